@@ -1,0 +1,456 @@
+// mtts_gemm.cu — the one tensor-core kernel of libmtts: a warp-specialised tcgen05 + TMA GEMM
+//
+//     C_z[M,N] (+)= alpha * sum_tap sum_kb  A(z,tap,kb)[M,K] * B(z,tap,kb)[N,K]^T
+//
+// which, by choice of TMA tensor maps / coordinate sources / operand majors, implements every dense
+// contraction of the FastSpeech2 hot path: Linear fwd/dgrad/wgrad, Conv1d (k taps as shifted TMA
+// loads with hardware zero fill = implicit im2col) fwd/dgrad/wgrad, and the batched attention
+// products QK^T, PV and their backward / tangent forms.  See include/mtts.h for the reference
+// call sites (SubLayers.py:39-41,54,88; Modules.py:16,23; modules.py:291-296; Layers.py:129-137).
+//
+// Layout of one CTA (192 threads, 1 CTA = 1 output tile of 128 x BN, persistent over its k-range):
+//   warp 0      TMA producer  (one elected lane)        global -> smem ring (128B-swizzled tiles)
+//   warp 1      MMA issuer    (one elected lane)        tcgen05.mma  smem x smem -> TMEM (fp32)
+//   warps 2..5  epilogue      (128 threads = 128 rows)  tcgen05.ld TMEM -> regs -> bias/act -> global
+// Pipelines: full[s]/empty[s] mbarriers for the smem ring, one tmem_full mbarrier MMA -> epilogue.
+//
+// bf16x3 mode (SPLIT == 3): operands arrive as hi/lo bf16 pairs; each k-step issues
+// hi*hi + hi*lo + lo*hi into the same TMEM accumulator (error ~2^-17, i.e. fp32-grade), which is
+// how the 1e-3 (fp32 relative) parity bar is met on bf16 tensor cores.
+#include "mtts_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;        // UMMA_M (cta_group::1)
+constexpr int BK = 64;         // bf16 elements per k-block = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_SMEM = 227 * 1024;
+
+struct OperandParams {
+  int32_t major;
+  int32_t src2, src3;
+  int32_t shift_src, shift_base, shift_step;
+};
+
+struct alignas(64) GemmParams {
+  CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
+  OperandParams a, b;
+  int32_t M, N, K;
+  int32_t ntaps, nkb, nz0, nz1, ksplit;
+  int32_t n_tiles;           // tiles along N
+  int32_t flags;
+  float alpha;
+  float* c_f32;
+  bf16* c_hi;
+  bf16* c_lo;
+  int64_t ldc, c_sz0, c_sz1;
+  const float* bias;
+  int64_t bias_sz0;
+  const bf16* gate;
+};
+
+template <int BN, int SPLIT>
+struct Cfg {
+  static constexpr int A_TILE = BM * BK * 2;                  // 16 KB
+  static constexpr int B_TILE = BN * BK * 2;
+  static constexpr int STAGE = (A_TILE + B_TILE) * (SPLIT == 3 ? 2 : 1);
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int STAGES_RAW = (MAX_SMEM - BAR_BYTES - 1024 /*align slack*/) / STAGE;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int SMEM = STAGES * STAGE + BAR_BYTES + 1024;
+  static_assert(STAGES >= 2, "need at least a double buffer");
+};
+
+__device__ __forceinline__ int pick_src(int src, int z0, int z1, int tap, int kb) {
+  return src == MTTS_SRC_Z0 ? z0 : src == MTTS_SRC_Z1 ? z1 : src == MTTS_SRC_TAP ? tap : src == MTTS_SRC_KB ? kb : 0;
+}
+
+template <int BN, int SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_constant__ GemmParams p) {
+  using C = Cfg<BN, SPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bar_base = smem + C::STAGES * C::STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tile = blockIdx.x;
+  const int m_tile = tile / p.n_tiles;
+  const int n_tile = tile - m_tile * p.n_tiles;
+  const int m0 = m_tile * BM;
+  const int n0 = n_tile * BN;
+  const int z0 = blockIdx.z % p.nz0;
+  const int z1 = blockIdx.z / p.nz0;
+
+  // this CTA's slice of the (tap, kb, kc) iteration space
+  const int kchunks = (p.K + BK - 1) / BK;
+  const int total_iters = p.ntaps * p.nkb * kchunks;
+  const int per_split = (total_iters + p.ksplit - 1) / p.ksplit;
+  const int it_begin = blockIdx.y * per_split;
+  const int it_end = min(total_iters, it_begin + per_split);
+  const int n_iters = max(0, it_end - it_begin);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_a_hi);
+    tma_prefetch_desc(&p.map_b_hi);
+    if (SPLIT == 3) {
+      tma_prefetch_desc(&p.map_a_lo);
+      tma_prefetch_desc(&p.map_b_lo);
+    }
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<BN>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer ==========================================
+    if (lane == 0 && n_iters > 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = it_begin; it < it_end; ++it) {
+        const int kc = it % kchunks;
+        const int rest = it / kchunks;
+        const int kb = rest % p.nkb;
+        const int tap = rest / p.nkb;
+
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], C::STAGE);
+
+        uint8_t* sa = smem + stage * C::STAGE;
+        uint8_t* sa_lo = sa + C::A_TILE;
+        uint8_t* sb = sa + C::A_TILE * (SPLIT == 3 ? 2 : 1);
+        uint8_t* sb_lo = sb + C::B_TILE;
+
+        {  // A operand
+          const int shift = p.a.shift_base + p.a.shift_step * pick_src(p.a.shift_src, z0, z1, tap, kb);
+          const int c2 = pick_src(p.a.src2, z0, z1, tap, kb);
+          const int c3 = pick_src(p.a.src3, z0, z1, tap, kb);
+          if (p.a.major == MTTS_MAJOR_K) {
+            tma_load_4d(sa, &p.map_a_hi, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
+            if (SPLIT == 3) tma_load_4d(sa_lo, &p.map_a_lo, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) {
+              tma_load_4d(sa + i * (BK * 128), &p.map_a_hi, &full_bar[stage], m0 + 64 * i, kc * BK + shift, c2, c3);
+              if (SPLIT == 3)
+                tma_load_4d(sa_lo + i * (BK * 128), &p.map_a_lo, &full_bar[stage], m0 + 64 * i, kc * BK + shift, c2, c3);
+            }
+          }
+        }
+        {  // B operand
+          const int shift = p.b.shift_base + p.b.shift_step * pick_src(p.b.shift_src, z0, z1, tap, kb);
+          const int c2 = pick_src(p.b.src2, z0, z1, tap, kb);
+          const int c3 = pick_src(p.b.src3, z0, z1, tap, kb);
+          if (p.b.major == MTTS_MAJOR_K) {
+            tma_load_4d(sb, &p.map_b_hi, &full_bar[stage], kc * BK, n0 + shift, c2, c3);
+            if (SPLIT == 3) tma_load_4d(sb_lo, &p.map_b_lo, &full_bar[stage], kc * BK, n0 + shift, c2, c3);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) {
+              tma_load_4d(sb + i * (BK * 128), &p.map_b_hi, &full_bar[stage], n0 + 64 * i, kc * BK + shift, c2, c3);
+              if (SPLIT == 3)
+                tma_load_4d(sb_lo + i * (BK * 128), &p.map_b_lo, &full_bar[stage], n0 + 64 * i, kc * BK + shift, c2, c3);
+            }
+          }
+        }
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer ============================================
+    if (lane == 0 && n_iters > 0) {
+      const uint32_t idesc = make_idesc_bf16(BN, p.a.major == MTTS_MAJOR_MN, p.b.major == MTTS_MAJOR_MN);
+      // per-UMMA_K advance of the descriptor start address and LBO, by operand major
+      const uint32_t a_step = (p.a.major == MTTS_MAJOR_K) ? UMMA_K * 2 : UMMA_K * 128;
+      const uint32_t b_step = (p.b.major == MTTS_MAJOR_K) ? UMMA_K * 2 : UMMA_K * 128;
+      const uint32_t a_lbo = (p.a.major == MTTS_MAJOR_K) ? 16 : BK * 128;
+      const uint32_t b_lbo = (p.b.major == MTTS_MAJOR_K) ? 16 : BK * 128;
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t accumulate = 0;
+      for (int it = 0; it < n_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * C::STAGE);
+        const uint32_t sa_lo = sa + C::A_TILE;
+        const uint32_t sb = sa + C::A_TILE * (SPLIT == 3 ? 2 : 1);
+        const uint32_t sb_lo = sb + C::B_TILE;
+#pragma unroll
+        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+          const uint64_t da = make_umma_desc(sa + kk * a_step, a_lbo, 1024);
+          const uint64_t db = make_umma_desc(sb + kk * b_step, b_lbo, 1024);
+          umma_bf16(tmem_base, da, db, idesc, accumulate);
+          accumulate = 1;
+          if (SPLIT == 3) {
+            const uint64_t da_lo = make_umma_desc(sa_lo + kk * a_step, a_lbo, 1024);
+            const uint64_t db_lo = make_umma_desc(sb_lo + kk * b_step, b_lbo, 1024);
+            umma_bf16(tmem_base, da, db_lo, idesc, 1);
+            umma_bf16(tmem_base, da_lo, db, idesc, 1);
+          }
+        }
+        umma_commit(&empty_bar[stage]);   // frees this smem slot once the MMAs above have read it
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tmem_full_bar);          // accumulator complete -> epilogue
+    }
+  } else {
+    // ===================================== epilogue ==============================================
+    // TMEM lane quarter accessible to a warp is (warp_id % 4); warps 2,3,4,5 -> quarters 2,3,0,1.
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    if (n_iters > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      const bool row_ok = row < p.M;
+      const int64_t c_off = int64_t(z0) * p.c_sz0 + int64_t(z1) * p.c_sz1 + int64_t(row) * p.ldc;
+      const float* bias = p.bias ? p.bias + int64_t(z0) * p.bias_sz0 : nullptr;
+      const bool vec_ok = ((p.ldc & 7) == 0) && ((p.c_sz0 & 7) == 0) && ((p.c_sz1 & 7) == 0);
+      const float bias_row = (bias && (p.flags & MTTS_EPI_BIAS_ROW) && row_ok) ? bias[row] : 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        __syncwarp();                       // tcgen05.ld is .sync.aligned: reconverge after guards
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (!row_ok || col0 >= p.N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        if (bias) {
+          if (p.flags & MTTS_EPI_BIAS_ROW) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += bias_row;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += __ldg(bias + col0 + j);
+          }
+        }
+        if (p.flags & MTTS_EPI_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.flags & MTTS_EPI_GATE) {
+          const bf16* g = p.gate + c_off + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N && !(__bfloat162float(g[j]) > 0.f)) v[j] = 0.f;
+        }
+        const bool full = (col0 + 32 <= p.N) && vec_ok;
+        if (p.c_f32) {
+          float* dst = p.c_f32 + c_off + col0;
+          if (p.flags & MTTS_EPI_ACCUM) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) atomicAdd(dst + j, v[j]);
+          } else if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) dst[j] = v[j];
+          }
+        }
+        if (p.c_hi) {
+          bf16* dh = p.c_hi + c_off + col0;
+          bf16* dl = p.c_lo ? p.c_lo + c_off + col0 : nullptr;
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t h[4], l[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                bf16 h0, l0, h1, l1;
+                split_bf16(v[j + 2 * t], h0, l0);
+                split_bf16(v[j + 2 * t + 1], h1, l1);
+                h[t] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
+                l[t] = uint32_t(__bfloat16_as_ushort(l0)) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
+              }
+              *reinterpret_cast<uint4*>(dh + j) = make_uint4(h[0], h[1], h[2], h[3]);
+              if (dl) *reinterpret_cast<uint4*>(dl + j) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) {
+                bf16 h0, l0;
+                split_bf16(v[j], h0, l0);
+                dh[j] = h0;
+                if (dl) dl[j] = l0;
+              }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(f);
+  }
+  return fn;
+}
+
+int encode_operand_map(CUtensorMap* map, const void* ptr, const mtts_operand& op, int block_mn, const char* name) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    mtts_set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return MTTS_ECUDA;
+  }
+  MTTS_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "gemm: operand %s base not 16B aligned", name);
+  MTTS_REQUIRE(op.strides[0] == 1, "gemm: operand %s strides[0] must be 1", name);
+  cuuint64_t gdim[4];
+  cuuint64_t gstride[3];
+  for (int i = 0; i < 4; ++i) {
+    MTTS_REQUIRE(op.dims[i] >= 1, "gemm: operand %s dims[%d]=%lld < 1", name, i, (long long)op.dims[i]);
+    gdim[i] = static_cast<cuuint64_t>(op.dims[i]);
+  }
+  for (int i = 1; i < 4; ++i) {
+    int64_t st = op.strides[i];
+    if (op.dims[i] == 1 && (st <= 0 || (st % 8) != 0)) st = 8;   // unused dim: any legal stride
+    MTTS_REQUIRE(st > 0 && (st % 8) == 0, "gemm: operand %s strides[%d]=%lld must be a positive multiple of 8",
+                 name, i, (long long)st);
+    gstride[i - 1] = static_cast<cuuint64_t>(st) * 2;
+  }
+  cuuint32_t box[4] = {64u, op.major == MTTS_MAJOR_K ? static_cast<cuuint32_t>(block_mn) : 64u, 1u, 1u};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mtts_set_error("cuTensorMapEncodeTiled(%s) failed: CUresult %d (dims %lld %lld %lld %lld strides %lld %lld %lld)",
+                   name, (int)r, (long long)op.dims[0], (long long)op.dims[1], (long long)op.dims[2],
+                   (long long)op.dims[3], (long long)op.strides[1], (long long)op.strides[2],
+                   (long long)op.strides[3]);
+    return MTTS_ECUDA;
+  }
+  return MTTS_OK;
+}
+
+template <int BN, int SPLIT>
+int launch(const GemmParams& p, dim3 grid, cudaStream_t stream) {
+  using C = Cfg<BN, SPLIT>;
+  static bool configured = false;
+  if (!configured) {
+    MTTS_CHECK_CUDA(cudaFuncSetAttribute(mtts_gemm_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM));
+    configured = true;
+  }
+  mtts_gemm_kernel<BN, SPLIT><<<grid, NUM_THREADS, C::SMEM, stream>>>(p);
+  MTTS_CHECK_LAUNCH();
+  return MTTS_OK;
+}
+
+}  // namespace
+
+extern "C" int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(d != nullptr, "gemm: null descriptor");
+  MTTS_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "gemm: bad M/N/K %d %d %d", d->M, d->N, d->K);
+  MTTS_REQUIRE(d->ntaps >= 1 && d->nkb >= 1 && d->nz0 >= 1 && d->nz1 >= 1, "gemm: bad loop extents");
+  MTTS_REQUIRE(d->split == 1 || d->split == 3, "gemm: split must be 1 or 3");
+  MTTS_REQUIRE(d->a.hi && d->b.hi, "gemm: null operand");
+  MTTS_REQUIRE(d->split == 1 || (d->a.lo && d->b.lo), "gemm: split=3 needs lo operands");
+  MTTS_REQUIRE(d->c_f32 || d->c_hi, "gemm: no output");
+  MTTS_REQUIRE(!(d->c_lo && !d->c_hi), "gemm: c_lo without c_hi");
+  MTTS_REQUIRE(!(d->flags & MTTS_EPI_GATE) || d->gate, "gemm: GATE flag without gate pointer");
+  const int ksplit = d->ksplit < 1 ? 1 : d->ksplit;
+  MTTS_REQUIRE(ksplit == 1 || ((d->flags & MTTS_EPI_ACCUM) && d->c_f32 && !d->c_hi),
+               "gemm: ksplit>1 requires ACCUM into c_f32 only");
+  MTTS_REQUIRE(!(d->flags & MTTS_EPI_ACCUM) || d->c_f32, "gemm: ACCUM requires c_f32");
+
+  int bn = d->block_n;
+  if (bn == 0) {
+    if (d->N <= 64) bn = 64;
+    else if (d->N <= 128 || d->split == 3) bn = 128;
+    else bn = 256;
+  }
+  MTTS_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: block_n must be 64/128/256");
+  MTTS_REQUIRE(!(d->split == 3 && bn == 256), "gemm: block_n 256 not available in split=3 mode");
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = encode_operand_map(&p.map_a_hi, d->a.hi, d->a, BM, "A.hi")) != MTTS_OK) return rc;
+  if ((rc = encode_operand_map(&p.map_b_hi, d->b.hi, d->b, bn, "B.hi")) != MTTS_OK) return rc;
+  if (d->split == 3) {
+    if ((rc = encode_operand_map(&p.map_a_lo, d->a.lo, d->a, BM, "A.lo")) != MTTS_OK) return rc;
+    if ((rc = encode_operand_map(&p.map_b_lo, d->b.lo, d->b, bn, "B.lo")) != MTTS_OK) return rc;
+  }
+  p.a = {d->a.major, d->a.src2, d->a.src3, d->a.shift_src, d->a.shift_base, d->a.shift_step};
+  p.b = {d->b.major, d->b.src2, d->b.src3, d->b.shift_src, d->b.shift_base, d->b.shift_step};
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.ntaps = d->ntaps; p.nkb = d->nkb; p.nz0 = d->nz0; p.nz1 = d->nz1;
+  const int kchunks = mtts_cdiv(d->K, BK);
+  const int total_iters = d->ntaps * d->nkb * kchunks;
+  p.ksplit = ksplit > total_iters ? total_iters : ksplit;
+  // every split must own >= 1 iteration
+  while (p.ksplit > 1 && mtts_cdiv(total_iters, p.ksplit) * (p.ksplit - 1) >= total_iters) --p.ksplit;
+  p.n_tiles = mtts_cdiv(d->N, bn);
+  p.flags = d->flags;
+  p.alpha = d->alpha;
+  p.c_f32 = d->c_f32;
+  p.c_hi = static_cast<bf16*>(d->c_hi);
+  p.c_lo = static_cast<bf16*>(d->c_lo);
+  p.ldc = d->ldc; p.c_sz0 = d->c_sz0; p.c_sz1 = d->c_sz1;
+  p.bias = d->bias; p.bias_sz0 = d->bias_sz0;
+  p.gate = static_cast<const bf16*>(d->gate);
+
+  const int m_tiles = mtts_cdiv(d->M, BM);
+  dim3 grid(m_tiles * p.n_tiles, p.ksplit, d->nz0 * d->nz1);
+  MTTS_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "gemm: grid too large");
+
+  if (d->split == 1) {
+    if (bn == 64) return launch<64, 1>(p, grid, stream);
+    if (bn == 128) return launch<128, 1>(p, grid, stream);
+    return launch<256, 1>(p, grid, stream);
+  } else {
+    if (bn == 64) return launch<64, 3>(p, grid, stream);
+    return launch<128, 3>(p, grid, stream);
+  }
+}

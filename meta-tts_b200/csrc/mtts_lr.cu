@@ -1,0 +1,174 @@
+// mtts_lr.cu — LengthRegulator: duration-driven row gather (forward) and segment sum (backward).
+//
+// Reference: lightning/model/modules.py:167-194 (Python double loop, one `.item()` host sync per
+// phoneme, `expand` + `cat`) followed by utils/tools.py:304-322 `pad`.  Closed form used here
+// (SURVEY.md §8 a11):  idx[b,t] = searchsorted(cumsum(max(int(d[b,:]),0)), t, right=True),
+// out[b,t,:] = x[b,idx,:] for t < mel_len[b] = sum_j max(int(d[b,j]),0), else 0.
+// The index path is integer arithmetic and bit-exact; the payload is copied unchanged (exact).
+//
+// HBM-bound: forward moves B*(L_touched + T)*C*4 bytes.  One warp per output row, 128-bit
+// vectorised loads/stores, no host sync, shapes static => CUDA-graph capturable.
+#include "mtts_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ long long dur_at(const int64_t* di, const float* df, int i) {
+  long long v = di ? static_cast<long long>(di[i]) : static_cast<long long>(df[i]);  // int() truncates toward 0
+  return v > 0 ? v : 0;
+}
+
+// One CTA per batch row: inclusive scan of the clamped durations in shared memory, then every
+// thread binary-searches its frames.  L <= 4096.
+__global__ void lr_index_kernel(const int64_t* __restrict__ di, const float* __restrict__ df, int L, int T,
+                                int32_t* __restrict__ idx, int64_t* __restrict__ mel_len) {
+  extern __shared__ long long cum[];   // [L]
+  const int b = blockIdx.x;
+  // serial-in-chunks inclusive scan (L is small: <= a few hundred phonemes)
+  __shared__ long long chunk_tot[32];
+  const int nthr = blockDim.x;
+  const int per = (L + nthr - 1) / nthr;
+  const int beg = threadIdx.x * per;
+  const int end = min(L, beg + per);
+  long long s = 0;
+  for (int i = beg; i < end; ++i) {
+    s += dur_at(di, df, b * L + i);
+    cum[i] = s;
+  }
+  // exclusive scan of per-thread totals via warp shuffles + one smem hop
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  long long incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    long long n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) chunk_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    long long t = lane < (nthr >> 5) ? chunk_tot[lane] : 0;
+    long long ti = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      long long n = __shfl_up_sync(0xffffffffu, ti, o);
+      if (lane >= o) ti += n;
+    }
+    chunk_tot[lane] = ti - t;   // exclusive
+  }
+  __syncthreads();
+  const long long offset = chunk_tot[warp] + (incl - s);
+  for (int i = beg; i < end; ++i) cum[i] += offset;
+  __syncthreads();
+  const long long total = L > 0 ? cum[L - 1] : 0;
+  if (threadIdx.x == 0) mel_len[b] = total;
+  for (int t = threadIdx.x; t < T; t += nthr) {
+    int r = -1;
+    if (t < total) {
+      // first j with cum[j] > t   (searchsorted right)
+      int lo = 0, hi = L;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (cum[mid] <= t) lo = mid + 1; else hi = mid;
+      }
+      r = lo;
+    }
+    idx[b * T + t] = r;
+  }
+}
+
+// out[b,t,:] = idx>=0 ? x[b,idx,:] : 0.  One warp per (b,t) row, float4 lanes.
+__global__ void lr_gather_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int L, int T, int C,
+                                 long long rows, float* __restrict__ out) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int b = static_cast<int>(row / T);
+  const int j = idx[row];
+  float* o = out + row * C;
+  if ((C & 3) == 0) {
+    float4* o4 = reinterpret_cast<float4*>(o);
+    if (j >= 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(x + (static_cast<long long>(b) * L + j) * C);
+      for (int c = lane; c < (C >> 2); c += 32) o4[c] = __ldg(s4 + c);
+    } else {
+      for (int c = lane; c < (C >> 2); c += 32) o4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else {
+    const float* s = x + (static_cast<long long>(b) * L + (j >= 0 ? j : 0)) * C;
+    for (int c = lane; c < C; c += 32) o[c] = j >= 0 ? s[c] : 0.f;
+  }
+}
+
+// dx[b,j,:] = sum over the frames of phoneme j (a contiguous run [start, start+d) clipped to T):
+// one warp per (b,j), serial over its run => deterministic, no atomics.
+__global__ void lr_segsum_kernel(const float* __restrict__ dy, const int64_t* __restrict__ di,
+                                 const float* __restrict__ df, int L, int T, int C, long long rows,
+                                 float* __restrict__ dx) {
+  const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int b = static_cast<int>(row / L);
+  const int j = static_cast<int>(row - static_cast<long long>(b) * L);
+  // start = sum_{i<j} d[b,i]  (warp-cooperative)
+  long long part = 0;
+  for (int i = lane; i < j; i += 32) part += dur_at(di, df, b * L + i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  const long long start = part;
+  long long len = dur_at(di, df, b * L + j);
+  long long stop = start + len;
+  if (stop > T) stop = T;
+  float* o = dx + row * C;
+  for (int c = lane * 4; c < C; c += 128) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c + 3 < C && (C & 3) == 0) {
+      for (long long t = start; t < stop; ++t) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(dy + (static_cast<long long>(b) * T + t) * C + c));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(o + c) = acc;
+    } else {
+      for (int cc = c; cc < min(C, c + 4); ++cc) {
+        float a = 0.f;
+        for (long long t = start; t < stop; ++t) a += dy[(static_cast<long long>(b) * T + t) * C + cc];
+        o[cc] = a;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int mtts_length_regulate_index(const int64_t* dur_i64, const float* dur_f32, int B, int L, int T,
+                                          int32_t* idx, int64_t* mel_len, mtts_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE((dur_i64 != nullptr) != (dur_f32 != nullptr), "length_regulate: pass exactly one duration pointer");
+  MTTS_REQUIRE(B > 0 && L > 0 && T > 0 && L <= 4096, "length_regulate: bad B/L/T %d %d %d", B, L, T);
+  lr_index_kernel<<<B, 256, L * sizeof(long long), stream>>>(dur_i64, dur_f32, L, T, idx, mel_len);
+  MTTS_CHECK_LAUNCH();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_length_regulate_fwd(const float* x, const int32_t* idx, int B, int L, int T, int C, float* out,
+                                        mtts_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(B > 0 && L > 0 && T > 0 && C > 0, "length_regulate_fwd: bad shape");
+  const long long rows = static_cast<long long>(B) * T;
+  const int threads = 256;
+  const long long blocks = mtts_cdiv64(rows * 32, threads);
+  lr_gather_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(x, idx, L, T, C, rows, out);
+  MTTS_CHECK_LAUNCH();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_length_regulate_bwd(const float* dy, const int64_t* dur_i64, const float* dur_f32, int B, int L,
+                                        int T, int C, float* dx, mtts_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE((dur_i64 != nullptr) != (dur_f32 != nullptr), "length_regulate_bwd: pass exactly one duration pointer");
+  MTTS_REQUIRE(B > 0 && L > 0 && T > 0 && C > 0, "length_regulate_bwd: bad shape");
+  const long long rows = static_cast<long long>(B) * L;
+  const int threads = 256;
+  const long long blocks = mtts_cdiv64(rows * 32, threads);
+  lr_segsum_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(dy, dur_i64, dur_f32, L, T, C, rows, dx);
+  MTTS_CHECK_LAUNCH();
+  return MTTS_OK;
+}

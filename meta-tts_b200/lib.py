@@ -1,0 +1,101 @@
+"""ctypes binding of libmtts.so (include/mtts.h).  Fails loudly: there is no CPU fallback.
+
+The library is built in-tree by `meta-tts_b200/build.py` (nvcc, sm_100a).  Importing this module
+does not need a GPU; calling any compute entry point without one raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmtts.so")
+
+# enums (include/mtts.h)
+SRC_ZERO, SRC_Z0, SRC_Z1, SRC_TAP, SRC_KB = 0, 1, 2, 3, 4
+MAJOR_K, MAJOR_MN = 0, 1
+EPI_RELU, EPI_ACCUM, EPI_GATE, EPI_BIAS_ROW = 1, 2, 4, 8
+
+
+class Operand(C.Structure):
+    _fields_ = [
+        ("hi", C.c_void_p),
+        ("lo", C.c_void_p),
+        ("major", C.c_int32),
+        ("src2", C.c_int32),
+        ("src3", C.c_int32),
+        ("shift_src", C.c_int32),
+        ("shift_base", C.c_int32),
+        ("shift_step", C.c_int32),
+        ("reserved", C.c_int32),
+        ("dims", C.c_int64 * 4),
+        ("strides", C.c_int64 * 4),
+    ]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("ntaps", C.c_int32), ("nkb", C.c_int32), ("nz0", C.c_int32), ("nz1", C.c_int32),
+        ("split", C.c_int32), ("block_n", C.c_int32), ("ksplit", C.c_int32), ("flags", C.c_int32),
+        ("alpha", C.c_float),
+        ("a", Operand), ("b", Operand),
+        ("c_f32", C.c_void_p), ("c_hi", C.c_void_p), ("c_lo", C.c_void_p),
+        ("ldc", C.c_int64), ("c_sz0", C.c_int64), ("c_sz1", C.c_int64),
+        ("bias", C.c_void_p), ("bias_sz0", C.c_int64),
+        ("gate", C.c_void_p),
+    ]
+
+
+class MttsError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libmtts.so; raise if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MttsError(
+            f"{LIB_PATH} is missing: build it with `python meta-tts_b200/build.py` "
+            "(or __graft_entry__.build()).  There is no CPU / PyTorch fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    lib.mtts_last_error.restype = C.c_char_p
+    lib.mtts_version.restype = C.c_int
+    _declare(lib)
+    _lib = lib
+    return lib
+
+
+# name -> argtypes; every function returns int (0 = ok)
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+SIGNATURES: dict[str, list] = {
+    "mtts_check_device": [],
+    "mtts_gemm": [C.POINTER(GemmDesc), _vp],
+    "mtts_length_regulate_index": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "mtts_length_regulate_fwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "mtts_length_regulate_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
+}
+
+
+def _declare(lib: C.CDLL) -> None:
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError => header / library mismatch: fail loudly
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().mtts_last_error().decode(errors="replace")
+        raise MttsError(f"libmtts {what} failed (rc={rc}): {msg}")
+
+
+def call(name: str, *args) -> None:
+    lib = load()
+    check(getattr(lib, name)(*args), name)

@@ -1,0 +1,217 @@
+"""GPU parity tests of the generic tcgen05 GEMM (mtts_gemm) through the C ABI.
+
+Checker: float64 torch matmul / conv restated in-line on the same inputs (for split=1 the inputs
+are the bf16-rounded values, so the only difference is fp32 accumulation order; for split=3 the
+inputs are fp32 and the kernel must be fp32-grade).  Tolerances are written per case.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from meta_tts_b200 import lib as L  # noqa: E402
+from meta_tts_b200 import ops  # noqa: E402
+
+
+def _rel(a, b):
+    a = a.double()
+    b = b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _prep(x, split):
+    """fp32 -> (hi, lo, value the kernel effectively sees)."""
+    hi, lo = ops.split_bf16(x)
+    if split == 1:
+        return hi, None, hi.double()
+    return hi, lo, x.double()
+
+
+TOL = {1: 2e-5, 3: 2e-5}   # relative Frobenius error vs float64 reference
+
+
+def _check(name, got, ref, split):
+    r = _rel(got, ref)
+    print(f"[gemm] {name:32s} split={split} rel_err={r:.3e}")
+    assert math.isfinite(r) and r < TOL[split], f"{name}: rel err {r}"
+
+
+@pytest.mark.parametrize("split", [1, 3])
+@pytest.mark.parametrize("block_n", [64, 128, 256])
+def test_linear_fwd(cuda_device, split, block_n):
+    if split == 3 and block_n == 256:
+        pytest.skip("BN=256 not built for split=3")
+    torch.manual_seed(0)
+    M, N, K = 300, 256, 320
+    X = torch.randn(M, K, device=cuda_device)
+    W = torch.randn(N, K, device=cuda_device) / math.sqrt(K)
+    bias = torch.randn(N, device=cuda_device)
+    xh, xl, xr = _prep(X, split)
+    wh, wl, wr = _prep(W, split)
+    out = torch.empty(M, N, device=cuda_device)
+    oh = torch.empty(M, N, device=cuda_device, dtype=torch.bfloat16)
+    ol = torch.empty(M, N, device=cuda_device, dtype=torch.bfloat16)
+    ops.gemm(ops.Opnd(xh, xl, L.MAJOR_K, (K, M), (1, K)), ops.Opnd(wh, wl, L.MAJOR_K, (K, N), (1, K)),
+             M, N, K, c_f32=out, c_hi=oh, c_lo=ol, ldc=N, bias=bias, flags=L.EPI_RELU, split=split,
+             block_n=block_n)
+    ref = torch.relu(xr @ wr.t() + bias.double())
+    _check(f"linear_fwd bn={block_n}", out, ref, split)
+    _check(f"linear_fwd hi+lo bn={block_n}", oh.float() + ol.float(), out, 3)
+    assert _rel(oh.float(), out) < 4e-3
+
+
+@pytest.mark.parametrize("split", [1, 3])
+def test_linear_dgrad_mn_major_b(cuda_device, split):
+    torch.manual_seed(1)
+    M, N, K = 260, 256, 192          # dX[M,K] = dY[M,N] W[N,K]
+    dY = torch.randn(M, N, device=cuda_device)
+    W = torch.randn(N, K, device=cuda_device) / math.sqrt(N)
+    yh, yl, yr = _prep(dY, split)
+    wh, wl, wr = _prep(W, split)
+    out = torch.empty(M, K, device=cuda_device)
+    ops.gemm(ops.Opnd(yh, yl, L.MAJOR_K, (N, M), (1, N)), ops.Opnd(wh, wl, L.MAJOR_MN, (K, N), (1, K)),
+             M, K, N, c_f32=out, ldc=K, split=split)
+    _check("linear_dgrad (B MN-major)", out, yr @ wr, split)
+
+
+@pytest.mark.parametrize("split", [1, 3])
+@pytest.mark.parametrize("ksplit", [1, 4])
+def test_linear_wgrad_mn_major_ab(cuda_device, split, ksplit):
+    torch.manual_seed(2)
+    T, N, K = 700, 256, 192          # dW[N,K] = dY[T,N]^T X[T,K]
+    dY = torch.randn(T, N, device=cuda_device)
+    X = torch.randn(T, K, device=cuda_device)
+    yh, yl, yr = _prep(dY, split)
+    xh, xl, xr = _prep(X, split)
+    out = torch.zeros(N, K, device=cuda_device)
+    ops.gemm(ops.Opnd(yh, yl, L.MAJOR_MN, (N, T), (1, N)), ops.Opnd(xh, xl, L.MAJOR_MN, (K, T), (1, K)),
+             N, K, T, c_f32=out, ldc=K, split=split, ksplit=ksplit, flags=L.EPI_ACCUM, alpha=0.5)
+    _check(f"linear_wgrad ksplit={ksplit}", out, 0.5 * (yr.t() @ xr), split)
+
+
+def _conv_ref(x, w_kio, bias, pad):
+    # x [B,T,Cin], w [k, Cout, Cin]
+    w = w_kio.permute(1, 2, 0).contiguous()   # [Cout, Cin, k]
+    y = torch.nn.functional.conv1d(x.transpose(1, 2), w, bias, padding=pad)
+    return y.transpose(1, 2).contiguous()
+
+
+@pytest.mark.parametrize("split", [1, 3])
+@pytest.mark.parametrize("k,cin,cout,T", [(9, 256, 256, 200), (5, 80, 512, 150), (3, 256, 256, 37)])
+def test_conv_fwd_dgrad_wgrad(cuda_device, split, k, cin, cout, T):
+    torch.manual_seed(3)
+    B, p = 3, (k - 1) // 2
+    X = torch.randn(B, T, cin, device=cuda_device)
+    W = torch.randn(k, cout, cin, device=cuda_device) / math.sqrt(cin * k)
+    bias = torch.randn(cout, device=cuda_device)
+    xh, xl, xr = _prep(X, split)
+    wh, wl, wr = _prep(W, split)
+    # forward
+    Y = torch.empty(B, T, cout, device=cuda_device)
+    ops.gemm(ops.Opnd(xh, xl, L.MAJOR_K, (cin, T, B), (1, cin, T * cin), src2=L.SRC_Z0,
+                      shift_src=L.SRC_TAP, shift_base=-p, shift_step=1),
+             ops.Opnd(wh, wl, L.MAJOR_K, (cin, cout, k), (1, cin, cout * cin), src2=L.SRC_TAP),
+             T, cout, cin, c_f32=Y, ldc=cout, c_sz0=T * cout, bias=bias, ntaps=k, nz0=B, split=split)
+    ref = _conv_ref(xr, wr, bias.double(), p)
+    _check(f"conv_fwd k={k} {cin}->{cout}", Y, ref, split)
+    # dgrad: dX[b,t] = sum_j dY[b,t-j+p] W_j
+    dY = torch.randn(B, T, cout, device=cuda_device)
+    yh, yl, yr = _prep(dY, split)
+    dX = torch.empty(B, T, cin, device=cuda_device)
+    ops.gemm(ops.Opnd(yh, yl, L.MAJOR_K, (cout, T, B), (1, cout, T * cout), src2=L.SRC_Z0,
+                      shift_src=L.SRC_TAP, shift_base=p, shift_step=-1),
+             ops.Opnd(wh, wl, L.MAJOR_MN, (cin, cout, k), (1, cin, cout * cin), src2=L.SRC_TAP),
+             T, cin, cout, c_f32=dX, ldc=cin, c_sz0=T * cin, ntaps=k, nz0=B, split=split)
+    xr_ = xr.clone().requires_grad_(True)
+    wr_ = wr.clone().requires_grad_(True)
+    _conv_ref(xr_, wr_, bias.double(), p).backward(yr)
+    _check(f"conv_dgrad k={k}", dX, xr_.grad, split)
+    # wgrad: dW[j] = sum_{b,t} dY[b,t]^T X[b,t+j-p]
+    dW = torch.zeros(k, cout, cin, device=cuda_device)
+    ops.gemm(ops.Opnd(yh, yl, L.MAJOR_MN, (cout, T, B), (1, cout, T * cout), src2=L.SRC_KB),
+             ops.Opnd(xh, xl, L.MAJOR_MN, (cin, T, B), (1, cin, T * cin), src2=L.SRC_KB,
+                      shift_src=L.SRC_Z0, shift_base=-p, shift_step=1),
+             cout, cin, T, c_f32=dW, ldc=cin, c_sz0=cout * cin, nkb=B, nz0=k, split=split,
+             flags=L.EPI_ACCUM, ksplit=2)
+    _check(f"conv_wgrad k={k}", dW, wr_.grad, split)
+
+
+@pytest.mark.parametrize("split", [1, 3])
+@pytest.mark.parametrize("Lq", [128, 200])
+def test_attention_products(cuda_device, split, Lq):
+    torch.manual_seed(4)
+    B, H, dk = 2, 2, 128
+    row = 3 * H * dk
+    QKV = torch.randn(B * Lq, row, device=cuda_device)
+    qh, ql, qr = _prep(QKV, split)
+    Lp = (Lq + 7) // 8 * 8
+    S = torch.zeros(B, H, Lq, Lp, device=cuda_device)
+    scale = 1.0 / math.sqrt(dk)
+    ops.gemm(ops.Opnd(qh, ql, L.MAJOR_K, (dk, Lq, H, B), (1, row, dk, Lq * row), src2=L.SRC_Z0, src3=L.SRC_Z1),
+             ops.Opnd(qh, ql, L.MAJOR_K, (dk, Lq, H, B), (1, row, dk, Lq * row), src2=L.SRC_Z0, src3=L.SRC_Z1,
+                      offset=H * dk),
+             Lq, Lq, dk, c_f32=S, ldc=Lp, c_sz0=Lq * Lp, c_sz1=H * Lq * Lp, alpha=scale, nz0=H, nz1=B,
+             split=split)
+    q4 = qr.view(B, Lq, 3, H, dk)
+    Sref = torch.einsum("blhd,bmhd->bhlm", q4[:, :, 0], q4[:, :, 1]) * scale
+    _check(f"attn QK^T L={Lq}", S[..., :Lq], Sref, split)
+    # P V with V MN-major
+    P = torch.softmax(Sref.float(), dim=-1)
+    Pp = torch.zeros(B, H, Lq, Lp, device=cuda_device)
+    Pp[..., :Lq] = P
+    ph, pl, pr = _prep(Pp, split)
+    O = torch.empty(B * Lq, H * dk, device=cuda_device)
+    ops.gemm(ops.Opnd(ph, pl, L.MAJOR_K, (Lq, Lq, H, B), (1, Lp, Lq * Lp, H * Lq * Lp), src2=L.SRC_Z0, src3=L.SRC_Z1),
+             ops.Opnd(qh, ql, L.MAJOR_MN, (dk, Lq, H, B), (1, row, dk, Lq * row), src2=L.SRC_Z0, src3=L.SRC_Z1,
+                      offset=2 * H * dk),
+             Lq, dk, Lq, c_f32=O, ldc=H * dk, c_sz0=dk, c_sz1=Lq * H * dk, nz0=H, nz1=B, split=split)
+    Oref = torch.einsum("bhlm,bmhd->blhd", pr[..., :Lq], q4[:, :, 2]).reshape(B * Lq, H * dk)
+    _check(f"attn PV L={Lq}", O, Oref, split)
+    # dV = P^T dO  (A MN-major from P, B MN-major from dO) -> [B, L, H, dk] layout
+    dO = torch.randn(B * Lq, H * dk, device=cuda_device)
+    dh, dl, dr = _prep(dO, split)
+    dV = torch.empty(B * Lq, H * dk, device=cuda_device)
+    ops.gemm(ops.Opnd(ph, pl, L.MAJOR_MN, (Lq, Lq, H, B), (1, Lp, Lq * Lp, H * Lq * Lp), src2=L.SRC_Z0, src3=L.SRC_Z1),
+             ops.Opnd(dh, dl, L.MAJOR_MN, (dk, Lq, H, B), (1, H * dk, dk, Lq * H * dk), src2=L.SRC_Z0, src3=L.SRC_Z1),
+             Lq, dk, Lq, c_f32=dV, ldc=H * dk, c_sz0=dk, c_sz1=Lq * H * dk, nz0=H, nz1=B, split=split)
+    dVref = torch.einsum("bhlm,blhd->bmhd", pr[..., :Lq], dr.view(B, Lq, H, dk)).reshape(B * Lq, H * dk)
+    _check(f"attn dV L={Lq}", dV, dVref, split)
+
+
+@pytest.mark.parametrize("split", [1, 3])
+def test_odd_sizes_and_gate(cuda_device, split):
+    torch.manual_seed(5)
+    M, N, K = 40, 80, 80
+    X = torch.randn(M, K, device=cuda_device)
+    W = torch.randn(N, K, device=cuda_device)
+    G = torch.randn(M, N, device=cuda_device)
+    xh, xl, xr = _prep(X, split)
+    wh, wl, wr = _prep(W, split)
+    out = torch.empty(M, N, device=cuda_device)
+    ops.gemm(ops.Opnd(xh, xl, L.MAJOR_K, (K, M), (1, K)), ops.Opnd(wh, wl, L.MAJOR_K, (K, N), (1, K)),
+             M, N, K, c_f32=out, ldc=N, split=split, gate=G.to(torch.bfloat16), flags=L.EPI_GATE)
+    ref = (xr @ wr.t()) * (G.to(torch.bfloat16).double() > 0)
+    _check("odd sizes + gate", out, ref, split)
+
+
+def test_large_decoder_shapes(cuda_device):
+    """BASELINE config-2 decoder conv k=9 shape (B*T = 4*864 tokens, 256 -> 1024)."""
+    torch.manual_seed(6)
+    B, T, cin, cout, k, p = 4, 864, 256, 1024, 9, 4
+    X = torch.randn(B, T, cin, device=cuda_device)
+    W = torch.randn(k, cout, cin, device=cuda_device) / math.sqrt(cin * k)
+    bias = torch.randn(cout, device=cuda_device)
+    for split in (1, 3):
+        xh, xl, xr = _prep(X, split)
+        wh, wl, wr = _prep(W, split)
+        Hh = torch.empty(B, T, cout, device=cuda_device, dtype=torch.bfloat16)
+        Hl = torch.empty(B, T, cout, device=cuda_device, dtype=torch.bfloat16)
+        ops.gemm(ops.Opnd(xh, xl, L.MAJOR_K, (cin, T, B), (1, cin, T * cin), src2=L.SRC_Z0,
+                          shift_src=L.SRC_TAP, shift_base=-p, shift_step=1),
+                 ops.Opnd(wh, wl, L.MAJOR_K, (cin, cout, k), (1, cin, cout * cin), src2=L.SRC_TAP),
+                 T, cout, cin, c_hi=Hh, c_lo=Hl, ldc=cout, c_sz0=T * cout, bias=bias, ntaps=k, nz0=B,
+                 split=split, flags=L.EPI_RELU)
+        ref = torch.relu(_conv_ref(xr, wr, bias.double(), p))
+        _check("decoder conv9 (hi+lo out)", Hh.float() + Hl.float(), ref, split)
