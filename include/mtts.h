@@ -76,7 +76,8 @@ enum {
   MTTS_EPI_RELU     = 1,   /* v = max(v, 0)                                                      */
   MTTS_EPI_ACCUM    = 2,   /* c_f32 += v  (red.global.add.f32; required when ksplit > 1)          */
   MTTS_EPI_GATE     = 4,   /* v = gate[m,n] > 0 ? v : 0   (ReLU backward; gate has C geometry)     */
-  MTTS_EPI_BIAS_ROW = 8    /* bias indexed by row m instead of column n                          */
+  MTTS_EPI_BIAS_ROW = 8,   /* bias indexed by row m instead of column n                          */
+  MTTS_EPI_ADD_C    = 16   /* v += c_f32[m,n] (non-atomic read-modify-write; ksplit must be 1)     */
 };
 
 typedef struct {
@@ -115,6 +116,118 @@ int mtts_length_regulate_fwd(const float* x /* [B,L,C] */, const int32_t* idx /*
 /* dx[b,j,:] = sum_{t: idx[b,t]==j} dy[b,t,:]  (segment sum; deterministic, no atomics) */
 int mtts_length_regulate_bwd(const float* dy /* [B,T,C] */, const int64_t* dur_i64, const float* dur_f32,
                              int B, int L, int T, int C, float* dx /* [B,L,C] */, mtts_stream stream);
+
+
+/* ------------------------------------------------------------------------------------------
+ * Row-wise kernels (one warp per token row).  `lens`/`T`: row r belongs to batch b = r / T,
+ * frame t = r % T and is a PADDED row when t >= lens[b] (lens == NULL: no padding).
+ * *_tfwd = tangent forward (JVP of the forward), *_tbwd = tangent backward (JVP of the backward):
+ * together they give exact Hessian-vector products for second-order MAML without autograd.
+ * ------------------------------------------------------------------------------------------ */
+
+/* LayerNorm(y + res) then pad-row zeroing.  nn.LayerNorm SubLayers.py:55,91; modules.py:221,233;
+ * masked_fill Layers.py:25,28.  z_out = y + res (saved for backward), stats[r] = (mean, rstd). */
+int mtts_ln_fwd(const float* y, const float* res, const float* gamma, const float* beta, const int64_t* lens, int T,
+                int64_t R, int C, float eps, float* z_out, float* stats, float* out, void* out_hi, void* out_lo,
+                mtts_stream stream);
+/* relu_gate != 0: the LN input z is a ReLU output and the gradient is also passed through the ReLU
+ * (dz *= z > 0) — the Conv->ReLU->LayerNorm order of modules.py:209-235.  dgamma/dbeta/dbias are
+ * ACCUMULATED (atomicAdd); dbias = column sum of dz (bias of the producing Linear/Conv). */
+int mtts_ln_bwd(const float* dy, const float* z, const float* stats, const float* gamma, const int64_t* lens, int T, int64_t R,
+                int C, int relu_gate, float* dz, void* dz_hi, void* dz_lo, float* dgamma, float* dbeta, float* dbias,
+                mtts_stream stream);
+int mtts_ln_tfwd(const float* ydot, const float* resdot, const float* z, const float* stats, const float* gamma,
+                 const float* gdot, const float* bdot, const int64_t* lens, int T, int64_t R, int C, float* zdot_out, float* out,
+                 void* out_hi, void* out_lo, mtts_stream stream);
+int mtts_ln_tbwd(const float* dy, const float* ddy, const float* z, const float* zdot, const float* stats, const float* gamma,
+                 const float* gdot, const int64_t* lens, int T, int64_t R, int C, int relu_gate, float* ddz, void* ddz_hi,
+                 void* ddz_lo, float* ddgamma, float* ddbeta, float* ddbias, mtts_stream stream);
+
+/* VariancePredictor head: Linear(C,1) + masked_fill(mask, 0)  (modules.py:240-250).
+ * hdot != NULL selects the tangent form  out = hdot.w + h.wdot + bdot. */
+int mtts_rowdot_fwd(const float* h, const float* hdot, const float* w, const float* wdot, const float* b, const float* bdot,
+                    const int64_t* lens, int T, int64_t R, int C, float* out, mtts_stream stream);
+/* ddout == NULL: dh = dout*w, dw += sum dout*h, db += sum dout.
+ * ddout != NULL: tangent-backward  ddh = ddout*w + dout*wdot, ddw += sum(ddout*h + dout*hdot), ddb += sum ddout. */
+int mtts_rowdot_bwd(const float* dout, const float* ddout, const float* h, const float* hdot, const float* w, const float* wdot,
+                    const int64_t* lens, int T, int64_t R, int C, float* dh, float* dw, float* db, mtts_stream stream);
+
+/* Masked softmax over attention-score rows S[z][q][0..Lk) (leading dim ld), z = b*H + h, keys
+ * j >= klens[b] masked (Modules.py:16-22).  P / outputs are bf16 hi(/lo).
+ *   mode 0: P   = softmax(A)                                   A = S
+ *   mode 1: out = P*(A - sum(P*A))                             backward (A = dP) and tangent fwd (A = Sdot)
+ *   mode 2: out = Pd*(A - d) + P*(Bm - dd)                     tangent backward (A = dP, Bm = ddP) */
+int mtts_softmax(int mode, const float* A, const float* Bm, const void* p_hi, const void* p_lo, const void* pd_hi,
+                 const void* pd_lo, const int64_t* klens, int nz, int H, int Lq, int Lk, int ld, void* o_hi, void* o_lo,
+                 mtts_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Gathers, broadcasts, column sums
+ * ------------------------------------------------------------------------------------------ */
+/* out[r,:] = table[idx[r],:] (+ base[r,:]) (+ pos[r % T,:]).  nn.Embedding + position_enc Models.py:89-91;
+ * pitch / energy embedding add modules.py:80-100,119-126. */
+int mtts_embed_fwd(const int64_t* idx, const float* table, const float* base, const float* pos, int T, int64_t R, int C,
+                   float* out, void* hi, void* lo, mtts_stream stream);
+/* dtable[idx[r],:] += scale*dy[r,:], rows with idx == skip_idx skipped (padding_idx=0, Models.py:56-58). */
+int mtts_embed_bwd(const int64_t* idx, const float* dy, int64_t R, int C, int64_t skip_idx, float scale, float* dtable,
+                   mtts_stream stream);
+/* torch.bucketize(v, bins) (modules.py:83,94): out[r] = #{bins < v[r]}.  Integer path, bit-exact. */
+int mtts_bucketize(const float* v, const float* bins, int nb, int64_t R, int64_t* out, mtts_stream stream);
+/* out[b,t,:] = x[b,t,:] + vec[b*vec_bstride + :] (+ pos[t,:]).  Speaker-embedding add
+ * base_adaptor.py:69-70,80-84 fused with the decoder's position_enc add Models.py:158-160. */
+int mtts_add_rowvec(const float* x, const float* vec, int64_t vec_bstride, const float* pos, int B, int T, int C, float* out,
+                    void* hi, void* lo, mtts_stream stream);
+/* speaker_emb(speaker_args) (+ mean over the support set, base_adaptor.py:64-67). */
+int mtts_spk_embed(const int64_t* ids, const float* table, int n, int C, int average, int n_out, float* out, mtts_stream stream);
+int mtts_spk_embed_bwd(const int64_t* ids, const float* dspk, int n, int C, int average, int n_out, float scale, float* dtable,
+                       mtts_stream stream);
+/* out[z,c] += sum_r src[z,r,c]; src is fp32 or bf16 hi(+lo).  Bias gradients. */
+int mtts_colsum(const float* f32, const void* hi, const void* lo, int nb, int64_t R, int C, float* out, mtts_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BatchNorm1d in train mode (+ optional tanh), PostNet Layers.py:129-137.  Statistics over all
+ * R = B*T rows (padded frames included, as the reference).  stats = (mean[C], rstd[C]).
+ * ------------------------------------------------------------------------------------------ */
+int mtts_bn_fwd(const float* x, const float* gamma, const float* beta, int64_t R, int C, float eps, float momentum, int tanh_flag,
+                float* running_mean, float* running_var, float* ws /*[2C]*/, float* stats /*[2C]*/, float* out, void* hi,
+                void* lo, mtts_stream stream);
+int mtts_bn_bwd(const float* dout, const float* o, const float* x, const float* stats, const float* gamma, int64_t R, int C,
+                int tanh_flag, float* ws /*[2C]*/, float* dx, void* hi, void* lo, float* dgamma, float* dbeta, mtts_stream stream);
+int mtts_bn_tfwd(const float* xdot, const float* x, const float* stats, const float* gamma, const float* gdot, const float* bdot,
+                 const float* o, int64_t R, int C, int tanh_flag, float* ws /*[2C]*/, float* tsums /*[2C]*/, float* odot, void* hi,
+                 void* lo, mtts_stream stream);
+int mtts_bn_tbwd(const float* dout, const float* ddout, const float* o, const float* odot, const float* x, const float* xdot,
+                 const float* stats, const float* tsums, const float* gamma, const float* gdot, int64_t R, int C, int tanh_flag,
+                 float* ws /*[4C]*/, float* ddx, void* hi, void* lo, float* ddgamma, float* ddbeta, mtts_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * FastSpeech2Loss (lightning/model/loss.py:19-92): masked L1 (mel, postnet mel) + masked MSE
+ * (pitch, energy, log-duration), means over valid elements.  out6 = (total, mel, postnet_mel,
+ * pitch, energy, duration); counts = (n_valid_mel_elements, n_valid_phonemes).
+ * loss_bwd(tangent=0): d total*scale / d predictions.  tangent=1: the JVP of those gradients given
+ * prediction tangents in (p, e, logd) — L1 has zero curvature so dmel = dpost = 0.
+ * ------------------------------------------------------------------------------------------ */
+int mtts_loss_fwd(const float* mel, const float* post, const float* mel_tgt, const int64_t* mel_lens, const float* p,
+                  const float* p_tgt, const float* e, const float* e_tgt, const float* logd, const int64_t* dur,
+                  const int64_t* src_lens, int B, int T, int L, int NM, float* ws /*[8]*/, float* out6, float* counts /*[2]*/,
+                  mtts_stream stream);
+int mtts_loss_bwd(const float* mel, const float* post, const float* mel_tgt, const int64_t* mel_lens, const float* p,
+                  const float* p_tgt, const float* e, const float* e_tgt, const float* logd, const int64_t* dur,
+                  const int64_t* src_lens, int B, int T, int L, int NM, const float* counts, float scale, int tangent, float* dmel,
+                  float* dpost, float* dp, float* de, float* dlogd, mtts_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Flat-arena elementwise kernels (n % 4 == 0).
+ * ------------------------------------------------------------------------------------------ */
+int mtts_split(const float* src, void* hi, void* lo, int64_t n, mtts_stream stream);
+/* l2l maml_update: out = theta - lr*g, fused with the bf16 hi/lo operand preparation. */
+int mtts_sgd_split(const float* theta, const float* g, float lr, float* out, void* hi, void* lo, int64_t n, mtts_stream stream);
+int mtts_axpby(float a, const float* x, float b, float* y, int64_t n, mtts_stream stream);
+int mtts_sumsq(const float* x, int64_t n, float* out, mtts_stream stream);
+/* clip_grad_norm_(max_norm) + Adam (lightning/optimizer.py:6-16, main.py:61).  sumsq = sum g^2 of
+ * the UNSCALED buffer, gscale multiplies g first (1/(n_tasks)); hyper = device (lr, 1-b1^t, 1-b2^t). */
+int mtts_adam_clip(float* p, const float* g, float* m, float* v, const float* sumsq, float gscale, float max_norm,
+                   const float* hyper, float beta1, float beta2, float eps, void* hi, void* lo, int64_t n, mtts_stream stream);
 
 #ifdef __cplusplus
 }

@@ -249,6 +249,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
               if (col0 + j < p.N) v[j] += __ldg(bias + col0 + j);
           }
         }
+        if (p.flags & MTTS_EPI_ADD_C) {
+          const float* src = p.c_f32 + c_off + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) v[j] += src[j];
+        }
         if (p.flags & MTTS_EPI_RELU) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -403,6 +409,8 @@ extern "C" int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream_) {
   MTTS_REQUIRE(ksplit == 1 || ((d->flags & MTTS_EPI_ACCUM) && d->c_f32 && !d->c_hi),
                "gemm: ksplit>1 requires ACCUM into c_f32 only");
   MTTS_REQUIRE(!(d->flags & MTTS_EPI_ACCUM) || d->c_f32, "gemm: ACCUM requires c_f32");
+  MTTS_REQUIRE(!(d->flags & MTTS_EPI_ADD_C) || (d->c_f32 && ksplit == 1 && !(d->flags & MTTS_EPI_ACCUM)),
+               "gemm: ADD_C requires c_f32, ksplit == 1 and no ACCUM");
 
   int bn = d->block_n;
   if (bn == 0) {

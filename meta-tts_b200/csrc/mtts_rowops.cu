@@ -87,8 +87,8 @@ __device__ __forceinline__ float row_dot(const RowVec<NV>& a, const RowVec<NV>& 
   for (int i = 0; i < NV; ++i) s += (a.v[i].x * b.v[i].x + a.v[i].y * b.v[i].y) + (a.v[i].z * b.v[i].z + a.v[i].w * b.v[i].w);
   return warp_sum(s);
 }
-#define ROW_FOREACH(NVv, i, expr)            \
-  _Pragma("unroll") for (int i = 0; i < NVv; ++i) { expr }
+#define ROW_FOREACH(NVv, i, ...)              \
+  _Pragma("unroll") for (int i = 0; i < NVv; ++i) { __VA_ARGS__ }
 
 // elementwise helpers on float4
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }

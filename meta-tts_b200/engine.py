@@ -1,0 +1,1055 @@
+"""Functional FastSpeech2 engine over the libmtts op set: forward, backward, tangent-forward (JVP)
+and tangent-backward (JVP of the backward) passes, written without autograd.
+
+This is the host side of the hot path `forward_learner -> FastSpeech2 -> FastSpeech2Loss`
+(lightning/systems/base_adaptor.py:41-95, lightning/model/fastspeech2.py:40-112, loss.py:19-92 of
+the reference).  The four passes are what the MAML engine (`maml.py`) composes:
+
+    inner step k :  forward(theta_k) ; backward -> g_k ; theta_{k+1} = theta_k - lr*g_k
+    query        :  forward(theta_K) ; backward -> lambda_K (adapted params), grad_phi (encoder)
+    second order :  for k = K-1..0:  tfwd(theta_k; v = lambda_{k+1}) ; tbwd -> H_k v
+                    lambda_k = lambda_{k+1} - lr * (H v)[adapted] ; grad_phi -= lr * (H v)[encoder]
+
+All tensors live in preallocated `Tape`s (stable addresses => the whole step is CUDA-graph
+capturable); every op is one libmtts kernel launch through the backend `be` (ops.CudaOps).
+Activations are token-major [B, T, C]; anything consumed by a GEMM is kept as bf16 hi(/lo).
+
+Internal parameter layout (`ParamLayout`): one flat fp32 arena + bf16 hi/lo arenas of the same
+geometry; Conv1d weights are stored [k, out, in] (K-major GEMM operand per tap), w_qs/w_ks/w_vs are
+adjacent so the QKV projection is one N=768 GEMM.  `pack`/`unpack` convert from/to the reference's
+state_dict (same keys, Conv1d [out, in, k]).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import lib as L
+from .ops import Opnd
+
+N_SYMBOLS = 360      # len(text.symbols.symbols), text/symbols.py:21-29
+N_MEL = 80
+POSTNET_CH = [N_MEL, 512, 512, 512, 512, N_MEL]
+
+
+def _rup(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# =================================================================================================
+# parameters
+# =================================================================================================
+def param_specs(cfg, n_speaker: int) -> List[Tuple[str, Tuple[int, ...]]]:
+    """Trainable parameters (reference state_dict names and shapes), in arena order."""
+    tr = cfg["transformer"]
+    d = tr["encoder_hidden"]
+    di = tr["conv_filter_size"]
+    k1, k2 = tr["conv_kernel_size"]
+    specs: List[Tuple[str, Tuple[int, ...]]] = []
+
+    def fft(prefix, dm, nh):
+        for n in ("w_qs", "w_ks", "w_vs"):
+            specs.append((f"{prefix}.slf_attn.{n}.weight", (dm, dm)))
+        for n in ("w_qs", "w_ks", "w_vs"):
+            specs.append((f"{prefix}.slf_attn.{n}.bias", (dm,)))
+        specs.extend([(f"{prefix}.slf_attn.layer_norm.weight", (dm,)), (f"{prefix}.slf_attn.layer_norm.bias", (dm,)),
+                      (f"{prefix}.slf_attn.fc.weight", (dm, dm)), (f"{prefix}.slf_attn.fc.bias", (dm,)),
+                      (f"{prefix}.pos_ffn.w_1.weight", (di, dm, k1)), (f"{prefix}.pos_ffn.w_1.bias", (di,)),
+                      (f"{prefix}.pos_ffn.w_2.weight", (dm, di, k2)), (f"{prefix}.pos_ffn.w_2.bias", (dm,)),
+                      (f"{prefix}.pos_ffn.layer_norm.weight", (dm,)), (f"{prefix}.pos_ffn.layer_norm.bias", (dm,))])
+
+    specs.append(("encoder.src_word_emb.weight", (N_SYMBOLS + 1, d)))
+    for i in range(tr["encoder_layer"]):
+        fft(f"encoder.layer_stack.{i}", d, tr["encoder_head"])
+    f = cfg["variance_predictor"]["filter_size"]
+    kv = cfg["variance_predictor"]["kernel_size"]
+    for p in ("duration_predictor", "pitch_predictor", "energy_predictor"):
+        pre = f"variance_adaptor.{p}"
+        specs.extend([(f"{pre}.conv_layer.conv1d_1.conv.weight", (f, d, kv)), (f"{pre}.conv_layer.conv1d_1.conv.bias", (f,)),
+                      (f"{pre}.conv_layer.layer_norm_1.weight", (f,)), (f"{pre}.conv_layer.layer_norm_1.bias", (f,)),
+                      (f"{pre}.conv_layer.conv1d_2.conv.weight", (f, f, kv)), (f"{pre}.conv_layer.conv1d_2.conv.bias", (f,)),
+                      (f"{pre}.conv_layer.layer_norm_2.weight", (f,)), (f"{pre}.conv_layer.layer_norm_2.bias", (f,)),
+                      (f"{pre}.linear_layer.weight", (1, f)), (f"{pre}.linear_layer.bias", (1,))])
+    nb = cfg["variance_embedding"]["n_bins"]
+    specs.append(("variance_adaptor.pitch_embedding.weight", (nb, d)))
+    specs.append(("variance_adaptor.energy_embedding.weight", (nb, d)))
+    dd = tr["decoder_hidden"]
+    for i in range(tr["decoder_layer"]):
+        fft(f"decoder.layer_stack.{i}", dd, tr["decoder_head"])
+    specs.extend([("mel_linear.weight", (N_MEL, dd)), ("mel_linear.bias", (N_MEL,))])
+    for i in range(5):
+        specs.extend([(f"postnet.convolutions.{i}.0.conv.weight", (POSTNET_CH[i + 1], POSTNET_CH[i], 5)),
+                      (f"postnet.convolutions.{i}.0.conv.bias", (POSTNET_CH[i + 1],)),
+                      (f"postnet.convolutions.{i}.1.weight", (POSTNET_CH[i + 1],)),
+                      (f"postnet.convolutions.{i}.1.bias", (POSTNET_CH[i + 1],))])
+    specs.append(("speaker_emb.model.weight", (n_speaker, d)))
+    return specs
+
+
+def const_names(cfg) -> List[str]:
+    names = ["encoder.position_enc", "decoder.position_enc", "variance_adaptor.pitch_bins", "variance_adaptor.energy_bins"]
+    for i in range(5):
+        names += [f"postnet.convolutions.{i}.1.running_mean", f"postnet.convolutions.{i}.1.running_var",
+                  f"postnet.convolutions.{i}.1.num_batches_tracked"]
+    return names
+
+
+@dataclass
+class PEntry:
+    name: str
+    sd_shape: Tuple[int, ...]       # reference state_dict shape
+    shape: Tuple[int, ...]          # internal shape ([k,out,in] for Conv1d weights)
+    offset: int
+    numel: int
+    adapted: bool
+
+
+class ParamLayout:
+    """Flat arena layout: [ non-adapted trainable | adapted trainable ], 64-element aligned entries."""
+
+    def __init__(self, cfg, n_speaker: int, adapt_modules: Sequence[str]):
+        self.cfg = cfg
+        self.n_speaker = n_speaker
+        self.adapt_modules = tuple(adapt_modules)
+        specs = param_specs(cfg, n_speaker)
+        self.entries: Dict[str, PEntry] = {}
+        off = 0
+        self.order: List[str] = []
+        for want_adapted in (False, True):
+            if want_adapted:
+                self.adapt_begin = off
+            for name, shp in specs:
+                ad = name.split(".")[0] in self.adapt_modules
+                if ad != want_adapted:
+                    continue
+                ishape = (shp[2], shp[0], shp[1]) if len(shp) == 3 else shp
+                n = int(math.prod(shp))
+                self.entries[name] = PEntry(name, tuple(shp), tuple(ishape), off, n, ad)
+                self.order.append(name)
+                off = _rup(off + n, 64)
+        self.total = off
+        self.n_adapt = self.total - self.adapt_begin
+        self.n_trainable = sum(e.numel for e in self.entries.values())
+        self.n_adapted_params = sum(e.numel for e in self.entries.values() if e.adapted)
+
+    def is_adapted_module(self, prefix: str) -> bool:
+        return prefix.split(".")[0] in self.adapt_modules
+
+    # ---- conversion from / to the reference state_dict (host-side plumbing, not on the hot path) ----
+    def pack(self, state_dict, flat: torch.Tensor) -> None:
+        flat.zero_()
+        for name, e in self.entries.items():
+            t = state_dict[name].detach().to(torch.float32)
+            assert tuple(t.shape) == e.sd_shape, f"{name}: {tuple(t.shape)} != {e.sd_shape}"
+            if len(e.sd_shape) == 3:
+                t = t.permute(2, 0, 1).contiguous()
+            flat[e.offset:e.offset + e.numel].copy_(t.reshape(-1))
+
+    def unpack(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        out = {}
+        for name, e in self.entries.items():
+            t = flat[e.offset:e.offset + e.numel].reshape(e.shape)
+            if len(e.sd_shape) == 3:
+                t = t.permute(1, 2, 0)
+            out[name] = t.contiguous().clone()
+        return out
+
+
+class Wt:
+    """One parameter's views: fp32 master and bf16 hi/lo (GEMM operand layout)."""
+    __slots__ = ("f32", "hi", "lo", "shape")
+
+    def __init__(self, f32, hi, lo, shape):
+        self.f32, self.hi, self.lo, self.shape = f32, hi, lo, shape
+
+
+class ParamSet:
+    """Name -> views over (flat f32, hi, lo) arenas; the adapted region may come from separate
+    (fast-weight) arenas of length layout.n_adapt.  hi/lo may be None (gradient arenas)."""
+
+    def __init__(self, layout: ParamLayout, base_f32, base_hi=None, base_lo=None, fast_f32=None, fast_hi=None,
+                 fast_lo=None, only_adapted: bool = False):
+        self.layout = layout
+        self.base = (base_f32, base_hi, base_lo)
+        self.fast = (fast_f32, fast_hi, fast_lo)
+        self.only_adapted = only_adapted
+        self._cache: Dict[str, Wt] = {}
+
+    def has(self, name: str) -> bool:
+        e = self.layout.entries[name]
+        return e.adapted or not self.only_adapted
+
+    def get(self, name: str) -> Optional[Wt]:
+        if name in self._cache:
+            return self._cache[name]
+        e = self.layout.entries[name]
+        if self.only_adapted and not e.adapted:
+            return None
+        if e.adapted and self.fast[0] is not None:
+            arenas, off = self.fast, e.offset - self.layout.adapt_begin
+        else:
+            arenas, off = self.base, e.offset
+        v = [a[off:off + e.numel].view(e.shape) if a is not None else None for a in arenas]
+        w = Wt(v[0], v[1], v[2], e.shape)
+        self._cache[name] = w
+        return w
+
+    def span(self, first: str, last: str, shape) -> Optional[Wt]:
+        """A view covering adjacent entries first..last (e.g. w_qs|w_ks|w_vs -> [768, 256])."""
+        key = f"{first}|{last}"
+        if key in self._cache:
+            return self._cache[key]
+        e0, e1 = self.layout.entries[first], self.layout.entries[last]
+        if self.only_adapted and not e0.adapted:
+            return None
+        n = e1.offset + e1.numel - e0.offset
+        assert n == math.prod(shape), "span is not contiguous"
+        if e0.adapted and self.fast[0] is not None:
+            arenas, off = self.fast, e0.offset - self.layout.adapt_begin
+        else:
+            arenas, off = self.base, e0.offset
+        v = [a[off:off + n].view(shape) if a is not None else None for a in arenas]
+        w = Wt(v[0], v[1], v[2], tuple(shape))
+        self._cache[key] = w
+        return w
+
+
+# =================================================================================================
+# buffers
+# =================================================================================================
+class Act:
+    """An activation: fp32 and/or bf16 hi(/lo) tensors of logical shape [B, T, C]."""
+    __slots__ = ("f32", "hi", "lo", "B", "T", "C")
+
+    def __init__(self, f32, hi, lo, B, T, C):
+        self.f32, self.hi, self.lo, self.B, self.T, self.C = f32, hi, lo, B, T, C
+
+
+class Tape:
+    """Named, lazily allocated, persistent device buffers (stable addresses across replays)."""
+
+    def __init__(self, be, split: int):
+        self.be = be
+        self.split = split
+        self.t: Dict[str, torch.Tensor] = {}
+
+    def buf(self, name, shape, dtype=torch.float32, zero=False):
+        t = self.t.get(name)
+        if t is None:
+            t = self.be.zeros(tuple(shape), dtype) if zero else self.be.empty(tuple(shape), dtype)
+            self.t[name] = t
+        assert tuple(t.shape) == tuple(shape), f"tape buffer {name}: {tuple(t.shape)} vs {tuple(shape)}"
+        return t
+
+    def f32(self, name, shape):
+        return self.buf(name + ":f", shape)
+
+    def bf(self, name, shape):
+        hi = self.buf(name + ":h", shape, torch.bfloat16)
+        lo = self.buf(name + ":l", shape, torch.bfloat16) if self.split == 3 else None
+        return hi, lo
+
+    def act(self, name, B, T, C, f32=True, bf=True) -> Act:
+        f = self.f32(name, (B, T, C)) if f32 else None
+        h, l = self.bf(name, (B, T, C)) if bf else (None, None)
+        return Act(f, h, l, B, T, C)
+
+    def scratch(self, name, shape, dtype=torch.float32):
+        """Shape-keyed scratch buffer (support / query / encoder / decoder shapes differ)."""
+        return self.buf(f"{name}[{'x'.join(str(int(v)) for v in shape)}]:s", shape, dtype)
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.t.values())
+
+
+@dataclass
+class Batch:
+    """Device-resident teacher-forced batch (the reference 12-tuple's tensor fields, collate.py:47-60)."""
+    spk_ids: torch.Tensor        # i64 [n_spk_ids]  ids fed to speaker_emb (support ids for the query pass)
+    average_spk: bool
+    texts: torch.Tensor          # i64 [B, L]
+    src_lens: torch.Tensor       # i64 [B]
+    mels: torch.Tensor           # f32 [B, T, 80]
+    mel_lens: torch.Tensor       # i64 [B]
+    pitches: torch.Tensor        # f32 [B, L]
+    energies: torch.Tensor       # f32 [B, L]
+    durations: torch.Tensor      # i64 [B, L]
+    B: int
+    L: int
+    T: int
+
+
+# =================================================================================================
+# GEMM builders
+# =================================================================================================
+@dataclass
+class BMat:
+    """Batched matrix X[b,h][r,c] = buf[off + b*sb + h*sh + r*sr + c]."""
+    hi: Optional[torch.Tensor]
+    lo: Optional[torch.Tensor]
+    off: int
+    sb: int
+    sh: int
+    sr: int
+    rows: int
+    cols: int
+    f32: Optional[torch.Tensor] = None
+
+
+def _wgrad_ksplit(tiles: int, iters: int) -> int:
+    ks = max(1, 148 // max(tiles, 1))
+    return max(1, min(ks, iters // 2 if iters >= 2 else 1, 32))
+
+
+class Gemm:
+    """Descriptor construction for the contractions of the model (all through be.gemm)."""
+
+    def __init__(self, be):
+        self.be = be
+
+    # y[b,t,:] = sum_j x[b,t+j-p,:] W_j^T (+bias) ; W: [k, N, Cin]
+    def conv_fwd(self, x: Act, w: Wt, bias, out_f32, out_hi, out_lo, relu=False, gate=None, add_c=False):
+        k, N, Cin = w.shape if len(w.shape) == 3 else (1,) + tuple(w.shape)
+        assert Cin == x.C
+        p = (k - 1) // 2
+        flags = (L.EPI_RELU if relu else 0) | (L.EPI_GATE if gate is not None else 0) | (L.EPI_ADD_C if add_c else 0)
+        wop = Opnd(w.hi, w.lo, L.MAJOR_K, (Cin, N, k), (1, Cin, N * Cin), src2=L.SRC_TAP)
+        if k == 1:
+            a = Opnd(x.hi, x.lo, L.MAJOR_K, (Cin, x.B * x.T), (1, Cin))
+            self.be.gemm(a, wop, x.B * x.T, N, Cin, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=N, bias=bias,
+                         gate=gate, flags=flags)
+        else:
+            a = Opnd(x.hi, x.lo, L.MAJOR_K, (Cin, x.T, x.B), (1, Cin, x.T * Cin), src2=L.SRC_Z0,
+                     shift_src=L.SRC_TAP, shift_base=-p, shift_step=1)
+            self.be.gemm(a, wop, x.T, N, Cin, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=N, c_sz0=x.T * N, bias=bias,
+                         gate=gate, flags=flags, ntaps=k, nz0=x.B)
+
+    # dx[b,t,:] = sum_j dy[b,t-j+p,:] W_j
+    def conv_dgrad(self, dy: Act, w: Wt, out_f32, out_hi, out_lo, gate=None, add_c=False):
+        k, N, Cin = w.shape if len(w.shape) == 3 else (1,) + tuple(w.shape)
+        assert N == dy.C
+        p = (k - 1) // 2
+        flags = (L.EPI_GATE if gate is not None else 0) | (L.EPI_ADD_C if add_c else 0)
+        wop = Opnd(w.hi, w.lo, L.MAJOR_MN, (Cin, N, k), (1, Cin, N * Cin), src2=L.SRC_TAP)
+        if k == 1:
+            a = Opnd(dy.hi, dy.lo, L.MAJOR_K, (N, dy.B * dy.T), (1, N))
+            self.be.gemm(a, wop, dy.B * dy.T, Cin, N, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=Cin, gate=gate,
+                         flags=flags)
+        else:
+            a = Opnd(dy.hi, dy.lo, L.MAJOR_K, (N, dy.T, dy.B), (1, N, dy.T * N), src2=L.SRC_Z0,
+                     shift_src=L.SRC_TAP, shift_base=p, shift_step=-1)
+            self.be.gemm(a, wop, dy.T, Cin, N, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=Cin, c_sz0=dy.T * Cin,
+                         gate=gate, flags=flags, ntaps=k, nz0=dy.B)
+
+    # dW_j[n,c] += sum_{b,t} dy[b,t,n] x[b,t+j-p,c]
+    def conv_wgrad(self, dy: Act, x: Act, dw_f32: torch.Tensor, scale: float = 1.0):
+        shp = tuple(dw_f32.shape)
+        k, N, Cin = shp if len(shp) == 3 else (1,) + shp
+        assert N == dy.C and Cin == x.C and dy.B == x.B and dy.T == x.T
+        p = (k - 1) // 2
+        bn = 64 if Cin <= 64 else 128
+        tiles = ((N + 127) // 128) * ((Cin + bn - 1) // bn) * k
+        if k == 1:
+            R = dy.B * dy.T
+            a = Opnd(dy.hi, dy.lo, L.MAJOR_MN, (N, R), (1, N))
+            b = Opnd(x.hi, x.lo, L.MAJOR_MN, (Cin, R), (1, Cin))
+            self.be.gemm(a, b, N, Cin, R, c_f32=dw_f32, ldc=Cin, flags=L.EPI_ACCUM, alpha=scale,
+                         ksplit=_wgrad_ksplit(tiles, (R + 63) // 64), block_n=bn)
+        else:
+            a = Opnd(dy.hi, dy.lo, L.MAJOR_MN, (N, dy.T, dy.B), (1, N, dy.T * N), src2=L.SRC_KB)
+            b = Opnd(x.hi, x.lo, L.MAJOR_MN, (Cin, x.T, x.B), (1, Cin, x.T * Cin), src2=L.SRC_KB,
+                     shift_src=L.SRC_Z0, shift_base=-p, shift_step=1)
+            self.be.gemm(a, b, N, Cin, dy.T, c_f32=dw_f32, ldc=Cin, c_sz0=N * Cin, flags=L.EPI_ACCUM, alpha=scale,
+                         nkb=dy.B, nz0=k, ksplit=_wgrad_ksplit(tiles, dy.B * ((dy.T + 63) // 64)), block_n=bn)
+
+    # C[b,h] = alpha * op(A)[M,K] op(B)[N,K]^T   (op = identity or transpose, see BMat)
+    def bmm(self, A: BMat, a_t: bool, Bm: BMat, b_t: bool, Cm: BMat, nb: int, nh: int, alpha=1.0, add_c=False):
+        M = A.cols if a_t else A.rows
+        K = A.rows if a_t else A.cols
+        N = Bm.cols if b_t else Bm.rows
+        assert K == (Bm.rows if b_t else Bm.cols)
+        a = Opnd(A.hi, A.lo, L.MAJOR_MN if a_t else L.MAJOR_K, (A.cols, A.rows, nh, nb), (1, A.sr, A.sh, A.sb),
+                 src2=L.SRC_Z0, src3=L.SRC_Z1, offset=A.off)
+        b = Opnd(Bm.hi, Bm.lo, L.MAJOR_MN if b_t else L.MAJOR_K, (Bm.cols, Bm.rows, nh, nb), (1, Bm.sr, Bm.sh, Bm.sb),
+                 src2=L.SRC_Z0, src3=L.SRC_Z1, offset=Bm.off)
+        self.be.gemm(a, b, M, N, K, c_f32=Cm.f32, c_hi=Cm.hi, c_lo=Cm.lo, ldc=Cm.sr, c_off=Cm.off, c_sz0=Cm.sh,
+                     c_sz1=Cm.sb, alpha=alpha, flags=(L.EPI_ADD_C if add_c else 0), nz0=nh, nz1=nb)
+
+
+# =================================================================================================
+# the model
+# =================================================================================================
+class FS2Engine:
+    """Four-pass functional FastSpeech2 (+ loss) over a backend."""
+
+    def __init__(self, be, cfg, layout: ParamLayout, consts: Dict[str, torch.Tensor]):
+        self.be = be
+        self.cfg = cfg
+        self.layout = layout
+        self.consts = consts
+        self.g = Gemm(be)
+        self.split = be.split
+        tr = cfg["transformer"]
+        self.d = tr["encoder_hidden"]
+        self.n_enc, self.n_dec = tr["encoder_layer"], tr["decoder_layer"]
+        self.h_enc, self.h_dec = tr["encoder_head"], tr["decoder_head"]
+        self.d_inner = tr["conv_filter_size"]
+        self.nbins = cfg["variance_embedding"]["n_bins"]
+        self.scr = Tape(be, self.split)        # shared scratch (never read across passes)
+        assert self.d % 128 == 0
+
+    def new_tape(self) -> Tape:
+        return Tape(self.be, self.split)
+
+    # ---------------------------------------------------------------------------------------------
+    # FFT block
+    # ---------------------------------------------------------------------------------------------
+    def _attn_geom(self, B, T, H):
+        d = self.d
+        dk = d // H
+        Tp = _rup(T, 8)
+        row = 3 * d
+        q = lambda buf_hi, buf_lo, which, f32=None: BMat(buf_hi, buf_lo, which * d, T * row, dk, row, T, dk, f32)  # noqa: E731
+        pm = lambda hi, lo, f32=None: BMat(hi, lo, 0, H * T * Tp, T * Tp, Tp, T, T, f32)  # noqa: E731
+        om = lambda hi, lo, f32=None: BMat(hi, lo, 0, T * d, dk, d, T, dk, f32)  # noqa: E731
+        return dk, Tp, q, pm, om
+
+    def _fft_names(self, pf):
+        a, f = f"{pf}.slf_attn", f"{pf}.pos_ffn"
+        return a, f
+
+    def _qkv(self, P: ParamSet, pf):
+        a = f"{pf}.slf_attn"
+        d = self.d
+        w = P.span(f"{a}.w_qs.weight", f"{a}.w_vs.weight", (3 * d, d))
+        b = P.span(f"{a}.w_qs.bias", f"{a}.w_vs.bias", (3 * d,))
+        return w, b
+
+    def fft_fwd(self, P: ParamSet, pf: str, tp: Tape, x: Act, lens, H: int) -> Act:
+        be, g, scr = self.be, self.g, self.scr
+        B, T, d = x.B, x.T, self.d
+        R = B * T
+        a_, f_ = self._fft_names(pf)
+        dk, Tp, qm, pm, om = self._attn_geom(B, T, H)
+        wqkv, bqkv = self._qkv(P, pf)
+        qkv_h, qkv_l = tp.bf(f"{pf}.qkv", (R, 3 * d))
+        g.conv_fwd(x, wqkv, bqkv.f32, None, qkv_h, qkv_l)
+        S = scr.scratch("S", (B, H, T, Tp))
+        g.bmm(qm(qkv_h, qkv_l, 0), False, qm(qkv_h, qkv_l, 1), False, pm(None, None, S), B, H, alpha=1.0 / math.sqrt(dk))
+        p_h, p_l = tp.bf(f"{pf}.P", (B, H, T, Tp))
+        be.softmax(0, S, None, None, None, None, None, lens, B * H, H, T, T, Tp, p_h, p_l)
+        o = tp.act(f"{pf}.o", B, T, d, f32=False)
+        g.bmm(pm(p_h, p_l), False, qm(qkv_h, qkv_l, 2), True, om(o.hi, o.lo), B, H)
+        y0 = scr.scratch("y0", (B, T, d))
+        g.conv_fwd(o, P.get(f"{a_}.fc.weight"), P.get(f"{a_}.fc.bias").f32, y0, None, None)
+        y1 = tp.act(f"{pf}.y1", B, T, d)
+        be.ln_fwd(y0, x.f32, P.get(f"{a_}.layer_norm.weight").f32, P.get(f"{a_}.layer_norm.bias").f32, lens, T, R, d,
+                  tp.f32(f"{pf}.z1", (B, T, d)), tp.f32(f"{pf}.st1", (R, 2)), y1.f32, y1.hi, y1.lo)
+        h = tp.act(f"{pf}.h", B, T, self.d_inner, f32=False)
+        g.conv_fwd(y1, P.get(f"{f_}.w_1.weight"), P.get(f"{f_}.w_1.bias").f32, None, h.hi, h.lo, relu=True)
+        y2 = scr.scratch("y0", (B, T, d))
+        g.conv_fwd(h, P.get(f"{f_}.w_2.weight"), P.get(f"{f_}.w_2.bias").f32, y2, None, None)
+        out = tp.act(f"{pf}.out", B, T, d)
+        be.ln_fwd(y2, y1.f32, P.get(f"{f_}.layer_norm.weight").f32, P.get(f"{f_}.layer_norm.bias").f32, lens, T, R, d,
+                  tp.f32(f"{pf}.z2", (B, T, d)), tp.f32(f"{pf}.st2", (R, 2)), out.f32, out.hi, out.lo)
+        return out
+
+    def fft_bwd(self, P: ParamSet, G: ParamSet, pf: str, tp: Tape, x: Act, lens, H: int, dout: torch.Tensor,
+                dx_out: torch.Tensor):
+        """dout: dL/d(out) fp32 [B,T,d] (kept: the tangent-backward pass re-reads it);
+        dx_out: destination for dL/d(x)."""
+        be, g, scr = self.be, self.g, self.scr
+        B, T, d = x.B, x.T, self.d
+        R = B * T
+        a_, f_ = self._fft_names(pf)
+        dk, Tp, qm, pm, om = self._attn_geom(B, T, H)
+        wqkv, _ = self._qkv(P, pf)
+        gwqkv, gbqkv = self._qkv(G, pf)
+        qkv_h, qkv_l = tp.bf(f"{pf}.qkv", (R, 3 * d))
+        p_h, p_l = tp.bf(f"{pf}.P", (B, H, T, Tp))
+        o = tp.act(f"{pf}.o", B, T, d, f32=False)
+        y1 = tp.act(f"{pf}.y1", B, T, d)
+        h = tp.act(f"{pf}.h", B, T, self.d_inner, f32=False)
+        # LN2
+        dz2 = tp.act(f"{pf}.dz2", B, T, d)          # f32 part becomes dL/dy1 (total) after the ADD_C below
+        be.ln_bwd(dout, tp.f32(f"{pf}.z2", (B, T, d)), tp.f32(f"{pf}.st2", (R, 2)), P.get(f"{f_}.layer_norm.weight").f32,
+                  lens, T, R, d, 0, dz2.f32, dz2.hi, dz2.lo, G.get(f"{f_}.layer_norm.weight").f32,
+                  G.get(f"{f_}.layer_norm.bias").f32, G.get(f"{f_}.w_2.bias").f32)
+        # conv k=1 (w_2), ReLU gate, conv k=9 (w_1)
+        dh = tp.act(f"{pf}.dh", B, T, self.d_inner, f32=False)
+        g.conv_dgrad(dz2, P.get(f"{f_}.w_2.weight"), None, dh.hi, dh.lo, gate=h.hi)
+        g.conv_wgrad(dz2, h, G.get(f"{f_}.w_2.weight").f32)
+        be.colsum(None, dh.hi, dh.lo, 1, R, self.d_inner, G.get(f"{f_}.w_1.bias").f32)
+        g.conv_dgrad(dh, P.get(f"{f_}.w_1.weight"), dz2.f32, None, None, add_c=True)       # dz2.f32 := dL/dy1
+        g.conv_wgrad(dh, y1, G.get(f"{f_}.w_1.weight").f32)
+        # LN1  (f32 result goes straight into dx_out; the QKV dgrad below adds onto it)
+        dz1 = Act(dx_out, *tp.bf(f"{pf}.dz1", (B, T, d)), B, T, d)
+        be.ln_bwd(dz2.f32, tp.f32(f"{pf}.z1", (B, T, d)), tp.f32(f"{pf}.st1", (R, 2)), P.get(f"{a_}.layer_norm.weight").f32,
+                  lens, T, R, d, 0, dz1.f32, dz1.hi, dz1.lo, G.get(f"{a_}.layer_norm.weight").f32,
+                  G.get(f"{a_}.layer_norm.bias").f32, G.get(f"{a_}.fc.bias").f32)
+        do = tp.act(f"{pf}.do", B, T, d, f32=False)
+        g.conv_dgrad(dz1, P.get(f"{a_}.fc.weight"), None, do.hi, do.lo)
+        g.conv_wgrad(dz1, o, G.get(f"{a_}.fc.weight").f32)
+        # attention
+        dP = tp.f32(f"{pf}.dP", (B, H, T, Tp))
+        g.bmm(om(do.hi, do.lo), False, qm(qkv_h, qkv_l, 2), False, pm(None, None, dP), B, H)
+        ds_h, ds_l = tp.bf(f"{pf}.dS", (B, H, T, Tp))
+        be.softmax(1, dP, None, p_h, p_l, None, None, lens, B * H, H, T, T, Tp, ds_h, ds_l)
+        dq_h, dq_l = tp.bf(f"{pf}.dqkv", (R, 3 * d))
+        sc = 1.0 / math.sqrt(dk)
+        g.bmm(pm(p_h, p_l), True, om(do.hi, do.lo), True, qm(dq_h, dq_l, 2), B, H)                      # dV = P^T dO
+        g.bmm(pm(ds_h, ds_l), False, qm(qkv_h, qkv_l, 1), True, qm(dq_h, dq_l, 0), B, H, alpha=sc)       # dQ = dS K
+        g.bmm(pm(ds_h, ds_l), True, qm(qkv_h, qkv_l, 0), True, qm(dq_h, dq_l, 1), B, H, alpha=sc)        # dK = dS^T Q
+        dqkv = Act(None, dq_h, dq_l, B, T, 3 * d)
+        g.conv_wgrad(dqkv, x, gwqkv.f32)
+        be.colsum(None, dq_h, dq_l, 1, R, 3 * d, gbqkv.f32)
+        g.conv_dgrad(dqkv, wqkv, dx_out, None, None, add_c=True)
+
+    def _lin_t(self, x: Act, xd: Optional[Act], w: Wt, wd: Optional[Wt], bd, out_f32, out_hi, out_lo, relu_gate=None):
+        """Tangent of y = conv(x, W) + b:  yd = conv(xd, W) + conv(x, Wd) + bd (then optional ReLU gate).
+        out_f32 is required as the accumulation buffer when both terms exist."""
+        terms = []
+        if xd is not None:
+            terms.append((xd, w))
+        if wd is not None:
+            terms.append((x, wd))
+        assert terms, "tangent of a linear op with zero input and weight tangents"
+        n = len(terms)
+        assert n == 1 or out_f32 is not None
+        for i, (xx, ww) in enumerate(terms):
+            last = i == n - 1
+            self.g.conv_fwd(xx, ww, bd if i == 0 else None, out_f32, out_hi if last else None, out_lo if last else None,
+                            gate=relu_gate if last else None, add_c=i > 0)
+
+    def _dgrad_t(self, dy: Act, ddy: Act, w: Wt, wd: Optional[Wt], out_f32, out_hi, out_lo, gate=None, add_c=False):
+        """Tangent of dx = dgrad(dy, W):  ddx = dgrad(ddy, W) + dgrad(dy, Wd)  (+ existing out_f32 if add_c)."""
+        g = self.g
+        if wd is None:
+            g.conv_dgrad(ddy, w, out_f32, out_hi, out_lo, gate=gate, add_c=add_c)
+            return
+        assert out_f32 is not None
+        g.conv_dgrad(ddy, w, out_f32, None, None, add_c=add_c)
+        g.conv_dgrad(dy, wd, out_f32, out_hi, out_lo, gate=gate, add_c=True)
+
+    def _wgrad_t(self, dy: Act, ddy: Act, x: Act, xd: Optional[Act], hv_w: torch.Tensor):
+        """Tangent of dW = wgrad(dy, x):  ddW += wgrad(ddy, x) + wgrad(dy, xd)."""
+        self.g.conv_wgrad(ddy, x, hv_w)
+        if xd is not None:
+            self.g.conv_wgrad(dy, xd, hv_w)
+
+    def fft_tfwd(self, P: ParamSet, Pd: ParamSet, pf: str, tp: Tape, tt: Tape, x: Act, xd: Optional[Act], lens, H: int) -> Act:
+        """Tangent forward; xd = input tangent (None = zero), Pd = parameter tangents."""
+        be, g, scr = self.be, self.g, self.scr
+        B, T, d = x.B, x.T, self.d
+        R = B * T
+        a_, f_ = self._fft_names(pf)
+        dk, Tp, qm, pm, om = self._attn_geom(B, T, H)
+        wqkv, _ = self._qkv(P, pf)
+        wdqkv, bdqkv = self._qkv(Pd, pf)
+        gd = lambda n: (Pd.get(n).f32 if Pd.has(n) else None)  # noqa: E731
+        wdt = lambda n: (Pd.get(n) if Pd.has(n) else None)  # noqa: E731
+        qkv_h, qkv_l = tp.bf(f"{pf}.qkv", (R, 3 * d))
+        p_h, p_l = tp.bf(f"{pf}.P", (B, H, T, Tp))
+        o = tp.act(f"{pf}.o", B, T, d, f32=False)
+        y1 = tp.act(f"{pf}.y1", B, T, d)
+        h = tp.act(f"{pf}.h", B, T, self.d_inner, f32=False)
+        # qkv tangent
+        qd_h, qd_l = tt.bf(f"{pf}.qkvd", (R, 3 * d))
+        qd_f = scr.scratch("qkv_f", (R, 3 * d))
+        self._lin_t(x, xd, wqkv, wdqkv, bdqkv.f32 if bdqkv is not None else None, qd_f, qd_h, qd_l)
+        # Sdot = scale (Qd K^T + Q Kd^T)
+        Sd = scr.scratch("S", (B, H, T, Tp))
+        sc = 1.0 / math.sqrt(dk)
+        g.bmm(qm(qd_h, qd_l, 0), False, qm(qkv_h, qkv_l, 1), False, pm(None, None, Sd), B, H, alpha=sc)
+        g.bmm(qm(qkv_h, qkv_l, 0), False, qm(qd_h, qd_l, 1), False, pm(None, None, Sd), B, H, alpha=sc, add_c=True)
+        pd_h, pd_l = tt.bf(f"{pf}.Pd", (B, H, T, Tp))
+        be.softmax(1, Sd, None, p_h, p_l, None, None, lens, B * H, H, T, T, Tp, pd_h, pd_l)
+        # Od = Pd V + P Vd
+        od = tt.act(f"{pf}.od", B, T, d, f32=False)
+        od_f = scr.scratch("o_f", (B, T, d))
+        g.bmm(pm(pd_h, pd_l), False, qm(qkv_h, qkv_l, 2), True, om(None, None, od_f), B, H)
+        g.bmm(pm(p_h, p_l), False, qm(qd_h, qd_l, 2), True, om(od.hi, od.lo, od_f), B, H, add_c=True)
+        # fc + LN1
+        y0d = scr.scratch("y0", (B, T, d))
+        self._lin_t(o, od, P.get(f"{a_}.fc.weight"), wdt(f"{a_}.fc.weight"), gd(f"{a_}.fc.bias"), y0d, None, None)
+        y1d = tt.act(f"{pf}.y1d", B, T, d)
+        be.ln_tfwd(y0d, xd.f32 if xd is not None else None, tp.f32(f"{pf}.z1", (B, T, d)), tp.f32(f"{pf}.st1", (R, 2)),
+                   P.get(f"{a_}.layer_norm.weight").f32, gd(f"{a_}.layer_norm.weight"), gd(f"{a_}.layer_norm.bias"), lens, T,
+                   R, d, tt.f32(f"{pf}.z1d", (B, T, d)), y1d.f32, y1d.hi, y1d.lo)
+        # conv9 + relu gate, conv1, LN2
+        hd = tt.act(f"{pf}.hd", B, T, self.d_inner, f32=False)
+        hd_f = scr.scratch("h_f", (B, T, self.d_inner))
+        self._lin_t(y1, y1d, P.get(f"{f_}.w_1.weight"), wdt(f"{f_}.w_1.weight"), gd(f"{f_}.w_1.bias"), hd_f, hd.hi, hd.lo,
+                    relu_gate=h.hi)
+        y2d = scr.scratch("y0", (B, T, d))
+        self._lin_t(h, hd, P.get(f"{f_}.w_2.weight"), wdt(f"{f_}.w_2.weight"), gd(f"{f_}.w_2.bias"), y2d, None, None)
+        outd = tt.act(f"{pf}.outd", B, T, d)
+        be.ln_tfwd(y2d, y1d.f32, tp.f32(f"{pf}.z2", (B, T, d)), tp.f32(f"{pf}.st2", (R, 2)),
+                   P.get(f"{f_}.layer_norm.weight").f32, gd(f"{f_}.layer_norm.weight"), gd(f"{f_}.layer_norm.bias"), lens, T,
+                   R, d, tt.f32(f"{pf}.z2d", (B, T, d)), outd.f32, outd.hi, outd.lo)
+        return outd
+
+    def fft_tbwd(self, P: ParamSet, Pd: ParamSet, HV: ParamSet, pf: str, tp: Tape, tt: Tape, x: Act, xd: Optional[Act],
+                 lens, H: int, dout: torch.Tensor, ddout: torch.Tensor, ddx_out: torch.Tensor):
+        """Tangent backward: given the primal tape (forward + backward signals), the tangent tape and
+        ddout = tangent of dL/d(out), accumulate (H v) into HV and write the tangent of dL/dx."""
+        be, g, scr = self.be, self.g, self.scr
+        B, T, d = x.B, x.T, self.d
+        R = B * T
+        a_, f_ = self._fft_names(pf)
+        dk, Tp, qm, pm, om = self._attn_geom(B, T, H)
+        wqkv, _ = self._qkv(P, pf)
+        wdqkv, _ = self._qkv(Pd, pf)
+        hvwqkv, hvbqkv = self._qkv(HV, pf)
+        gd = lambda n: (Pd.get(n).f32 if Pd.has(n) else None)  # noqa: E731
+        wdt = lambda n: (Pd.get(n) if Pd.has(n) else None)  # noqa: E731
+        hv = lambda n: HV.get(n).f32  # noqa: E731
+        qkv_h, qkv_l = tp.bf(f"{pf}.qkv", (R, 3 * d))
+        p_h, p_l = tp.bf(f"{pf}.P", (B, H, T, Tp))
+        o = tp.act(f"{pf}.o", B, T, d, f32=False)
+        y1 = tp.act(f"{pf}.y1", B, T, d)
+        h = tp.act(f"{pf}.h", B, T, self.d_inner, f32=False)
+        dz2 = tp.act(f"{pf}.dz2", B, T, d)             # .f32 holds dL/dy1 (total), hi/lo hold dz2
+        dh = tp.act(f"{pf}.dh", B, T, self.d_inner, f32=False)
+        dz1 = Act(None, *tp.bf(f"{pf}.dz1", (B, T, d)), B, T, d)
+        do = tp.act(f"{pf}.do", B, T, d, f32=False)
+        dP = tp.f32(f"{pf}.dP", (B, H, T, Tp))
+        ds_h, ds_l = tp.bf(f"{pf}.dS", (B, H, T, Tp))
+        dq_h, dq_l = tp.bf(f"{pf}.dqkv", (R, 3 * d))
+        qd_h, qd_l = tt.bf(f"{pf}.qkvd", (R, 3 * d))
+        pd_h, pd_l = tt.bf(f"{pf}.Pd", (B, H, T, Tp))
+        od = tt.act(f"{pf}.od", B, T, d, f32=False)
+        y1d = tt.act(f"{pf}.y1d", B, T, d)
+        hd = tt.act(f"{pf}.hd", B, T, self.d_inner, f32=False)
+        # ---- LN2 ----
+        ddz2 = tt.act(f"{pf}.ddz2", B, T, d)
+        be.ln_tbwd(dout, ddout, tp.f32(f"{pf}.z2", (B, T, d)), tt.f32(f"{pf}.z2d", (B, T, d)), tp.f32(f"{pf}.st2", (R, 2)),
+                   P.get(f"{f_}.layer_norm.weight").f32, gd(f"{f_}.layer_norm.weight"), lens, T, R, d, 0, ddz2.f32, ddz2.hi,
+                   ddz2.lo, hv(f"{f_}.layer_norm.weight"), hv(f"{f_}.layer_norm.bias"), hv(f"{f_}.w_2.bias"))
+        # ---- w_2 (k=1) with ReLU gate ----
+        ddh = tt.act(f"{pf}.ddh", B, T, self.d_inner, f32=False)
+        ddh_f = scr.scratch("h_f", (B, T, self.d_inner))
+        self._dgrad_t(dz2, ddz2, P.get(f"{f_}.w_2.weight"), wdt(f"{f_}.w_2.weight"), ddh_f, ddh.hi, ddh.lo, gate=h.hi)
+        self._wgrad_t(dz2, ddz2, h, hd, hv(f"{f_}.w_2.weight"))
+        be.colsum(None, ddh.hi, ddh.lo, 1, R, self.d_inner, hv(f"{f_}.w_1.bias"))
+        # ---- w_1 (k=9): ddy1 = dgrad(ddh, W1) + dgrad(dh, W1d) + ddz2 (residual) ----
+        self._dgrad_t(dh, ddh, P.get(f"{f_}.w_1.weight"), wdt(f"{f_}.w_1.weight"), ddz2.f32, None, None, add_c=True)
+        self._wgrad_t(dh, ddh, y1, y1d, hv(f"{f_}.w_1.weight"))
+        # ---- LN1 ----
+        ddz1 = Act(ddx_out, *tt.bf(f"{pf}.ddz1", (B, T, d)), B, T, d)
+        be.ln_tbwd(dz2.f32, ddz2.f32, tp.f32(f"{pf}.z1", (B, T, d)), tt.f32(f"{pf}.z1d", (B, T, d)),
+                   tp.f32(f"{pf}.st1", (R, 2)), P.get(f"{a_}.layer_norm.weight").f32, gd(f"{a_}.layer_norm.weight"), lens, T,
+                   R, d, 0, ddz1.f32, ddz1.hi, ddz1.lo, hv(f"{a_}.layer_norm.weight"), hv(f"{a_}.layer_norm.bias"),
+                   hv(f"{a_}.fc.bias"))
+        # ---- fc ----
+        ddo = tt.act(f"{pf}.ddo", B, T, d, f32=False)
+        ddo_f = scr.scratch("o_f", (B, T, d))
+        self._dgrad_t(dz1, ddz1, P.get(f"{a_}.fc.weight"), wdt(f"{a_}.fc.weight"), ddo_f, ddo.hi, ddo.lo)
+        self._wgrad_t(dz1, ddz1, o, od, hv(f"{a_}.fc.weight"))
+        # ---- attention ----
+        sc = 1.0 / math.sqrt(dk)
+        ddP = scr.scratch("S", (B, H, T, Tp))
+        g.bmm(om(ddo.hi, ddo.lo), False, qm(qkv_h, qkv_l, 2), False, pm(None, None, ddP), B, H)            # ddO V^T
+        g.bmm(om(do.hi, do.lo), False, qm(qd_h, qd_l, 2), False, pm(None, None, ddP), B, H, add_c=True)    # dO Vd^T
+        dds_h, dds_l = tt.bf(f"{pf}.ddS", (B, H, T, Tp))
+        be.softmax(2, dP, ddP, p_h, p_l, pd_h, pd_l, lens, B * H, H, T, T, Tp, dds_h, dds_l)
+        ddq_h, ddq_l = tt.bf(f"{pf}.ddqkv", (R, 3 * d))
+        ddq_f = scr.scratch("qkv_f", (R, 3 * d))
+        # ddV = Pd^T dO + P^T ddO
+        g.bmm(pm(pd_h, pd_l), True, om(do.hi, do.lo), True, qm(None, None, 2, ddq_f), B, H)
+        g.bmm(pm(p_h, p_l), True, om(ddo.hi, ddo.lo), True, qm(ddq_h, ddq_l, 2, ddq_f), B, H, add_c=True)
+        # ddQ = scale (ddS K + dS Kd)
+        g.bmm(pm(dds_h, dds_l), False, qm(qkv_h, qkv_l, 1), True, qm(None, None, 0, ddq_f), B, H, alpha=sc)
+        g.bmm(pm(ds_h, ds_l), False, qm(qd_h, qd_l, 1), True, qm(ddq_h, ddq_l, 0, ddq_f), B, H, alpha=sc, add_c=True)
+        # ddK = scale (ddS^T Q + dS^T Qd)
+        g.bmm(pm(dds_h, dds_l), True, qm(qkv_h, qkv_l, 0), True, qm(None, None, 1, ddq_f), B, H, alpha=sc)
+        g.bmm(pm(ds_h, ds_l), True, qm(qd_h, qd_l, 0), True, qm(ddq_h, ddq_l, 1, ddq_f), B, H, alpha=sc, add_c=True)
+        dqkv = Act(None, dq_h, dq_l, B, T, 3 * d)
+        ddqkv = Act(None, ddq_h, ddq_l, B, T, 3 * d)
+        self._wgrad_t(dqkv, ddqkv, x, xd, hvwqkv.f32)
+        be.colsum(None, ddq_h, ddq_l, 1, R, 3 * d, hvbqkv.f32)
+        self._dgrad_t(dqkv, ddqkv, wqkv, wdqkv, ddx_out, None, None, add_c=True)
+
+    # ---------------------------------------------------------------------------------------------
+    # VariancePredictor (modules.py:197-250)
+    # ---------------------------------------------------------------------------------------------
+    def vp_fwd(self, P, pf, tp, x: Act, lens, out: torch.Tensor):
+        be, g = self.be, self.g
+        B, Lq, d = x.B, x.T, self.d
+        R = B * Lq
+        c = f"{pf}.conv_layer"
+        h1 = tp.f32(f"{pf}.h1", (B, Lq, d))
+        g.conv_fwd(x, P.get(f"{c}.conv1d_1.conv.weight"), P.get(f"{c}.conv1d_1.conv.bias").f32, h1, None, None, relu=True)
+        a1 = tp.act(f"{pf}.a1", B, Lq, d)
+        be.ln_fwd(h1, None, P.get(f"{c}.layer_norm_1.weight").f32, P.get(f"{c}.layer_norm_1.bias").f32, None, Lq, R, d, None,
+                  tp.f32(f"{pf}.st1", (R, 2)), a1.f32, a1.hi, a1.lo)
+        h2 = tp.f32(f"{pf}.h2", (B, Lq, d))
+        g.conv_fwd(a1, P.get(f"{c}.conv1d_2.conv.weight"), P.get(f"{c}.conv1d_2.conv.bias").f32, h2, None, None, relu=True)
+        a2 = tp.f32(f"{pf}.a2", (B, Lq, d))
+        be.ln_fwd(h2, None, P.get(f"{c}.layer_norm_2.weight").f32, P.get(f"{c}.layer_norm_2.bias").f32, None, Lq, R, d, None,
+                  tp.f32(f"{pf}.st2", (R, 2)), a2, None, None)
+        be.rowdot_fwd(a2, None, P.get(f"{pf}.linear_layer.weight").f32, None, P.get(f"{pf}.linear_layer.bias").f32, None, lens,
+                      Lq, R, d, out)
+
+    def vp_bwd(self, P, G, pf, tp, x: Act, lens, dpred: torch.Tensor, dx_acc: torch.Tensor):
+        """dx_acc += dL/dx (fp32 [B,L,d])."""
+        be, g = self.be, self.g
+        B, Lq, d = x.B, x.T, self.d
+        R = B * Lq
+        c = f"{pf}.conv_layer"
+        a1 = tp.act(f"{pf}.a1", B, Lq, d)
+        da2 = tp.f32(f"{pf}.da2", (B, Lq, d))
+        be.rowdot_bwd(dpred, None, tp.f32(f"{pf}.a2", (B, Lq, d)), None, P.get(f"{pf}.linear_layer.weight").f32, None, lens,
+                      Lq, R, d, da2, G.get(f"{pf}.linear_layer.weight").f32, G.get(f"{pf}.linear_layer.bias").f32)
+        dc2 = tp.act(f"{pf}.dc2", B, Lq, d, f32=False)
+        be.ln_bwd(da2, tp.f32(f"{pf}.h2", (B, Lq, d)), tp.f32(f"{pf}.st2", (R, 2)), P.get(f"{c}.layer_norm_2.weight").f32,
+                  None, Lq, R, d, 1, None, dc2.hi, dc2.lo, G.get(f"{c}.layer_norm_2.weight").f32,
+                  G.get(f"{c}.layer_norm_2.bias").f32, G.get(f"{c}.conv1d_2.conv.bias").f32)
+        g.conv_wgrad(dc2, a1, G.get(f"{c}.conv1d_2.conv.weight").f32)
+        da1 = tp.f32(f"{pf}.da1", (B, Lq, d))
+        g.conv_dgrad(dc2, P.get(f"{c}.conv1d_2.conv.weight"), da1, None, None)
+        dc1 = tp.act(f"{pf}.dc1", B, Lq, d, f32=False)
+        be.ln_bwd(da1, tp.f32(f"{pf}.h1", (B, Lq, d)), tp.f32(f"{pf}.st1", (R, 2)), P.get(f"{c}.layer_norm_1.weight").f32,
+                  None, Lq, R, d, 1, None, dc1.hi, dc1.lo, G.get(f"{c}.layer_norm_1.weight").f32,
+                  G.get(f"{c}.layer_norm_1.bias").f32, G.get(f"{c}.conv1d_1.conv.bias").f32)
+        g.conv_wgrad(dc1, x, G.get(f"{c}.conv1d_1.conv.weight").f32)
+        g.conv_dgrad(dc1, P.get(f"{c}.conv1d_1.conv.weight"), dx_acc, None, None, add_c=True)
+
+    def vp_tfwd(self, P, Pd, pf, tp, tt, x: Act, xd: Optional[Act], lens, outd: torch.Tensor):
+        be = self.be
+        B, Lq, d = x.B, x.T, self.d
+        R = B * Lq
+        c = f"{pf}.conv_layer"
+        gd = lambda n: (Pd.get(n).f32 if Pd.has(n) else None)  # noqa: E731
+        wdt = lambda n: (Pd.get(n) if Pd.has(n) else None)  # noqa: E731
+        h1 = tp.f32(f"{pf}.h1", (B, Lq, d))
+        h2 = tp.f32(f"{pf}.h2", (B, Lq, d))
+        a1 = tp.act(f"{pf}.a1", B, Lq, d)
+        # relu gate needs a bf16 view of h1/h2: gate on the fp32 relu output via a hi copy kept in the tape
+        h1g, _ = tp.bf(f"{pf}.h1g", (B, Lq, d))
+        h2g, _ = tp.bf(f"{pf}.h2g", (B, Lq, d))
+        be.split_(h1, h1g, None)
+        be.split_(h2, h2g, None)
+        h1d = tt.f32(f"{pf}.h1d", (B, Lq, d))
+        self._lin_t(x, xd, P.get(f"{c}.conv1d_1.conv.weight"), wdt(f"{c}.conv1d_1.conv.weight"), gd(f"{c}.conv1d_1.conv.bias"),
+                    h1d, None, None, relu_gate=h1g)
+        a1d = tt.act(f"{pf}.a1d", B, Lq, d)
+        be.ln_tfwd(h1d, None, h1, tp.f32(f"{pf}.st1", (R, 2)), P.get(f"{c}.layer_norm_1.weight").f32,
+                   gd(f"{c}.layer_norm_1.weight"), gd(f"{c}.layer_norm_1.bias"), None, Lq, R, d, None, a1d.f32, a1d.hi, a1d.lo)
+        h2d = tt.f32(f"{pf}.h2d", (B, Lq, d))
+        self._lin_t(a1, a1d, P.get(f"{c}.conv1d_2.conv.weight"), wdt(f"{c}.conv1d_2.conv.weight"), gd(f"{c}.conv1d_2.conv.bias"),
+                    h2d, None, None, relu_gate=h2g)
+        a2d = tt.f32(f"{pf}.a2d", (B, Lq, d))
+        be.ln_tfwd(h2d, None, h2, tp.f32(f"{pf}.st2", (R, 2)), P.get(f"{c}.layer_norm_2.weight").f32,
+                   gd(f"{c}.layer_norm_2.weight"), gd(f"{c}.layer_norm_2.bias"), None, Lq, R, d, None, a2d, None, None)
+        be.rowdot_fwd(tp.f32(f"{pf}.a2", (B, Lq, d)), a2d, P.get(f"{pf}.linear_layer.weight").f32, gd(f"{pf}.linear_layer.weight"),
+                      None, gd(f"{pf}.linear_layer.bias"), lens, Lq, R, d, outd)
+
+    def vp_tbwd(self, P, Pd, HV, pf, tp, tt, x: Act, xd: Optional[Act], lens, dpred, ddpred, ddx_acc: torch.Tensor):
+        be, g = self.be, self.g
+        B, Lq, d = x.B, x.T, self.d
+        R = B * Lq
+        c = f"{pf}.conv_layer"
+        gd = lambda n: (Pd.get(n).f32 if Pd.has(n) else None)  # noqa: E731
+        wdt = lambda n: (Pd.get(n) if Pd.has(n) else None)  # noqa: E731
+        hv = lambda n: HV.get(n).f32  # noqa: E731
+        a1 = tp.act(f"{pf}.a1", B, Lq, d)
+        a1d = tt.act(f"{pf}.a1d", B, Lq, d)
+        dc2 = tp.act(f"{pf}.dc2", B, Lq, d, f32=False)
+        dc1 = tp.act(f"{pf}.dc1", B, Lq, d, f32=False)
+        dda2 = tt.f32(f"{pf}.dda2", (B, Lq, d))
+        be.rowdot_bwd(dpred, ddpred, tp.f32(f"{pf}.a2", (B, Lq, d)), tt.f32(f"{pf}.a2d", (B, Lq, d)),
+                      P.get(f"{pf}.linear_layer.weight").f32, gd(f"{pf}.linear_layer.weight"), lens, Lq, R, d, dda2,
+                      hv(f"{pf}.linear_layer.weight"), hv(f"{pf}.linear_layer.bias"))
+        ddc2 = tt.act(f"{pf}.ddc2", B, Lq, d, f32=False)
+        be.ln_tbwd(tp.f32(f"{pf}.da2", (B, Lq, d)), dda2, tp.f32(f"{pf}.h2", (B, Lq, d)), tt.f32(f"{pf}.h2d", (B, Lq, d)),
+                   tp.f32(f"{pf}.st2", (R, 2)), P.get(f"{c}.layer_norm_2.weight").f32, gd(f"{c}.layer_norm_2.weight"), None, Lq,
+                   R, d, 1, None, ddc2.hi, ddc2.lo, hv(f"{c}.layer_norm_2.weight"), hv(f"{c}.layer_norm_2.bias"),
+                   hv(f"{c}.conv1d_2.conv.bias"))
+        self._wgrad_t(dc2, ddc2, a1, a1d, hv(f"{c}.conv1d_2.conv.weight"))
+        dda1 = tt.f32(f"{pf}.dda1", (B, Lq, d))
+        self._dgrad_t(dc2, ddc2, P.get(f"{c}.conv1d_2.conv.weight"), wdt(f"{c}.conv1d_2.conv.weight"), dda1, None, None)
+        ddc1 = tt.act(f"{pf}.ddc1", B, Lq, d, f32=False)
+        be.ln_tbwd(tp.f32(f"{pf}.da1", (B, Lq, d)), dda1, tp.f32(f"{pf}.h1", (B, Lq, d)), tt.f32(f"{pf}.h1d", (B, Lq, d)),
+                   tp.f32(f"{pf}.st1", (R, 2)), P.get(f"{c}.layer_norm_1.weight").f32, gd(f"{c}.layer_norm_1.weight"), None, Lq,
+                   R, d, 1, None, ddc1.hi, ddc1.lo, hv(f"{c}.layer_norm_1.weight"), hv(f"{c}.layer_norm_1.bias"),
+                   hv(f"{c}.conv1d_1.conv.bias"))
+        self._wgrad_t(dc1, ddc1, x, xd, hv(f"{c}.conv1d_1.conv.weight"))
+        self._dgrad_t(dc1, ddc1, P.get(f"{c}.conv1d_1.conv.weight"), wdt(f"{c}.conv1d_1.conv.weight"), ddx_acc, None, None,
+                      add_c=True)
+
+    # ---------------------------------------------------------------------------------------------
+    # whole model
+    # ---------------------------------------------------------------------------------------------
+    def forward(self, P: ParamSet, bt: Batch, tp: Tape, update_bn: bool = True):
+        """Teacher-forced forward + loss.  Returns dict with the reference's prediction tensors."""
+        be, g, scr, d = self.be, self.g, self.scr, self.d
+        B, Lq, T = bt.B, bt.L, bt.T
+        assert T <= self.cfg["max_seq_len"] and Lq <= self.cfg["max_seq_len"], "sequence longer than max_seq_len"
+        # ---- encoder (Models.py:73-100) ----
+        x = tp.act("enc.x0", B, Lq, d)
+        be.embed_fwd(bt.texts, P.get("encoder.src_word_emb.weight").f32, None, self.consts["encoder.position_enc"], Lq,
+                     B * Lq, d, x.f32, x.hi, x.lo)
+        for i in range(self.n_enc):
+            x = self.fft_fwd(P, f"encoder.layer_stack.{i}", tp, x, bt.src_lens, self.h_enc)
+        # ---- speaker embedding (base_adaptor.py:64-70) ----
+        spk = tp.f32("spk", (B, d))
+        be.spk_embed(bt.spk_ids, P.get("speaker_emb.model.weight").f32, bt.spk_ids.numel(), d, bt.average_spk, B, spk)
+        x0 = tp.act("va.x0", B, Lq, d)
+        be.add_rowvec(x.f32, spk, d, None, B, Lq, d, x0.f32, x0.hi, x0.lo)
+        # ---- variance adaptor (modules.py:102-158) ----
+        va = "variance_adaptor"
+        logd = tp.f32("logd", (B, Lq))
+        ppred = tp.f32("ppred", (B, Lq))
+        epred = tp.f32("epred", (B, Lq))
+        self.vp_fwd(P, f"{va}.duration_predictor", tp, x0, bt.src_lens, logd)
+        self.vp_fwd(P, f"{va}.pitch_predictor", tp, x0, bt.src_lens, ppred)
+        idx_p = tp.buf("va.idx_p", (B, Lq), torch.int64)
+        idx_e = tp.buf("va.idx_e", (B, Lq), torch.int64)
+        be.bucketize(bt.pitches, self.consts[f"{va}.pitch_bins"], self.nbins - 1, B * Lq, idx_p)
+        be.bucketize(bt.energies, self.consts[f"{va}.energy_bins"], self.nbins - 1, B * Lq, idx_e)
+        x1 = tp.act("va.x1", B, Lq, d)
+        be.embed_fwd(idx_p, P.get(f"{va}.pitch_embedding.weight").f32, x0.f32, None, Lq, B * Lq, d, x1.f32, x1.hi, x1.lo)
+        self.vp_fwd(P, f"{va}.energy_predictor", tp, x1, bt.src_lens, epred)
+        x2 = scr.scratch("va.x2", (B, Lq, d))
+        be.embed_fwd(idx_e, P.get(f"{va}.energy_embedding.weight").f32, x1.f32, None, Lq, B * Lq, d, x2, None, None)
+        lr_idx = tp.buf("lr.idx", (B, T), torch.int32)
+        lr_len = tp.buf("lr.mel_len", (B,), torch.int64)
+        be.lr_index(bt.durations, T, lr_idx, lr_len)
+        xr = scr.scratch("lr.out", (B, T, d))
+        be.lr_fwd(x2, lr_idx, xr)
+        # ---- decoder (Models.py:139-171) ----
+        y = tp.act("dec.x0", B, T, d)
+        be.add_rowvec(xr, spk, d, self.consts["decoder.position_enc"], B, T, d, y.f32, y.hi, y.lo)
+        for i in range(self.n_dec):
+            y = self.fft_fwd(P, f"decoder.layer_stack.{i}", tp, y, bt.mel_lens, self.h_dec)
+        # ---- mel_linear + postnet (fastspeech2.py:97-99, Layers.py:129-137) ----
+        mel = tp.act("mel", B, T, N_MEL)
+        g.conv_fwd(y, P.get("mel_linear.weight"), P.get("mel_linear.bias").f32, mel.f32, mel.hi, mel.lo)
+        xin = mel
+        R = B * T
+        for i in range(5):
+            pre = f"postnet.convolutions.{i}"
+            co = POSTNET_CH[i + 1]
+            c = tp.f32(f"post.{i}.c", (B, T, co))
+            g.conv_fwd(xin, P.get(f"{pre}.0.conv.weight"), P.get(f"{pre}.0.conv.bias").f32, c, None, None)
+            o = tp.act(f"post.{i}.o", B, T, co, bf=(i < 4))
+            rm = self.consts[f"{pre}.1.running_mean"] if update_bn else None
+            rv = self.consts[f"{pre}.1.running_var"] if update_bn else None
+            be.bn_fwd(c, P.get(f"{pre}.1.weight").f32, P.get(f"{pre}.1.bias").f32, R, co, i < 4, rm, rv,
+                      scr.scratch("bn.ws", (4 * 512,)), tp.f32(f"post.{i}.st", (2 * co,)), o.f32, o.hi, o.lo)
+            xin = o
+        post = xin.f32
+        be.axpby(1.0, mel.f32, 1.0, post)                    # postnet(output) + output
+        loss6 = tp.f32("loss6", (6,))
+        be.loss_fwd(mel.f32, post, bt.mels, bt.mel_lens, ppred, bt.pitches, epred, bt.energies, logd, bt.durations,
+                    bt.src_lens, B, T, Lq, N_MEL, scr.scratch("loss.ws", (8,)), loss6, tp.f32("loss.counts", (2,)))
+        return {"mel": mel.f32, "postnet": post, "pitch": ppred, "energy": epred, "logd": logd, "loss6": loss6,
+                "mel_len": lr_len}
+
+    def backward(self, P: ParamSet, G: ParamSet, bt: Batch, tp: Tape, loss_scale: float = 1.0, into_encoder: bool = True):
+        """dL*loss_scale/dparams accumulated into G (G must be zeroed by the caller when needed)."""
+        be, g, scr, d = self.be, self.g, self.scr, self.d
+        B, Lq, T = bt.B, bt.L, bt.T
+        R = B * T
+        va = "variance_adaptor"
+        mel = tp.act("mel", B, T, N_MEL)
+        post = tp.f32("post.4.o", (B, T, N_MEL))
+        dmel = tp.act("dmel", B, T, N_MEL)                   # total dL/dmel (L1 + residual + postnet path)
+        dpost = tp.f32("post.4.dout", (B, T, N_MEL))
+        dp, de, dlogd = tp.f32("dp", (B, Lq)), tp.f32("de", (B, Lq)), tp.f32("dlogd", (B, Lq))
+        be.loss_bwd(mel.f32, post, bt.mels, bt.mel_lens, tp.f32("ppred", (B, Lq)), bt.pitches, tp.f32("epred", (B, Lq)),
+                    bt.energies, tp.f32("logd", (B, Lq)), bt.durations, bt.src_lens, B, T, Lq, N_MEL,
+                    tp.f32("loss.counts", (2,)), loss_scale, 0, dmel.f32, dpost, dp, de, dlogd)
+        be.axpby(1.0, dpost, 1.0, dmel.f32)                  # residual: postnet_output = postnet(mel) + mel
+        # ---- postnet ----
+        for i in range(4, -1, -1):
+            pre = f"postnet.convolutions.{i}"
+            ci, co = POSTNET_CH[i], POSTNET_CH[i + 1]
+            xin = mel if i == 0 else tp.act(f"post.{i - 1}.o", B, T, ci)
+            dout = tp.f32(f"post.{i}.dout", (B, T, co))
+            dc = tp.act(f"post.{i}.dc", B, T, co)
+            be.bn_bwd(dout, tp.f32(f"post.{i}.o", (B, T, co)) if i < 4 else None, tp.f32(f"post.{i}.c", (B, T, co)),
+                      tp.f32(f"post.{i}.st", (2 * co,)), P.get(f"{pre}.1.weight").f32, R, co, i < 4, scr.scratch("bn.ws", (4 * 512,)),
+                      dc.f32, dc.hi, dc.lo, G.get(f"{pre}.1.weight").f32, G.get(f"{pre}.1.bias").f32,
+                      beta=P.get(f"{pre}.1.bias").f32)
+            be.colsum(dc.f32, None, None, 1, R, co, G.get(f"{pre}.0.conv.bias").f32)
+            g.conv_wgrad(dc, xin, G.get(f"{pre}.0.conv.weight").f32)
+            if i > 0:
+                g.conv_dgrad(dc, P.get(f"{pre}.0.conv.weight"), tp.f32(f"post.{i - 1}.dout", (B, T, ci)), None, None)
+            else:
+                g.conv_dgrad(dc, P.get(f"{pre}.0.conv.weight"), dmel.f32, None, None, add_c=True)
+        # ---- mel_linear ----
+        be.split_(dmel.f32, dmel.hi, dmel.lo)
+        be.colsum(dmel.f32, None, None, 1, R, N_MEL, G.get("mel_linear.bias").f32)
+        ylast = tp.act(f"decoder.layer_stack.{self.n_dec - 1}.out", B, T, d)
+        g.conv_wgrad(dmel, ylast, G.get("mel_linear.weight").f32)
+        dcur = tp.f32(f"decoder.layer_stack.{self.n_dec - 1}.dout", (B, T, d))
+        g.conv_dgrad(dmel, P.get("mel_linear.weight"), dcur, None, None)
+        # ---- decoder ----
+        for i in range(self.n_dec - 1, -1, -1):
+            pf = f"decoder.layer_stack.{i}"
+            xin = tp.act(f"decoder.layer_stack.{i - 1}.out", B, T, d) if i > 0 else tp.act("dec.x0", B, T, d)
+            dnext = tp.f32(f"decoder.layer_stack.{i - 1}.dout", (B, T, d)) if i > 0 else tp.f32("dec.din", (B, T, d))
+            self.fft_bwd(P, G, pf, tp, xin, bt.mel_lens, self.h_dec, dcur, dnext)
+            dcur = dnext
+        # ---- speaker add / length regulator ----
+        dspk = tp.f32("dspk", (B, d))
+        be.zero_(dspk)
+        be.colsum(dcur, None, None, B, T, d, dspk)
+        dx = tp.f32("va.dx", (B, Lq, d))
+        be.lr_bwd(dcur, bt.durations, Lq, dx)
+        # ---- variance adaptor ----
+        x0 = tp.act("va.x0", B, Lq, d)
+        x1 = tp.act("va.x1", B, Lq, d)
+        be.embed_bwd(tp.buf("va.idx_e", (B, Lq), torch.int64), dx, B * Lq, d, -1, 1.0, G.get(f"{va}.energy_embedding.weight").f32)
+        self.vp_bwd(P, G, f"{va}.energy_predictor", tp, x1, bt.src_lens, de, dx)
+        be.embed_bwd(tp.buf("va.idx_p", (B, Lq), torch.int64), dx, B * Lq, d, -1, 1.0, G.get(f"{va}.pitch_embedding.weight").f32)
+        self.vp_bwd(P, G, f"{va}.pitch_predictor", tp, x0, bt.src_lens, dp, dx)
+        self.vp_bwd(P, G, f"{va}.duration_predictor", tp, x0, bt.src_lens, dlogd, dx)
+        be.colsum(dx, None, None, B, Lq, d, dspk)
+        be.spk_embed_bwd(bt.spk_ids, dspk, bt.spk_ids.numel(), d, bt.average_spk, B, 1.0, G.get("speaker_emb.model.weight").f32)
+        # ---- encoder ----
+        if into_encoder:
+            self._encoder_bwd(P, G, bt, tp, dx)
+
+    def _encoder_bwd(self, P, G, bt: Batch, tp: Tape, d_encout: torch.Tensor):
+        """Plain backward through the encoder from dL/d(encoder output)."""
+        be, d = self.be, self.d
+        B, Lq = bt.B, bt.L
+        dcur = d_encout
+        for i in range(self.n_enc - 1, -1, -1):
+            pf = f"encoder.layer_stack.{i}"
+            xin = tp.act(f"encoder.layer_stack.{i - 1}.out", B, Lq, d) if i > 0 else tp.act("enc.x0", B, Lq, d)
+            dnext = tp.f32(f"encoder.layer_stack.{i}.din", (B, Lq, d))
+            self.fft_bwd(P, G, pf, tp, xin, bt.src_lens, self.h_enc, dcur, dnext)
+            dcur = dnext
+        be.embed_bwd(bt.texts, dcur, B * Lq, d, 0, 1.0, G.get("encoder.src_word_emb.weight").f32)
+
+    # ---------------------------------------------------------------------------------------------
+    # Hessian-vector product at the tape's parameters:  HV += d/d(eps) grad L(P + eps*Pd)
+    # (Pd is non-zero on adapted parameters only; encoder = non-adapted => zero forward tangent.)
+    # ---------------------------------------------------------------------------------------------
+    def hvp(self, P: ParamSet, Pd: ParamSet, HV: ParamSet, bt: Batch, tp: Tape, tt: Tape, loss_scale: float = 1.0):
+        be, g, scr, d = self.be, self.g, self.scr, self.d
+        B, Lq, T = bt.B, bt.L, bt.T
+        R = B * T
+        va = "variance_adaptor"
+        lay = self.layout
+        assert not lay.is_adapted_module("encoder"), "HVP with an adapted encoder is not implemented"
+        gd = lambda n: (Pd.get(n).f32 if Pd.has(n) else None)  # noqa: E731
+        wdt = lambda n: (Pd.get(n) if Pd.has(n) else None)  # noqa: E731
+        hv = lambda n: HV.get(n).f32  # noqa: E731
+        # ================= tangent forward =================
+        x0 = tp.act("va.x0", B, Lq, d)
+        x1 = tp.act("va.x1", B, Lq, d)
+        spkd = None
+        x0d = None
+        if Pd.has("speaker_emb.model.weight"):
+            spkd = tt.f32("spkd", (B, d))
+            be.spk_embed(bt.spk_ids, Pd.get("speaker_emb.model.weight").f32, bt.spk_ids.numel(), d, bt.average_spk, B, spkd)
+            x0d = tt.act("va.x0d", B, Lq, d)
+            zl = scr.scratch("zeros.L", (B, Lq, d))
+            be.zero_(zl)
+            be.add_rowvec(zl, spkd, d, None, B, Lq, d, x0d.f32, x0d.hi, x0d.lo)
+        va_adapted = lay.is_adapted_module(va)
+        assert va_adapted and spkd is not None, "HVP expects speaker_emb and variance_adaptor in adapt.modules"
+        logdd, ppd, epd = tt.f32("logdd", (B, Lq)), tt.f32("ppredd", (B, Lq)), tt.f32("epredd", (B, Lq))
+        self.vp_tfwd(P, Pd, f"{va}.duration_predictor", tp, tt, x0, x0d, bt.src_lens, logdd)
+        self.vp_tfwd(P, Pd, f"{va}.pitch_predictor", tp, tt, x0, x0d, bt.src_lens, ppd)
+        idx_p = tp.buf("va.idx_p", (B, Lq), torch.int64)
+        idx_e = tp.buf("va.idx_e", (B, Lq), torch.int64)
+        x1d = tt.act("va.x1d", B, Lq, d)
+        be.embed_fwd(idx_p, Pd.get(f"{va}.pitch_embedding.weight").f32, x0d.f32, None, Lq, B * Lq, d, x1d.f32, x1d.hi, x1d.lo)
+        self.vp_tfwd(P, Pd, f"{va}.energy_predictor", tp, tt, x1, x1d, bt.src_lens, epd)
+        x2d = scr.scratch("va.x2", (B, Lq, d))
+        be.embed_fwd(idx_e, Pd.get(f"{va}.energy_embedding.weight").f32, x1d.f32, None, Lq, B * Lq, d, x2d, None, None)
+        xrd = scr.scratch("lr.out", (B, T, d))
+        be.lr_fwd(x2d, tp.buf("lr.idx", (B, T), torch.int32), xrd)
+        yd = tt.act("dec.x0d", B, T, d)
+        be.add_rowvec(xrd, spkd, d, None, B, T, d, yd.f32, yd.hi, yd.lo)
+        y = tp.act("dec.x0", B, T, d)
+        for i in range(self.n_dec):
+            pf = f"decoder.layer_stack.{i}"
+            ynext = tp.act(f"{pf}.out", B, T, d)
+            yd = self.fft_tfwd(P, Pd, pf, tp, tt, y, yd, bt.mel_lens, self.h_dec)
+            y = ynext
+        mel = tp.act("mel", B, T, N_MEL)
+        meld = tt.act("meld", B, T, N_MEL)
+        self._lin_t(y, yd, P.get("mel_linear.weight"), wdt("mel_linear.weight"), gd("mel_linear.bias"), meld.f32, meld.hi, meld.lo)
+        xin, xind = mel, meld
+        for i in range(5):
+            pre = f"postnet.convolutions.{i}"
+            co = POSTNET_CH[i + 1]
+            cd = tt.f32(f"post.{i}.cd", (B, T, co))
+            self._lin_t(xin, xind, P.get(f"{pre}.0.conv.weight"), wdt(f"{pre}.0.conv.weight"), gd(f"{pre}.0.conv.bias"), cd, None, None)
+            od = tt.act(f"post.{i}.od", B, T, co, bf=(i < 4))
+            be.bn_tfwd(cd, tp.f32(f"post.{i}.c", (B, T, co)), tp.f32(f"post.{i}.st", (2 * co,)), P.get(f"{pre}.1.weight").f32,
+                       gd(f"{pre}.1.weight"), gd(f"{pre}.1.bias"), tp.f32(f"post.{i}.o", (B, T, co)) if i < 4 else None, R, co,
+                       i < 4, scr.scratch("bn.ws", (4 * 512,)), tt.f32(f"post.{i}.ts", (2 * co,)), od.f32, od.hi, od.lo,
+                       beta=P.get(f"{pre}.1.bias").f32)
+            xin = tp.act(f"post.{i}.o", B, T, co, bf=(i < 4))
+            xind = od
+        # (postnet_output tangent = od4 + meld, but the L1 losses have zero curvature: not needed)
+        # ================= tangent backward =================
+        ddmel = tt.act("ddmel", B, T, N_MEL)
+        ddpost = tt.f32("post.4.ddout", (B, T, N_MEL))
+        ddp, dde, ddlogd = tt.f32("ddp", (B, Lq)), tt.f32("dde", (B, Lq)), tt.f32("ddlogd", (B, Lq))
+        be.loss_bwd(None, None, None, bt.mel_lens, ppd, None, epd, None, logdd, None, bt.src_lens, B, T, Lq, N_MEL,
+                    tp.f32("loss.counts", (2,)), loss_scale, 1, ddmel.f32, ddpost, ddp, dde, ddlogd)
+        # ddmel = 0 + ddpost(=0) so far; postnet chain
+        for i in range(4, -1, -1):
+            pre = f"postnet.convolutions.{i}"
+            ci, co = POSTNET_CH[i], POSTNET_CH[i + 1]
+            xin = mel if i == 0 else tp.act(f"post.{i - 1}.o", B, T, ci)
+            xind = meld if i == 0 else tt.act(f"post.{i - 1}.od", B, T, ci)
+            dc = tp.act(f"post.{i}.dc", B, T, co)
+            ddc = tt.act(f"post.{i}.ddc", B, T, co)
+            be.bn_tbwd(tp.f32(f"post.{i}.dout", (B, T, co)), tt.f32(f"post.{i}.ddout", (B, T, co)),
+                       tp.f32(f"post.{i}.o", (B, T, co)) if i < 4 else None, tt.f32(f"post.{i}.od", (B, T, co)) if i < 4 else None,
+                       tp.f32(f"post.{i}.c", (B, T, co)), tt.f32(f"post.{i}.cd", (B, T, co)), tp.f32(f"post.{i}.st", (2 * co,)),
+                       tt.f32(f"post.{i}.ts", (2 * co,)), P.get(f"{pre}.1.weight").f32, gd(f"{pre}.1.weight"), R, co, i < 4,
+                       scr.scratch("bn.ws", (4 * 512,)), ddc.f32, ddc.hi, ddc.lo, hv(f"{pre}.1.weight"), hv(f"{pre}.1.bias"),
+                       beta=P.get(f"{pre}.1.bias").f32, bdot=gd(f"{pre}.1.bias"))
+            be.colsum(ddc.f32, None, None, 1, R, co, hv(f"{pre}.0.conv.bias"))
+            self._wgrad_t(dc, ddc, xin, xind, hv(f"{pre}.0.conv.weight"))
+            if i > 0:
+                self._dgrad_t(dc, ddc, P.get(f"{pre}.0.conv.weight"), wdt(f"{pre}.0.conv.weight"),
+                              tt.f32(f"post.{i - 1}.ddout", (B, T, ci)), None, None)
+            else:
+                self._dgrad_t(dc, ddc, P.get(f"{pre}.0.conv.weight"), wdt(f"{pre}.0.conv.weight"), ddmel.f32, None, None,
+                              add_c=True)
+        # mel_linear
+        dmel = tp.act("dmel", B, T, N_MEL)
+        be.split_(ddmel.f32, ddmel.hi, ddmel.lo)
+        be.colsum(ddmel.f32, None, None, 1, R, N_MEL, hv("mel_linear.bias"))
+        ylast = tp.act(f"decoder.layer_stack.{self.n_dec - 1}.out", B, T, d)
+        ylastd = tt.act(f"decoder.layer_stack.{self.n_dec - 1}.outd", B, T, d)
+        self._wgrad_t(dmel, ddmel, ylast, ylastd, hv("mel_linear.weight"))
+        ddcur = tt.f32(f"decoder.layer_stack.{self.n_dec - 1}.ddout", (B, T, d))
+        self._dgrad_t(dmel, ddmel, P.get("mel_linear.weight"), wdt("mel_linear.weight"), ddcur, None, None)
+        # decoder
+        for i in range(self.n_dec - 1, -1, -1):
+            pf = f"decoder.layer_stack.{i}"
+            xin = tp.act(f"decoder.layer_stack.{i - 1}.out", B, T, d) if i > 0 else tp.act("dec.x0", B, T, d)
+            xind = tt.act(f"decoder.layer_stack.{i - 1}.outd", B, T, d) if i > 0 else tt.act("dec.x0d", B, T, d)
+            ddnext = tt.f32(f"decoder.layer_stack.{i - 1}.ddout", (B, T, d)) if i > 0 else tt.f32("dec.ddin", (B, T, d))
+            self.fft_tbwd(P, Pd, HV, pf, tp, tt, xin, xind, bt.mel_lens, self.h_dec, tp.f32(f"{pf}.dout", (B, T, d)), ddcur, ddnext)
+            ddcur = ddnext
+        ddspk = tt.f32("ddspk", (B, d))
+        be.zero_(ddspk)
+        be.colsum(ddcur, None, None, B, T, d, ddspk)
+        ddx = tt.f32("va.ddx", (B, Lq, d))
+        be.lr_bwd(ddcur, bt.durations, Lq, ddx)
+        be.embed_bwd(idx_e, ddx, B * Lq, d, -1, 1.0, hv(f"{va}.energy_embedding.weight"))
+        self.vp_tbwd(P, Pd, HV, f"{va}.energy_predictor", tp, tt, x1, x1d, bt.src_lens, tp.f32("de", (B, Lq)), dde, ddx)
+        be.embed_bwd(idx_p, ddx, B * Lq, d, -1, 1.0, hv(f"{va}.pitch_embedding.weight"))
+        self.vp_tbwd(P, Pd, HV, f"{va}.pitch_predictor", tp, tt, x0, x0d, bt.src_lens, tp.f32("dp", (B, Lq)), ddp, ddx)
+        self.vp_tbwd(P, Pd, HV, f"{va}.duration_predictor", tp, tt, x0, x0d, bt.src_lens, tp.f32("dlogd", (B, Lq)), ddlogd, ddx)
+        be.colsum(ddx, None, None, B, Lq, d, ddspk)
+        be.spk_embed_bwd(bt.spk_ids, ddspk, bt.spk_ids.numel(), d, bt.average_spk, B, 1.0, hv("speaker_emb.model.weight"))
+        # encoder: zero forward tangent => the tangent backward is a plain backward of ddx (mixed partials)
+        self._encoder_bwd(P, HV, bt, tp, ddx)

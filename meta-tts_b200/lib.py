@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmtts.so")
 # enums (include/mtts.h)
 SRC_ZERO, SRC_Z0, SRC_Z1, SRC_TAP, SRC_KB = 0, 1, 2, 3, 4
 MAJOR_K, MAJOR_MN = 0, 1
-EPI_RELU, EPI_ACCUM, EPI_GATE, EPI_BIAS_ROW = 1, 2, 4, 8
+EPI_RELU, EPI_ACCUM, EPI_GATE, EPI_BIAS_ROW, EPI_ADD_C = 1, 2, 4, 8, 16
 
 
 class Operand(C.Structure):
@@ -80,6 +80,31 @@ SIGNATURES: dict[str, list] = {
     "mtts_length_regulate_index": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "mtts_length_regulate_fwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "mtts_length_regulate_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "mtts_ln_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mtts_ln_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mtts_ln_tfwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp],
+    "mtts_ln_tbwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mtts_rowdot_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp],
+    "mtts_rowdot_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp],
+    "mtts_softmax": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "mtts_embed_fwd": [_vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp],
+    "mtts_embed_bwd": [_vp, _vp, _i64, _i, _i64, _f, _vp, _vp],
+    "mtts_bucketize": [_vp, _vp, _i, _i64, _vp, _vp],
+    "mtts_add_rowvec": [_vp, _vp, _i64, _vp, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "mtts_spk_embed": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
+    "mtts_spk_embed_bwd": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp],
+    "mtts_colsum": [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp],
+    "mtts_bn_fwd": [_vp, _vp, _vp, _i64, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mtts_bn_bwd": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mtts_bn_tfwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mtts_bn_tbwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mtts_loss_fwd": [_vp] * 11 + [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "mtts_loss_bwd": [_vp] * 11 + [_i, _i, _i, _i, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mtts_split": [_vp, _vp, _vp, _i64, _vp],
+    "mtts_sgd_split": [_vp, _vp, _f, _vp, _vp, _vp, _i64, _vp],
+    "mtts_axpby": [_f, _vp, _f, _vp, _i64, _vp],
+    "mtts_sumsq": [_vp, _i64, _vp, _vp],
+    "mtts_adam_clip": [_vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _f, _f, _f, _vp, _vp, _i64, _vp],
 }
 
 

@@ -101,14 +101,17 @@ def gemm(a: Opnd, b: Opnd, M: int, N: int, K: int, *,
 # ---------------------------------------------------------------------------------------------
 # LengthRegulator
 # ---------------------------------------------------------------------------------------------
-def length_regulate_index(dur: torch.Tensor, T: int):
+def length_regulate_index(dur: torch.Tensor, T: int, idx: Optional[torch.Tensor] = None,
+                          mel_len: Optional[torch.Tensor] = None):
     """dur [B,L] int64 (targets) or float32 (predicted) -> (idx [B,T] int32, mel_len [B] int64)."""
     global launch_count
     _need_cuda(dur)
     B, Lp = dur.shape
-    dur = dur.contiguous()
-    idx = torch.empty((B, T), dtype=torch.int32, device=dur.device)
-    mel_len = torch.empty((B,), dtype=torch.int64, device=dur.device)
+    assert dur.is_contiguous()
+    if idx is None:
+        idx = torch.empty((B, T), dtype=torch.int32, device=dur.device)
+    if mel_len is None:
+        mel_len = torch.empty((B,), dtype=torch.int64, device=dur.device)
     if dur.dtype == torch.int64:
         di, df = dur.data_ptr(), None
     elif dur.dtype == torch.float32:
@@ -142,3 +145,155 @@ def length_regulate_bwd(dy: torch.Tensor, dur: torch.Tensor, Lp: int, out: Optio
     L.call("mtts_length_regulate_bwd", dy.data_ptr(), di, df, B, Lp, T, Cc, out.data_ptr(), _stream())
     launch_count += 1
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CudaOps: the op set the engine is written against.  Every method is one (or a fixed handful of)
+# libmtts kernel launch(es) on the current stream; tensors are preallocated by the caller.
+# ---------------------------------------------------------------------------------------------
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class CudaOps:
+    """sm_100a backend.  `split` = 1 (bf16) or 3 (bf16x3 hi/lo, fp32-grade)."""
+
+    name = "cuda"
+
+    def __init__(self, split: int = 3, device: str = "cuda:0"):
+        if not torch.cuda.is_available():
+            raise L.MttsError("CudaOps needs a CUDA device (B200): there is no CPU fallback")
+        L.call("mtts_check_device")
+        assert split in (1, 3)
+        self.split = split
+        self.device = torch.device(device)
+
+    # ---- allocation helpers (plumbing) ----
+    def empty(self, shape, dtype=torch.float32):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype=torch.float32):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    def zero_(self, t):
+        t.zero_()          # cudaMemsetAsync on the current stream
+
+    def _call(self, name, *args):
+        global launch_count
+        L.call(name, *args, _stream())
+        launch_count += 1
+
+    # ---- GEMM ----
+    def gemm(self, a: Opnd, b: Opnd, M, N, K, **kw):
+        kw.setdefault("split", self.split)
+        gemm(a, b, M, N, K, **kw)
+
+    # ---- length regulator ----
+    def lr_index(self, dur, T, idx=None, mel_len=None):
+        return length_regulate_index(dur, T, idx, mel_len)
+
+    def lr_fwd(self, x, idx, out):
+        return length_regulate_fwd(x, idx, out)
+
+    def lr_bwd(self, dy, dur, Lp, out):
+        return length_regulate_bwd(dy, dur, Lp, out)
+
+    # ---- row ops ----
+    def ln_fwd(self, y, res, gamma, beta, lens, T, R, C, z_out, stats, out, out_hi, out_lo, eps=1e-5):
+        self._call("mtts_ln_fwd", _p(y), _p(res), _p(gamma), _p(beta), _p(lens), T, R, C, eps, _p(z_out), _p(stats),
+                   _p(out), _p(out_hi), _p(out_lo))
+
+    def ln_bwd(self, dy, z, stats, gamma, lens, T, R, C, relu_gate, dz, dz_hi, dz_lo, dgamma, dbeta, dbias):
+        self._call("mtts_ln_bwd", _p(dy), _p(z), _p(stats), _p(gamma), _p(lens), T, R, C, int(relu_gate), _p(dz),
+                   _p(dz_hi), _p(dz_lo), _p(dgamma), _p(dbeta), _p(dbias))
+
+    def ln_tfwd(self, ydot, resdot, z, stats, gamma, gdot, bdot, lens, T, R, C, zdot_out, out, out_hi, out_lo):
+        self._call("mtts_ln_tfwd", _p(ydot), _p(resdot), _p(z), _p(stats), _p(gamma), _p(gdot), _p(bdot), _p(lens),
+                   T, R, C, _p(zdot_out), _p(out), _p(out_hi), _p(out_lo))
+
+    def ln_tbwd(self, dy, ddy, z, zdot, stats, gamma, gdot, lens, T, R, C, relu_gate, ddz, ddz_hi, ddz_lo,
+                ddgamma, ddbeta, ddbias):
+        self._call("mtts_ln_tbwd", _p(dy), _p(ddy), _p(z), _p(zdot), _p(stats), _p(gamma), _p(gdot), _p(lens), T, R, C,
+                   int(relu_gate), _p(ddz), _p(ddz_hi), _p(ddz_lo), _p(ddgamma), _p(ddbeta), _p(ddbias))
+
+    def rowdot_fwd(self, h, hdot, w, wdot, b, bdot, lens, T, R, C, out):
+        self._call("mtts_rowdot_fwd", _p(h), _p(hdot), _p(w), _p(wdot), _p(b), _p(bdot), _p(lens), T, R, C, _p(out))
+
+    def rowdot_bwd(self, dout, ddout, h, hdot, w, wdot, lens, T, R, C, dh, dw, db):
+        self._call("mtts_rowdot_bwd", _p(dout), _p(ddout), _p(h), _p(hdot), _p(w), _p(wdot), _p(lens), T, R, C,
+                   _p(dh), _p(dw), _p(db))
+
+    def softmax(self, mode, A, Bm, p_hi, p_lo, pd_hi, pd_lo, klens, nz, H, Lq, Lk, ld, o_hi, o_lo):
+        self._call("mtts_softmax", mode, _p(A), _p(Bm), _p(p_hi), _p(p_lo), _p(pd_hi), _p(pd_lo), _p(klens), nz, H,
+                   Lq, Lk, ld, _p(o_hi), _p(o_lo))
+
+    # ---- gathers / broadcasts / sums ----
+    def embed_fwd(self, idx, table, base, pos, T, R, C, out, hi, lo):
+        self._call("mtts_embed_fwd", _p(idx), _p(table), _p(base), _p(pos), T, R, C, _p(out), _p(hi), _p(lo))
+
+    def embed_bwd(self, idx, dy, R, C, skip_idx, scale, dtable):
+        self._call("mtts_embed_bwd", _p(idx), _p(dy), R, C, skip_idx, scale, _p(dtable))
+
+    def bucketize(self, v, bins, nb, R, out):
+        self._call("mtts_bucketize", _p(v), _p(bins), nb, R, _p(out))
+
+    def add_rowvec(self, x, vec, vec_bstride, pos, B, T, C, out, hi, lo):
+        self._call("mtts_add_rowvec", _p(x), _p(vec), vec_bstride, _p(pos), B, T, C, _p(out), _p(hi), _p(lo))
+
+    def spk_embed(self, ids, table, n, C, average, n_out, out):
+        self._call("mtts_spk_embed", _p(ids), _p(table), n, C, int(average), n_out, _p(out))
+
+    def spk_embed_bwd(self, ids, dspk, n, C, average, n_out, scale, dtable):
+        self._call("mtts_spk_embed_bwd", _p(ids), _p(dspk), n, C, int(average), n_out, scale, _p(dtable))
+
+    def colsum(self, f32, hi, lo, nb, R, C, out):
+        self._call("mtts_colsum", _p(f32), _p(hi), _p(lo), nb, R, C, _p(out))
+
+    # ---- batch norm ----
+    def bn_fwd(self, x, gamma, beta, R, C, tanh_flag, running_mean, running_var, ws, stats, out, hi, lo,
+               eps=1e-5, momentum=0.1):
+        self._call("mtts_bn_fwd", _p(x), _p(gamma), _p(beta), R, C, eps, momentum, int(tanh_flag), _p(running_mean),
+                   _p(running_var), _p(ws), _p(stats), _p(out), _p(hi), _p(lo))
+
+    def bn_bwd(self, dout, o, x, stats, gamma, R, C, tanh_flag, ws, dx, hi, lo, dgamma, dbeta, beta=None):
+        self._call("mtts_bn_bwd", _p(dout), _p(o), _p(x), _p(stats), _p(gamma), R, C, int(tanh_flag), _p(ws), _p(dx),
+                   _p(hi), _p(lo), _p(dgamma), _p(dbeta))
+
+    def bn_tfwd(self, xdot, x, stats, gamma, gdot, bdot, o, R, C, tanh_flag, ws, tsums, odot, hi, lo, beta=None):
+        self._call("mtts_bn_tfwd", _p(xdot), _p(x), _p(stats), _p(gamma), _p(gdot), _p(bdot), _p(o), R, C,
+                   int(tanh_flag), _p(ws), _p(tsums), _p(odot), _p(hi), _p(lo))
+
+    def bn_tbwd(self, dout, ddout, o, odot, x, xdot, stats, tsums, gamma, gdot, R, C, tanh_flag, ws, ddx, hi, lo,
+                ddgamma, ddbeta, beta=None, bdot=None):
+        # beta / bdot are only used by the CPU restatement (the kernels use the saved tanh output o / odot)
+        self._call("mtts_bn_tbwd", _p(dout), _p(ddout), _p(o), _p(odot), _p(x), _p(xdot), _p(stats), _p(tsums),
+                   _p(gamma), _p(gdot), R, C, int(tanh_flag), _p(ws), _p(ddx), _p(hi), _p(lo), _p(ddgamma), _p(ddbeta))
+
+    # ---- loss ----
+    def loss_fwd(self, mel, post, mel_tgt, mel_lens, p, p_tgt, e, e_tgt, logd, dur, src_lens, B, T, Lp, NM, ws, out6,
+                 counts):
+        self._call("mtts_loss_fwd", _p(mel), _p(post), _p(mel_tgt), _p(mel_lens), _p(p), _p(p_tgt), _p(e), _p(e_tgt),
+                   _p(logd), _p(dur), _p(src_lens), B, T, Lp, NM, _p(ws), _p(out6), _p(counts))
+
+    def loss_bwd(self, mel, post, mel_tgt, mel_lens, p, p_tgt, e, e_tgt, logd, dur, src_lens, B, T, Lp, NM, counts,
+                 scale, tangent, dmel, dpost, dp, de, dlogd):
+        self._call("mtts_loss_bwd", _p(mel), _p(post), _p(mel_tgt), _p(mel_lens), _p(p), _p(p_tgt), _p(e), _p(e_tgt),
+                   _p(logd), _p(dur), _p(src_lens), B, T, Lp, NM, _p(counts), scale, int(tangent), _p(dmel), _p(dpost),
+                   _p(dp), _p(de), _p(dlogd))
+
+    # ---- flat elementwise ----
+    def split_(self, src, hi, lo):
+        self._call("mtts_split", _p(src), _p(hi), _p(lo), src.numel())
+
+    def sgd_split(self, theta, g, lr, out, hi, lo):
+        self._call("mtts_sgd_split", _p(theta), _p(g), lr, _p(out), _p(hi), _p(lo), theta.numel())
+
+    def axpby(self, a, x, b, y):
+        self._call("mtts_axpby", a, _p(x), b, _p(y), x.numel())
+
+    def sumsq(self, x, out):
+        self._call("mtts_sumsq", _p(x), x.numel(), _p(out))
+
+    def adam_clip(self, p, g, m, v, sumsq, gscale, max_norm, hyper, beta1, beta2, eps, hi, lo):
+        self._call("mtts_adam_clip", _p(p), _p(g), _p(m), _p(v), _p(sumsq), gscale, max_norm, _p(hyper), beta1, beta2,
+                   eps, _p(hi), _p(lo), p.numel())
