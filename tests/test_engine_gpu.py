@@ -1,0 +1,127 @@
+"""End-to-end parity of the CUDA path (C ABI kernels driven by the engine) against
+(a) the autograd oracle on the same seeded inputs and (b) the golden vectors produced by the REAL
+reference modules (tests/golden/fs2_golden.npz).  Tolerance: north_star's 1e-3 relative (fp32) for
+mel / pitch / energy / duration outputs in bf16x3 mode; gradients compared against the total
+gradient norm.  The LengthRegulator index path is checked bit-exact (mel_len / idx)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from meta_tts_b200.maml import MamlEngine, batch_from_tuple  # noqa: E402
+from meta_tts_b200.ops import CudaOps  # noqa: E402
+from oracle import fs2_oracle as O  # noqa: E402
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "fs2_golden.npz"), allow_pickle=False)
+REL_OUT = 1e-3            # BASELINE.json north_star tolerance
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _engine(P, cfg, split=3, K=2):
+    be = CudaOps(split=split)
+    m = MamlEngine(be, cfg, n_speaker=16, adapt_modules=O.ADAPT_MODULES, inner_lr=0.001, max_inner_steps=K)
+    m.load_state_dict({k: v.detach().clone() for k, v in P.items()})
+    return m
+
+
+def _check_task(m, P, cfg, sup, qry, steps, first_order, grad_tol, label):
+    Pc = {k: v.detach().clone() for k, v in P.items()}
+    losses, preds, grads, fast = O.maml_task_step(Pc, cfg, sup, qry, steps, 0.001, first_order, return_fast_weights=True)
+    dev = m.theta.device
+    bs = batch_from_tuple(sup, dev)
+    bq = batch_from_tuple(qry, dev, spk_ids=sup[2], average_spk=True)
+    loss6, out = m.task_step(bs, bq, steps, first_order)
+    torch.cuda.synchronize()
+    r_loss = _rel(loss6, torch.stack(losses))
+    r_mel = _rel(out["mel"].reshape(preds[0].shape), preds[0])
+    r_post = _rel(out["postnet"].reshape(preds[1].shape), preds[1])
+    r_p, r_e, r_d = _rel(out["pitch"], preds[2]), _rel(out["energy"], preds[3]), _rel(out["logd"], preds[4])
+    assert torch.equal(out["mel_len"].cpu(), preds[9]), "LengthRegulator mel_len must be bit-exact"
+    fw = m.fast_weights(steps)
+    r_fast = max(_rel(fw[k], fast[k]) for k in fast)
+    got = m.task_grads()
+    tot_ref = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values()))
+    tot_err = torch.sqrt(sum(((got[k].double() - grads[k].double()) ** 2).sum() for k in grads))
+    r_grad = (tot_err / tot_ref).item()
+    worst = max(((got[k].double() - grads[k].double()).norm() / tot_ref).item() for k in grads)
+    print(f"[engine] {label}: loss {r_loss:.2e} mel {r_mel:.2e} post {r_post:.2e} pitch {r_p:.2e} energy {r_e:.2e} "
+          f"logd {r_d:.2e} fast {r_fast:.2e} grad(total) {r_grad:.2e} grad(worst tensor/total) {worst:.2e}")
+    assert max(r_loss, r_mel, r_post, r_p, r_e, r_d) < REL_OUT
+    assert r_fast < 1e-4
+    assert r_grad < grad_tol
+
+
+def test_small_model_all_modes(cuda_device):
+    cfg = O.small_model_config(1, 1)
+    P = O.init_params(seed=0, model_config=cfg)
+    m = _engine(P, cfg)
+    sup, qry = O.synth_task(task=3, shots=2, queries=2, L=6, T=18, ragged=True)
+    for steps, fo in ((1, True), (1, False), (2, False)):
+        m.load_state_dict({k: v.detach().clone() for k, v in P.items()})
+        _check_task(m, P, cfg, sup, qry, steps, fo, 1e-3, f"small K={steps} fo={fo}")
+
+
+def test_base_model_ragged_second_order(cuda_device):
+    cfg = O.BASE_MODEL_CONFIG
+    P = O.init_params(seed=0)
+    m = _engine(P, cfg, K=2)
+    sup, qry = O.synth_task(task=1, shots=3, queries=2, L=40, T=150, ragged=True)
+    _check_task(m, P, cfg, sup, qry, 2, False, 1e-3, "base ragged K=2 second-order")
+
+
+def test_golden_reference_task_steps(cuda_device):
+    """Against the goldens generated from the real reference modules + restated learn2learn."""
+    cfg = O.BASE_MODEL_CONFIG
+    for tag in ("maml_so_k2", "maml_fo_k2", "maml_so_k1"):
+        K, fo, S, Q, L, T, task = [int(v) for v in G[f"{tag}_cfg"]]
+        P = O.init_params(seed=0)
+        m = _engine(P, cfg, K=2)
+        sup, qry = O.synth_task(task=task, shots=S, queries=Q, L=L, T=T, ragged=True)
+        dev = m.theta.device
+        loss6, out = m.task_step(batch_from_tuple(sup, dev), batch_from_tuple(qry, dev, spk_ids=sup[2], average_spk=True),
+                                 K, bool(fo))
+        torch.cuda.synchronize()
+        ref_losses = torch.from_numpy(G[f"{tag}_losses"])
+        assert _rel(loss6, ref_losses) < REL_OUT
+        assert _rel(out["mel"].reshape(G[f"{tag}_mel"].shape), torch.from_numpy(G[f"{tag}_mel"])) < REL_OUT
+        got = m.task_grads()
+        names = [str(k) for k in G[f"{tag}_grad_names"]]
+        gn = torch.tensor([got[k].double().norm().item() for k in names])
+        ref_gn = torch.from_numpy(G[f"{tag}_grad_norm"])
+        tot = ref_gn.norm()
+        assert ((gn - ref_gn).abs().max() / tot).item() < 1e-3
+        heads = np.stack([np.pad(got[k].flatten()[:8].numpy(), (0, max(0, 8 - got[k].numel()))) for k in names])
+        assert np.abs(heads - G[f"{tag}_grad_head"]).max() / np.abs(G[f"{tag}_grad_head"]).max() < 2e-3
+        print(f"[engine] golden {tag}: loss rel {_rel(loss6, ref_losses):.2e}")
+
+
+def test_config2_full_size_parity(cuda_device):
+    """BASELINE configs[1]: MAML 1 inner step, 1 task, 4-shot support / query, 128 phonemes -> 864 frames."""
+    cfg = O.BASE_MODEL_CONFIG
+    P = O.init_params(seed=0)
+    m = _engine(P, cfg, K=1)
+    sup, qry = O.synth_task(task=0, shots=4, queries=4, L=128, T=864)
+    _check_task(m, P, cfg, sup, qry, 1, False, 1e-3, "config2 full size second-order")
+
+
+def test_bf16_single_pass_mode_runs(cuda_device):
+    """split=1 (plain bf16 operands): documented looser tolerance (bf16 rounding ~4e-3 per product)."""
+    cfg = O.small_model_config(1, 1)
+    P = O.init_params(seed=0, model_config=cfg)
+    m = _engine(P, cfg, split=1)
+    sup, qry = O.synth_task(task=3, shots=2, queries=2, L=6, T=18, ragged=True)
+    Pc = {k: v.detach().clone() for k, v in P.items()}
+    losses, preds, grads = O.maml_task_step(Pc, cfg, sup, qry, 1, 0.001, False)
+    dev = m.theta.device
+    loss6, out = m.task_step(batch_from_tuple(sup, dev), batch_from_tuple(qry, dev, spk_ids=sup[2], average_spk=True), 1, False)
+    torch.cuda.synchronize()
+    r = _rel(out["mel"].reshape(preds[0].shape), preds[0])
+    print(f"[engine] bf16 single-pass mel rel {r:.2e}, loss rel {_rel(loss6, torch.stack(losses)):.2e}")
+    assert r < 3e-2 and _rel(loss6, torch.stack(losses)) < 3e-2

@@ -1,0 +1,192 @@
+"""Every libmtts row / reduction / elementwise kernel vs the independent CPU restatement
+(oracle/ops_reference.RefOps; tangent forms there come from torch.func jvp/vjp).  Tolerance: 1e-5
+relative (fp32 kernels; fast-math exp/rsqrt), bit-exact for integer paths."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from meta_tts_b200.ops import CudaOps  # noqa: E402
+from oracle.ops_reference import RefOps  # noqa: E402
+
+TOL = 2e-5
+
+
+def _both(cuda_device, name, args, kwargs=None, tol=TOL, split=3, skip=()):
+    """Run op `name` on RefOps (CPU) and CudaOps (GPU); compare every tensor argument afterwards."""
+    kwargs = kwargs or {}
+    ref, cu = RefOps(split=split), CudaOps(split=split)
+    cargs = [a.clone() if torch.is_tensor(a) else a for a in args]
+    gargs = [a.to(cuda_device) if torch.is_tensor(a) else a for a in args]
+    ckw = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in kwargs.items()}
+    gkw = {k: (v.to(cuda_device) if torch.is_tensor(v) else v) for k, v in kwargs.items()}
+    getattr(ref, name)(*cargs, **ckw)
+    getattr(cu, name)(*gargs, **gkw)
+    torch.cuda.synchronize()
+    for i, (c, g) in enumerate(zip(cargs, gargs)):
+        if not torch.is_tensor(c) or i in skip:
+            continue
+        g = g.cpu()
+        if c.dtype in (torch.int64, torch.int32):
+            assert torch.equal(c, g), f"{name}: int arg {i} differs"
+            continue
+        c64, g64 = c.double(), g.double()
+        assert torch.isfinite(g64).all(), f"{name}: arg {i} has non-finite values"
+        scale = c64.abs().max().clamp_min(1e-30)
+        err = (c64 - g64).abs().max() / scale
+        lim = tol if c.dtype == torch.float32 else 1e-2   # bf16 hi halves compare loosely; hi+lo checked below
+        assert err < lim, f"{name}: arg {i} max err {err:.3e} (scale {scale:.3e})"
+    return cargs, [g.cpu() if torch.is_tensor(g) else g for g in gargs]
+
+
+def _hl_check(c_hi, c_lo, g_hi, g_lo, tol=TOL):
+    c = c_hi.double() + c_lo.double()
+    g = g_hi.double() + g_lo.double()
+    assert ((c - g).abs().max() / c.abs().max().clamp_min(1e-30)) < tol
+
+
+def R_(*s, seed=0):
+    return torch.randn(*s, generator=torch.Generator().manual_seed(seed))
+
+
+def bf(*s):
+    return torch.zeros(*s, dtype=torch.bfloat16)
+
+
+@pytest.mark.parametrize("with_res,with_lens", [(True, True), (False, False)])
+def test_layernorm_family(cuda_device, with_res, with_lens):
+    B, T, C = 3, 37, 256
+    R = B * T
+    lens = torch.tensor([37, 20, 5]) if with_lens else None
+    y, res = R_(R, C, seed=1), (R_(R, C, seed=2) if with_res else None)
+    gamma, beta = 1 + 0.1 * R_(C, seed=3), 0.1 * R_(C, seed=4)
+    z, st, out, oh, ol = torch.zeros(R, C), torch.zeros(R, 2), torch.zeros(R, C), bf(R, C), bf(R, C)
+    c, g = _both(cuda_device, "ln_fwd", [y, res, gamma, beta, lens, T, R, C, z, st, out, oh, ol])
+    _hl_check(c[11], c[12], g[11], g[12])
+    z, st = c[8], c[9]
+    dy = R_(R, C, seed=5)
+    for gate in (0, 1):
+        dz, dh, dl = torch.zeros(R, C), bf(R, C), bf(R, C)
+        dg, db, dbias = torch.zeros(C), torch.zeros(C), torch.zeros(C)
+        c2, g2 = _both(cuda_device, "ln_bwd", [dy, z, st, gamma, lens, T, R, C, gate, dz, dh, dl, dg, db, dbias])
+        _hl_check(c2[10], c2[11], g2[10], g2[11])
+    ydot, resdot = R_(R, C, seed=6), (R_(R, C, seed=7) if with_res else None)
+    gdot, bdot = R_(C, seed=8), R_(C, seed=9)
+    zd, od, odh, odl = torch.zeros(R, C), torch.zeros(R, C), bf(R, C), bf(R, C)
+    c3, _ = _both(cuda_device, "ln_tfwd", [ydot, resdot, z, st, gamma, gdot, bdot, lens, T, R, C, zd, od, odh, odl])
+    zd = c3[11]
+    ddy = R_(R, C, seed=10)
+    for gate in (0, 1):
+        ddz, dh, dl = torch.zeros(R, C), bf(R, C), bf(R, C)
+        dg, db, dbias = torch.zeros(C), torch.zeros(C), torch.zeros(C)
+        _both(cuda_device, "ln_tbwd", [dy, ddy, z, zd, st, gamma, gdot, lens, T, R, C, gate, ddz, dh, dl, dg, db, dbias],
+              tol=5e-5)
+
+
+def test_rowdot(cuda_device):
+    B, T, C = 2, 19, 256
+    R = B * T
+    lens = torch.tensor([19, 7])
+    h, hd, w, wd, b, bd = R_(R, C, seed=1), R_(R, C, seed=2), R_(C, seed=3), R_(C, seed=4), R_(1, seed=5), R_(1, seed=6)
+    _both(cuda_device, "rowdot_fwd", [h, None, w, None, b, None, lens, T, R, C, torch.zeros(R)])
+    _both(cuda_device, "rowdot_fwd", [h, hd, w, wd, None, bd, lens, T, R, C, torch.zeros(R)])
+    dout, ddout = R_(R, seed=7), R_(R, seed=8)
+    _both(cuda_device, "rowdot_bwd", [dout, None, h, None, w, None, lens, T, R, C, torch.zeros(R, C), torch.zeros(C), torch.zeros(1)])
+    _both(cuda_device, "rowdot_bwd", [dout, ddout, h, hd, w, wd, lens, T, R, C, torch.zeros(R, C), torch.zeros(C), torch.zeros(1)])
+
+
+@pytest.mark.parametrize("Lq", [24, 50])
+def test_softmax_family(cuda_device, Lq):
+    B, H = 2, 2
+    nz, ld = B * H, (Lq + 7) // 8 * 8
+    kl = torch.tensor([Lq, Lq // 2])
+    S = 3 * R_(nz, Lq, ld, seed=1)
+    ph, pl = bf(nz, Lq, ld), bf(nz, Lq, ld)
+    c, g = _both(cuda_device, "softmax", [0, S, None, None, None, None, None, kl, nz, H, Lq, Lq, ld, ph, pl])
+    _hl_check(c[13], c[14], g[13], g[14])
+    ph, pl = c[13], c[14]
+    dP = R_(nz, Lq, ld, seed=2)
+    oh, ol = bf(nz, Lq, ld), bf(nz, Lq, ld)
+    c1, g1 = _both(cuda_device, "softmax", [1, dP, None, ph, pl, None, None, kl, nz, H, Lq, Lq, ld, oh, ol])
+    _hl_check(c1[13], c1[14], g1[13], g1[14])
+    pdh, pdl = c1[13], c1[14]
+    ddP = R_(nz, Lq, ld, seed=3)
+    oh, ol = bf(nz, Lq, ld), bf(nz, Lq, ld)
+    c2, g2 = _both(cuda_device, "softmax", [2, dP, ddP, ph, pl, pdh, pdl, kl, nz, H, Lq, Lq, ld, oh, ol])
+    _hl_check(c2[13], c2[14], g2[13], g2[14])
+
+
+def test_gathers_and_sums(cuda_device):
+    B, T, C, V = 3, 11, 256, 40
+    R = B * T
+    g = torch.Generator().manual_seed(0)
+    idx = torch.randint(0, V, (R,), generator=g)
+    table, base, pos = R_(V, C, seed=1), R_(R, C, seed=2), R_(T + 3, C, seed=3)
+    _both(cuda_device, "embed_fwd", [idx, table, base, pos, T, R, C, torch.zeros(R, C), bf(R, C), bf(R, C)])
+    _both(cuda_device, "embed_fwd", [idx, table, None, None, T, R, C, torch.zeros(R, C), None, None])
+    _both(cuda_device, "embed_bwd", [idx, R_(R, C, seed=4), R, C, 0, 0.5, torch.zeros(V, C)], tol=5e-5)
+    bins = torch.linspace(-2.9, 10.2, 255)
+    v = torch.cat([3 * R_(R - 3, seed=5), bins[[0, 100, 254]]])          # exact boundary hits included
+    _both(cuda_device, "bucketize", [v, bins, 255, R, torch.zeros(R, dtype=torch.int64)])
+    vec = R_(B, C, seed=6)
+    _both(cuda_device, "add_rowvec", [R_(B, T, C, seed=7), vec, C, pos, B, T, C, torch.zeros(B, T, C), bf(B, T, C), bf(B, T, C)])
+    _both(cuda_device, "add_rowvec", [R_(B, T, C, seed=7), vec, C, None, B, T, C, torch.zeros(B, T, C), None, None])
+    ids = torch.tensor([3, 3, 7])
+    for avg, n_out in ((False, 3), (True, 5)):
+        _both(cuda_device, "spk_embed", [ids, table, 3, C, avg, n_out, torch.zeros(n_out, C)])
+        _both(cuda_device, "spk_embed_bwd", [ids, R_(n_out, C, seed=8), 3, C, avg, n_out, 1.0, torch.zeros(V, C)])
+    x = R_(B, T, C, seed=9)
+    _both(cuda_device, "colsum", [x, None, None, B, T, C, torch.zeros(B, C)], tol=5e-5)
+    xh = x.to(torch.bfloat16)
+    xl = (x - xh.float()).to(torch.bfloat16)
+    _both(cuda_device, "colsum", [None, xh, xl, 1, R, C, torch.zeros(C)], tol=5e-5)
+
+
+@pytest.mark.parametrize("C,tanh", [(512, True), (80, False)])
+def test_batchnorm_family(cuda_device, C, tanh):
+    R = 4 * 53
+    x, xd = 2 * R_(R, C, seed=1) + 0.5, R_(R, C, seed=2)
+    gamma, beta, gd, bd = 1 + 0.1 * R_(C, seed=3), 0.1 * R_(C, seed=4), R_(C, seed=5), R_(C, seed=6)
+    rm, rv = torch.zeros(C), torch.ones(C)
+    ws, st, out, oh, ol = torch.zeros(4 * 512), torch.zeros(2 * C), torch.zeros(R, C), bf(R, C), bf(R, C)
+    c, g = _both(cuda_device, "bn_fwd", [x, gamma, beta, R, C, tanh, rm, rv, ws, st, out, oh, ol], tol=5e-5, skip=(8,))
+    st, o = c[9], c[10]
+    dout, ddout = R_(R, C, seed=7), R_(R, C, seed=8)
+    _both(cuda_device, "bn_bwd", [dout, o if tanh else None, x, st, gamma, R, C, tanh, ws, torch.zeros(R, C), bf(R, C), bf(R, C),
+                                  torch.zeros(C), torch.zeros(C)], {"beta": beta}, tol=1e-4, skip=(8,))
+    ts, od = torch.zeros(2 * C), torch.zeros(R, C)
+    c2, _ = _both(cuda_device, "bn_tfwd", [xd, x, st, gamma, gd, bd, o if tanh else None, R, C, tanh, ws, ts, od, bf(R, C), bf(R, C)],
+                  {"beta": beta}, tol=1e-4, skip=(10,))
+    ts, od = c2[11], c2[12]
+    _both(cuda_device, "bn_tbwd", [dout, ddout, o if tanh else None, od if tanh else None, x, xd, st, ts, gamma, gd, R, C, tanh, ws,
+                                   torch.zeros(R, C), bf(R, C), bf(R, C), torch.zeros(C), torch.zeros(C)],
+          {"beta": beta, "bdot": bd}, tol=2e-4, skip=(13,))
+
+
+def test_loss_family(cuda_device):
+    B, T, Lq, NM = 3, 20, 7, 80
+    mel_lens, src_lens = torch.tensor([20, 11, 3]), torch.tensor([7, 4, 2])
+    mel, post, tgt = R_(B, T, NM, seed=1), R_(B, T, NM, seed=2), R_(B, T, NM, seed=3)
+    p, pt, e, et, logd = R_(B, Lq, seed=4), R_(B, Lq, seed=5), R_(B, Lq, seed=6), R_(B, Lq, seed=7), R_(B, Lq, seed=8)
+    dur = torch.randint(0, 9, (B, Lq), generator=torch.Generator().manual_seed(9))
+    c, _ = _both(cuda_device, "loss_fwd", [mel, post, tgt, mel_lens, p, pt, e, et, logd, dur, src_lens, B, T, Lq, NM, torch.zeros(8),
+                                           torch.zeros(6), torch.zeros(2)], skip=(15,))
+    counts = c[17]
+    outs = [torch.zeros(B, T, NM), torch.zeros(B, T, NM), torch.zeros(B, Lq), torch.zeros(B, Lq), torch.zeros(B, Lq)]
+    _both(cuda_device, "loss_bwd", [mel, post, tgt, mel_lens, p, pt, e, et, logd, dur, src_lens, B, T, Lq, NM, counts, 0.7, 0, *outs])
+    _both(cuda_device, "loss_bwd", [None, None, None, mel_lens, p, None, e, None, logd, None, src_lens, B, T, Lq, NM, counts, 0.7, 1,
+                                    *[torch.ones_like(o) for o in outs]])
+
+
+def test_elementwise(cuda_device):
+    n = 4096 + 64
+    x, g = R_(n, seed=1), R_(n, seed=2)
+    c, gg = _both(cuda_device, "split_", [x, bf(n), bf(n)])
+    _hl_check(c[1], c[2], gg[1], gg[2])
+    _both(cuda_device, "sgd_split", [x, g, 0.001, torch.zeros(n), bf(n), bf(n)])
+    _both(cuda_device, "axpby", [-0.3, x, 1.5, g.clone()])
+    _both(cuda_device, "sumsq", [x, torch.zeros(1)])
+    hyper = torch.tensor([0.01, 1 - 0.9, 1 - 0.98, 0.0])
+    ss = (g.double() ** 2).sum().float().reshape(1)
+    _both(cuda_device, "adam_clip", [x.clone(), g, 0.1 * R_(n, seed=3), R_(n, seed=4).abs(), ss, 0.5, 1.0, hyper, 0.9, 0.98, 1e-9,
+                                     bf(n), bf(n)], tol=5e-5)
