@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — mel-frames/sec per outer meta-step of the B200-native Meta-TTS MAML step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): second-order MAML, 1 inner step, 1 task per GPU per outer step,
+4-shot support + 4 queries, LibriTTS-shaped synthetic utterances (128 phonemes -> 864 mel frames, full
+length), FastSpeech2 base config, random-init weights (no corpus / checkpoint in the sandbox).
+One "step" = one outer meta-step: task step (inner SGD step, query forward, outer backward incl. the
+exact Hessian-vector recursion) on every rank -> ONE NCCL allreduce of the flat outer gradient ->
+clip + Adam.  N > 1 is weak scaling (meta-batch = N tasks), launched with torch.distributed.run.
+
+value : throughput with the task batch already resident in HBM (CUDA-graph replay + allreduce + Adam)
+e2e   : the same through the public API MetaSystem.training_step(host batch) + optimizer_step():
+        per step the batch goes pinned-host -> device and the 6 query losses come back to the host.
+roofline    : the tcgen05 GEMM kernel (every dense contraction of the step), algorithmic FLOPs / CUDA-event
+              time of its launches in an instrumented eager pass, against MEASURED_PEAKS.json.
+cpu_baseline: the oracle (CPU restatement of the reference path, PyTorch fp32 autograd) on the host cores,
+              same workload, bounded sample.  --impl reference prints that arm alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SHOTS, QUERIES, L_PHON, T_MEL, K_INNER = 4, 4, 128, 864, 1
+METRIC = "mel-frames/sec per outer meta-step"
+UNIT = "mel-frames/s"
+
+
+def workload_config(n_gpus, split):
+    return {
+        "workload": f"second-order MAML K={K_INNER}, 1 task/GPU, {SHOTS}-shot support + {QUERIES} queries, "
+                    f"{L_PHON} phonemes -> {T_MEL} frames (BASELINE configs[1])",
+        "tasks_per_step": n_gpus, "shots": SHOTS, "queries": QUERIES, "phonemes": L_PHON, "frames": T_MEL,
+        "inner_steps": K_INNER, "order": "second", "precision": "bf16x3 hi/lo split (fp32-grade)" if split == 3 else "bf16",
+        "dropout": "identity (parity mode; the oracle neutralises it too)", "parallelism": f"dp{n_gpus} (1 task per GPU)",
+        "l2": "per-step working set (activation tapes ~GBs + 280 MB weights) >> 126 MB L2: no flush needed",
+    }
+
+
+def frames_per_task():
+    return (SHOTS + QUERIES) * T_MEL
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (restated reference path) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(steps, warmup, shots=SHOTS, queries=QUERIES, budget_s=150.0):
+    from oracle import fs2_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.BASE_MODEL_CONFIG
+    P = O.init_params(seed=0)
+    times = []
+    total = steps + warmup
+    sample_shots, sample_q = shots, queries
+    t_start = time.perf_counter()
+    for i in range(total):
+        sup, qry = O.synth_task(task=i, shots=sample_shots, queries=sample_q, L=L_PHON, T=T_MEL)
+        t0 = time.perf_counter()
+        O.maml_task_step(P, cfg, sup, qry, K_INNER, 0.001, first_order=False)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append((dt, (sample_shots + sample_q) * T_MEL))
+        # keep the whole arm inside the budget: shrink the per-step sample (throughput is per frame)
+        done = i + 1
+        if done < total and (time.perf_counter() - t_start) / done * total > budget_s and sample_shots > 1:
+            sample_shots, sample_q = max(1, sample_shots // 2), max(1, sample_q // 2)
+    frames = sum(f for _, f in times)
+    secs = sum(t for t, _ in times)
+    return {"value": frames / secs, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{len(times)} timed task-step(s) of the same workload (last sample {sample_shots}+{sample_q} utterances), "
+                      f"oracle/fs2_oracle.maml_task_step, fp32 autograd, dropout identity",
+            "ms_per_step": 1e3 * secs / max(len(times), 1)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_arm(args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus, 3),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "the reference is pure Python (PyTorch + learn2learn + Lightning) and is absent on the GPU box: this arm "
+                    "times oracle/, its CPU restatement validated against the real reference modules (tests/golden)"}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM roofline instrumentation (eager pass, CUDA events around every mtts_gemm launch)
+# ------------------------------------------------------------------------------------------------
+def instrument_gemm(be):
+    """Wrap be.gemm: record (algorithmic flops, start event, end event) per launch."""
+    rec = []
+    orig = be.gemm
+
+    def wrapped(a, b, M, N, K, **kw):
+        nz = kw.get("nz0", 1) * kw.get("nz1", 1)
+        flops = 2.0 * M * N * K * kw.get("ntaps", 1) * kw.get("nkb", 1) * nz
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(a, b, M, N, K, **kw)
+        e1.record()
+        rec.append((flops, e0, e1, (M, N, K, kw.get("ntaps", 1), kw.get("nkb", 1), nz)))
+
+    be.gemm = wrapped
+    return rec, orig
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "hbm_gbs": d.get("hbm_gbs"),
+                "source": "MEASURED_PEAKS.json (bf16_tflops_sustained: kernel timed inside a long step)"}
+    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md: ~1.4 PF/s sustained, 6.65 TB/s)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------
+def run_own_arm(args):
+    import torch.distributed as dist
+
+    from meta_tts_b200 import ops as mops
+    from meta_tts_b200.systems import DEFAULT_ALGORITHM_CONFIG, DEFAULT_MODEL_CONFIG, DEFAULT_TRAIN_CONFIG, MetaSystem
+    from oracle import fs2_oracle as O   # synthetic task generator + seeded init only (never on the measured path)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = f"cuda:{local}"
+    split = args.split
+
+    import copy
+    algo = copy.deepcopy(DEFAULT_ALGORITHM_CONFIG)
+    algo["adapt"]["train"]["steps"] = K_INNER
+    algo["adapt"]["test"]["steps"] = K_INNER
+    sysm = MetaSystem(None, DEFAULT_MODEL_CONFIG, DEFAULT_TRAIN_CONFIG, algo, n_speaker=16, device=dev, split=split)
+    P = O.init_params(seed=0)
+    sysm.load_state_dict({k: v.detach() for k, v in P.items()})
+    n_steps_total = args.warmup + args.steps
+    tasks = [O.synth_task(task=rank + world * i, shots=SHOTS, queries=QUERIES, L=L_PHON, T=T_MEL) for i in range(4)]
+    batches = [[([t[0]], [t[1]])] for t in tasks]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------- (1) device-resident timing: graph replay + allreduce + Adam ----------
+    sysm.training_step(batches[0], 0)              # builds static buffers, warm-up + CUDA-graph capture
+    sysm.optimizer_step()
+    key, ent = next(iter(sysm._graphs.items()))
+    graph = ent[2]
+    launches_task = sysm.launches_per_task_step
+    launches_step = launches_task + 2               # + sumsq + adam_clip (the allreduce is NCCL's kernel)
+
+    def device_step():
+        graph.replay()
+        sysm.optimizer_step()
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        device_step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = ms.item() / args.steps
+    value = world * frames_per_task() / (ms_per_step * 1e-3)
+
+    # ---------- (2) end-to-end through the public API with host buffers ----------
+    for i in range(min(args.warmup, 3)):
+        sysm.training_step(batches[i % len(batches)], i)
+        sysm.optimizer_step()
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        out = sysm.training_step(batches[i % len(batches)], i)     # H2D of the batch + D2H of the losses inside
+        sysm.optimizer_step()
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = ms2.item() / args.steps
+    e2e_value = world * frames_per_task() / (e2e_ms * 1e-3)
+    last_loss = float(out["loss"])
+
+    line = None
+    if rank == 0:
+        # ---------- (3) roofline of the GEMM kernel: instrumented eager pass ----------
+        rec, orig = instrument_gemm(sysm.be)
+        sysm.use_cuda_graph = False
+        sysm.training_step(batches[0], 0)
+        torch.cuda.synchronize()
+        rec.clear()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        sysm.training_step(batches[1], 1)
+        t1.record()
+        torch.cuda.synchronize()
+        sysm.be.gemm = orig
+        sysm.use_cuda_graph = True
+        sysm.be.zero_(sysm.maml.g_outer)
+        gemm_ms = sum(a.elapsed_time(b) for _, a, b, _ in rec)
+        gemm_flops = sum(f for f, _, _, _ in rec)
+        by_shape = {}
+        for f, a, b, shp in rec:
+            d = by_shape.setdefault(shp, [0.0, 0.0, 0])
+            d[0] += f
+            d[1] += a.elapsed_time(b)
+            d[2] += 1
+        top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:5]
+        peaks = load_peaks()
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        mma_mult = 3 if split == 3 else 1
+        roofline = {"bound": "tensor", "kernel": "mtts_gemm_kernel (tcgen05 + TMA; all dense contractions of the step)",
+                    "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+                    "traffic": None, "peak_source": peaks["source"],
+                    "launches": len(rec), "avg_launch_us": 1e3 * gemm_ms / max(len(rec), 1),
+                    "gemm_share_of_eager_step": gemm_ms / t0.elapsed_time(t1),
+                    "algorithmic_gflop_per_step": gemm_flops / 1e9,
+                    "tensor_pipe_work_multiplier": mma_mult,
+                    "frac_of_issued_mma": mma_mult * achieved / peaks["bf16_tflops"],
+                    "top_shapes_MNK_taps_kb_z": [{"shape": list(k), "launches": v[2], "ms": v[1], "tflops": v[0] / (v[1] * 1e-3) / 1e12}
+                                                 for k, v in top]}
+        # ---------- (4) CPU baseline (bounded sample) ----------
+        cb = cpu_arm(steps=2, warmup=1, budget_s=60.0) if not args.no_cpu else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16x3" if split == 3 else "bf16", "data": "synthetic", "config": workload_config(world, split),
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": sysm.h2d_bytes_per_step,
+                        "d2h_bytes_per_step": sysm.d2h_bytes_per_step, "api": "MetaSystem.training_step + optimizer_step"},
+                "gpu_launches": launches_step * args.steps, "gpu_launches_per_step": launches_step,
+                "roofline": roofline, "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),
+                "last_query_loss": last_loss, "hbm_bytes_resident": sysm.maml.memory_bytes()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--split", type=int, default=3, choices=[1, 3], help="3: bf16x3 (parity-grade, default); 1: plain bf16")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_own_arm(args)
+
+
+if __name__ == "__main__":
+    main()

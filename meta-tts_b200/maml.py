@@ -91,9 +91,14 @@ class MamlEngine:
                 t = t[0]
             self.consts[name] = t.contiguous().to(self.theta.device)
         self.engine = FS2Engine(be, self.cfg, lay, self.consts)
-        self.tapes = [self.engine.new_tape() for _ in range(self.K_max)]
-        self.tape_q = self.engine.new_tape()
-        self.tape_t = self.engine.new_tape()
+        self.use_tapes(self.new_tapes())
+
+    def new_tapes(self):
+        """(support tapes x K_max, query tape, tangent tape): one set per input-shape signature."""
+        return ([self.engine.new_tape() for _ in range(self.K_max)], self.engine.new_tape(), self.engine.new_tape())
+
+    def use_tapes(self, tapes) -> None:
+        self.tapes, self.tape_q, self.tape_t = tapes
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         sd = self.layout.unpack(self.theta.detach().cpu())

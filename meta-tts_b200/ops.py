@@ -178,10 +178,13 @@ class CudaOps:
     def zero_(self, t):
         t.zero_()          # cudaMemsetAsync on the current stream
 
+    # kernels launched per C-ABI call (memsets not counted)
+    KERNELS = {"mtts_bn_fwd": 3, "mtts_bn_bwd": 2, "mtts_bn_tfwd": 2, "mtts_bn_tbwd": 2, "mtts_loss_fwd": 2}
+
     def _call(self, name, *args):
         global launch_count
         L.call(name, *args, _stream())
-        launch_count += 1
+        launch_count += self.KERNELS.get(name, 1)
 
     # ---- GEMM ----
     def gemm(self, a: Opnd, b: Opnd, M, N, K, **kw):

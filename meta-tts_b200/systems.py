@@ -1,0 +1,279 @@
+"""Drop-in host API for the MAML step: same names / arguments / return values as the reference's
+`lightning.systems` classes for the hot path, minus Lightning (which only orchestrates).
+
+    reference                                         here
+    ------------------------------------------------  -------------------------------------------
+    MAML(module, lr).clone()/adapt_()                 MAML (compatibility shim over MamlEngine)
+      lightning/systems/utils.py:17-77
+    BaseAdaptorSystem.adapt(batch, steps, ...)        MetaSystem.adapt        (base_adaptor.py:98-112)
+    BaseAdaptorSystem.meta_learn(batch, idx, train)   MetaSystem.meta_learn   (base_adaptor.py:114-124)
+    MetaSystem.training_step(batch, idx)              MetaSystem.training_step (meta.py:68-80)
+    Lightning: backward, DDP allreduce, clip, Adam    MetaSystem.optimizer_step (main.py:57-64,
+      + LambdaLR                                        optimizer.py:6-16, scheduler.py:6-29)
+
+`batch` keeps the reference layout `[ ( [sup 12-tuple], [qry 12-tuple] ) ]` (base_adaptor.py:126-131).
+The autograd-free engine cannot accept a bare loss tensor in `MAML.adapt_(loss)`; the fused path is
+exposed at adapt()/meta_learn() level with the reference signatures.
+
+The whole task step (K inner steps + query + outer backward [+ HVP recursion]) is captured once per
+input shape in a CUDA graph and replayed; per step the host copies the batch into static device
+buffers (pinned H2D) and reads back the 6 query losses.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops as _ops
+from .engine import Batch, N_MEL
+from .maml import MamlEngine, batch_from_tuple
+from .ops import CudaOps
+
+
+def _assert_meta_batch(batch) -> None:
+    """base_adaptor.py:126-131"""
+    assert len(batch) == 1, "meta_batch_per_gpu"
+    assert len(batch[0]) == 2, "sup + qry"
+    assert len(batch[0][0]) == 1, "n_batch == 1"
+    assert len(batch[0][0][0]) == 12, "data with 12 elements"
+
+
+class _StaticBatch:
+    """Static device buffers + pinned host staging for one 12-tuple shape."""
+
+    def __init__(self, device, n: int, L: int, T: int, n_spk_ids: int, average_spk: bool):
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)  # noqa: E731
+        self.dev = Batch(spk_ids=z((n_spk_ids,), torch.int64), average_spk=average_spk, texts=z((n, L), torch.int64),
+                         src_lens=z((n,), torch.int64), mels=z((n, T, N_MEL), torch.float32), mel_lens=z((n,), torch.int64),
+                         pitches=z((n, L), torch.float32), energies=z((n, L), torch.float32),
+                         durations=z((n, L), torch.int64), B=n, L=L, T=T)
+        self.fields = ("spk_ids", "texts", "src_lens", "mels", "mel_lens", "pitches", "energies", "durations")
+        pin = torch.cuda.is_available()
+        self.pinned = {f: (torch.empty_like(getattr(self.dev, f), device="cpu").pin_memory() if pin
+                           else torch.empty_like(getattr(self.dev, f), device="cpu")) for f in self.fields}
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.pinned.values())
+
+    def upload(self, b12, spk_ids=None) -> None:
+        (_, _, spk, texts, src_lens, _, mels, mel_lens, _, pitches, energies, durs) = b12
+        src = {"spk_ids": spk if spk_ids is None else spk_ids, "texts": texts, "src_lens": src_lens, "mels": mels,
+               "mel_lens": mel_lens, "pitches": pitches, "energies": energies, "durations": durs}
+        for f in self.fields:
+            p = self.pinned[f]
+            p.copy_(torch.as_tensor(src[f]).to(p.dtype).reshape(p.shape))
+            getattr(self.dev, f).copy_(p, non_blocking=True)
+
+
+DEFAULT_MODEL_CONFIG = {
+    "transformer": {"encoder_layer": 4, "encoder_head": 2, "encoder_hidden": 256, "decoder_layer": 6, "decoder_head": 2,
+                    "decoder_hidden": 256, "conv_filter_size": 1024, "conv_kernel_size": [9, 1],
+                    "encoder_dropout": 0.2, "decoder_dropout": 0.2},
+    "variance_predictor": {"filter_size": 256, "kernel_size": 3, "dropout": 0.5},
+    "variance_embedding": {"pitch_quantization": "linear", "energy_quantization": "linear", "n_bins": 256},
+    "multi_speaker": True, "max_seq_len": 1000,
+}                                                                      # config/model/base.yaml
+DEFAULT_ALGORITHM_CONFIG = {
+    "name": "meta_emb_vad", "type": "meta",
+    "adapt": {"type": "spk", "speaker_emb": "table",
+              "modules": ["speaker_emb", "variance_adaptor", "decoder", "mel_linear", "postnet"],
+              "task": {"ways": 1, "shots": 5, "queries": 5, "lr": 0.001},
+              "train": {"steps": 5, "meta_batch_size": 8}, "test": {"steps": 100}},
+}                                                                      # config/algorithm/meta_emb_vad.yaml
+DEFAULT_TRAIN_CONFIG = {
+    "optimizer": {"betas": [0.9, 0.98], "eps": 1e-9, "weight_decay": 0.0, "grad_clip_thresh": 1.0, "grad_acc_step": 1,
+                  "warm_up_step": 4000, "anneal_steps": [300000, 400000, 500000], "anneal_rate": 0.3},
+}                                                                      # config/train/base.yaml
+
+
+def _metasystem_init(self, preprocess_config=None, model_config=None, train_config=None, algorithm_config=None,
+                     log_dir=None, result_dir=None, *, n_speaker: int = 16, device: str = "cuda:0", split: int = 3,
+                     use_cuda_graph: bool = True, second_order: bool = True, process_group=None, backend=None):
+    self.preprocess_config = preprocess_config
+    self.model_config = model_config or DEFAULT_MODEL_CONFIG
+    self.train_config = train_config or DEFAULT_TRAIN_CONFIG
+    self.algorithm_config = algorithm_config or DEFAULT_ALGORITHM_CONFIG
+    ad = self.algorithm_config["adapt"]
+    self.adaptation_steps = ad["train"]["steps"]
+    self.test_adaptation_steps = ad["test"]["steps"]
+    assert self.test_adaptation_steps % self.adaptation_steps == 0        # base_adaptor.py:39
+    assert ad.get("speaker_emb", "table") == "table", "only the table speaker embedding is on the hot path"
+    self.device = torch.device(device)
+    self.second_order = second_order       # reference: first_order = not train  (base_adaptor.py:107)
+    # `backend` exists for host-logic tests (tests inject the CPU restatement); the product path is CudaOps,
+    # which raises without a B200 — there is no fallback.
+    self.be = backend if backend is not None else CudaOps(split=split, device=device)
+    self.maml = MamlEngine(self.be, self.model_config, n_speaker, ad["modules"], inner_lr=ad["task"]["lr"],
+                           max_inner_steps=self.adaptation_steps)
+    self.use_cuda_graph = use_cuda_graph
+    self.process_group = process_group
+    self._graphs: Dict[Tuple, Tuple] = {}
+    self._pending_tasks = 0
+    self.launches_per_task_step: Optional[int] = None
+    self.h2d_bytes_per_step = 0
+    self.d2h_bytes_per_step = 6 * 4
+
+
+
+
+def _load_state_dict(self, state_dict, strict: bool = True):
+    """Accepts the reference's FastSpeech2 state_dict (optionally with Lightning's 'model.' prefix)."""
+    sd = {(k[6:] if k.startswith("model.") else k): v for k, v in state_dict.items()}
+    self.maml.load_state_dict(sd)
+    self._graphs.clear()
+
+
+def _state_dict(self):
+    return self.maml.state_dict()
+
+
+def _get_task(self, sup12, qry12, steps: int, first_order: bool):
+    S, Q = sup12[3].shape[0], qry12[3].shape[0]
+    Ls, Ts, Lq, Tq = int(sup12[5]), int(sup12[8]), int(qry12[5]), int(qry12[8])
+    key = (S, Ls, Ts, Q, Lq, Tq, steps, first_order)
+    ent = self._graphs.get(key)
+    if ent is None:
+        sb = _StaticBatch(self.device, S, Ls, Ts, S, False)
+        qb = _StaticBatch(self.device, Q, Lq, Tq, S, True)
+        ent = [sb, qb, None, None, self.maml.new_tapes()]
+        self._graphs[key] = ent
+        self.h2d_bytes_per_step = sb.h2d_bytes + qb.h2d_bytes
+    return key, ent
+
+
+def _run_task(self, sup12, qry12, steps: int, first_order: bool, accumulate_scale: Optional[float]):
+    key, ent = _get_task(self, sup12, qry12, steps, first_order)
+    sb, qb, graph, result, tapes = ent
+    self.maml.use_tapes(tapes)
+    sb.upload(sup12)
+    qb.upload(qry12, spk_ids=sup12[2])            # query uses the SUPPORT speaker ids, averaged (base_adaptor.py:122)
+    if not self.use_cuda_graph:
+        n0 = _ops.launch_count
+        result = self.maml.task_step(sb.dev, qb.dev, steps, first_order, accumulate_scale)
+        self.launches_per_task_step = _ops.launch_count - n0
+        return result
+    if graph is None:
+        # eager warm-up run: allocates every tape buffer and sets kernel attributes outside capture
+        bn0 = self.maml.bn_batches
+        saved = {k: v.clone() for k, v in self.maml.consts.items() if k.endswith(("running_mean", "running_var"))}
+        g_outer_saved = self.maml.g_outer.clone()
+        self.maml.task_step(sb.dev, qb.dev, steps, first_order, accumulate_scale)
+        torch.cuda.synchronize()
+        for k, v in saved.items():
+            self.maml.consts[k].copy_(v)           # the warm-up must not advance BatchNorm running statistics
+        self.maml.g_outer.copy_(g_outer_saved)
+        self.maml.bn_batches = bn0
+        graph = torch.cuda.CUDAGraph()
+        n0 = _ops.launch_count
+        with torch.cuda.graph(graph):
+            result = self.maml.task_step(sb.dev, qb.dev, steps, first_order, accumulate_scale)
+        self.launches_per_task_step = _ops.launch_count - n0
+        self.maml.bn_batches = bn0
+        ent[2], ent[3] = graph, result
+    graph.replay()
+    self.maml.bn_batches += steps + 1
+    return ent[3]
+
+
+def _scale(self) -> float:
+    acc = self.train_config["optimizer"].get("grad_acc_step", 1)
+    world = torch.distributed.get_world_size(self.process_group) if torch.distributed.is_initialized() else 1
+    return 1.0 / (acc * world)
+
+
+def adapt(self, batch, adaptation_steps: int = 5, learner=None, train: bool = True):
+    """base_adaptor.py:98-112.  Returns the number of inner steps held in the fast-weight arenas
+    (the reference returns the adapted learner object; here the engine owns the fast weights)."""
+    _assert_meta_batch(batch)
+    sup12 = batch[0][0][0]
+    start = int(learner) if learner is not None else 0
+    sb = _StaticBatch(self.device, sup12[3].shape[0], int(sup12[5]), int(sup12[8]), sup12[3].shape[0], False)
+    sb.upload(sup12)
+    self.maml.adapt(sb.dev, adaptation_steps, start=start)
+    return start + adaptation_steps
+
+
+def meta_learn(self, batch, batch_idx, train: bool = True):
+    """base_adaptor.py:114-124 -> (6-tuple losses, 10-tuple predictions).  Also leaves this task's
+    outer gradient (Lightning's later `loss.backward()`) accumulated, pre-scaled by 1/(acc*world)."""
+    _assert_meta_batch(batch)
+    sup12, qry12 = batch[0][0][0], batch[0][1][0]
+    steps = min(self.adaptation_steps, self.test_adaptation_steps)
+    first_order = (not train) or (not self.second_order)
+    loss6, out = _run_task(self, sup12, qry12, steps, first_order, _scale(self) if train else None)
+    self._pending_tasks += 1 if train else 0
+    l = loss6.cpu()                                    # D2H read of the 6 losses (the step's result)
+    losses = tuple(l[i] for i in range(6))
+    B, Lq, T = qry12[3].shape[0], int(qry12[5]), int(qry12[8])
+    ar_l = torch.arange(Lq, device=self.device)[None, :]
+    ar_t = torch.arange(T, device=self.device)[None, :]
+    src_lens = _ent_dev(self, sup12, qry12, steps, first_order).src_lens
+    mel_lens = _ent_dev(self, sup12, qry12, steps, first_order).mel_lens
+    preds = (out["mel"], out["postnet"], out["pitch"], out["energy"], out["logd"], qry12[11],
+             ar_l >= src_lens[:, None], ar_t >= mel_lens[:, None], src_lens, out["mel_len"])
+    return losses, preds
+
+
+def _ent_dev(self, sup12, qry12, steps, first_order):
+    _, ent = _get_task(self, sup12, qry12, steps, first_order)
+    return ent[1].dev
+
+
+def training_step(self, batch, batch_idx):
+    """meta.py:68-80"""
+    train_loss, predictions = self.meta_learn(batch, batch_idx, train=True)
+    qry_batch = batch[0][1][0]
+    return {"loss": train_loss[0], "losses": train_loss, "output": predictions, "_batch": qry_batch}
+
+
+def validation_step(self, batch, batch_idx):
+    """meta.py:85-97 (NB: the reference validates with train=True, i.e. second order; no optimizer step follows)."""
+    val_loss, predictions = self.meta_learn(batch, batch_idx, train=False)
+    return {"losses": val_loss, "output": predictions, "_batch": batch[0][1][0]}
+
+
+def optimizer_step(self):
+    """What Lightning does after `accumulate_grad_batches` training_steps: DDP mean-allreduce of the
+    outer gradient (one flat buffer, summed; the 1/(acc*world) scale was folded in at accumulation),
+    clip_grad_norm_(grad_clip_thresh), Adam, LambdaLR; then zero the accumulation buffer."""
+    m = self.maml
+    if torch.distributed.is_initialized() and torch.distributed.get_world_size(self.process_group) > 1:
+        torch.distributed.all_reduce(m.g_outer, group=self.process_group)
+    opt = self.train_config["optimizer"]
+    m.outer_update(1.0, float(opt.get("grad_clip_thresh", 1.0)), tuple(opt["betas"]), float(opt["eps"]))
+    self.be.zero_(m.g_outer)
+    self._pending_tasks = 0
+
+
+class MetaSystem:
+    """B200-native counterpart of `lightning.systems.meta.MetaSystem` (hot path only)."""
+
+    __init__ = _metasystem_init
+    load_state_dict = _load_state_dict
+    state_dict = _state_dict
+    adapt = adapt
+    meta_learn = meta_learn
+    training_step = training_step
+    validation_step = validation_step
+    optimizer_step = optimizer_step
+    _on_meta_batch_start = staticmethod(_assert_meta_batch)
+
+
+class MAML:
+    """Compatibility shim for `lightning.systems.utils.MAML` (l2l.algorithms.MAML): exposes `.lr`,
+    `.module` names and `clone()`; `adapt_` with a bare loss tensor is not meaningful without an
+    autograd graph and raises with a pointer to MetaSystem.adapt / meta_learn."""
+
+    def __init__(self, module, lr, first_order=False, allow_unused=None, allow_nograd=False):
+        self.module, self.lr, self.first_order = module, lr, first_order
+        self.allow_unused, self.allow_nograd = allow_unused, allow_nograd
+
+    def clone(self, first_order=None, allow_unused=None, allow_nograd=None):
+        return MAML(self.module, self.lr, self.first_order if first_order is None else first_order,
+                    allow_unused, allow_nograd)
+
+    def adapt_(self, loss, first_order=None, allow_unused=None, allow_nograd=None):
+        raise RuntimeError("the B200 engine adapts without an autograd graph: call MetaSystem.adapt(batch, steps) / "
+                           "meta_learn(batch, idx) (same signatures as lightning/systems/base_adaptor.py:98-124)")
+
+    adapt = adapt_

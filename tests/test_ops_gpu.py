@@ -23,19 +23,34 @@ def _both(cuda_device, name, args, kwargs=None, tol=TOL, split=3, skip=()):
     getattr(ref, name)(*cargs, **ckw)
     getattr(cu, name)(*gargs, **gkw)
     torch.cuda.synchronize()
-    for i, (c, g) in enumerate(zip(cargs, gargs)):
+    i = 0
+    while i < len(cargs):
+        c, g = cargs[i], gargs[i]
         if not torch.is_tensor(c) or i in skip:
+            i += 1
             continue
         g = g.cpu()
         if c.dtype in (torch.int64, torch.int32):
             assert torch.equal(c, g), f"{name}: int arg {i} differs"
-            continue
-        c64, g64 = c.double(), g.double()
-        assert torch.isfinite(g64).all(), f"{name}: arg {i} has non-finite values"
-        scale = c64.abs().max().clamp_min(1e-30)
-        err = (c64 - g64).abs().max() / scale
-        lim = tol if c.dtype == torch.float32 else 1e-2   # bf16 hi halves compare loosely; hi+lo checked below
-        assert err < lim, f"{name}: arg {i} max err {err:.3e} (scale {scale:.3e})"
+        elif c.dtype == torch.bfloat16:
+            # (hi, lo) pairs: the halves may round differently; their SUM is the fp32-grade value
+            nxt = cargs[i + 1] if i + 1 < len(cargs) else None
+            if torch.is_tensor(nxt) and nxt.dtype == torch.bfloat16:
+                cs, gs = c.double() + nxt.double(), g.double() + gargs[i + 1].cpu().double()
+                i += 1
+                lim = tol
+            else:
+                cs, gs, lim = c.double(), g.double(), 1e-2
+            assert torch.isfinite(gs).all(), f"{name}: arg {i} has non-finite values"
+            err = (cs - gs).abs().max() / cs.abs().max().clamp_min(1e-30)
+            assert err < lim, f"{name}: bf16 arg {i} max err {err:.3e}"
+        else:
+            c64, g64 = c.double(), g.double()
+            assert torch.isfinite(g64).all(), f"{name}: arg {i} has non-finite values"
+            scale = c64.abs().max().clamp_min(1e-30)
+            err = (c64 - g64).abs().max() / scale
+            assert err < tol, f"{name}: arg {i} max err {err:.3e} (scale {scale:.3e})"
+        i += 1
     return cargs, [g.cpu() if torch.is_tensor(g) else g for g in gargs]
 
 
