@@ -784,17 +784,52 @@ class FS2Engine:
     # ---------------------------------------------------------------------------------------------
     # whole model
     # ---------------------------------------------------------------------------------------------
+    def encoder_fwd(self, P: ParamSet, texts, src_lens, B: int, Lq: int, tp: Tape) -> Act:
+        """Encoder.forward (Models.py:73-100): embedding + position_enc, then the FFT blocks."""
+        d = self.d
+        x = tp.act("enc.x0", B, Lq, d)
+        self.be.embed_fwd(texts, P.get("encoder.src_word_emb.weight").f32, None, self.consts["encoder.position_enc"], Lq,
+                          B * Lq, d, x.f32, x.hi, x.lo)
+        for i in range(self.n_enc):
+            x = self.fft_fwd(P, f"encoder.layer_stack.{i}", tp, x, src_lens, self.h_enc)
+        return x
+
+    def decoder_fwd(self, P: ParamSet, xin_f32, spk, mel_lens, B: int, T: int, tp: Tape) -> Act:
+        """Decoder.forward (Models.py:139-171) on (x + spk_emb): + position_enc, then the FFT blocks.
+        `spk` may be None (plain Decoder module)."""
+        d = self.d
+        y = tp.act("dec.x0", B, T, d)
+        self.be.add_rowvec(xin_f32, spk, d, self.consts["decoder.position_enc"], B, T, d, y.f32, y.hi, y.lo)
+        for i in range(self.n_dec):
+            y = self.fft_fwd(P, f"decoder.layer_stack.{i}", tp, y, mel_lens, self.h_dec)
+        return y
+
+    def postnet_fwd(self, P: ParamSet, mel: Act, tp: Tape, update_bn: bool = True) -> Act:
+        """PostNet.forward (Layers.py:129-137): 4 x tanh(BN(conv5)) + BN(conv5), batch statistics."""
+        be, g, scr = self.be, self.g, self.scr
+        B, T = mel.B, mel.T
+        R = B * T
+        xin = mel
+        for i in range(5):
+            pre = f"postnet.convolutions.{i}"
+            co = POSTNET_CH[i + 1]
+            c = tp.f32(f"post.{i}.c", (B, T, co))
+            g.conv_fwd(xin, P.get(f"{pre}.0.conv.weight"), P.get(f"{pre}.0.conv.bias").f32, c, None, None)
+            o = tp.act(f"post.{i}.o", B, T, co, bf=(i < 4))
+            rm = self.consts[f"{pre}.1.running_mean"] if update_bn else None
+            rv = self.consts[f"{pre}.1.running_var"] if update_bn else None
+            be.bn_fwd(c, P.get(f"{pre}.1.weight").f32, P.get(f"{pre}.1.bias").f32, R, co, i < 4, rm, rv,
+                      scr.scratch("bn.ws", (4 * 512,)), tp.f32(f"post.{i}.st", (2 * co,)), o.f32, o.hi, o.lo)
+            xin = o
+        return xin
+
     def forward(self, P: ParamSet, bt: Batch, tp: Tape, update_bn: bool = True):
         """Teacher-forced forward + loss.  Returns dict with the reference's prediction tensors."""
         be, g, scr, d = self.be, self.g, self.scr, self.d
         B, Lq, T = bt.B, bt.L, bt.T
         assert T <= self.cfg["max_seq_len"] and Lq <= self.cfg["max_seq_len"], "sequence longer than max_seq_len"
         # ---- encoder (Models.py:73-100) ----
-        x = tp.act("enc.x0", B, Lq, d)
-        be.embed_fwd(bt.texts, P.get("encoder.src_word_emb.weight").f32, None, self.consts["encoder.position_enc"], Lq,
-                     B * Lq, d, x.f32, x.hi, x.lo)
-        for i in range(self.n_enc):
-            x = self.fft_fwd(P, f"encoder.layer_stack.{i}", tp, x, bt.src_lens, self.h_enc)
+        x = self.encoder_fwd(P, bt.texts, bt.src_lens, B, Lq, tp)
         # ---- speaker embedding (base_adaptor.py:64-70) ----
         spk = tp.f32("spk", (B, d))
         be.spk_embed(bt.spk_ids, P.get("speaker_emb.model.weight").f32, bt.spk_ids.numel(), d, bt.average_spk, B, spk)
@@ -822,26 +857,11 @@ class FS2Engine:
         xr = scr.scratch("lr.out", (B, T, d))
         be.lr_fwd(x2, lr_idx, xr)
         # ---- decoder (Models.py:139-171) ----
-        y = tp.act("dec.x0", B, T, d)
-        be.add_rowvec(xr, spk, d, self.consts["decoder.position_enc"], B, T, d, y.f32, y.hi, y.lo)
-        for i in range(self.n_dec):
-            y = self.fft_fwd(P, f"decoder.layer_stack.{i}", tp, y, bt.mel_lens, self.h_dec)
+        y = self.decoder_fwd(P, xr, spk, bt.mel_lens, B, T, tp)
         # ---- mel_linear + postnet (fastspeech2.py:97-99, Layers.py:129-137) ----
         mel = tp.act("mel", B, T, N_MEL)
         g.conv_fwd(y, P.get("mel_linear.weight"), P.get("mel_linear.bias").f32, mel.f32, mel.hi, mel.lo)
-        xin = mel
-        R = B * T
-        for i in range(5):
-            pre = f"postnet.convolutions.{i}"
-            co = POSTNET_CH[i + 1]
-            c = tp.f32(f"post.{i}.c", (B, T, co))
-            g.conv_fwd(xin, P.get(f"{pre}.0.conv.weight"), P.get(f"{pre}.0.conv.bias").f32, c, None, None)
-            o = tp.act(f"post.{i}.o", B, T, co, bf=(i < 4))
-            rm = self.consts[f"{pre}.1.running_mean"] if update_bn else None
-            rv = self.consts[f"{pre}.1.running_var"] if update_bn else None
-            be.bn_fwd(c, P.get(f"{pre}.1.weight").f32, P.get(f"{pre}.1.bias").f32, R, co, i < 4, rm, rv,
-                      scr.scratch("bn.ws", (4 * 512,)), tp.f32(f"post.{i}.st", (2 * co,)), o.f32, o.hi, o.lo)
-            xin = o
+        xin = self.postnet_fwd(P, mel, tp, update_bn)
         post = xin.f32
         be.axpby(1.0, mel.f32, 1.0, post)                    # postnet(output) + output
         loss6 = tp.f32("loss6", (6,))

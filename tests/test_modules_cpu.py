@@ -1,0 +1,82 @@
+"""Drop-in module classes: identical state_dict keys / seeded init as the reference (via the pinned
+oracle.init_params) and forward parity of Encoder / Decoder / PostNet / VariancePredictor / FastSpeech2 /
+LengthRegulator semantics, with the CPU restatement of the op set injected as backend."""
+import json
+import os
+import tempfile
+
+import pytest
+import torch
+
+from meta_tts_b200 import modules as M
+from oracle import fs2_oracle as O
+from oracle.ops_reference import RefOps
+
+CFG = O.small_model_config(1, 1)
+
+
+@pytest.fixture(scope="module")
+def pre_cfg():
+    d = tempfile.mkdtemp(prefix="mtts_pre_")
+    json.dump(O.DEFAULT_STATS, open(os.path.join(d, "stats.json"), "w"))
+    json.dump({f"s{i}": i for i in range(16)}, open(os.path.join(d, "speakers.json"), "w"))
+    return {"path": {"preprocessed_path": d},
+            "preprocessing": {"pitch": {"feature": "phoneme_level"}, "energy": {"feature": "phoneme_level"},
+                              "mel": {"n_mel_channels": 80}}}
+
+
+ALGO = {"adapt": {"type": "spk", "speaker_emb": "table"}}
+
+
+def test_state_dict_keys_and_seeded_init_match_reference(pre_cfg):
+    torch.manual_seed(0)
+    model = M.FastSpeech2(pre_cfg, O.BASE_MODEL_CONFIG, ALGO)
+    P = O.init_params(seed=0)          # bit-identical to the real reference (tests/test_oracle_golden.py)
+    sd = model.state_dict()
+    assert sorted(sd.keys()) == sorted(P.keys())
+    for k in P:
+        assert torch.equal(sd[k], P[k].detach()), k
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def test_forward_parity_with_injected_backend(pre_cfg):
+    be = RefOps(split=3)
+    M._B200Module._backend = be
+    try:
+        torch.manual_seed(0)
+        model = M.FastSpeech2(pre_cfg, CFG, ALGO).train()
+        P = O.init_params(seed=0, model_config=CFG)
+        b12 = O.synth_batch(2, 7, 20, seed=4, speaker=1, ragged=True)
+        with torch.no_grad():
+            ref = O.fs2_forward({k: v.detach().clone() for k, v in P.items()}, CFG, *b12[2:])
+        out = model(*b12[2:])
+        for i in range(5):
+            assert _rel(out[i].reshape(ref[i].shape), ref[i]) < 2e-5, i
+        assert torch.equal(out[6], ref[6]) and torch.equal(out[7], ref[7]) and torch.equal(out[9], ref[9])
+        # stand-alone Encoder / Decoder keep the reference signatures
+        src_mask, mel_mask = ref[6], ref[7]
+        enc_o = model.encoder(b12[3], src_mask)
+        assert _rel(enc_o, O.encoder({k: v.detach() for k, v in P.items()}, CFG, b12[3], src_mask)) < 2e-5
+        x = torch.randn(2, 20, 256, generator=torch.Generator().manual_seed(1))
+        dec_o, m2 = model.decoder(x, mel_mask)
+        dref, mref = O.decoder({k: v.detach() for k, v in P.items()}, CFG, x, mel_mask)
+        assert _rel(dec_o, dref) < 2e-5 and torch.equal(m2, mref)
+        post = model.postnet(ref[0])
+        pref = O.postnet({k: v.detach().clone() for k, v in P.items()}, ref[0], True)
+        assert _rel(post, pref) < 2e-5
+        vp = model.variance_adaptor.duration_predictor(enc_o, src_mask)
+        vref = O.variance_predictor({k: v.detach() for k, v in P.items()}, "variance_adaptor.duration_predictor", enc_o, src_mask)
+        assert _rel(vp, vref) < 5e-5
+    finally:
+        M._B200Module._backend = None
+
+
+def test_product_modules_refuse_to_run_without_gpu(pre_cfg):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    enc = M.Encoder(CFG)
+    with pytest.raises(Exception):
+        enc(torch.ones(1, 4, dtype=torch.long), torch.zeros(1, 4, dtype=torch.bool))
