@@ -45,6 +45,7 @@ int         mtts_check_device(void);
 /* ------------------------------------------------------------------------------------------
  * Generic tcgen05 GEMM:   for every z = (z0, z1):
  *     C_z[M,N] (+)= alpha * sum_{tap < ntaps} sum_{kb < nkb}  A(z,tap,kb)[M,K] * B(z,tap,kb)[N,K]^T
+ * (epilogue order: v = alpha*acc + bias; +C; ReLU; gate; store)
  * operands are bf16 (optionally hi/lo split => 3 MMAs per k-step, fp32-grade result), the
  * accumulator is fp32 in TMEM, operand tiles are fetched with TMA (4-D tensor maps, 128B swizzle,
  * out-of-bounds = 0 which implements conv zero padding and all ragged edges).
@@ -96,6 +97,9 @@ typedef struct {
   const float* bias;       /* [N] (or [M] with MTTS_EPI_BIAS_ROW) or NULL; added after alpha        */
   int64_t   bias_sz0;      /* bias stride per z0 (0 = shared)                                       */
   const void* gate;        /* bf16, C geometry, or NULL                                             */
+  /* optional SECOND product term accumulated into the same tile: C += A2 * B2^T with the geometry of
+   * a / b (only the base pointers differ).  Tangent passes: d(xW^T) = xdot W^T + x Wdot^T in one launch. */
+  const void* a2_hi; const void* a2_lo; const void* b2_hi; const void* b2_lo;
 } mtts_gemm_desc;
 
 int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream);

@@ -35,7 +35,9 @@ struct OperandParams {
 
 struct alignas(64) GemmParams {
   CUtensorMap map_a_hi, map_a_lo, map_b_hi, map_b_lo;
+  CUtensorMap map_a2_hi, map_a2_lo, map_b2_hi, map_b2_lo;   // optional second product term (same geometry)
   OperandParams a, b;
+  int32_t nterms;
   int32_t M, N, K;
   int32_t ntaps, nkb, nz0, nz1, ksplit;
   int32_t n_tiles;           // tiles along N
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
 
   // this CTA's slice of the (tap, kb, kc) iteration space
   const int kchunks = (p.K + BK - 1) / BK;
-  const int total_iters = p.ntaps * p.nkb * kchunks;
+  const int total_iters = p.nterms * p.ntaps * p.nkb * kchunks;
   const int per_split = (total_iters + p.ksplit - 1) / p.ksplit;
   const int it_begin = blockIdx.y * per_split;
   const int it_end = min(total_iters, it_begin + per_split);
@@ -102,6 +104,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
     if (SPLIT == 3) {
       tma_prefetch_desc(&p.map_a_lo);
       tma_prefetch_desc(&p.map_b_lo);
+    }
+    if (p.nterms > 1) {
+      tma_prefetch_desc(&p.map_a2_hi);
+      tma_prefetch_desc(&p.map_b2_hi);
+      if (SPLIT == 3) {
+        tma_prefetch_desc(&p.map_a2_lo);
+        tma_prefetch_desc(&p.map_b2_lo);
+      }
     }
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -127,7 +137,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
         const int kc = it % kchunks;
         const int rest = it / kchunks;
         const int kb = rest % p.nkb;
-        const int tap = rest / p.nkb;
+        const int rest2 = rest / p.nkb;
+        const int tap = rest2 % p.ntaps;
+        const bool t2 = rest2 >= p.ntaps;                 // second product term (tangent passes)
+        const CUtensorMap* ma_hi = t2 ? &p.map_a2_hi : &p.map_a_hi;
+        const CUtensorMap* ma_lo = t2 ? &p.map_a2_lo : &p.map_a_lo;
+        const CUtensorMap* mb_hi = t2 ? &p.map_b2_hi : &p.map_b_hi;
+        const CUtensorMap* mb_lo = t2 ? &p.map_b2_lo : &p.map_b_lo;
 
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full_bar[stage], C::STAGE);
@@ -142,14 +158,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
           const int c2 = pick_src(p.a.src2, z0, z1, tap, kb);
           const int c3 = pick_src(p.a.src3, z0, z1, tap, kb);
           if (p.a.major == MTTS_MAJOR_K) {
-            tma_load_4d(sa, &p.map_a_hi, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
-            if (SPLIT == 3) tma_load_4d(sa_lo, &p.map_a_lo, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
+            tma_load_4d(sa, ma_hi, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
+            if (SPLIT == 3) tma_load_4d(sa_lo, ma_lo, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
           } else {
 #pragma unroll
             for (int i = 0; i < BM / 64; ++i) {
-              tma_load_4d(sa + i * (BK * 128), &p.map_a_hi, &full_bar[stage], m0 + 64 * i, kc * BK + shift, c2, c3);
+              tma_load_4d(sa + i * (BK * 128), ma_hi, &full_bar[stage], m0 + 64 * i, kc * BK + shift, c2, c3);
               if (SPLIT == 3)
-                tma_load_4d(sa_lo + i * (BK * 128), &p.map_a_lo, &full_bar[stage], m0 + 64 * i, kc * BK + shift, c2, c3);
+                tma_load_4d(sa_lo + i * (BK * 128), ma_lo, &full_bar[stage], m0 + 64 * i, kc * BK + shift, c2, c3);
             }
           }
         }
@@ -158,14 +174,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
           const int c2 = pick_src(p.b.src2, z0, z1, tap, kb);
           const int c3 = pick_src(p.b.src3, z0, z1, tap, kb);
           if (p.b.major == MTTS_MAJOR_K) {
-            tma_load_4d(sb, &p.map_b_hi, &full_bar[stage], kc * BK, n0 + shift, c2, c3);
-            if (SPLIT == 3) tma_load_4d(sb_lo, &p.map_b_lo, &full_bar[stage], kc * BK, n0 + shift, c2, c3);
+            tma_load_4d(sb, mb_hi, &full_bar[stage], kc * BK, n0 + shift, c2, c3);
+            if (SPLIT == 3) tma_load_4d(sb_lo, mb_lo, &full_bar[stage], kc * BK, n0 + shift, c2, c3);
           } else {
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i) {
-              tma_load_4d(sb + i * (BK * 128), &p.map_b_hi, &full_bar[stage], n0 + 64 * i, kc * BK + shift, c2, c3);
+              tma_load_4d(sb + i * (BK * 128), mb_hi, &full_bar[stage], n0 + 64 * i, kc * BK + shift, c2, c3);
               if (SPLIT == 3)
-                tma_load_4d(sb_lo + i * (BK * 128), &p.map_b_lo, &full_bar[stage], n0 + 64 * i, kc * BK + shift, c2, c3);
+                tma_load_4d(sb_lo + i * (BK * 128), mb_lo, &full_bar[stage], n0 + 64 * i, kc * BK + shift, c2, c3);
             }
           }
         }
@@ -243,17 +259,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
           if (p.flags & MTTS_EPI_BIAS_ROW) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += bias_row;
+          } else if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+              v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) v[j] += __ldg(bias + col0 + j);
           }
         }
+        const bool full = (col0 + 32 <= p.N) && vec_ok;
         if (p.flags & MTTS_EPI_ADD_C) {
           const float* src = p.c_f32 + c_off + col0;
+          if (full) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) v[j] += src[j];
+            for (int j = 0; j < 32; j += 4) {
+              const float4 cc = *reinterpret_cast<const float4*>(src + j);
+              v[j] += cc.x; v[j + 1] += cc.y; v[j + 2] += cc.z; v[j + 3] += cc.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += src[j];
+          }
         }
         if (p.flags & MTTS_EPI_RELU) {
 #pragma unroll
@@ -261,11 +292,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
         }
         if (p.flags & MTTS_EPI_GATE) {
           const bf16* g = p.gate + c_off + col0;
+          if (full) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N && !(__bfloat162float(g[j]) > 0.f)) v[j] = 0.f;
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 gg = *reinterpret_cast<const uint4*>(g + j);
+              const uint32_t w[4] = {gg.x, gg.y, gg.z, gg.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                const uint32_t lo16 = w[t] & 0xFFFFu, hi16 = w[t] >> 16;
+                if (!((lo16 & 0x8000u) == 0 && (lo16 & 0x7FFFu) != 0)) v[j + 2 * t] = 0.f;
+                if (!((hi16 & 0x8000u) == 0 && (hi16 & 0x7FFFu) != 0)) v[j + 2 * t + 1] = 0.f;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N && !(__bfloat162float(g[j]) > 0.f)) v[j] = 0.f;
+          }
         }
-        const bool full = (col0 + 32 <= p.N) && vec_ok;
         if (p.c_f32) {
           float* dst = p.c_f32 + c_off + col0;
           if (p.flags & MTTS_EPI_ACCUM) {
@@ -415,11 +460,10 @@ extern "C" int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream_) {
   int bn = d->block_n;
   if (bn == 0) {
     if (d->N <= 64) bn = 64;
-    else if (d->N <= 128 || d->split == 3) bn = 128;
+    else if (d->N <= 128) bn = 128;
     else bn = 256;
   }
   MTTS_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: block_n must be 64/128/256");
-  MTTS_REQUIRE(!(d->split == 3 && bn == 256), "gemm: block_n 256 not available in split=3 mode");
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -430,12 +474,23 @@ extern "C" int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream_) {
     if ((rc = encode_operand_map(&p.map_a_lo, d->a.lo, d->a, BM, "A.lo")) != MTTS_OK) return rc;
     if ((rc = encode_operand_map(&p.map_b_lo, d->b.lo, d->b, bn, "B.lo")) != MTTS_OK) return rc;
   }
+  const bool two = d->a2_hi != nullptr || d->b2_hi != nullptr;
+  if (two) {
+    MTTS_REQUIRE(d->a2_hi && d->b2_hi && (d->split == 1 || (d->a2_lo && d->b2_lo)), "gemm: incomplete second term");
+    if ((rc = encode_operand_map(&p.map_a2_hi, d->a2_hi, d->a, BM, "A2.hi")) != MTTS_OK) return rc;
+    if ((rc = encode_operand_map(&p.map_b2_hi, d->b2_hi, d->b, bn, "B2.hi")) != MTTS_OK) return rc;
+    if (d->split == 3) {
+      if ((rc = encode_operand_map(&p.map_a2_lo, d->a2_lo, d->a, BM, "A2.lo")) != MTTS_OK) return rc;
+      if ((rc = encode_operand_map(&p.map_b2_lo, d->b2_lo, d->b, bn, "B2.lo")) != MTTS_OK) return rc;
+    }
+  }
+  p.nterms = two ? 2 : 1;
   p.a = {d->a.major, d->a.src2, d->a.src3, d->a.shift_src, d->a.shift_base, d->a.shift_step};
   p.b = {d->b.major, d->b.src2, d->b.src3, d->b.shift_src, d->b.shift_base, d->b.shift_step};
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.ntaps = d->ntaps; p.nkb = d->nkb; p.nz0 = d->nz0; p.nz1 = d->nz1;
   const int kchunks = mtts_cdiv(d->K, BK);
-  const int total_iters = d->ntaps * d->nkb * kchunks;
+  const int total_iters = p.nterms * d->ntaps * d->nkb * kchunks;
   p.ksplit = ksplit > total_iters ? total_iters : ksplit;
   // every split must own >= 1 iteration
   while (p.ksplit > 1 && mtts_cdiv(total_iters, p.ksplit) * (p.ksplit - 1) >= total_iters) --p.ksplit;
@@ -459,6 +514,7 @@ extern "C" int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream_) {
     return launch<256, 1>(p, grid, stream);
   } else {
     if (bn == 64) return launch<64, 3>(p, grid, stream);
-    return launch<128, 3>(p, grid, stream);
+    if (bn == 128) return launch<128, 3>(p, grid, stream);
+    return launch<256, 3>(p, grid, stream);
   }
 }

@@ -304,79 +304,115 @@ def _wgrad_ksplit(tiles: int, iters: int) -> int:
     return max(1, min(ks, iters // 2 if iters >= 2 else 1, 32))
 
 
+def _pick_bn(row_tiles: int, N: int) -> int:
+    """Largest N-tile that still gives ~a wave of CTAs: bigger tiles cut operand traffic per flop (the GEMM
+    is L2-throughput bound at 128x128 in bf16x3, profiles/r01_ncu_summary.md); tiny grids get BN=64."""
+    for bn, need in ((256, 100), (128, 120)):
+        if N > bn // 2 and row_tiles * ((N + bn - 1) // bn) >= need:
+            return bn
+    return 64 if N > 64 or row_tiles * ((N + 63) // 64) >= 1 else 64
+
+
 class Gemm:
-    """Descriptor construction for the contractions of the model (all through be.gemm)."""
+    """Descriptor construction for the contractions of the model (all through be.gemm).
+    `x2/w2`-style arguments add a SECOND product term in the same launch (tangent passes)."""
 
     def __init__(self, be):
         self.be = be
 
-    # y[b,t,:] = sum_j x[b,t+j-p,:] W_j^T (+bias) ; W: [k, N, Cin]
-    def conv_fwd(self, x: Act, w: Wt, bias, out_f32, out_hi, out_lo, relu=False, gate=None, add_c=False):
+    # y[b,t,:] = sum_j x[b,t+j-p,:] W_j^T (+bias) [+ sum_j x2[b,t+j-p,:] W2_j^T] ; W: [k, N, Cin]
+    def conv_fwd(self, x: Act, w: Wt, bias, out_f32, out_hi, out_lo, relu=False, gate=None, add_c=False,
+                 x2: Optional[Act] = None, w2: Optional[Wt] = None):
         k, N, Cin = w.shape if len(w.shape) == 3 else (1,) + tuple(w.shape)
-        assert Cin == x.C
+        assert Cin == x.C and (x2 is None) == (w2 is None)
         p = (k - 1) // 2
         flags = (L.EPI_RELU if relu else 0) | (L.EPI_GATE if gate is not None else 0) | (L.EPI_ADD_C if add_c else 0)
+        h2 = (lambda t: (t.hi, t.lo)) if x2 is not None else (lambda t: (None, None))
         wop = Opnd(w.hi, w.lo, L.MAJOR_K, (Cin, N, k), (1, Cin, N * Cin), src2=L.SRC_TAP)
+        if w2 is not None:
+            wop.hi2, wop.lo2 = w2.hi, w2.lo
         if k == 1:
             a = Opnd(x.hi, x.lo, L.MAJOR_K, (Cin, x.B * x.T), (1, Cin))
+            if x2 is not None:
+                a.hi2, a.lo2 = x2.hi, x2.lo
             self.be.gemm(a, wop, x.B * x.T, N, Cin, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=N, bias=bias,
-                         gate=gate, flags=flags)
+                         gate=gate, flags=flags, block_n=_pick_bn((x.B * x.T + 127) // 128, N))
         else:
             a = Opnd(x.hi, x.lo, L.MAJOR_K, (Cin, x.T, x.B), (1, Cin, x.T * Cin), src2=L.SRC_Z0,
                      shift_src=L.SRC_TAP, shift_base=-p, shift_step=1)
+            if x2 is not None:
+                a.hi2, a.lo2 = x2.hi, x2.lo
             self.be.gemm(a, wop, x.T, N, Cin, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=N, c_sz0=x.T * N, bias=bias,
-                         gate=gate, flags=flags, ntaps=k, nz0=x.B)
+                         gate=gate, flags=flags, ntaps=k, nz0=x.B, block_n=_pick_bn(x.B * ((x.T + 127) // 128), N))
 
-    # dx[b,t,:] = sum_j dy[b,t-j+p,:] W_j
-    def conv_dgrad(self, dy: Act, w: Wt, out_f32, out_hi, out_lo, gate=None, add_c=False):
+    # dx[b,t,:] = sum_j dy[b,t-j+p,:] W_j  [+ sum_j dy2[b,t-j+p,:] W2_j]
+    def conv_dgrad(self, dy: Act, w: Wt, out_f32, out_hi, out_lo, gate=None, add_c=False,
+                   dy2: Optional[Act] = None, w2: Optional[Wt] = None):
         k, N, Cin = w.shape if len(w.shape) == 3 else (1,) + tuple(w.shape)
-        assert N == dy.C
+        assert N == dy.C and (dy2 is None) == (w2 is None)
         p = (k - 1) // 2
         flags = (L.EPI_GATE if gate is not None else 0) | (L.EPI_ADD_C if add_c else 0)
         wop = Opnd(w.hi, w.lo, L.MAJOR_MN, (Cin, N, k), (1, Cin, N * Cin), src2=L.SRC_TAP)
+        if w2 is not None:
+            wop.hi2, wop.lo2 = w2.hi, w2.lo
         if k == 1:
             a = Opnd(dy.hi, dy.lo, L.MAJOR_K, (N, dy.B * dy.T), (1, N))
+            if dy2 is not None:
+                a.hi2, a.lo2 = dy2.hi, dy2.lo
             self.be.gemm(a, wop, dy.B * dy.T, Cin, N, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=Cin, gate=gate,
-                         flags=flags)
+                         flags=flags, block_n=_pick_bn((dy.B * dy.T + 127) // 128, Cin))
         else:
             a = Opnd(dy.hi, dy.lo, L.MAJOR_K, (N, dy.T, dy.B), (1, N, dy.T * N), src2=L.SRC_Z0,
                      shift_src=L.SRC_TAP, shift_base=p, shift_step=-1)
+            if dy2 is not None:
+                a.hi2, a.lo2 = dy2.hi, dy2.lo
             self.be.gemm(a, wop, dy.T, Cin, N, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=Cin, c_sz0=dy.T * Cin,
-                         gate=gate, flags=flags, ntaps=k, nz0=dy.B)
+                         gate=gate, flags=flags, ntaps=k, nz0=dy.B, block_n=_pick_bn(dy.B * ((dy.T + 127) // 128), Cin))
 
-    # dW_j[n,c] += sum_{b,t} dy[b,t,n] x[b,t+j-p,c]
-    def conv_wgrad(self, dy: Act, x: Act, dw_f32: torch.Tensor, scale: float = 1.0):
+    # dW_j[n,c] += sum_{b,t} dy[b,t,n] x[b,t+j-p,c]  [+ dy2 (x) x2]
+    def conv_wgrad(self, dy: Act, x: Act, dw_f32: torch.Tensor, scale: float = 1.0,
+                   dy2: Optional[Act] = None, x2: Optional[Act] = None):
         shp = tuple(dw_f32.shape)
         k, N, Cin = shp if len(shp) == 3 else (1,) + shp
-        assert N == dy.C and Cin == x.C and dy.B == x.B and dy.T == x.T
+        assert N == dy.C and Cin == x.C and dy.B == x.B and dy.T == x.T and (dy2 is None) == (x2 is None)
         p = (k - 1) // 2
         bn = 64 if Cin <= 64 else 128
         tiles = ((N + 127) // 128) * ((Cin + bn - 1) // bn) * k
+        nt = 2 if dy2 is not None else 1
         if k == 1:
             R = dy.B * dy.T
             a = Opnd(dy.hi, dy.lo, L.MAJOR_MN, (N, R), (1, N))
             b = Opnd(x.hi, x.lo, L.MAJOR_MN, (Cin, R), (1, Cin))
+            if dy2 is not None:
+                a.hi2, a.lo2, b.hi2, b.lo2 = dy2.hi, dy2.lo, x2.hi, x2.lo
             self.be.gemm(a, b, N, Cin, R, c_f32=dw_f32, ldc=Cin, flags=L.EPI_ACCUM, alpha=scale,
-                         ksplit=_wgrad_ksplit(tiles, (R + 63) // 64), block_n=bn)
+                         ksplit=_wgrad_ksplit(tiles, nt * ((R + 63) // 64)), block_n=bn)
         else:
             a = Opnd(dy.hi, dy.lo, L.MAJOR_MN, (N, dy.T, dy.B), (1, N, dy.T * N), src2=L.SRC_KB)
             b = Opnd(x.hi, x.lo, L.MAJOR_MN, (Cin, x.T, x.B), (1, Cin, x.T * Cin), src2=L.SRC_KB,
                      shift_src=L.SRC_Z0, shift_base=-p, shift_step=1)
+            if dy2 is not None:
+                a.hi2, a.lo2, b.hi2, b.lo2 = dy2.hi, dy2.lo, x2.hi, x2.lo
             self.be.gemm(a, b, N, Cin, dy.T, c_f32=dw_f32, ldc=Cin, c_sz0=N * Cin, flags=L.EPI_ACCUM, alpha=scale,
-                         nkb=dy.B, nz0=k, ksplit=_wgrad_ksplit(tiles, dy.B * ((dy.T + 63) // 64)), block_n=bn)
+                         nkb=dy.B, nz0=k, ksplit=_wgrad_ksplit(tiles, nt * dy.B * ((dy.T + 63) // 64)), block_n=bn)
 
-    # C[b,h] = alpha * op(A)[M,K] op(B)[N,K]^T   (op = identity or transpose, see BMat)
-    def bmm(self, A: BMat, a_t: bool, Bm: BMat, b_t: bool, Cm: BMat, nb: int, nh: int, alpha=1.0, add_c=False):
+    # C[b,h] = alpha * ( op(A) op(B)^T [+ op(A2) op(B2)^T] )   (op = identity or transpose, see BMat)
+    def bmm(self, A: BMat, a_t: bool, Bm: BMat, b_t: bool, Cm: BMat, nb: int, nh: int, alpha=1.0, add_c=False,
+            A2: Optional[BMat] = None, B2: Optional[BMat] = None):
         M = A.cols if a_t else A.rows
         K = A.rows if a_t else A.cols
         N = Bm.cols if b_t else Bm.rows
-        assert K == (Bm.rows if b_t else Bm.cols)
+        assert K == (Bm.rows if b_t else Bm.cols) and (A2 is None) == (B2 is None)
         a = Opnd(A.hi, A.lo, L.MAJOR_MN if a_t else L.MAJOR_K, (A.cols, A.rows, nh, nb), (1, A.sr, A.sh, A.sb),
                  src2=L.SRC_Z0, src3=L.SRC_Z1, offset=A.off)
         b = Opnd(Bm.hi, Bm.lo, L.MAJOR_MN if b_t else L.MAJOR_K, (Bm.cols, Bm.rows, nh, nb), (1, Bm.sr, Bm.sh, Bm.sb),
                  src2=L.SRC_Z0, src3=L.SRC_Z1, offset=Bm.off)
+        if A2 is not None:
+            assert (A2.off, A2.sr, A2.sh, A2.sb) == (A.off, A.sr, A.sh, A.sb) and (B2.off, B2.sr, B2.sh, B2.sb) == (Bm.off, Bm.sr, Bm.sh, Bm.sb)
+            a.hi2, a.lo2, b.hi2, b.lo2 = A2.hi, A2.lo, B2.hi, B2.lo
         self.be.gemm(a, b, M, N, K, c_f32=Cm.f32, c_hi=Cm.hi, c_lo=Cm.lo, ldc=Cm.sr, c_off=Cm.off, c_sz0=Cm.sh,
-                     c_sz1=Cm.sb, alpha=alpha, flags=(L.EPI_ADD_C if add_c else 0), nz0=nh, nz1=nb)
+                     c_sz1=Cm.sb, alpha=alpha, flags=(L.EPI_ADD_C if add_c else 0), nz0=nh, nz1=nb,
+                     block_n=_pick_bn(nb * nh * ((M + 127) // 128), N))
 
 
 # =================================================================================================
@@ -509,36 +545,29 @@ class FS2Engine:
         g.conv_dgrad(dqkv, wqkv, dx_out, None, None, add_c=True)
 
     def _lin_t(self, x: Act, xd: Optional[Act], w: Wt, wd: Optional[Wt], bd, out_f32, out_hi, out_lo, relu_gate=None):
-        """Tangent of y = conv(x, W) + b:  yd = conv(xd, W) + conv(x, Wd) + bd (then optional ReLU gate).
-        out_f32 is required as the accumulation buffer when both terms exist."""
-        terms = []
-        if xd is not None:
-            terms.append((xd, w))
-        if wd is not None:
-            terms.append((x, wd))
-        assert terms, "tangent of a linear op with zero input and weight tangents"
-        n = len(terms)
-        assert n == 1 or out_f32 is not None
-        for i, (xx, ww) in enumerate(terms):
-            last = i == n - 1
-            self.g.conv_fwd(xx, ww, bd if i == 0 else None, out_f32, out_hi if last else None, out_lo if last else None,
-                            gate=relu_gate if last else None, add_c=i > 0)
+        """Tangent of y = conv(x, W) + b:  yd = conv(xd, W) + conv(x, Wd) + bd (then optional ReLU gate),
+        ONE launch (two product terms accumulate in the same TMEM tile)."""
+        assert xd is not None or wd is not None, "tangent of a linear op with zero input and weight tangents"
+        if xd is not None and wd is not None:
+            self.g.conv_fwd(xd, w, bd, out_f32, out_hi, out_lo, gate=relu_gate, x2=x, w2=wd)
+        elif xd is not None:
+            self.g.conv_fwd(xd, w, bd, out_f32, out_hi, out_lo, gate=relu_gate)
+        else:
+            self.g.conv_fwd(x, wd, bd, out_f32, out_hi, out_lo, gate=relu_gate)
 
     def _dgrad_t(self, dy: Act, ddy: Act, w: Wt, wd: Optional[Wt], out_f32, out_hi, out_lo, gate=None, add_c=False):
         """Tangent of dx = dgrad(dy, W):  ddx = dgrad(ddy, W) + dgrad(dy, Wd)  (+ existing out_f32 if add_c)."""
-        g = self.g
         if wd is None:
-            g.conv_dgrad(ddy, w, out_f32, out_hi, out_lo, gate=gate, add_c=add_c)
-            return
-        assert out_f32 is not None
-        g.conv_dgrad(ddy, w, out_f32, None, None, add_c=add_c)
-        g.conv_dgrad(dy, wd, out_f32, out_hi, out_lo, gate=gate, add_c=True)
+            self.g.conv_dgrad(ddy, w, out_f32, out_hi, out_lo, gate=gate, add_c=add_c)
+        else:
+            self.g.conv_dgrad(ddy, w, out_f32, out_hi, out_lo, gate=gate, add_c=add_c, dy2=dy, w2=wd)
 
     def _wgrad_t(self, dy: Act, ddy: Act, x: Act, xd: Optional[Act], hv_w: torch.Tensor):
         """Tangent of dW = wgrad(dy, x):  ddW += wgrad(ddy, x) + wgrad(dy, xd)."""
-        self.g.conv_wgrad(ddy, x, hv_w)
-        if xd is not None:
-            self.g.conv_wgrad(dy, xd, hv_w)
+        if xd is None:
+            self.g.conv_wgrad(ddy, x, hv_w)
+        else:
+            self.g.conv_wgrad(ddy, x, hv_w, dy2=dy, x2=xd)
 
     def fft_tfwd(self, P: ParamSet, Pd: ParamSet, pf: str, tp: Tape, tt: Tape, x: Act, xd: Optional[Act], lens, H: int) -> Act:
         """Tangent forward; xd = input tangent (None = zero), Pd = parameter tangents."""
@@ -563,15 +592,13 @@ class FS2Engine:
         # Sdot = scale (Qd K^T + Q Kd^T)
         Sd = scr.scratch("S", (B, H, T, Tp))
         sc = 1.0 / math.sqrt(dk)
-        g.bmm(qm(qd_h, qd_l, 0), False, qm(qkv_h, qkv_l, 1), False, pm(None, None, Sd), B, H, alpha=sc)
-        g.bmm(qm(qkv_h, qkv_l, 0), False, qm(qd_h, qd_l, 1), False, pm(None, None, Sd), B, H, alpha=sc, add_c=True)
+        g.bmm(qm(qd_h, qd_l, 0), False, qm(qkv_h, qkv_l, 1), False, pm(None, None, Sd), B, H, alpha=sc,
+              A2=qm(qkv_h, qkv_l, 0), B2=qm(qd_h, qd_l, 1))
         pd_h, pd_l = tt.bf(f"{pf}.Pd", (B, H, T, Tp))
         be.softmax(1, Sd, None, p_h, p_l, None, None, lens, B * H, H, T, T, Tp, pd_h, pd_l)
         # Od = Pd V + P Vd
         od = tt.act(f"{pf}.od", B, T, d, f32=False)
-        od_f = scr.scratch("o_f", (B, T, d))
-        g.bmm(pm(pd_h, pd_l), False, qm(qkv_h, qkv_l, 2), True, om(None, None, od_f), B, H)
-        g.bmm(pm(p_h, p_l), False, qm(qd_h, qd_l, 2), True, om(od.hi, od.lo, od_f), B, H, add_c=True)
+        g.bmm(pm(pd_h, pd_l), False, qm(qkv_h, qkv_l, 2), True, om(od.hi, od.lo), B, H, A2=pm(p_h, p_l), B2=qm(qd_h, qd_l, 2))
         # fc + LN1
         y0d = scr.scratch("y0", (B, T, d))
         self._lin_t(o, od, P.get(f"{a_}.fc.weight"), wdt(f"{a_}.fc.weight"), gd(f"{a_}.fc.bias"), y0d, None, None)
@@ -652,21 +679,19 @@ class FS2Engine:
         # ---- attention ----
         sc = 1.0 / math.sqrt(dk)
         ddP = scr.scratch("S", (B, H, T, Tp))
-        g.bmm(om(ddo.hi, ddo.lo), False, qm(qkv_h, qkv_l, 2), False, pm(None, None, ddP), B, H)            # ddO V^T
-        g.bmm(om(do.hi, do.lo), False, qm(qd_h, qd_l, 2), False, pm(None, None, ddP), B, H, add_c=True)    # dO Vd^T
+        g.bmm(om(ddo.hi, ddo.lo), False, qm(qkv_h, qkv_l, 2), False, pm(None, None, ddP), B, H,             # ddO V^T + dO Vd^T
+              A2=om(do.hi, do.lo), B2=qm(qd_h, qd_l, 2))
         dds_h, dds_l = tt.bf(f"{pf}.ddS", (B, H, T, Tp))
         be.softmax(2, dP, ddP, p_h, p_l, pd_h, pd_l, lens, B * H, H, T, T, Tp, dds_h, dds_l)
         ddq_h, ddq_l = tt.bf(f"{pf}.ddqkv", (R, 3 * d))
-        ddq_f = scr.scratch("qkv_f", (R, 3 * d))
         # ddV = Pd^T dO + P^T ddO
-        g.bmm(pm(pd_h, pd_l), True, om(do.hi, do.lo), True, qm(None, None, 2, ddq_f), B, H)
-        g.bmm(pm(p_h, p_l), True, om(ddo.hi, ddo.lo), True, qm(ddq_h, ddq_l, 2, ddq_f), B, H, add_c=True)
+        g.bmm(pm(pd_h, pd_l), True, om(do.hi, do.lo), True, qm(ddq_h, ddq_l, 2), B, H, A2=pm(p_h, p_l), B2=om(ddo.hi, ddo.lo))
         # ddQ = scale (ddS K + dS Kd)
-        g.bmm(pm(dds_h, dds_l), False, qm(qkv_h, qkv_l, 1), True, qm(None, None, 0, ddq_f), B, H, alpha=sc)
-        g.bmm(pm(ds_h, ds_l), False, qm(qd_h, qd_l, 1), True, qm(ddq_h, ddq_l, 0, ddq_f), B, H, alpha=sc, add_c=True)
+        g.bmm(pm(dds_h, dds_l), False, qm(qkv_h, qkv_l, 1), True, qm(ddq_h, ddq_l, 0), B, H, alpha=sc,
+              A2=pm(ds_h, ds_l), B2=qm(qd_h, qd_l, 1))
         # ddK = scale (ddS^T Q + dS^T Qd)
-        g.bmm(pm(dds_h, dds_l), True, qm(qkv_h, qkv_l, 0), True, qm(None, None, 1, ddq_f), B, H, alpha=sc)
-        g.bmm(pm(ds_h, ds_l), True, qm(qd_h, qd_l, 0), True, qm(ddq_h, ddq_l, 1, ddq_f), B, H, alpha=sc, add_c=True)
+        g.bmm(pm(dds_h, dds_l), True, qm(qkv_h, qkv_l, 0), True, qm(ddq_h, ddq_l, 1), B, H, alpha=sc,
+              A2=pm(ds_h, ds_l), B2=qm(qd_h, qd_l, 0))
         dqkv = Act(None, dq_h, dq_l, B, T, 3 * d)
         ddqkv = Act(None, ddq_h, ddq_l, B, T, 3 * d)
         self._wgrad_t(dqkv, ddqkv, x, xd, hvwqkv.f32)

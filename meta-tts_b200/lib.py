@@ -44,6 +44,7 @@ class GemmDesc(C.Structure):
         ("ldc", C.c_int64), ("c_sz0", C.c_int64), ("c_sz1", C.c_int64),
         ("bias", C.c_void_p), ("bias_sz0", C.c_int64),
         ("gate", C.c_void_p),
+        ("a2_hi", C.c_void_p), ("a2_lo", C.c_void_p), ("b2_hi", C.c_void_p), ("b2_lo", C.c_void_p),
     ]
 
 

@@ -56,6 +56,8 @@ class Opnd:
     shift_base: int = 0
     shift_step: int = 0
     offset: int = 0                 # element offset into hi/lo
+    hi2: Optional[torch.Tensor] = None   # second product term (same geometry / offset), see mtts_gemm_desc.a2_hi
+    lo2: Optional[torch.Tensor] = None
 
     def fill(self, o: L.Operand) -> None:
         esz = 2
@@ -94,6 +96,12 @@ def gemm(a: Opnd, b: Opnd, M: int, N: int, K: int, *,
     d.bias = _ptr(bias)
     d.bias_sz0 = bias_sz0
     d.gate = (gate.data_ptr() + 2 * c_off) if gate is not None else None
+    if a.hi2 is not None or b.hi2 is not None:
+        assert a.hi2 is not None and b.hi2 is not None, "second product term needs both operands"
+        d.a2_hi = a.hi2.data_ptr() + 2 * a.offset
+        d.a2_lo = (a.lo2.data_ptr() + 2 * a.offset) if a.lo2 is not None else None
+        d.b2_hi = b.hi2.data_ptr() + 2 * b.offset
+        d.b2_lo = (b.lo2.data_ptr() + 2 * b.offset) if b.lo2 is not None else None
     L.call("mtts_gemm", C.byref(d), _stream())
     launch_count += 1
 

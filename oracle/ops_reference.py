@@ -77,17 +77,18 @@ class RefOps:
     # ------------------------------------------------------------------------------------------
     # GEMM descriptor emulator (semantics of mtts_gemm: TMA coordinates, OOB zero fill, epilogue)
     # ------------------------------------------------------------------------------------------
-    def _fetch(self, op, n_mn, K, z0, z1, tap, kb, split):
+    def _fetch(self, op, n_mn, K, z0, z1, tap, kb, split, term=0):
         pick = lambda s: {SRC_ZERO: 0, SRC_Z0: z0, SRC_Z1: z1, SRC_TAP: tap, SRC_KB: kb}[s]  # noqa: E731
         d = list(op.dims) + [1] * (4 - len(op.dims))
         s = list(op.strides) + [0] * (4 - len(op.strides))
         c2, c3 = pick(op.src2), pick(op.src3)
         shift = op.shift_base + op.shift_step * pick(op.shift_src)
-        flat_hi = op.hi.reshape(-1)
+        t_hi, t_lo = (op.hi, op.lo) if term == 0 else (op.hi2, op.lo2)
+        flat_hi = t_hi.reshape(-1)
         flat = flat_hi.float()
         if split == 3:
-            assert op.lo is not None, "split=3 operand without lo"
-            flat = flat + op.lo.reshape(-1).float()
+            assert t_lo is not None, "split=3 operand without lo"
+            flat = flat + t_lo.reshape(-1).float()
         mn = torch.arange(n_mn)
         kk = torch.arange(K)
         if c2 >= d[2] or c3 >= d[3]:
@@ -124,11 +125,13 @@ class RefOps:
         for z1 in range(nz1):
             for z0 in range(nz0):
                 acc = torch.zeros(M, N, dtype=self.acc)
-                for tap in range(ntaps):
-                    for kb in range(nkb):
-                        A = self._fetch(a, M, K, z0, z1, tap, kb, split)
-                        Bm = self._fetch(b, N, K, z0, z1, tap, kb, split)
-                        acc += A @ Bm.t()
+                nterms = 2 if (getattr(a, "hi2", None) is not None or getattr(b, "hi2", None) is not None) else 1
+                for term in range(nterms):
+                    for tap in range(ntaps):
+                        for kb in range(nkb):
+                            A = self._fetch(a, M, K, z0, z1, tap, kb, split, term)
+                            Bm = self._fetch(b, N, K, z0, z1, tap, kb, split, term)
+                            acc += A @ Bm.t()
                 v = acc * alpha
                 if bias is not None:
                     bv = bias.reshape(-1)[z0 * bias_sz0:]

@@ -215,3 +215,23 @@ def test_large_decoder_shapes(cuda_device):
                  split=split, flags=L.EPI_RELU)
         ref = torch.relu(_conv_ref(xr, wr, bias.double(), p))
         _check("decoder conv9 (hi+lo out)", Hh.float() + Hl.float(), ref, split)
+
+
+@pytest.mark.parametrize("split", [1, 3])
+@pytest.mark.parametrize("block_n", [64, 128, 256])
+def test_two_term_conv_and_bn256(cuda_device, split, block_n):
+    """C = conv(x1, W1) + conv(x2, W2) + bias in ONE launch (tangent passes), all tile widths incl. BN=256 in bf16x3."""
+    torch.manual_seed(7)
+    B, T, cin, cout, k, p = 2, 300, 256, 512, 3, 1
+    X1, X2 = torch.randn(B, T, cin, device=cuda_device), torch.randn(B, T, cin, device=cuda_device)
+    W1, W2 = (torch.randn(k, cout, cin, device=cuda_device) / 30 for _ in range(2))
+    bias = torch.randn(cout, device=cuda_device)
+    (x1h, x1l, x1r), (x2h, x2l, x2r) = _prep(X1, split), _prep(X2, split)
+    (w1h, w1l, w1r), (w2h, w2l, w2r) = _prep(W1, split), _prep(W2, split)
+    Y = torch.empty(B, T, cout, device=cuda_device)
+    ops.gemm(ops.Opnd(x1h, x1l, L.MAJOR_K, (cin, T, B), (1, cin, T * cin), src2=L.SRC_Z0, shift_src=L.SRC_TAP,
+                      shift_base=-p, shift_step=1, hi2=x2h, lo2=x2l),
+             ops.Opnd(w1h, w1l, L.MAJOR_K, (cin, cout, k), (1, cin, cout * cin), src2=L.SRC_TAP, hi2=w2h, lo2=w2l),
+             T, cout, cin, c_f32=Y, ldc=cout, c_sz0=T * cout, bias=bias, ntaps=k, nz0=B, split=split, block_n=block_n)
+    ref = _conv_ref(x1r, w1r, bias.double(), p) + _conv_ref(x2r, w2r, None, p)
+    _check(f"two-term conv bn={block_n}", Y, ref, split)
