@@ -100,6 +100,8 @@ typedef struct {
   /* optional SECOND product term accumulated into the same tile: C += A2 * B2^T with the geometry of
    * a / b (only the base pointers differ).  Tangent passes: d(xW^T) = xdot W^T + x Wdot^T in one launch. */
   const void* a2_hi; const void* a2_lo; const void* b2_hi; const void* b2_lo;
+  int32_t pair;            /* != 0: 2-CTA kernel (tcgen05 cta_group::2, 256 x block_n tile per CTA pair; block_n 128/256) */
+  int32_t reserved2;
 } mtts_gemm_desc;
 
 int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream);

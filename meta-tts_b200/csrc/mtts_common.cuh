@@ -193,15 +193,64 @@ __device__ __forceinline__ uint64_t make_umma_desc(uint32_t smem_addr, uint32_t 
   d |= static_cast<uint64_t>(2) << 61;   // SWIZZLE_128B
   return d;
 }
-// instruction descriptor, kind::f16: bf16 x bf16 -> fp32, M = 128
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int n, int a_mn_major, int b_mn_major) {
+// instruction descriptor, kind::f16: bf16 x bf16 -> fp32, M = 128 (cta_group::1) or 256 (cta_group::2)
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int n, int a_mn_major, int b_mn_major, int m = 128) {
   return (1u << 4)                       // c_format  = F32
          | (1u << 7)                     // a_format  = BF16
          | (1u << 10)                    // b_format  = BF16
          | (uint32_t(a_mn_major) << 15)  // a_major
          | (uint32_t(b_mn_major) << 16)  // b_major
          | (uint32_t(n >> 3) << 17)      // n_dim
-         | (uint32_t(128 >> 4) << 24);   // m_dim
+         | (uint32_t(m >> 4) << 24);     // m_dim
+}
+
+// ---- 2-CTA (cta_group::2) variants: a CTA pair in one cluster shares one 256-row UMMA --------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_slot) {   // one warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// D[tmem of both CTAs, 256 rows] (+)= A[smem of both CTAs] * B[smem halves of both CTAs]^T ; leader CTA, one thread
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all prior MMAs completed) on the mbarrier at the same smem offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// TMA load into THIS CTA's smem whose completion bytes are counted on the LEADER CTA's mbarrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_4d_2cta(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                                 int c3) {
+  const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
 }
 
 #endif  // __CUDACC__

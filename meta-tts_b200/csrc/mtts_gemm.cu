@@ -68,6 +68,131 @@ __device__ __forceinline__ int pick_src(int src, int z0, int z1, int tap, int kb
   return src == MTTS_SRC_Z0 ? z0 : src == MTTS_SRC_Z1 ? z1 : src == MTTS_SRC_TAP ? tap : src == MTTS_SRC_KB ? kb : 0;
 }
 
+// TMEM accumulator tile (128 lanes x BN columns) -> alpha, bias, +C, ReLU, gate -> global (fp32 / bf16 hi,lo / red.add)
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_base, int q, int lane, int m0, int n0, int z0,
+                                              int z1) {
+  const int row = m0 + q * 32 + lane;
+  const bool row_ok = row < p.M;
+  const int64_t c_off = int64_t(z0) * p.c_sz0 + int64_t(z1) * p.c_sz1 + int64_t(row) * p.ldc;
+  const float* bias = p.bias ? p.bias + int64_t(z0) * p.bias_sz0 : nullptr;
+  const bool vec_ok = ((p.ldc & 7) == 0) && ((p.c_sz0 & 7) == 0) && ((p.c_sz1 & 7) == 0);
+  const float bias_row = (bias && (p.flags & MTTS_EPI_BIAS_ROW) && row_ok) ? bias[row] : 0.f;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    __syncwarp();                       // tcgen05.ld is .sync.aligned: reconverge after guards
+    uint32_t r[32];
+    tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), r);
+    tmem_ld_wait();
+    const int col0 = n0 + c * 32;
+    if (!row_ok || col0 >= p.N) continue;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+    if (bias) {
+      if (p.flags & MTTS_EPI_BIAS_ROW) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += bias_row;
+      } else if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+          v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) v[j] += __ldg(bias + col0 + j);
+      }
+    }
+    const bool full = (col0 + 32 <= p.N) && vec_ok;
+    if (p.flags & MTTS_EPI_ADD_C) {
+      const float* src = p.c_f32 + c_off + col0;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 cc = *reinterpret_cast<const float4*>(src + j);
+          v[j] += cc.x; v[j + 1] += cc.y; v[j + 2] += cc.z; v[j + 3] += cc.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) v[j] += src[j];
+      }
+    }
+    if (p.flags & MTTS_EPI_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (p.flags & MTTS_EPI_GATE) {
+      const bf16* g = p.gate + c_off + col0;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const uint4 gg = *reinterpret_cast<const uint4*>(g + j);
+          const uint32_t w[4] = {gg.x, gg.y, gg.z, gg.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+            const uint32_t lo16 = w[t] & 0xFFFFu, hi16 = w[t] >> 16;
+            if (!((lo16 & 0x8000u) == 0 && (lo16 & 0x7FFFu) != 0)) v[j + 2 * t] = 0.f;
+            if (!((hi16 & 0x8000u) == 0 && (hi16 & 0x7FFFu) != 0)) v[j + 2 * t + 1] = 0.f;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N && !(__bfloat162float(g[j]) > 0.f)) v[j] = 0.f;
+      }
+    }
+    if (p.c_f32) {
+      float* dst = p.c_f32 + c_off + col0;
+      if (p.flags & MTTS_EPI_ACCUM) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) atomicAdd(dst + j, v[j]);
+      } else if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) dst[j] = v[j];
+      }
+    }
+    if (p.c_hi) {
+      bf16* dh = p.c_hi + c_off + col0;
+      bf16* dl = p.c_lo ? p.c_lo + c_off + col0 : nullptr;
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            bf16 h0, l0, h1, l1;
+            split_bf16(v[j + 2 * t], h0, l0);
+            split_bf16(v[j + 2 * t + 1], h1, l1);
+            h[t] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
+            l[t] = uint32_t(__bfloat16_as_ushort(l0)) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
+          }
+          *reinterpret_cast<uint4*>(dh + j) = make_uint4(h[0], h[1], h[2], h[3]);
+          if (dl) *reinterpret_cast<uint4*>(dl + j) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) {
+            bf16 h0, l0;
+            split_bf16(v[j], h0, l0);
+            dh[j] = h0;
+            if (dl) dl[j] = l0;
+          }
+      }
+    }
+  }
+}
+
 template <int BN, int SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN, SPLIT>;
@@ -235,128 +360,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
     // ===================================== epilogue ==============================================
     // TMEM lane quarter accessible to a warp is (warp_id % 4); warps 2,3,4,5 -> quarters 2,3,0,1.
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
     if (n_iters > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
-      const bool row_ok = row < p.M;
-      const int64_t c_off = int64_t(z0) * p.c_sz0 + int64_t(z1) * p.c_sz1 + int64_t(row) * p.ldc;
-      const float* bias = p.bias ? p.bias + int64_t(z0) * p.bias_sz0 : nullptr;
-      const bool vec_ok = ((p.ldc & 7) == 0) && ((p.c_sz0 & 7) == 0) && ((p.c_sz1 & 7) == 0);
-      const float bias_row = (bias && (p.flags & MTTS_EPI_BIAS_ROW) && row_ok) ? bias[row] : 0.f;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        __syncwarp();                       // tcgen05.ld is .sync.aligned: reconverge after guards
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), r);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (!row_ok || col0 >= p.N) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-        if (bias) {
-          if (p.flags & MTTS_EPI_BIAS_ROW) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += bias_row;
-          } else if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
-              v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) v[j] += __ldg(bias + col0 + j);
-          }
-        }
-        const bool full = (col0 + 32 <= p.N) && vec_ok;
-        if (p.flags & MTTS_EPI_ADD_C) {
-          const float* src = p.c_f32 + c_off + col0;
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 cc = *reinterpret_cast<const float4*>(src + j);
-              v[j] += cc.x; v[j + 1] += cc.y; v[j + 2] += cc.z; v[j + 3] += cc.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) v[j] += src[j];
-          }
-        }
-        if (p.flags & MTTS_EPI_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (p.flags & MTTS_EPI_GATE) {
-          const bf16* g = p.gate + c_off + col0;
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 gg = *reinterpret_cast<const uint4*>(g + j);
-              const uint32_t w[4] = {gg.x, gg.y, gg.z, gg.w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                const uint32_t lo16 = w[t] & 0xFFFFu, hi16 = w[t] >> 16;
-                if (!((lo16 & 0x8000u) == 0 && (lo16 & 0x7FFFu) != 0)) v[j + 2 * t] = 0.f;
-                if (!((hi16 & 0x8000u) == 0 && (hi16 & 0x7FFFu) != 0)) v[j + 2 * t + 1] = 0.f;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N && !(__bfloat162float(g[j]) > 0.f)) v[j] = 0.f;
-          }
-        }
-        if (p.c_f32) {
-          float* dst = p.c_f32 + c_off + col0;
-          if (p.flags & MTTS_EPI_ACCUM) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) atomicAdd(dst + j, v[j]);
-          } else if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) dst[j] = v[j];
-          }
-        }
-        if (p.c_hi) {
-          bf16* dh = p.c_hi + c_off + col0;
-          bf16* dl = p.c_lo ? p.c_lo + c_off + col0 : nullptr;
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint32_t h[4], l[4];
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                bf16 h0, l0, h1, l1;
-                split_bf16(v[j + 2 * t], h0, l0);
-                split_bf16(v[j + 2 * t + 1], h1, l1);
-                h[t] = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
-                l[t] = uint32_t(__bfloat16_as_ushort(l0)) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
-              }
-              *reinterpret_cast<uint4*>(dh + j) = make_uint4(h[0], h[1], h[2], h[3]);
-              if (dl) *reinterpret_cast<uint4*>(dl + j) = make_uint4(l[0], l[1], l[2], l[3]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) {
-                bf16 h0, l0;
-                split_bf16(v[j], h0, l0);
-                dh[j] = h0;
-                if (dl) dl[j] = l0;
-              }
-          }
-        }
-      }
+      epilogue_tile<BN>(p, tmem_base, q, lane, m0, n0, z0, z1);
     }
   }
 
@@ -365,6 +372,199 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<BN>(tmem_base);
+  }
+}
+
+// ================================================================================================
+// 2-CTA variant: a cluster of two CTAs computes one 256 x BN tile with tcgen05.mma.cta_group::2.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows), so the operand bytes
+// fetched from L2 per flop halve compared with two independent 128 x BN tiles — the 1-CTA kernel is
+// L2-throughput bound in bf16x3 (profiles/r01_ncu_summary.md).  The leader CTA (cluster rank 0) issues
+// the MMAs for both; tcgen05.commit multicasts the smem-slot release and the accumulator-ready signal to
+// both CTAs; every CTA runs its own TMA producer (completion bytes land on the leader's full barrier)
+// and its own epilogue over its 128 TMEM lanes.  The two CTAs' row tiles are consecutive m-tiles of the
+// same z; an odd tail gets a dummy partner (all-OOB A rows, nothing stored).
+// ================================================================================================
+template <int BN, int SPLIT>
+struct Cfg2 {
+  static constexpr int A_TILE = BM * BK * 2;                  // this CTA's 128 rows
+  static constexpr int B_TILE = (BN / 2) * BK * 2;            // this CTA's half of the B tile
+  static constexpr int STAGE = (A_TILE + B_TILE) * (SPLIT == 3 ? 2 : 1);
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int STAGES_RAW = (MAX_SMEM - BAR_BYTES - 1024) / STAGE;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int SMEM = STAGES * STAGE + BAR_BYTES + 1024;
+  static_assert(STAGES >= 2, "need at least a double buffer");
+};
+
+template <int BN, int SPLIT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mtts_gemm_pair_kernel(const __grid_constant__ GemmParams p) {
+  using C = Cfg2<BN, SPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bar_base = smem + C::STAGES * C::STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();       // 0 = leader
+
+  const int pair = blockIdx.x >> 1;
+  const int pair_m = pair / p.n_tiles;
+  const int n_tile = pair - pair_m * p.n_tiles;
+  const int m0 = (2 * pair_m + int(rank)) * BM;  // may be >= M for the dummy partner of an odd tail
+  const int n0 = n_tile * BN;
+  const int nb0 = n0 + int(rank) * (BN / 2);     // this CTA's half of the B tile
+  const int z0 = blockIdx.z % p.nz0;
+  const int z1 = blockIdx.z / p.nz0;
+
+  const int kchunks = (p.K + BK - 1) / BK;
+  const int total_iters = p.nterms * p.ntaps * p.nkb * kchunks;
+  const int per_split = (total_iters + p.ksplit - 1) / p.ksplit;
+  const int it_begin = blockIdx.y * per_split;
+  const int it_end = min(total_iters, it_begin + per_split);
+  const int n_iters = max(0, it_end - it_begin);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.map_a_hi);
+    tma_prefetch_desc(&p.map_b_hi);
+    if (SPLIT == 3) {
+      tma_prefetch_desc(&p.map_a_lo);
+      tma_prefetch_desc(&p.map_b_lo);
+    }
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta<BN>(tmem_slot);
+  }
+  tc_fence_before();
+  cluster_sync_all();                            // peer barriers initialised before any remote complete_tx / arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) ===============================
+    if (lane == 0 && n_iters > 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = it_begin; it < it_end; ++it) {
+        const int kc = it % kchunks;
+        const int rest = it / kchunks;
+        const int kb = rest % p.nkb;
+        const int rest2 = rest / p.nkb;
+        const int tap = rest2 % p.ntaps;
+        const bool t2 = rest2 >= p.ntaps;
+        const CUtensorMap* ma_hi = t2 ? &p.map_a2_hi : &p.map_a_hi;
+        const CUtensorMap* ma_lo = t2 ? &p.map_a2_lo : &p.map_a_lo;
+        const CUtensorMap* mb_hi = t2 ? &p.map_b2_hi : &p.map_b_hi;
+        const CUtensorMap* mb_lo = t2 ? &p.map_b2_lo : &p.map_b_lo;
+
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE);   // bytes of both CTAs
+
+        uint8_t* sa = smem + stage * C::STAGE;
+        uint8_t* sa_lo = sa + C::A_TILE;
+        uint8_t* sb = sa + C::A_TILE * (SPLIT == 3 ? 2 : 1);
+        uint8_t* sb_lo = sb + C::B_TILE;
+        {
+          const int shift = p.a.shift_base + p.a.shift_step * pick_src(p.a.shift_src, z0, z1, tap, kb);
+          const int c2 = pick_src(p.a.src2, z0, z1, tap, kb);
+          const int c3 = pick_src(p.a.src3, z0, z1, tap, kb);
+          if (p.a.major == MTTS_MAJOR_K) {
+            tma_load_4d_2cta(sa, ma_hi, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
+            if (SPLIT == 3) tma_load_4d_2cta(sa_lo, ma_lo, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) {
+              tma_load_4d_2cta(sa + i * (BK * 128), ma_hi, &full_bar[stage], m0 + 64 * i, kc * BK + shift, c2, c3);
+              if (SPLIT == 3)
+                tma_load_4d_2cta(sa_lo + i * (BK * 128), ma_lo, &full_bar[stage], m0 + 64 * i, kc * BK + shift, c2, c3);
+            }
+          }
+        }
+        {
+          const int shift = p.b.shift_base + p.b.shift_step * pick_src(p.b.shift_src, z0, z1, tap, kb);
+          const int c2 = pick_src(p.b.src2, z0, z1, tap, kb);
+          const int c3 = pick_src(p.b.src3, z0, z1, tap, kb);
+          if (p.b.major == MTTS_MAJOR_K) {
+            tma_load_4d_2cta(sb, mb_hi, &full_bar[stage], kc * BK, nb0 + shift, c2, c3);
+            if (SPLIT == 3) tma_load_4d_2cta(sb_lo, mb_lo, &full_bar[stage], kc * BK, nb0 + shift, c2, c3);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 128; ++i) {
+              tma_load_4d_2cta(sb + i * (BK * 128), mb_hi, &full_bar[stage], nb0 + 64 * i, kc * BK + shift, c2, c3);
+              if (SPLIT == 3)
+                tma_load_4d_2cta(sb_lo + i * (BK * 128), mb_lo, &full_bar[stage], nb0 + 64 * i, kc * BK + shift, c2, c3);
+            }
+          }
+        }
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA only) ===========================
+    if (rank == 0 && lane == 0 && n_iters > 0) {
+      const uint32_t idesc = make_idesc_bf16(BN, p.a.major == MTTS_MAJOR_MN, p.b.major == MTTS_MAJOR_MN, 256);
+      const uint32_t a_step = (p.a.major == MTTS_MAJOR_K) ? UMMA_K * 2 : UMMA_K * 128;
+      const uint32_t b_step = (p.b.major == MTTS_MAJOR_K) ? UMMA_K * 2 : UMMA_K * 128;
+      const uint32_t a_lbo = (p.a.major == MTTS_MAJOR_K) ? 16 : BK * 128;
+      const uint32_t b_lbo = (p.b.major == MTTS_MAJOR_K) ? 16 : BK * 128;
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t accumulate = 0;
+      for (int it = 0; it < n_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * C::STAGE);
+        const uint32_t sa_lo = sa + C::A_TILE;
+        const uint32_t sb = sa + C::A_TILE * (SPLIT == 3 ? 2 : 1);
+        const uint32_t sb_lo = sb + C::B_TILE;
+#pragma unroll
+        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+          const uint64_t da = make_umma_desc(sa + kk * a_step, a_lbo, 1024);
+          const uint64_t db = make_umma_desc(sb + kk * b_step, b_lbo, 1024);
+          umma_bf16_2cta(tmem_base, da, db, idesc, accumulate);
+          accumulate = 1;
+          if (SPLIT == 3) {
+            const uint64_t da_lo = make_umma_desc(sa_lo + kk * a_step, a_lbo, 1024);
+            const uint64_t db_lo = make_umma_desc(sb_lo + kk * b_step, b_lbo, 1024);
+            umma_bf16_2cta(tmem_base, da, db_lo, idesc, 1);
+            umma_bf16_2cta(tmem_base, da_lo, db, idesc, 1);
+          }
+        }
+        umma_commit_2cta(&empty_bar[stage], 3);   // both CTAs may refill this slot
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit_2cta(tmem_full_bar, 3);          // both CTAs' epilogues
+    }
+  } else {
+    const int q = warp & 3;
+    if (n_iters > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      epilogue_tile<BN>(p, tmem_base, q, lane, m0, n0, z0, z1);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                            // no CTA exits while its peer may still signal / read its smem
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta<BN>(tmem_base);
   }
 }
 
@@ -424,6 +624,20 @@ int encode_operand_map(CUtensorMap* map, const void* ptr, const mtts_operand& op
 }
 
 template <int BN, int SPLIT>
+int launch_pair(const GemmParams& p, dim3 grid, cudaStream_t stream) {
+  using C = Cfg2<BN, SPLIT>;
+  static bool configured = false;
+  if (!configured) {
+    MTTS_CHECK_CUDA(cudaFuncSetAttribute(mtts_gemm_pair_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM));
+    configured = true;
+  }
+  mtts_gemm_pair_kernel<BN, SPLIT><<<grid, NUM_THREADS, C::SMEM, stream>>>(p);   // __cluster_dims__(2,1,1)
+  MTTS_CHECK_LAUNCH();
+  return MTTS_OK;
+}
+
+template <int BN, int SPLIT>
 int launch(const GemmParams& p, dim3 grid, cudaStream_t stream) {
   using C = Cfg<BN, SPLIT>;
   static bool configured = false;
@@ -464,24 +678,27 @@ extern "C" int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream_) {
     else bn = 256;
   }
   MTTS_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: block_n must be 64/128/256");
+  const bool pair = d->pair != 0;
+  MTTS_REQUIRE(!pair || bn >= 128, "gemm: the 2-CTA kernel needs block_n 128 or 256");
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
   int rc;
   if ((rc = encode_operand_map(&p.map_a_hi, d->a.hi, d->a, BM, "A.hi")) != MTTS_OK) return rc;
-  if ((rc = encode_operand_map(&p.map_b_hi, d->b.hi, d->b, bn, "B.hi")) != MTTS_OK) return rc;
+  const int b_rows = pair ? bn / 2 : bn;         // 2-CTA: each CTA stages half of the B tile
+  if ((rc = encode_operand_map(&p.map_b_hi, d->b.hi, d->b, b_rows, "B.hi")) != MTTS_OK) return rc;
   if (d->split == 3) {
     if ((rc = encode_operand_map(&p.map_a_lo, d->a.lo, d->a, BM, "A.lo")) != MTTS_OK) return rc;
-    if ((rc = encode_operand_map(&p.map_b_lo, d->b.lo, d->b, bn, "B.lo")) != MTTS_OK) return rc;
+    if ((rc = encode_operand_map(&p.map_b_lo, d->b.lo, d->b, b_rows, "B.lo")) != MTTS_OK) return rc;
   }
   const bool two = d->a2_hi != nullptr || d->b2_hi != nullptr;
   if (two) {
     MTTS_REQUIRE(d->a2_hi && d->b2_hi && (d->split == 1 || (d->a2_lo && d->b2_lo)), "gemm: incomplete second term");
     if ((rc = encode_operand_map(&p.map_a2_hi, d->a2_hi, d->a, BM, "A2.hi")) != MTTS_OK) return rc;
-    if ((rc = encode_operand_map(&p.map_b2_hi, d->b2_hi, d->b, bn, "B2.hi")) != MTTS_OK) return rc;
+    if ((rc = encode_operand_map(&p.map_b2_hi, d->b2_hi, d->b, b_rows, "B2.hi")) != MTTS_OK) return rc;
     if (d->split == 3) {
       if ((rc = encode_operand_map(&p.map_a2_lo, d->a2_lo, d->a, BM, "A2.lo")) != MTTS_OK) return rc;
-      if ((rc = encode_operand_map(&p.map_b2_lo, d->b2_lo, d->b, bn, "B2.lo")) != MTTS_OK) return rc;
+      if ((rc = encode_operand_map(&p.map_b2_lo, d->b2_lo, d->b, b_rows, "B2.lo")) != MTTS_OK) return rc;
     }
   }
   p.nterms = two ? 2 : 1;
@@ -507,6 +724,11 @@ extern "C" int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream_) {
   const int m_tiles = mtts_cdiv(d->M, BM);
   dim3 grid(m_tiles * p.n_tiles, p.ksplit, d->nz0 * d->nz1);
   MTTS_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "gemm: grid too large");
+  if (pair) {
+    grid.x = 2 * mtts_cdiv(m_tiles, 2) * p.n_tiles;
+    if (d->split == 1) return bn == 128 ? launch_pair<128, 1>(p, grid, stream) : launch_pair<256, 1>(p, grid, stream);
+    return bn == 128 ? launch_pair<128, 3>(p, grid, stream) : launch_pair<256, 3>(p, grid, stream);
+  }
 
   if (d->split == 1) {
     if (bn == 64) return launch<64, 1>(p, grid, stream);

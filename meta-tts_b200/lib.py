@@ -45,6 +45,7 @@ class GemmDesc(C.Structure):
         ("bias", C.c_void_p), ("bias_sz0", C.c_int64),
         ("gate", C.c_void_p),
         ("a2_hi", C.c_void_p), ("a2_lo", C.c_void_p), ("b2_hi", C.c_void_p), ("b2_lo", C.c_void_p),
+        ("pair", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 

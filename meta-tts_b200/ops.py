@@ -79,13 +79,14 @@ def gemm(a: Opnd, b: Opnd, M: int, N: int, K: int, *,
          alpha: float = 1.0, bias: Optional[torch.Tensor] = None, bias_sz0: int = 0,
          gate: Optional[torch.Tensor] = None, flags: int = 0,
          ntaps: int = 1, nkb: int = 1, nz0: int = 1, nz1: int = 1,
-         split: int = 1, block_n: int = 0, ksplit: int = 1) -> None:
+         split: int = 1, block_n: int = 0, ksplit: int = 1, pair: bool = False) -> None:
     global launch_count
     _need_cuda(a.hi, b.hi, c_f32, c_hi, c_lo, bias, gate)
     d = L.GemmDesc()
     d.M, d.N, d.K = M, N, K
     d.ntaps, d.nkb, d.nz0, d.nz1 = ntaps, nkb, nz0, nz1
     d.split, d.block_n, d.ksplit, d.flags = split, block_n, ksplit, flags
+    d.pair = 1 if pair else 0
     d.alpha = alpha
     a.fill(d.a)
     b.fill(d.b)

@@ -107,7 +107,7 @@ class RefOps:
         return torch.where(valid, v, torch.zeros((), dtype=self.acc))
 
     def gemm(self, a, b, M, N, K, *, c_f32=None, c_hi=None, c_lo=None, ldc, c_off=0, c_sz0=0, c_sz1=0, alpha=1.0,
-             bias=None, bias_sz0=0, gate=None, flags=0, ntaps=1, nkb=1, nz0=1, nz1=1, split=None, block_n=0, ksplit=1):
+             bias=None, bias_sz0=0, gate=None, flags=0, ntaps=1, nkb=1, nz0=1, nz1=1, split=None, block_n=0, ksplit=1, pair=False):
         self.n_calls += 1
         split = split or self.split
         assert c_f32 is not None or c_hi is not None

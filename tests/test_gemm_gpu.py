@@ -41,8 +41,6 @@ def _check(name, got, ref, split):
 @pytest.mark.parametrize("split", [1, 3])
 @pytest.mark.parametrize("block_n", [64, 128, 256])
 def test_linear_fwd(cuda_device, split, block_n):
-    if split == 3 and block_n == 256:
-        pytest.skip("BN=256 not built for split=3")
     torch.manual_seed(0)
     M, N, K = 300, 256, 320
     X = torch.randn(M, K, device=cuda_device)
@@ -235,3 +233,102 @@ def test_two_term_conv_and_bn256(cuda_device, split, block_n):
              T, cout, cin, c_f32=Y, ldc=cout, c_sz0=T * cout, bias=bias, ntaps=k, nz0=B, split=split, block_n=block_n)
     ref = _conv_ref(x1r, w1r, bias.double(), p) + _conv_ref(x2r, w2r, None, p)
     _check(f"two-term conv bn={block_n}", Y, ref, split)
+
+
+# ---------------------------------------------------------------------------------------------
+# 2-CTA kernel (tcgen05 cta_group::2, one 256 x BN tile per CTA pair)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("split", [1, 3])
+@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("M", [300, 128, 700])          # odd / even m-tile counts (dummy partner CTA for odd tails)
+def test_pair_linear_all_majors(cuda_device, split, block_n, M):
+    torch.manual_seed(11)
+    N, K = 384, 320
+    X = torch.randn(M, K, device=cuda_device)
+    W = torch.randn(N, K, device=cuda_device) / math.sqrt(K)
+    bias = torch.randn(N, device=cuda_device)
+    xh, xl, xr = _prep(X, split)
+    wh, wl, wr = _prep(W, split)
+    out = torch.empty(M, N, device=cuda_device)
+    oh = torch.empty(M, N, device=cuda_device, dtype=torch.bfloat16)
+    ol = torch.empty(M, N, device=cuda_device, dtype=torch.bfloat16)
+    ops.gemm(ops.Opnd(xh, xl, L.MAJOR_K, (K, M), (1, K)), ops.Opnd(wh, wl, L.MAJOR_K, (K, N), (1, K)),
+             M, N, K, c_f32=out, c_hi=oh, c_lo=ol, ldc=N, bias=bias, flags=L.EPI_RELU, split=split, block_n=block_n, pair=True)
+    _check(f"pair linear_fwd bn={block_n} M={M}", out, torch.relu(xr @ wr.t() + bias.double()), split)
+    _check("pair hi+lo", oh.float() + ol.float(), out, 3)
+    # dgrad (B MN-major): dX[M,K] = dY[M,N] W[N,K]
+    dY = torch.randn(M, N, device=cuda_device)
+    yh, yl, yr = _prep(dY, split)
+    dX = torch.empty(M, K, device=cuda_device)
+    ops.gemm(ops.Opnd(yh, yl, L.MAJOR_K, (N, M), (1, N)), ops.Opnd(wh, wl, L.MAJOR_MN, (K, N), (1, K)),
+             M, K, N, c_f32=dX, ldc=K, split=split, block_n=block_n, pair=True)
+    _check(f"pair dgrad (B MN-major) bn={block_n}", dX, yr @ wr, split)
+    # wgrad (A and B MN-major, split-K accumulate): dW[N,K] = dY^T X
+    dW = torch.zeros(N, K, device=cuda_device)
+    ops.gemm(ops.Opnd(yh, yl, L.MAJOR_MN, (N, M), (1, N)), ops.Opnd(xh, xl, L.MAJOR_MN, (K, M), (1, K)),
+             N, K, M, c_f32=dW, ldc=K, split=split, ksplit=2, flags=L.EPI_ACCUM, block_n=block_n, pair=True)
+    _check(f"pair wgrad (A,B MN-major) bn={block_n}", dW, yr.t() @ xr, split)
+
+
+@pytest.mark.parametrize("split", [1, 3])
+def test_pair_conv_taps_and_two_terms(cuda_device, split):
+    torch.manual_seed(12)
+    B, T, cin, cout, k, p = 3, 864, 256, 1024, 9, 4
+    X1, X2 = torch.randn(B, T, cin, device=cuda_device), torch.randn(B, T, cin, device=cuda_device)
+    W1, W2 = (torch.randn(k, cout, cin, device=cuda_device) / 40 for _ in range(2))
+    bias = torch.randn(cout, device=cuda_device)
+    (x1h, x1l, x1r), (x2h, x2l, x2r) = _prep(X1, split), _prep(X2, split)
+    (w1h, w1l, w1r), (w2h, w2l, w2r) = _prep(W1, split), _prep(W2, split)
+    Y = torch.empty(B, T, cout, device=cuda_device)
+    ops.gemm(ops.Opnd(x1h, x1l, L.MAJOR_K, (cin, T, B), (1, cin, T * cin), src2=L.SRC_Z0, shift_src=L.SRC_TAP,
+                      shift_base=-p, shift_step=1, hi2=x2h, lo2=x2l),
+             ops.Opnd(w1h, w1l, L.MAJOR_K, (cin, cout, k), (1, cin, cout * cin), src2=L.SRC_TAP, hi2=w2h, lo2=w2l),
+             T, cout, cin, c_f32=Y, ldc=cout, c_sz0=T * cout, bias=bias, ntaps=k, nz0=B, split=split, block_n=256, pair=True)
+    ref = _conv_ref(x1r, w1r, bias.double(), p) + _conv_ref(x2r, w2r, None, p)
+    _check("pair two-term conv9 864x1024", Y, ref, split)
+    # conv dgrad through MN-major weights, N_gemm = cin
+    dY = torch.randn(B, T, cout, device=cuda_device)
+    yh, yl, yr = _prep(dY, split)
+    dX = torch.empty(B, T, cin, device=cuda_device)
+    ops.gemm(ops.Opnd(yh, yl, L.MAJOR_K, (cout, T, B), (1, cout, T * cout), src2=L.SRC_Z0, shift_src=L.SRC_TAP,
+                      shift_base=p, shift_step=-1),
+             ops.Opnd(w1h, w1l, L.MAJOR_MN, (cin, cout, k), (1, cin, cout * cin), src2=L.SRC_TAP),
+             T, cin, cout, c_f32=dX, ldc=cin, c_sz0=T * cin, ntaps=k, nz0=B, split=split, block_n=256, pair=True)
+    xr_ = x1r.clone().requires_grad_(True)
+    _conv_ref(xr_, w1r, None, p).backward(yr)
+    _check("pair conv9 dgrad", dX, xr_.grad, split)
+
+
+@pytest.mark.parametrize("split", [1, 3])
+def test_pair_attention_products(cuda_device, split):
+    torch.manual_seed(13)
+    B, H, dk, Lq = 2, 2, 128, 200
+    row = 3 * H * dk
+    QKV = torch.randn(B * Lq, row, device=cuda_device)
+    qh, ql, qr = _prep(QKV, split)
+    Lp = (Lq + 7) // 8 * 8
+    S = torch.zeros(B, H, Lq, Lp, device=cuda_device)
+    ops.gemm(ops.Opnd(qh, ql, L.MAJOR_K, (dk, Lq, H, B), (1, row, dk, Lq * row), src2=L.SRC_Z0, src3=L.SRC_Z1),
+             ops.Opnd(qh, ql, L.MAJOR_K, (dk, Lq, H, B), (1, row, dk, Lq * row), src2=L.SRC_Z0, src3=L.SRC_Z1, offset=H * dk),
+             Lq, Lq, dk, c_f32=S, ldc=Lp, c_sz0=Lq * Lp, c_sz1=H * Lq * Lp, nz0=H, nz1=B, split=split, block_n=256, pair=True)
+    q4 = qr.view(B, Lq, 3, H, dk)
+    Sref = torch.einsum("blhd,bmhd->bhlm", q4[:, :, 0], q4[:, :, 1])
+    _check("pair attn QK^T", S[..., :Lq], Sref, split)
+    P = torch.softmax(Sref.float() / 11.3, dim=-1)
+    Pp = torch.zeros(B, H, Lq, Lp, device=cuda_device)
+    Pp[..., :Lq] = P
+    ph, pl, pr = _prep(Pp, split)
+    O = torch.empty(B * Lq, H * dk, device=cuda_device)
+    ops.gemm(ops.Opnd(ph, pl, L.MAJOR_K, (Lq, Lq, H, B), (1, Lp, Lq * Lp, H * Lq * Lp), src2=L.SRC_Z0, src3=L.SRC_Z1),
+             ops.Opnd(qh, ql, L.MAJOR_MN, (dk, Lq, H, B), (1, row, dk, Lq * row), src2=L.SRC_Z0, src3=L.SRC_Z1, offset=2 * H * dk),
+             Lq, dk, Lq, c_f32=O, ldc=H * dk, c_sz0=dk, c_sz1=Lq * H * dk, nz0=H, nz1=B, split=split, block_n=128, pair=True)
+    Oref = torch.einsum("bhlm,bmhd->blhd", pr[..., :Lq], q4[:, :, 2]).reshape(B * Lq, H * dk)
+    _check("pair attn PV (B MN-major)", O, Oref, split)
+    dO = torch.randn(B * Lq, H * dk, device=cuda_device)
+    dh, dl, dr = _prep(dO, split)
+    dV = torch.empty(B * Lq, H * dk, device=cuda_device)
+    ops.gemm(ops.Opnd(ph, pl, L.MAJOR_MN, (Lq, Lq, H, B), (1, Lp, Lq * Lp, H * Lq * Lp), src2=L.SRC_Z0, src3=L.SRC_Z1),
+             ops.Opnd(dh, dl, L.MAJOR_MN, (dk, Lq, H, B), (1, H * dk, dk, Lq * H * dk), src2=L.SRC_Z0, src3=L.SRC_Z1),
+             Lq, dk, Lq, c_f32=dV, ldc=H * dk, c_sz0=dk, c_sz1=Lq * H * dk, nz0=H, nz1=B, split=split, block_n=128, pair=True)
+    dVref = torch.einsum("bhlm,blhd->bmhd", pr[..., :Lq], dr.view(B, Lq, H, dk)).reshape(B * Lq, H * dk)
+    _check("pair attn dV (A,B MN-major)", dV, dVref, split)
