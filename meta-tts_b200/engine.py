@@ -304,13 +304,43 @@ def _wgrad_ksplit(tiles: int, iters: int) -> int:
     return max(1, min(ks, iters // 2 if iters >= 2 else 1, 32))
 
 
-def _pick_bn(row_tiles: int, N: int) -> int:
-    """Largest N-tile that still gives ~a wave of CTAs: bigger tiles cut operand traffic per flop (the GEMM
-    is L2-throughput bound at 128x128 in bf16x3, profiles/r01_ncu_summary.md); tiny grids get BN=64."""
-    for bn, need in ((256, 100), (128, 120)):
-        if N > bn // 2 and row_tiles * ((N + bn - 1) // bn) >= need:
-            return bn
-    return 64 if N > 64 or row_tiles * ((N + 63) // 64) >= 1 else 64
+USE_PAIR = True        # 2-CTA (cta_group::2) tiles; set False to fall back to the 1-CTA kernel everywhere
+
+
+def _pick_cfg(mt: int, nz: int, N: int, k_iters: int, can_splitk: bool):
+    """(block_n, pair, ksplit) for an output of nz x mt row tiles (128 rows) by N columns.
+    Bigger / paired tiles cut L2->SMEM operand bytes per flop (the 1-CTA 128x128 tile is L2-throughput bound
+    in bf16x3, profiles/r01_ncu_summary.md); small grids are filled by split-K when the epilogue is a pure
+    fp32 accumulation, otherwise by narrower tiles."""
+    opts = []
+    if USE_PAIR and N >= 192:
+        opts.append((256, True))
+    if USE_PAIR and N >= 96:
+        opts.append((128, True))
+    if N >= 192:
+        opts.append((256, False))
+    if N > 64:
+        opts.append((128, False))
+    opts.append((64, False))
+
+    def ctas(o):
+        bn, pair = o
+        rows = 2 * ((mt + 1) // 2) if pair else mt
+        return nz * rows * ((N + bn - 1) // bn)
+
+    for o in opts:
+        if ctas(o) >= 96:
+            return o[0], o[1], 1
+    if can_splitk:
+        o = opts[0]
+        ks = max(1, min((140 + ctas(o) - 1) // ctas(o), max(1, k_iters // 6), 16))
+        return o[0], o[1], ks
+    # no split-K possible: widest tile that still yields >= 48 CTAs, else the most CTAs
+    for o in opts:
+        if ctas(o) >= 48:
+            return o[0], o[1], 1
+    o = max(opts, key=ctas)
+    return o[0], o[1], 1
 
 
 class Gemm:
@@ -335,15 +365,17 @@ class Gemm:
             a = Opnd(x.hi, x.lo, L.MAJOR_K, (Cin, x.B * x.T), (1, Cin))
             if x2 is not None:
                 a.hi2, a.lo2 = x2.hi, x2.lo
+            bn, pair, _ = _pick_cfg((x.B * x.T + 127) // 128, 1, N, 0, False)
             self.be.gemm(a, wop, x.B * x.T, N, Cin, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=N, bias=bias,
-                         gate=gate, flags=flags, block_n=_pick_bn((x.B * x.T + 127) // 128, N))
+                         gate=gate, flags=flags, block_n=bn, pair=pair)
         else:
             a = Opnd(x.hi, x.lo, L.MAJOR_K, (Cin, x.T, x.B), (1, Cin, x.T * Cin), src2=L.SRC_Z0,
                      shift_src=L.SRC_TAP, shift_base=-p, shift_step=1)
             if x2 is not None:
                 a.hi2, a.lo2 = x2.hi, x2.lo
+            bn, pair, _ = _pick_cfg((x.T + 127) // 128, x.B, N, 0, False)
             self.be.gemm(a, wop, x.T, N, Cin, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=N, c_sz0=x.T * N, bias=bias,
-                         gate=gate, flags=flags, ntaps=k, nz0=x.B, block_n=_pick_bn(x.B * ((x.T + 127) // 128), N))
+                         gate=gate, flags=flags, ntaps=k, nz0=x.B, block_n=bn, pair=pair)
 
     # dx[b,t,:] = sum_j dy[b,t-j+p,:] W_j  [+ sum_j dy2[b,t-j+p,:] W2_j]
     def conv_dgrad(self, dy: Act, w: Wt, out_f32, out_hi, out_lo, gate=None, add_c=False,
@@ -351,23 +383,31 @@ class Gemm:
         k, N, Cin = w.shape if len(w.shape) == 3 else (1,) + tuple(w.shape)
         assert N == dy.C and (dy2 is None) == (w2 is None)
         p = (k - 1) // 2
-        flags = (L.EPI_GATE if gate is not None else 0) | (L.EPI_ADD_C if add_c else 0)
         wop = Opnd(w.hi, w.lo, L.MAJOR_MN, (Cin, N, k), (1, Cin, N * Cin), src2=L.SRC_TAP)
         if w2 is not None:
             wop.hi2, wop.lo2 = w2.hi, w2.lo
+        nt = 2 if dy2 is not None else 1
+        # "+= into an fp32 buffer" epilogues may be split along the contraction (red.global.add instead of +C)
+        can_split = add_c and out_hi is None and gate is None
+        mt = (dy.B * dy.T + 127) // 128 if k == 1 else (dy.T + 127) // 128
+        bn, pair, ks = _pick_cfg(mt, 1 if k == 1 else dy.B, Cin, nt * k * ((N + 63) // 64), can_split)
+        if ks > 1:
+            flags = L.EPI_ACCUM
+        else:
+            flags = (L.EPI_GATE if gate is not None else 0) | (L.EPI_ADD_C if add_c else 0)
         if k == 1:
             a = Opnd(dy.hi, dy.lo, L.MAJOR_K, (N, dy.B * dy.T), (1, N))
             if dy2 is not None:
                 a.hi2, a.lo2 = dy2.hi, dy2.lo
             self.be.gemm(a, wop, dy.B * dy.T, Cin, N, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=Cin, gate=gate,
-                         flags=flags, block_n=_pick_bn((dy.B * dy.T + 127) // 128, Cin))
+                         flags=flags, block_n=bn, pair=pair, ksplit=ks)
         else:
             a = Opnd(dy.hi, dy.lo, L.MAJOR_K, (N, dy.T, dy.B), (1, N, dy.T * N), src2=L.SRC_Z0,
                      shift_src=L.SRC_TAP, shift_base=p, shift_step=-1)
             if dy2 is not None:
                 a.hi2, a.lo2 = dy2.hi, dy2.lo
             self.be.gemm(a, wop, dy.T, Cin, N, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=Cin, c_sz0=dy.T * Cin,
-                         gate=gate, flags=flags, ntaps=k, nz0=dy.B, block_n=_pick_bn(dy.B * ((dy.T + 127) // 128), Cin))
+                         gate=gate, flags=flags, ntaps=k, nz0=dy.B, block_n=bn, pair=pair, ksplit=ks)
 
     # dW_j[n,c] += sum_{b,t} dy[b,t,n] x[b,t+j-p,c]  [+ dy2 (x) x2]
     def conv_wgrad(self, dy: Act, x: Act, dw_f32: torch.Tensor, scale: float = 1.0,
@@ -376,17 +416,17 @@ class Gemm:
         k, N, Cin = shp if len(shp) == 3 else (1,) + shp
         assert N == dy.C and Cin == x.C and dy.B == x.B and dy.T == x.T and (dy2 is None) == (x2 is None)
         p = (k - 1) // 2
-        bn = 64 if Cin <= 64 else 128
-        tiles = ((N + 127) // 128) * ((Cin + bn - 1) // bn) * k
         nt = 2 if dy2 is not None else 1
+        iters = nt * ((dy.B * dy.T + 63) // 64) if k == 1 else nt * dy.B * ((dy.T + 63) // 64)
+        bn, pair, ks = _pick_cfg((N + 127) // 128, k, Cin, iters, True)
         if k == 1:
             R = dy.B * dy.T
             a = Opnd(dy.hi, dy.lo, L.MAJOR_MN, (N, R), (1, N))
             b = Opnd(x.hi, x.lo, L.MAJOR_MN, (Cin, R), (1, Cin))
             if dy2 is not None:
                 a.hi2, a.lo2, b.hi2, b.lo2 = dy2.hi, dy2.lo, x2.hi, x2.lo
-            self.be.gemm(a, b, N, Cin, R, c_f32=dw_f32, ldc=Cin, flags=L.EPI_ACCUM, alpha=scale,
-                         ksplit=_wgrad_ksplit(tiles, nt * ((R + 63) // 64)), block_n=bn)
+            self.be.gemm(a, b, N, Cin, R, c_f32=dw_f32, ldc=Cin, flags=L.EPI_ACCUM, alpha=scale, ksplit=ks, block_n=bn,
+                         pair=pair)
         else:
             a = Opnd(dy.hi, dy.lo, L.MAJOR_MN, (N, dy.T, dy.B), (1, N, dy.T * N), src2=L.SRC_KB)
             b = Opnd(x.hi, x.lo, L.MAJOR_MN, (Cin, x.T, x.B), (1, Cin, x.T * Cin), src2=L.SRC_KB,
@@ -394,7 +434,7 @@ class Gemm:
             if dy2 is not None:
                 a.hi2, a.lo2, b.hi2, b.lo2 = dy2.hi, dy2.lo, x2.hi, x2.lo
             self.be.gemm(a, b, N, Cin, dy.T, c_f32=dw_f32, ldc=Cin, c_sz0=N * Cin, flags=L.EPI_ACCUM, alpha=scale,
-                         nkb=dy.B, nz0=k, ksplit=_wgrad_ksplit(tiles, nt * dy.B * ((dy.T + 63) // 64)), block_n=bn)
+                         nkb=dy.B, nz0=k, ksplit=ks, block_n=bn, pair=pair)
 
     # C[b,h] = alpha * ( op(A) op(B)^T [+ op(A2) op(B2)^T] )   (op = identity or transpose, see BMat)
     def bmm(self, A: BMat, a_t: bool, Bm: BMat, b_t: bool, Cm: BMat, nb: int, nh: int, alpha=1.0, add_c=False,
@@ -410,9 +450,10 @@ class Gemm:
         if A2 is not None:
             assert (A2.off, A2.sr, A2.sh, A2.sb) == (A.off, A.sr, A.sh, A.sb) and (B2.off, B2.sr, B2.sh, B2.sb) == (Bm.off, Bm.sr, Bm.sh, Bm.sb)
             a.hi2, a.lo2, b.hi2, b.lo2 = A2.hi, A2.lo, B2.hi, B2.lo
+        bn, pair, _ = _pick_cfg((M + 127) // 128, nb * nh, N, 0, False)
         self.be.gemm(a, b, M, N, K, c_f32=Cm.f32, c_hi=Cm.hi, c_lo=Cm.lo, ldc=Cm.sr, c_off=Cm.off, c_sz0=Cm.sh,
                      c_sz1=Cm.sb, alpha=alpha, flags=(L.EPI_ADD_C if add_c else 0), nz0=nh, nz1=nb,
-                     block_n=_pick_bn(nb * nh * ((M + 127) // 128), N))
+                     block_n=bn, pair=pair)
 
 
 # =================================================================================================

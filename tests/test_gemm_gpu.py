@@ -29,7 +29,7 @@ def _prep(x, split):
     return hi, lo, x.double()
 
 
-TOL = {1: 2e-5, 3: 2e-5}   # relative Frobenius error vs float64 reference
+TOL = {1: 2e-5, 3: 5e-5}   # relative Frobenius error vs float64 reference (bf16x3: ~2^-17 per operand, grows ~sqrt(K))
 
 
 def _check(name, got, ref, split):
