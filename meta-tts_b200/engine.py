@@ -328,13 +328,13 @@ def _pick_cfg(mt: int, nz: int, N: int, k_iters: int, can_splitk: bool):
         rows = 2 * ((mt + 1) // 2) if pair else mt
         return nz * rows * ((N + bn - 1) // bn)
 
+    if can_splitk:
+        o = opts[0]                      # widest tile; fill the machine along the contraction instead
+        ks = max(1, min(148 // max(ctas(o), 1), max(1, k_iters // 6), 16))
+        return o[0], o[1], ks
     for o in opts:
         if ctas(o) >= 96:
             return o[0], o[1], 1
-    if can_splitk:
-        o = opts[0]
-        ks = max(1, min((140 + ctas(o) - 1) // ctas(o), max(1, k_iters // 6), 16))
-        return o[0], o[1], ks
     # no split-K possible: widest tile that still yields >= 48 CTAs, else the most CTAs
     for o in opts:
         if ctas(o) >= 48:
