@@ -227,6 +227,38 @@ def run_own_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.kineto:
+        # per-kernel device time of real CUDA-graph replays at boost clocks (CUPTI activity trace via torch.profiler)
+        from torch.profiler import ProfilerActivity, profile
+        sysm.training_step(batches[0], 0)
+        sysm.optimizer_step()
+        key, ent = next(iter(sysm._graphs.items()))
+        for _ in range(3):
+            ent[2].replay()
+            sysm.optimizer_step()
+        torch.cuda.synchronize()
+        nrep = 3
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(nrep):
+                ent[2].replay()
+                sysm.optimizer_step()
+            e1.record()
+            torch.cuda.synchronize()
+        agg = {}
+        for ev in prof.events():
+            if ev.device_type.name != "CUDA":
+                continue
+            d = agg.setdefault(ev.name[:90], [0, 0.0])
+            d[0] += 1
+            d[1] += ev.device_time_total if hasattr(ev, "device_time_total") else ev.cuda_time_total
+        tot = sum(v[1] for v in agg.values())
+        print(f"# kineto: {nrep} graph replays, wall(events) {e0.elapsed_time(e1) / nrep:.3f} ms/step, sum of kernel time {tot / nrep / 1e3:.3f} ms/step")
+        for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
+            print(f"{k:90s} n/step={n / nrep:7.1f}  {v / nrep / 1e3:8.3f} ms  {100 * v / tot:5.1f}%  avg {v / n:7.1f} us")
+        return
+
     if args.profile_step:
         sysm.use_cuda_graph = False
         sysm.training_step(batches[0], 0)          # warm-up: allocations, kernel attributes
@@ -353,6 +385,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--split", type=int, default=3, choices=[1, 3], help="3: bf16x3 (parity-grade, default); 1: plain bf16")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--kineto", action="store_true", help="print a per-kernel device-time table of real graph replays")
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager (non-graph) outer step between cudaProfilerStart/Stop and exit (for ncu "
                          "--profile-from-start off); prints nothing to judge")
