@@ -447,6 +447,8 @@ __device__ __forceinline__ void st_split(bf16* hi, bf16* lo, long long i, float 
 //         (also the tangent forward: Pdot = P*(Sdot - sum(P*Sdot)) with A = Sdot)
 // mode 2: ddS = Pd*(dP - d) + P*(ddP - dd),  d = sum(P*dP), dd = sum(Pd*dP + P*ddP)
 //                                                         in: P, Pd (hi/lo), A = dP, Bm = ddP (f32)
+// Single pass over HBM: the row (<= 32*NPL keys) lives in registers, one read + one write per element.
+template <int NPL>
 __global__ void __launch_bounds__(ROW_THREADS) softmax_kernel(int mode, const float* __restrict__ A, const float* __restrict__ Bm,
                                                               const bf16* __restrict__ p_hi, const bf16* __restrict__ p_lo,
                                                               const bf16* __restrict__ pd_hi, const bf16* __restrict__ pd_lo,
@@ -458,43 +460,73 @@ __global__ void __launch_bounds__(ROW_THREADS) softmax_kernel(int mode, const fl
     const int b = static_cast<int>(zidx / H);
     const int kl = klens ? static_cast<int>(min(static_cast<long long>(Lk), static_cast<long long>(klens[b]))) : Lk;
     const long long base = r * ld;
+    float v[NPL];
     if (mode == 0) {
       float m = -INFINITY;
-      for (int j = lane; j < kl; j += 32) m = fmaxf(m, A[base + j]);
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int j = lane + 32 * i;
+        v[i] = j < kl ? A[base + j] : -INFINITY;
+        m = fmaxf(m, v[i]);
+      }
       m = warp_max(m);
       float s = 0.f;
-      for (int j = lane; j < kl; j += 32) s += __expf(A[base + j] - m);
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        v[i] = (lane + 32 * i) < kl ? __expf(v[i] - m) : 0.f;
+        s += v[i];
+      }
       s = warp_sum(s);
       const float inv = 1.f / s;
-      for (int j = lane; j < ld; j += 32) {
-        const float p = j < kl ? __expf(A[base + j] - m) * inv : 0.f;
-        st_split(o_hi, o_lo, base + j, p);
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int j = lane + 32 * i;
+        if (j < ld) st_split(o_hi, o_lo, base + j, v[i] * inv);
       }
     } else if (mode == 1) {
+      float a[NPL];
       float d = 0.f;
-      for (int j = lane; j < kl; j += 32) d += ld_split(p_hi, p_lo, base + j) * A[base + j];
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int j = lane + 32 * i;
+        if (j < kl) {
+          v[i] = ld_split(p_hi, p_lo, base + j);
+          a[i] = A[base + j];
+        } else {
+          v[i] = 0.f;
+          a[i] = 0.f;
+        }
+        d += v[i] * a[i];
+      }
       d = warp_sum(d);
-      for (int j = lane; j < ld; j += 32) {
-        const float v = j < kl ? ld_split(p_hi, p_lo, base + j) * (A[base + j] - d) : 0.f;
-        st_split(o_hi, o_lo, base + j, v);
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int j = lane + 32 * i;
+        if (j < ld) st_split(o_hi, o_lo, base + j, v[i] * (a[i] - d));
       }
     } else {
+      float a[NPL], pd[NPL], bb[NPL];
       float d = 0.f, dd = 0.f;
-      for (int j = lane; j < kl; j += 32) {
-        const float p = ld_split(p_hi, p_lo, base + j), pd = ld_split(pd_hi, pd_lo, base + j);
-        const float a = A[base + j], bb = Bm[base + j];
-        d += p * a;
-        dd += pd * a + p * bb;
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int j = lane + 32 * i;
+        if (j < kl) {
+          v[i] = ld_split(p_hi, p_lo, base + j);
+          pd[i] = ld_split(pd_hi, pd_lo, base + j);
+          a[i] = A[base + j];
+          bb[i] = Bm[base + j];
+        } else {
+          v[i] = pd[i] = a[i] = bb[i] = 0.f;
+        }
+        d += v[i] * a[i];
+        dd += pd[i] * a[i] + v[i] * bb[i];
       }
       d = warp_sum(d);
       dd = warp_sum(dd);
-      for (int j = lane; j < ld; j += 32) {
-        float v = 0.f;
-        if (j < kl) {
-          const float p = ld_split(p_hi, p_lo, base + j), pd = ld_split(pd_hi, pd_lo, base + j);
-          v = pd * (A[base + j] - d) + p * (Bm[base + j] - dd);
-        }
-        st_split(o_hi, o_lo, base + j, v);
+#pragma unroll
+      for (int i = 0; i < NPL; ++i) {
+        const int j = lane + 32 * i;
+        if (j < ld) st_split(o_hi, o_lo, base + j, pd[i] * (a[i] - d) + v[i] * (bb[i] - dd));
       }
     }
   }
@@ -592,9 +624,17 @@ extern "C" int mtts_softmax(int mode, const float* A, const float* Bm, const voi
   MTTS_REQUIRE(mode == 0 || p_hi, "softmax: mode %d needs P", mode);
   MTTS_REQUIRE(mode != 2 || (pd_hi && Bm), "softmax: mode 2 needs Pdot and ddP");
   const long long rows = static_cast<long long>(nz) * Lq;
-  softmax_kernel<<<row_grid(rows), ROW_THREADS, 0, s>>>(mode, A, Bm, static_cast<const bf16*>(p_hi), static_cast<const bf16*>(p_lo),
-                                                        static_cast<const bf16*>(pd_hi), static_cast<const bf16*>(pd_lo), klens, H,
-                                                        Lq, Lk, ld, rows, static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo));
+  MTTS_REQUIRE(ld <= 1024, "softmax: rows longer than 1024 keys are not supported (max_seq_len = 1000)");
+#define SM_LAUNCH(NPL)                                                                                                          \
+  softmax_kernel<NPL><<<row_grid(rows), ROW_THREADS, 0, s>>>(mode, A, Bm, static_cast<const bf16*>(p_hi),                        \
+                                                              static_cast<const bf16*>(p_lo), static_cast<const bf16*>(pd_hi), \
+                                                              static_cast<const bf16*>(pd_lo), klens, H, Lq, Lk, ld, rows,      \
+                                                              static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo))
+  if (ld <= 128) SM_LAUNCH(4);
+  else if (ld <= 256) SM_LAUNCH(8);
+  else if (ld <= 512) SM_LAUNCH(16);
+  else SM_LAUNCH(32);
+#undef SM_LAUNCH
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }

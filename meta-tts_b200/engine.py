@@ -558,10 +558,11 @@ class FS2Engine:
         # conv k=1 (w_2), ReLU gate, conv k=9 (w_1)
         dh = tp.act(f"{pf}.dh", B, T, self.d_inner, f32=False)
         g.conv_dgrad(dz2, P.get(f"{f_}.w_2.weight"), None, dh.hi, dh.lo, gate=h.hi)
-        g.conv_wgrad(dz2, h, G.get(f"{f_}.w_2.weight").f32)
-        be.colsum(None, dh.hi, dh.lo, 1, R, self.d_inner, G.get(f"{f_}.w_1.bias").f32)
+        with be.side():
+            g.conv_wgrad(dz2, h, G.get(f"{f_}.w_2.weight").f32)
+            be.colsum(None, dh.hi, dh.lo, 1, R, self.d_inner, G.get(f"{f_}.w_1.bias").f32)
+            g.conv_wgrad(dh, y1, G.get(f"{f_}.w_1.weight").f32)
         g.conv_dgrad(dh, P.get(f"{f_}.w_1.weight"), dz2.f32, None, None, add_c=True)       # dz2.f32 := dL/dy1
-        g.conv_wgrad(dh, y1, G.get(f"{f_}.w_1.weight").f32)
         # LN1  (f32 result goes straight into dx_out; the QKV dgrad below adds onto it)
         dz1 = Act(dx_out, *tp.bf(f"{pf}.dz1", (B, T, d)), B, T, d)
         be.ln_bwd(dz2.f32, tp.f32(f"{pf}.z1", (B, T, d)), tp.f32(f"{pf}.st1", (R, 2)), P.get(f"{a_}.layer_norm.weight").f32,
@@ -569,7 +570,8 @@ class FS2Engine:
                   G.get(f"{a_}.layer_norm.bias").f32, G.get(f"{a_}.fc.bias").f32)
         do = tp.act(f"{pf}.do", B, T, d, f32=False)
         g.conv_dgrad(dz1, P.get(f"{a_}.fc.weight"), None, do.hi, do.lo)
-        g.conv_wgrad(dz1, o, G.get(f"{a_}.fc.weight").f32)
+        with be.side():
+            g.conv_wgrad(dz1, o, G.get(f"{a_}.fc.weight").f32)
         # attention
         dP = tp.f32(f"{pf}.dP", (B, H, T, Tp))
         g.bmm(om(do.hi, do.lo), False, qm(qkv_h, qkv_l, 2), False, pm(None, None, dP), B, H)
@@ -581,8 +583,9 @@ class FS2Engine:
         g.bmm(pm(ds_h, ds_l), False, qm(qkv_h, qkv_l, 1), True, qm(dq_h, dq_l, 0), B, H, alpha=sc)       # dQ = dS K
         g.bmm(pm(ds_h, ds_l), True, qm(qkv_h, qkv_l, 0), True, qm(dq_h, dq_l, 1), B, H, alpha=sc)        # dK = dS^T Q
         dqkv = Act(None, dq_h, dq_l, B, T, 3 * d)
-        g.conv_wgrad(dqkv, x, gwqkv.f32)
-        be.colsum(None, dq_h, dq_l, 1, R, 3 * d, gbqkv.f32)
+        with be.side():
+            g.conv_wgrad(dqkv, x, gwqkv.f32)
+            be.colsum(None, dq_h, dq_l, 1, R, 3 * d, gbqkv.f32)
         g.conv_dgrad(dqkv, wqkv, dx_out, None, None, add_c=True)
 
     def _lin_t(self, x: Act, xd: Optional[Act], w: Wt, wd: Optional[Wt], bd, out_f32, out_hi, out_lo, relu_gate=None):
@@ -701,11 +704,12 @@ class FS2Engine:
         ddh = tt.act(f"{pf}.ddh", B, T, self.d_inner, f32=False)
         ddh_f = scr.scratch("h_f", (B, T, self.d_inner))
         self._dgrad_t(dz2, ddz2, P.get(f"{f_}.w_2.weight"), wdt(f"{f_}.w_2.weight"), ddh_f, ddh.hi, ddh.lo, gate=h.hi)
-        self._wgrad_t(dz2, ddz2, h, hd, hv(f"{f_}.w_2.weight"))
-        be.colsum(None, ddh.hi, ddh.lo, 1, R, self.d_inner, hv(f"{f_}.w_1.bias"))
+        with be.side():
+            self._wgrad_t(dz2, ddz2, h, hd, hv(f"{f_}.w_2.weight"))
+            be.colsum(None, ddh.hi, ddh.lo, 1, R, self.d_inner, hv(f"{f_}.w_1.bias"))
+            self._wgrad_t(dh, ddh, y1, y1d, hv(f"{f_}.w_1.weight"))
         # ---- w_1 (k=9): ddy1 = dgrad(ddh, W1) + dgrad(dh, W1d) + ddz2 (residual) ----
         self._dgrad_t(dh, ddh, P.get(f"{f_}.w_1.weight"), wdt(f"{f_}.w_1.weight"), ddz2.f32, None, None, add_c=True)
-        self._wgrad_t(dh, ddh, y1, y1d, hv(f"{f_}.w_1.weight"))
         # ---- LN1 ----
         ddz1 = Act(ddx_out, *tt.bf(f"{pf}.ddz1", (B, T, d)), B, T, d)
         be.ln_tbwd(dz2.f32, ddz2.f32, tp.f32(f"{pf}.z1", (B, T, d)), tt.f32(f"{pf}.z1d", (B, T, d)),
@@ -716,7 +720,8 @@ class FS2Engine:
         ddo = tt.act(f"{pf}.ddo", B, T, d, f32=False)
         ddo_f = scr.scratch("o_f", (B, T, d))
         self._dgrad_t(dz1, ddz1, P.get(f"{a_}.fc.weight"), wdt(f"{a_}.fc.weight"), ddo_f, ddo.hi, ddo.lo)
-        self._wgrad_t(dz1, ddz1, o, od, hv(f"{a_}.fc.weight"))
+        with be.side():
+            self._wgrad_t(dz1, ddz1, o, od, hv(f"{a_}.fc.weight"))
         # ---- attention ----
         sc = 1.0 / math.sqrt(dk)
         ddP = scr.scratch("S", (B, H, T, Tp))
@@ -735,8 +740,9 @@ class FS2Engine:
               A2=pm(ds_h, ds_l), B2=qm(qd_h, qd_l, 0))
         dqkv = Act(None, dq_h, dq_l, B, T, 3 * d)
         ddqkv = Act(None, ddq_h, ddq_l, B, T, 3 * d)
-        self._wgrad_t(dqkv, ddqkv, x, xd, hvwqkv.f32)
-        be.colsum(None, ddq_h, ddq_l, 1, R, 3 * d, hvbqkv.f32)
+        with be.side():
+            self._wgrad_t(dqkv, ddqkv, x, xd, hvwqkv.f32)
+            be.colsum(None, ddq_h, ddq_l, 1, R, 3 * d, hvbqkv.f32)
         self._dgrad_t(dqkv, ddqkv, wqkv, wdqkv, ddx_out, None, None, add_c=True)
 
     # ---------------------------------------------------------------------------------------------
@@ -774,14 +780,16 @@ class FS2Engine:
         be.ln_bwd(da2, tp.f32(f"{pf}.h2", (B, Lq, d)), tp.f32(f"{pf}.st2", (R, 2)), P.get(f"{c}.layer_norm_2.weight").f32,
                   None, Lq, R, d, 1, None, dc2.hi, dc2.lo, G.get(f"{c}.layer_norm_2.weight").f32,
                   G.get(f"{c}.layer_norm_2.bias").f32, G.get(f"{c}.conv1d_2.conv.bias").f32)
-        g.conv_wgrad(dc2, a1, G.get(f"{c}.conv1d_2.conv.weight").f32)
+        with be.side():
+            g.conv_wgrad(dc2, a1, G.get(f"{c}.conv1d_2.conv.weight").f32)
         da1 = tp.f32(f"{pf}.da1", (B, Lq, d))
         g.conv_dgrad(dc2, P.get(f"{c}.conv1d_2.conv.weight"), da1, None, None)
         dc1 = tp.act(f"{pf}.dc1", B, Lq, d, f32=False)
         be.ln_bwd(da1, tp.f32(f"{pf}.h1", (B, Lq, d)), tp.f32(f"{pf}.st1", (R, 2)), P.get(f"{c}.layer_norm_1.weight").f32,
                   None, Lq, R, d, 1, None, dc1.hi, dc1.lo, G.get(f"{c}.layer_norm_1.weight").f32,
                   G.get(f"{c}.layer_norm_1.bias").f32, G.get(f"{c}.conv1d_1.conv.bias").f32)
-        g.conv_wgrad(dc1, x, G.get(f"{c}.conv1d_1.conv.weight").f32)
+        with be.side():
+            g.conv_wgrad(dc1, x, G.get(f"{c}.conv1d_1.conv.weight").f32)
         g.conv_dgrad(dc1, P.get(f"{c}.conv1d_1.conv.weight"), dx_acc, None, None, add_c=True)
 
     def vp_tfwd(self, P, Pd, pf, tp, tt, x: Act, xd: Optional[Act], lens, outd: torch.Tensor):
@@ -835,7 +843,8 @@ class FS2Engine:
                    tp.f32(f"{pf}.st2", (R, 2)), P.get(f"{c}.layer_norm_2.weight").f32, gd(f"{c}.layer_norm_2.weight"), None, Lq,
                    R, d, 1, None, ddc2.hi, ddc2.lo, hv(f"{c}.layer_norm_2.weight"), hv(f"{c}.layer_norm_2.bias"),
                    hv(f"{c}.conv1d_2.conv.bias"))
-        self._wgrad_t(dc2, ddc2, a1, a1d, hv(f"{c}.conv1d_2.conv.weight"))
+        with be.side():
+            self._wgrad_t(dc2, ddc2, a1, a1d, hv(f"{c}.conv1d_2.conv.weight"))
         dda1 = tt.f32(f"{pf}.dda1", (B, Lq, d))
         self._dgrad_t(dc2, ddc2, P.get(f"{c}.conv1d_2.conv.weight"), wdt(f"{c}.conv1d_2.conv.weight"), dda1, None, None)
         ddc1 = tt.act(f"{pf}.ddc1", B, Lq, d, f32=False)
@@ -843,7 +852,8 @@ class FS2Engine:
                    tp.f32(f"{pf}.st1", (R, 2)), P.get(f"{c}.layer_norm_1.weight").f32, gd(f"{c}.layer_norm_1.weight"), None, Lq,
                    R, d, 1, None, ddc1.hi, ddc1.lo, hv(f"{c}.layer_norm_1.weight"), hv(f"{c}.layer_norm_1.bias"),
                    hv(f"{c}.conv1d_1.conv.bias"))
-        self._wgrad_t(dc1, ddc1, x, xd, hv(f"{c}.conv1d_1.conv.weight"))
+        with be.side():
+            self._wgrad_t(dc1, ddc1, x, xd, hv(f"{c}.conv1d_1.conv.weight"))
         self._dgrad_t(dc1, ddc1, P.get(f"{c}.conv1d_1.conv.weight"), wdt(f"{c}.conv1d_1.conv.weight"), ddx_acc, None, None,
                       add_c=True)
 
@@ -962,17 +972,19 @@ class FS2Engine:
                       tp.f32(f"post.{i}.st", (2 * co,)), P.get(f"{pre}.1.weight").f32, R, co, i < 4, scr.scratch("bn.ws", (4 * 512,)),
                       dc.f32, dc.hi, dc.lo, G.get(f"{pre}.1.weight").f32, G.get(f"{pre}.1.bias").f32,
                       beta=P.get(f"{pre}.1.bias").f32)
-            be.colsum(dc.f32, None, None, 1, R, co, G.get(f"{pre}.0.conv.bias").f32)
-            g.conv_wgrad(dc, xin, G.get(f"{pre}.0.conv.weight").f32)
+            with be.side():
+                be.colsum(dc.f32, None, None, 1, R, co, G.get(f"{pre}.0.conv.bias").f32)
+                g.conv_wgrad(dc, xin, G.get(f"{pre}.0.conv.weight").f32)
             if i > 0:
                 g.conv_dgrad(dc, P.get(f"{pre}.0.conv.weight"), tp.f32(f"post.{i - 1}.dout", (B, T, ci)), None, None)
             else:
                 g.conv_dgrad(dc, P.get(f"{pre}.0.conv.weight"), dmel.f32, None, None, add_c=True)
         # ---- mel_linear ----
         be.split_(dmel.f32, dmel.hi, dmel.lo)
-        be.colsum(dmel.f32, None, None, 1, R, N_MEL, G.get("mel_linear.bias").f32)
         ylast = tp.act(f"decoder.layer_stack.{self.n_dec - 1}.out", B, T, d)
-        g.conv_wgrad(dmel, ylast, G.get("mel_linear.weight").f32)
+        with be.side():
+            be.colsum(dmel.f32, None, None, 1, R, N_MEL, G.get("mel_linear.bias").f32)
+            g.conv_wgrad(dmel, ylast, G.get("mel_linear.weight").f32)
         dcur = tp.f32(f"decoder.layer_stack.{self.n_dec - 1}.dout", (B, T, d))
         g.conv_dgrad(dmel, P.get("mel_linear.weight"), dcur, None, None)
         # ---- decoder ----
@@ -1001,6 +1013,7 @@ class FS2Engine:
         # ---- encoder ----
         if into_encoder:
             self._encoder_bwd(P, G, bt, tp, dx)
+        be.join_side()                                      # weight-gradient branch joins before anyone reads G
 
     def _encoder_bwd(self, P, G, bt: Batch, tp: Tape, d_encout: torch.Tensor):
         """Plain backward through the encoder from dL/d(encoder output)."""
@@ -1100,8 +1113,9 @@ class FS2Engine:
                        tt.f32(f"post.{i}.ts", (2 * co,)), P.get(f"{pre}.1.weight").f32, gd(f"{pre}.1.weight"), R, co, i < 4,
                        scr.scratch("bn.ws", (4 * 512,)), ddc.f32, ddc.hi, ddc.lo, hv(f"{pre}.1.weight"), hv(f"{pre}.1.bias"),
                        beta=P.get(f"{pre}.1.bias").f32, bdot=gd(f"{pre}.1.bias"))
-            be.colsum(ddc.f32, None, None, 1, R, co, hv(f"{pre}.0.conv.bias"))
-            self._wgrad_t(dc, ddc, xin, xind, hv(f"{pre}.0.conv.weight"))
+            with be.side():
+                be.colsum(ddc.f32, None, None, 1, R, co, hv(f"{pre}.0.conv.bias"))
+                self._wgrad_t(dc, ddc, xin, xind, hv(f"{pre}.0.conv.weight"))
             if i > 0:
                 self._dgrad_t(dc, ddc, P.get(f"{pre}.0.conv.weight"), wdt(f"{pre}.0.conv.weight"),
                               tt.f32(f"post.{i - 1}.ddout", (B, T, ci)), None, None)
@@ -1111,10 +1125,11 @@ class FS2Engine:
         # mel_linear
         dmel = tp.act("dmel", B, T, N_MEL)
         be.split_(ddmel.f32, ddmel.hi, ddmel.lo)
-        be.colsum(ddmel.f32, None, None, 1, R, N_MEL, hv("mel_linear.bias"))
         ylast = tp.act(f"decoder.layer_stack.{self.n_dec - 1}.out", B, T, d)
         ylastd = tt.act(f"decoder.layer_stack.{self.n_dec - 1}.outd", B, T, d)
-        self._wgrad_t(dmel, ddmel, ylast, ylastd, hv("mel_linear.weight"))
+        with be.side():
+            be.colsum(ddmel.f32, None, None, 1, R, N_MEL, hv("mel_linear.bias"))
+            self._wgrad_t(dmel, ddmel, ylast, ylastd, hv("mel_linear.weight"))
         ddcur = tt.f32(f"decoder.layer_stack.{self.n_dec - 1}.ddout", (B, T, d))
         self._dgrad_t(dmel, ddmel, P.get("mel_linear.weight"), wdt("mel_linear.weight"), ddcur, None, None)
         # decoder
@@ -1139,3 +1154,4 @@ class FS2Engine:
         be.spk_embed_bwd(bt.spk_ids, ddspk, bt.spk_ids.numel(), d, bt.average_spk, B, 1.0, hv("speaker_emb.model.weight"))
         # encoder: zero forward tangent => the tangent backward is a plain backward of ddx (mixed partials)
         self._encoder_bwd(P, HV, bt, tp, ddx)
+        be.join_side()

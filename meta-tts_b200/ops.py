@@ -164,6 +164,31 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+class _SideCtx:
+    """Fork: everything issued so far on the current stream happens-before the side work."""
+
+    def __init__(self, be):
+        self.be = be
+        self.ctx = None
+
+    def __enter__(self):
+        be = self.be
+        if not be.use_side_stream:
+            return self
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        be._side.wait_event(ev)
+        be._side_used = True
+        self.ctx = torch.cuda.stream(be._side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+        return False
+
+
 class CudaOps:
     """sm_100a backend.  `split` = 1 (bf16) or 3 (bf16x3 hi/lo, fp32-grade)."""
 
@@ -176,6 +201,20 @@ class CudaOps:
         assert split in (1, 3)
         self.split = split
         self.device = torch.device(device)
+        self._side = torch.cuda.Stream(device=self.device)      # weight-gradient GEMMs / bias column sums (off the critical path)
+        self._side_used = False
+        self.use_side_stream = True
+
+    # ---- side stream: work that nothing on the critical path waits for (captured as a parallel graph branch) ----
+    def side(self):
+        return _SideCtx(self)
+
+    def join_side(self):
+        if self._side_used:
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            torch.cuda.current_stream().wait_event(ev)
+            self._side_used = False
 
     # ---- allocation helpers (plumbing) ----
     def empty(self, shape, dtype=torch.float32):

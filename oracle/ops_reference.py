@@ -74,6 +74,13 @@ class RefOps:
     def zero_(self, t):
         t.zero_()
 
+    def side(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def join_side(self):
+        pass
+
     # ------------------------------------------------------------------------------------------
     # GEMM descriptor emulator (semantics of mtts_gemm: TMA coordinates, OOB zero fill, epilogue)
     # ------------------------------------------------------------------------------------------
