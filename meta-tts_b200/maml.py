@@ -178,14 +178,19 @@ class MamlEngine:
                 lr *= anneal_rate
         return self.cfg["transformer"]["encoder_hidden"] ** -0.5 * lr
 
-    def outer_update(self, gscale: float = 1.0, max_norm: float = 1.0, betas=(0.9, 0.98), eps: float = 1e-9) -> None:
+    def outer_update(self, gscale: float = 1.0, max_norm: float = 1.0, betas=(0.9, 0.98), eps: float = 1e-9,
+                     warmup: int = 4000, anneal_steps=(300000, 400000, 500000), anneal_rate: float = 0.3) -> None:
         """clip_grad_norm_(1.0) + Adam + LambdaLR on the flat arena (one norm pass + one update pass),
         also refreshing the bf16 operand copies of theta."""
         be = self.be
         t = self.opt_step + 1
-        hyper = torch.tensor([self.lr_schedule(self.opt_step), 1 - betas[0] ** t, 1 - betas[1] ** t, 0.0],
-                             dtype=torch.float32)
-        self.hyper.copy_(hyper, non_blocking=True)
+        if not hasattr(self, "_hyper_ring"):
+            pin = self.hyper.is_cuda
+            self._hyper_ring = [torch.zeros(4).pin_memory() if pin else torch.zeros(4) for _ in range(8)]
+        hb = self._hyper_ring[self.opt_step % len(self._hyper_ring)]
+        hb[0] = self.lr_schedule(self.opt_step, warmup, anneal_steps, anneal_rate)
+        hb[1], hb[2] = 1 - betas[0] ** t, 1 - betas[1] ** t
+        self.hyper.copy_(hb, non_blocking=True)
         be.sumsq(self.g_outer, self.sumsq)
         be.adam_clip(self.theta, self.g_outer, self.adam_m, self.adam_v, self.sumsq, gscale, max_norm, self.hyper,
                      betas[0], betas[1], eps, self.theta_hi, self.theta_lo)

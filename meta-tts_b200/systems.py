@@ -41,28 +41,75 @@ def _assert_meta_batch(batch) -> None:
 
 
 class _StaticBatch:
-    """Static device buffers + pinned host staging for one 12-tuple shape."""
+    """Static device buffers for one 12-tuple shape + a ring of pinned host staging buffers.
+    All tensor fields live in ONE contiguous byte buffer: one cudaMemcpyAsync per batch; the host may run
+    one step ahead of the device (ring of 2, guarded by events)."""
+    FIELDS = (("spk_ids", torch.int64), ("texts", torch.int64), ("src_lens", torch.int64), ("mels", torch.float32),
+              ("mel_lens", torch.int64), ("pitches", torch.float32), ("energies", torch.float32), ("durations", torch.int64))
+    RING = 2
 
     def __init__(self, device, n: int, L: int, T: int, n_spk_ids: int, average_spk: bool):
-        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)  # noqa: E731
-        self.dev = Batch(spk_ids=z((n_spk_ids,), torch.int64), average_spk=average_spk, texts=z((n, L), torch.int64),
-                         src_lens=z((n,), torch.int64), mels=z((n, T, N_MEL), torch.float32), mel_lens=z((n,), torch.int64),
-                         pitches=z((n, L), torch.float32), energies=z((n, L), torch.float32),
-                         durations=z((n, L), torch.int64), B=n, L=L, T=T)
-        self.fields = ("spk_ids", "texts", "src_lens", "mels", "mel_lens", "pitches", "energies", "durations")
-        pin = torch.cuda.is_available()
-        self.pinned = {f: (torch.empty_like(getattr(self.dev, f), device="cpu").pin_memory() if pin
-                           else torch.empty_like(getattr(self.dev, f), device="cpu")) for f in self.fields}
-        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.pinned.values())
+        shapes = {"spk_ids": (n_spk_ids,), "texts": (n, L), "src_lens": (n,), "mels": (n, T, N_MEL), "mel_lens": (n,),
+                  "pitches": (n, L), "energies": (n, L), "durations": (n, L)}
+        offs, off = {}, 0
+        for f, dt in self.FIELDS:
+            nbytes = int(torch.tensor([], dtype=dt).element_size()) * int(torch.Size(shapes[f]).numel())
+            offs[f] = (off, nbytes)
+            off = (off + nbytes + 63) // 64 * 64
+        self.nbytes = off
+        self.dev_buf = torch.zeros(off, dtype=torch.uint8, device=device)
+        view = lambda buf, f, dt: buf[offs[f][0]:offs[f][0] + offs[f][1]].view(dt).view(shapes[f])  # noqa: E731
+        d = {f: view(self.dev_buf, f, dt) for f, dt in self.FIELDS}
+        self.dev = Batch(average_spk=average_spk, B=n, L=L, T=T, **d)
+        pin = torch.cuda.is_available() and self.dev_buf.is_cuda
+        self.host_bufs = [torch.zeros(off, dtype=torch.uint8).pin_memory() if pin else torch.zeros(off, dtype=torch.uint8)
+                          for _ in range(self.RING)]
+        self.host = [{f: view(hb, f, dt) for f, dt in self.FIELDS} for hb in self.host_bufs]
+        self.events = [None] * self.RING
+        self.slot = 0
+        self.h2d_bytes = off
 
     def upload(self, b12, spk_ids=None) -> None:
         (_, _, spk, texts, src_lens, _, mels, mel_lens, _, pitches, energies, durs) = b12
         src = {"spk_ids": spk if spk_ids is None else spk_ids, "texts": texts, "src_lens": src_lens, "mels": mels,
                "mel_lens": mel_lens, "pitches": pitches, "energies": energies, "durations": durs}
-        for f in self.fields:
-            p = self.pinned[f]
-            p.copy_(torch.as_tensor(src[f]).to(p.dtype).reshape(p.shape))
-            getattr(self.dev, f).copy_(p, non_blocking=True)
+        k = self.slot
+        self.slot = (k + 1) % self.RING
+        if self.events[k] is not None:
+            self.events[k].synchronize()                 # the H2D that last used this staging slot has completed
+        for f, _ in self.FIELDS:
+            dst = self.host[k][f]
+            dst.copy_(torch.as_tensor(src[f]).reshape(dst.shape))      # dtype conversion + gather into pinned staging
+        self.dev_buf.copy_(self.host_bufs[k], non_blocking=True)       # ONE H2D per batch
+        if self.dev_buf.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            self.events[k] = ev
+
+
+class LazyLosses:
+    """The step's 6 query losses, copied device -> pinned host asynchronously right after the step was
+    enqueued (the reference returns CUDA tensors from training_step and only syncs when it logs).  Reading
+    a value waits for that copy.  Behaves like the reference's 6-tuple."""
+
+    def __init__(self, host: torch.Tensor, event):
+        self._host, self._event = host, event
+
+    def wait(self):
+        if self._event is not None:
+            self._event.synchronize()
+            self._event = None
+        return self._host
+
+    def __len__(self):
+        return 6
+
+    def __getitem__(self, i):
+        return self.wait()[i]
+
+    def __iter__(self):
+        h = self.wait()
+        return iter([h[i] for i in range(6)])
 
 
 DEFAULT_MODEL_CONFIG = {
@@ -202,15 +249,27 @@ def meta_learn(self, batch, batch_idx, train: bool = True):
     first_order = (not train) or (not self.second_order)
     loss6, out = _run_task(self, sup12, qry12, steps, first_order, _scale(self) if train else None)
     self._pending_tasks += 1 if train else 0
-    l = loss6.cpu()                                    # D2H read of the 6 losses (the step's result)
-    losses = tuple(l[i] for i in range(6))
-    B, Lq, T = qry12[3].shape[0], int(qry12[5]), int(qry12[8])
-    ar_l = torch.arange(Lq, device=self.device)[None, :]
-    ar_t = torch.arange(T, device=self.device)[None, :]
-    src_lens = _ent_dev(self, sup12, qry12, steps, first_order).src_lens
-    mel_lens = _ent_dev(self, sup12, qry12, steps, first_order).mel_lens
-    preds = (out["mel"], out["postnet"], out["pitch"], out["energy"], out["logd"], qry12[11],
-             ar_l >= src_lens[:, None], ar_t >= mel_lens[:, None], src_lens, out["mel_len"])
+    # D2H read of the 6 losses (the step's result): asynchronous copy into a pinned ring, waited on access
+    if not hasattr(self, "_loss_ring"):
+        pin = loss6.is_cuda
+        self._loss_ring = [torch.zeros(6).pin_memory() if pin else torch.zeros(6) for _ in range(4)]
+        self._loss_slot = 0
+    hbuf = self._loss_ring[self._loss_slot]
+    self._loss_slot = (self._loss_slot + 1) % len(self._loss_ring)
+    hbuf.copy_(loss6, non_blocking=True)
+    ev = None
+    if loss6.is_cuda:
+        ev = torch.cuda.Event()
+        ev.record()
+    losses = LazyLosses(hbuf, ev)
+    dev = _ent_dev(self, sup12, qry12, steps, first_order)
+    Lq, T = int(qry12[5]), int(qry12[8])
+    ar = self.__dict__.setdefault("_arange", {})
+    if (Lq, T) not in ar:
+        ar[(Lq, T)] = (torch.arange(Lq, device=self.device)[None, :], torch.arange(T, device=self.device)[None, :])
+    ar_l, ar_t = ar[(Lq, T)]
+    preds = (out["mel"], out["postnet"], out["pitch"], out["energy"], out["logd"], dev.durations,
+             ar_l >= dev.src_lens[:, None], ar_t >= dev.mel_lens[:, None], dev.src_lens, out["mel_len"])
     return losses, preds
 
 
@@ -240,7 +299,9 @@ def optimizer_step(self):
     if torch.distributed.is_initialized() and torch.distributed.get_world_size(self.process_group) > 1:
         torch.distributed.all_reduce(m.g_outer, group=self.process_group)
     opt = self.train_config["optimizer"]
-    m.outer_update(1.0, float(opt.get("grad_clip_thresh", 1.0)), tuple(opt["betas"]), float(opt["eps"]))
+    m.outer_update(1.0, float(opt.get("grad_clip_thresh", 1.0)), tuple(opt["betas"]), float(opt["eps"]),
+                   warmup=int(opt.get("warm_up_step", 4000)), anneal_steps=tuple(opt.get("anneal_steps", ())),
+                   anneal_rate=float(opt.get("anneal_rate", 0.3)))
     self.be.zero_(m.g_outer)
     self._pending_tasks = 0
 
