@@ -35,6 +35,7 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 SHOTS, QUERIES, L_PHON, T_MEL, K_INNER = 4, 4, 128, 864, 1
+_JSON_OUT = sys.stdout
 METRIC = "mel-frames/sec per outer meta-step"
 UNIT = "mel-frames/s"
 
@@ -114,7 +115,7 @@ def run_reference_arm(args):
             "gpu_launches": 0,
             "note": "the reference is pure Python (PyTorch + learn2learn + Lightning) and is absent on the GPU box: this arm "
                     "times oracle/, its CPU restatement validated against the real reference modules (tests/golden)"}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -374,13 +375,17 @@ def run_own_arm(args):
                 "gpu_launches": launches_step * args.steps, "gpu_launches_per_step": launches_step,
                 "roofline": roofline, "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),
                 "last_query_loss": last_loss, "hbm_bytes_resident": sysm.maml.memory_bytes()}
-        print(json.dumps(line))
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
+    # the JSON line is the ONLY thing on stdout: library chatter (NCCL banner, device printf) goes to stderr
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

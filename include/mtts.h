@@ -41,6 +41,8 @@ int         mtts_version(void);
 const char* mtts_last_error(void);
 /* 0 when a usable sm_100 device is current, MTTS_EARCH otherwise. */
 int         mtts_check_device(void);
+/* Programmatic Dependent Launch on/off (default on; env MTTS_PDL=0 disables). */
+int         mtts_set_pdl(int on);
 
 /* ------------------------------------------------------------------------------------------
  * Generic tcgen05 GEMM:   for every z = (z0, z1):

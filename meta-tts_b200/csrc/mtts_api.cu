@@ -1,4 +1,5 @@
 // mtts_api.cu — library-level entry points: version, error string, device check.
+#include <stdlib.h>
 #include "mtts_common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -22,5 +23,19 @@ extern "C" int mtts_check_device(void) {
     mtts_set_error("libmtts needs an sm_100 (B200) device, found sm_%d%d (%s)", prop.major, prop.minor, prop.name);
     return MTTS_EARCH;
   }
+  return MTTS_OK;
+}
+
+// Programmatic Dependent Launch toggle (default on; MTTS_PDL=0 in the environment disables it)
+static int g_pdl = -1;
+int mtts_pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("MTTS_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl;
+}
+extern "C" int mtts_set_pdl(int on) {
+  g_pdl = on ? 1 : 0;
   return MTTS_OK;
 }

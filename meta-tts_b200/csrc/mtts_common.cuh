@@ -44,6 +44,30 @@ void mtts_set_error(const char* fmt, ...);
     }                                                                                 \
   } while (0)
 
+// ------------------------------------------------------------------------------------------------
+// kernel launch with Programmatic Dependent Launch: the next kernel's CTAs may become resident and run
+// their prologue (smem carve-up, mbarrier init, TMEM alloc) while the previous kernel drains; every kernel
+// executes griddepcontrol.wait before its first global-memory access, so ordering is unchanged.
+// ------------------------------------------------------------------------------------------------
+int mtts_pdl_enabled();
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mtts_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                      Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = mtts_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline int mtts_cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t mtts_cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -53,6 +77,15 @@ static inline int64_t mtts_cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b
 #ifdef __CUDACC__
 
 typedef __nv_bfloat16 bf16;
+
+// PDL: let the dependent grid start launching, then wait until the grid we depend on has completed and
+// flushed its memory.  Must precede the first global-memory access of every kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -196,6 +196,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
 template <int BN, int SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN, SPLIT>;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bar_base = smem + C::STAGES * C::STAGE;
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                    // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================================== TMA producer ==========================================
@@ -400,6 +402,7 @@ struct Cfg2 {
 template <int BN, int SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mtts_gemm_pair_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg2<BN, SPLIT>;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bar_base = smem + C::STAGES * C::STAGE;
@@ -449,6 +452,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mtts
   cluster_sync_all();                            // peer barriers initialised before any remote complete_tx / arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                    // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================================== TMA producer (both CTAs) ===============================
@@ -632,7 +636,7 @@ int launch_pair(const GemmParams& p, dim3 grid, cudaStream_t stream) {
                                          C::SMEM));
     configured = true;
   }
-  mtts_gemm_pair_kernel<BN, SPLIT><<<grid, NUM_THREADS, C::SMEM, stream>>>(p);   // __cluster_dims__(2,1,1)
+  MTTS_CHECK_CUDA(mtts_launch(mtts_gemm_pair_kernel<BN, SPLIT>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, p));   // __cluster_dims__(2,1,1)
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -646,7 +650,7 @@ int launch(const GemmParams& p, dim3 grid, cudaStream_t stream) {
                                          C::SMEM));
     configured = true;
   }
-  mtts_gemm_kernel<BN, SPLIT><<<grid, NUM_THREADS, C::SMEM, stream>>>(p);
+  MTTS_CHECK_CUDA(mtts_launch(mtts_gemm_kernel<BN, SPLIT>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, p));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }

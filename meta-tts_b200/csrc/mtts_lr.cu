@@ -21,6 +21,7 @@ __device__ __forceinline__ long long dur_at(const int64_t* di, const float* df, 
 // thread binary-searches its frames.  L <= 4096.
 __global__ void lr_index_kernel(const int64_t* __restrict__ di, const float* __restrict__ df, int L, int T,
                                 int32_t* __restrict__ idx, int64_t* __restrict__ mel_len) {
+  pdl_enter();
   extern __shared__ long long cum[];   // [L]
   const int b = blockIdx.x;
   // serial-in-chunks inclusive scan (L is small: <= a few hundred phonemes)
@@ -78,6 +79,7 @@ __global__ void lr_index_kernel(const int64_t* __restrict__ di, const float* __r
 // out[b,t,:] = idx>=0 ? x[b,idx,:] : 0.  One warp per (b,t) row, float4 lanes.
 __global__ void lr_gather_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, int L, int T, int C,
                                  long long rows, float* __restrict__ out) {
+  pdl_enter();
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -103,6 +105,7 @@ __global__ void lr_gather_kernel(const float* __restrict__ x, const int32_t* __r
 __global__ void lr_segsum_kernel(const float* __restrict__ dy, const int64_t* __restrict__ di,
                                  const float* __restrict__ df, int L, int T, int C, long long rows,
                                  float* __restrict__ dx) {
+  pdl_enter();
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -143,7 +146,7 @@ extern "C" int mtts_length_regulate_index(const int64_t* dur_i64, const float* d
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE((dur_i64 != nullptr) != (dur_f32 != nullptr), "length_regulate: pass exactly one duration pointer");
   MTTS_REQUIRE(B > 0 && L > 0 && T > 0 && L <= 4096, "length_regulate: bad B/L/T %d %d %d", B, L, T);
-  lr_index_kernel<<<B, 256, L * sizeof(long long), stream>>>(dur_i64, dur_f32, L, T, idx, mel_len);
+  MTTS_CHECK_CUDA(mtts_launch(lr_index_kernel, dim3(B), dim3(256), L * sizeof(long long), stream, dur_i64, dur_f32, L, T, idx, mel_len));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -155,7 +158,7 @@ extern "C" int mtts_length_regulate_fwd(const float* x, const int32_t* idx, int 
   const long long rows = static_cast<long long>(B) * T;
   const int threads = 256;
   const long long blocks = mtts_cdiv64(rows * 32, threads);
-  lr_gather_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(x, idx, L, T, C, rows, out);
+  MTTS_CHECK_CUDA(mtts_launch(lr_gather_kernel, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, stream, x, idx, L, T, C, rows, out));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -168,7 +171,7 @@ extern "C" int mtts_length_regulate_bwd(const float* dy, const int64_t* dur_i64,
   const long long rows = static_cast<long long>(B) * L;
   const int threads = 256;
   const long long blocks = mtts_cdiv64(rows * 32, threads);
-  lr_segsum_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(dy, dur_i64, dur_f32, L, T, C, rows, dx);
+  MTTS_CHECK_CUDA(mtts_launch(lr_segsum_kernel, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, stream, dy, dur_i64, dur_f32, L, T, C, rows, dx));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }

@@ -39,6 +39,7 @@ __device__ __forceinline__ void store_split4(bf16* hi, bf16* lo, long long i, fl
 __global__ void embed_fwd_kernel(const int64_t* __restrict__ idx, const float* __restrict__ table,
                                  const float* __restrict__ base, const float* __restrict__ pos, int T, long long R, int C,
                                  float* __restrict__ out, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  pdl_enter();
   const int c4 = C >> 2;
   const long long total = R * c4;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -60,6 +61,7 @@ __global__ void embed_fwd_kernel(const int64_t* __restrict__ idx, const float* _
 // dtable[idx[r],:] += scale * dy[r,:]   (rows with idx == skip_idx are skipped: padding_idx)
 __global__ void embed_bwd_kernel(const int64_t* __restrict__ idx, const float* __restrict__ dy, long long R, int C,
                                  long long skip_idx, float scale, float* __restrict__ dtable) {
+  pdl_enter();
   const long long total = R * C;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / C;
@@ -72,6 +74,7 @@ __global__ void embed_bwd_kernel(const int64_t* __restrict__ idx, const float* _
 // torch.bucketize(v, bins) (right=False): out = #{ bins < v }  (lower bound)
 __global__ void bucketize_kernel(const float* __restrict__ v, const float* __restrict__ bins, int nb, long long R,
                                  int64_t* __restrict__ out) {
+  pdl_enter();
   const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= R) return;
   const float x = v[r];
@@ -87,6 +90,7 @@ __global__ void bucketize_kernel(const float* __restrict__ v, const float* __res
 __global__ void add_rowvec_kernel(const float* __restrict__ x, const float* __restrict__ vec, long long vec_bstride,
                                   const float* __restrict__ pos, int T, long long R, int C, float* __restrict__ out,
                                   bf16* __restrict__ hi, bf16* __restrict__ lo) {
+  pdl_enter();
   const int c4 = C >> 2;
   const long long total = R * c4;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -110,6 +114,7 @@ __global__ void add_rowvec_kernel(const float* __restrict__ x, const float* __re
 // speaker embedding: out[q,:] = average ? mean_i table[ids[i],:] : table[ids[q],:]
 __global__ void spk_embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ table, int n, int C, int average,
                                  int n_out, float* __restrict__ out) {
+  pdl_enter();
   const int q = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float v;
@@ -125,6 +130,7 @@ __global__ void spk_embed_kernel(const int64_t* __restrict__ ids, const float* _
 }
 __global__ void spk_embed_bwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ dspk, int n, int C,
                                      int average, int n_out, float scale, float* __restrict__ dtable) {
+  pdl_enter();
   for (int c = threadIdx.x + blockIdx.x * blockDim.x; c < C; c += blockDim.x * gridDim.x) {
     if (average) {
       float s = 0.f;
@@ -143,6 +149,7 @@ __global__ void spk_embed_bwd_kernel(const int64_t* __restrict__ ids, const floa
 // ================================================================================================
 __global__ void colsum_kernel(const float* __restrict__ f32, const bf16* __restrict__ hi, const bf16* __restrict__ lo,
                               long long R, int C, int rows_per_cta, float* __restrict__ out) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const long long zoff = static_cast<long long>(blockIdx.z) * R * C;
@@ -180,6 +187,7 @@ struct BnArgs {
 
 template <int MODE>
 __global__ void bn_reduce_kernel(BnArgs a, float* __restrict__ ws) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.C) return;
   const long long r0 = static_cast<long long>(blockIdx.y) * a.rows_per_cta;
@@ -218,6 +226,7 @@ __global__ void bn_fwd_apply_kernel(const float* __restrict__ x, const float* __
                                     float eps, float momentum, int tanh_flag, float* __restrict__ running_mean,
                                     float* __restrict__ running_var, float* __restrict__ stats, float* __restrict__ out,
                                     bf16* __restrict__ hi, bf16* __restrict__ lo, int rows_per_cta) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float mean = ws[c] / R;
@@ -252,6 +261,7 @@ __global__ void bn_fwd_apply_kernel(const float* __restrict__ x, const float* __
 __global__ void bn_bwd_apply_kernel(BnArgs a, const float* __restrict__ ws, const float* __restrict__ gamma,
                                     float* __restrict__ dx, bf16* __restrict__ hi, bf16* __restrict__ lo,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.C) return;
   const float mean = a.stats[c], rstd = a.stats[a.C + c];
@@ -283,6 +293,7 @@ __global__ void bn_tfwd_apply_kernel(BnArgs a, const float* __restrict__ ws, con
                                      const float* __restrict__ gdot, const float* __restrict__ bdot,
                                      float* __restrict__ tsums, float* __restrict__ od, bf16* __restrict__ hi,
                                      bf16* __restrict__ lo) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.C) return;
   const float mean = a.stats[c], rstd = a.stats[a.C + c];
@@ -310,6 +321,7 @@ __global__ void bn_tfwd_apply_kernel(BnArgs a, const float* __restrict__ ws, con
 __global__ void bn_tbwd_apply_kernel(BnArgs a, const float* __restrict__ ws, const float* __restrict__ gamma,
                                      const float* __restrict__ gdot, float* __restrict__ ddx, bf16* __restrict__ hi,
                                      bf16* __restrict__ lo, float* __restrict__ ddgamma, float* __restrict__ ddbeta) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.C) return;
   const float mean = a.stats[c], rstd = a.stats[a.C + c];
@@ -378,6 +390,7 @@ __device__ __forceinline__ float block_sum(float v) {
 }
 // ws[0..4] = sum|mel-t|, sum|post-t|, sum (p-pt)^2, sum (e-et)^2, sum (logd - log(d+1))^2
 __global__ void loss_sums_kernel(LossArgs a, float* __restrict__ ws) {
+  pdl_enter();
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
   const long long nmel = static_cast<long long>(a.B) * a.T * a.NM;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nmel; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -407,6 +420,7 @@ __global__ void loss_sums_kernel(LossArgs a, float* __restrict__ ws) {
 }
 // out6 = (total, mel, postnet_mel, pitch, energy, duration); counts[0] = n_mel_elems, counts[1] = n_src
 __global__ void loss_finalize_kernel(LossArgs a, const float* __restrict__ ws, float* __restrict__ out6, float* __restrict__ counts) {
+  pdl_enter();
   long long nm = 0, ns = 0;
   for (int b = 0; b < a.B; ++b) {
     nm += min(static_cast<long long>(a.T), static_cast<long long>(a.mel_lens[b]));
@@ -422,6 +436,7 @@ __global__ void loss_finalize_kernel(LossArgs a, const float* __restrict__ ws, f
 __global__ void loss_bwd_kernel(LossArgs a, const float* __restrict__ counts, float scale, int tangent,
                                 float* __restrict__ dmel, float* __restrict__ dpost, float* __restrict__ dp,
                                 float* __restrict__ de, float* __restrict__ dlogd) {
+  pdl_enter();
   const float n_mel = counts[0], n_src = counts[1];
   const long long nmel = static_cast<long long>(a.B) * a.T * a.NM;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nmel; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -461,12 +476,14 @@ __global__ void loss_bwd_kernel(LossArgs a, const float* __restrict__ counts, fl
 // flat-arena elementwise kernels (n % 4 == 0, 16B-aligned)
 // ================================================================================================
 __global__ void split_kernel(const float* __restrict__ src, bf16* __restrict__ hi, bf16* __restrict__ lo, long long n4) {
+  pdl_enter();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x)
     store_split4(hi, lo, i * 4, *reinterpret_cast<const float4*>(src + i * 4));
 }
 // theta_out = theta_in - lr * g ; (hi, lo) = split(theta_out)      (l2l maml_update + operand prep, fused)
 __global__ void sgd_split_kernel(const float* __restrict__ th, const float* __restrict__ g, float lr, float* __restrict__ out,
                                  bf16* __restrict__ hi, bf16* __restrict__ lo, long long n4) {
+  pdl_enter();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 a = *reinterpret_cast<const float4*>(th + i * 4);
     const float4 b = *reinterpret_cast<const float4*>(g + i * 4);
@@ -477,6 +494,7 @@ __global__ void sgd_split_kernel(const float* __restrict__ th, const float* __re
 }
 // y = a*x + b*y
 __global__ void axpby_kernel(float a, const float* __restrict__ x, float b, float* __restrict__ y, long long n4) {
+  pdl_enter();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 u = *reinterpret_cast<const float4*>(x + i * 4);
     float4 v = *reinterpret_cast<float4*>(y + i * 4);
@@ -485,6 +503,7 @@ __global__ void axpby_kernel(float a, const float* __restrict__ x, float b, floa
   }
 }
 __global__ void sumsq_kernel(const float* __restrict__ x, long long n4, float* __restrict__ out) {
+  pdl_enter();
   float s = 0.f;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 u = *reinterpret_cast<const float4*>(x + i * 4);
@@ -499,6 +518,7 @@ __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict_
                                  float* __restrict__ v, const float* __restrict__ sumsq, float gscale, float max_norm,
                                  const float* __restrict__ hyper, float beta1, float beta2, float eps,
                                  bf16* __restrict__ hi, bf16* __restrict__ lo, long long n4) {
+  pdl_enter();
   const float norm = sqrtf(sumsq[0]) * gscale;
   float coef = max_norm > 0.f ? max_norm / (norm + 1e-6f) : 1.f;
   coef = fminf(coef, 1.f) * gscale;
@@ -538,8 +558,8 @@ extern "C" int mtts_embed_fwd(const int64_t* idx, const float* table, const floa
                               int C, float* out, void* hi, void* lo, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(idx && table && R > 0 && C > 0 && (C % 4) == 0 && (!pos || T > 0), "embed_fwd: bad args");
-  embed_fwd_kernel<<<ew_grid(R * (C / 4), 1), EW_THREADS, 0, s>>>(idx, table, base, pos, T, R, C, out, static_cast<bf16*>(hi),
-                                                                 static_cast<bf16*>(lo));
+  MTTS_CHECK_CUDA(mtts_launch(embed_fwd_kernel, dim3(ew_grid(R * (C / 4), 1)), dim3(EW_THREADS), 0, s, idx, table, base, pos, T, R, C, out, static_cast<bf16*>(hi),
+                                                                 static_cast<bf16*>(lo)));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -547,14 +567,14 @@ extern "C" int mtts_embed_bwd(const int64_t* idx, const float* dy, int64_t R, in
                               float* dtable, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(idx && dy && dtable && R > 0 && C > 0, "embed_bwd: bad args");
-  embed_bwd_kernel<<<ew_grid(R * C, 1), EW_THREADS, 0, s>>>(idx, dy, R, C, skip_idx, scale, dtable);
+  MTTS_CHECK_CUDA(mtts_launch(embed_bwd_kernel, dim3(ew_grid(R * C, 1)), dim3(EW_THREADS), 0, s, idx, dy, R, C, skip_idx, scale, dtable));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
 extern "C" int mtts_bucketize(const float* v, const float* bins, int nb, int64_t R, int64_t* out, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(v && bins && out && nb > 0 && R > 0, "bucketize: bad args");
-  bucketize_kernel<<<static_cast<unsigned>(mtts_cdiv64(R, 256)), 256, 0, s>>>(v, bins, nb, R, out);
+  MTTS_CHECK_CUDA(mtts_launch(bucketize_kernel, dim3(static_cast<unsigned>(mtts_cdiv64(R, 256))), dim3(256), 0, s, v, bins, nb, R, out));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -563,8 +583,8 @@ extern "C" int mtts_add_rowvec(const float* x, const float* vec, int64_t vec_bst
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(x && B > 0 && T > 0 && C > 0 && (C % 4) == 0, "add_rowvec: bad args");
   const long long R = static_cast<long long>(B) * T;
-  add_rowvec_kernel<<<ew_grid(R * (C / 4), 1), EW_THREADS, 0, s>>>(x, vec, vec_bstride, pos, T, R, C, out, static_cast<bf16*>(hi),
-                                                                  static_cast<bf16*>(lo));
+  MTTS_CHECK_CUDA(mtts_launch(add_rowvec_kernel, dim3(ew_grid(R * (C / 4), 1)), dim3(EW_THREADS), 0, s, x, vec, vec_bstride, pos, T, R, C, out, static_cast<bf16*>(hi),
+                                                                  static_cast<bf16*>(lo)));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -572,7 +592,7 @@ extern "C" int mtts_spk_embed(const int64_t* ids, const float* table, int n, int
                               mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(ids && table && out && n > 0 && n_out > 0 && (average || n_out == n), "spk_embed: bad args");
-  spk_embed_kernel<<<n_out, 256, 0, s>>>(ids, table, n, C, average, n_out, out);
+  MTTS_CHECK_CUDA(mtts_launch(spk_embed_kernel, dim3(n_out), dim3(256), 0, s, ids, table, n, C, average, n_out, out));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -580,7 +600,7 @@ extern "C" int mtts_spk_embed_bwd(const int64_t* ids, const float* dspk, int n, 
                                   float* dtable, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(ids && dspk && dtable && n > 0 && n_out > 0 && (average || n_out == n), "spk_embed_bwd: bad args");
-  spk_embed_bwd_kernel<<<1, 256, 0, s>>>(ids, dspk, n, C, average, n_out, scale, dtable);
+  MTTS_CHECK_CUDA(mtts_launch(spk_embed_bwd_kernel, dim3(1), dim3(256), 0, s, ids, dspk, n, C, average, n_out, scale, dtable));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -594,8 +614,8 @@ extern "C" int mtts_colsum(const float* f32, const void* hi, const void* lo, int
   if (row_chunks > R) row_chunks = static_cast<int>(R);
   const int rows_per_cta = static_cast<int>(mtts_cdiv64(R, row_chunks));
   row_chunks = static_cast<int>(mtts_cdiv64(R, rows_per_cta));
-  colsum_kernel<<<dim3(col_blocks, row_chunks, nb), 128, 0, s>>>(f32, static_cast<const bf16*>(hi), static_cast<const bf16*>(lo), R,
-                                                                  C, rows_per_cta, out);
+  MTTS_CHECK_CUDA(mtts_launch(colsum_kernel, dim3(dim3(col_blocks, row_chunks, nb)), dim3(128), 0, s, f32, static_cast<const bf16*>(hi), static_cast<const bf16*>(lo), R,
+                                                                  C, rows_per_cta, out));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -611,10 +631,10 @@ extern "C" int mtts_bn_fwd(const float* x, const float* gamma, const float* beta
   BnArgs a{};
   a.x = x; a.R = R; a.C = C; a.tanh_flag = tanh_flag; a.rows_per_cta = rpc; a.ws_in = ws;
   MTTS_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s));
-  bn_reduce_kernel<0><<<grid, block, 0, s>>>(a, ws);
-  bn_reduce_kernel<1><<<grid, block, 0, s>>>(a, ws + C);
-  bn_fwd_apply_kernel<<<grid, block, 0, s>>>(x, ws, gamma, beta, R, C, eps, momentum, tanh_flag, running_mean, running_var, stats,
-                                             out, static_cast<bf16*>(hi), static_cast<bf16*>(lo), rpc);
+  MTTS_CHECK_CUDA(mtts_launch(bn_reduce_kernel<0>, dim3(grid), dim3(block), 0, s, a, ws));
+  MTTS_CHECK_CUDA(mtts_launch(bn_reduce_kernel<1>, dim3(grid), dim3(block), 0, s, a, ws + C));
+  MTTS_CHECK_CUDA(mtts_launch(bn_fwd_apply_kernel, dim3(grid), dim3(block), 0, s, x, ws, gamma, beta, R, C, eps, momentum, tanh_flag, running_mean, running_var, stats,
+                                             out, static_cast<bf16*>(hi), static_cast<bf16*>(lo), rpc));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -629,8 +649,8 @@ extern "C" int mtts_bn_bwd(const float* dout, const float* o, const float* x, co
   BnArgs a{};
   a.x = x; a.dout = dout; a.o = o; a.stats = stats; a.R = R; a.C = C; a.tanh_flag = tanh_flag; a.rows_per_cta = rpc;
   MTTS_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s));
-  bn_reduce_kernel<2><<<grid, block, 0, s>>>(a, ws);
-  bn_bwd_apply_kernel<<<grid, block, 0, s>>>(a, ws, gamma, dx, static_cast<bf16*>(hi), static_cast<bf16*>(lo), dgamma, dbeta);
+  MTTS_CHECK_CUDA(mtts_launch(bn_reduce_kernel<2>, dim3(grid), dim3(block), 0, s, a, ws));
+  MTTS_CHECK_CUDA(mtts_launch(bn_bwd_apply_kernel, dim3(grid), dim3(block), 0, s, a, ws, gamma, dx, static_cast<bf16*>(hi), static_cast<bf16*>(lo), dgamma, dbeta));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -645,8 +665,8 @@ extern "C" int mtts_bn_tfwd(const float* xdot, const float* x, const float* stat
   BnArgs a{};
   a.x = x; a.xdot = xdot; a.o = o; a.stats = stats; a.R = R; a.C = C; a.tanh_flag = tanh_flag; a.rows_per_cta = rpc;
   MTTS_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s));
-  bn_reduce_kernel<3><<<grid, block, 0, s>>>(a, ws);
-  bn_tfwd_apply_kernel<<<grid, block, 0, s>>>(a, ws, gamma, gdot, bdot, tsums, odot, static_cast<bf16*>(hi), static_cast<bf16*>(lo));
+  MTTS_CHECK_CUDA(mtts_launch(bn_reduce_kernel<3>, dim3(grid), dim3(block), 0, s, a, ws));
+  MTTS_CHECK_CUDA(mtts_launch(bn_tfwd_apply_kernel, dim3(grid), dim3(block), 0, s, a, ws, gamma, gdot, bdot, tsums, odot, static_cast<bf16*>(hi), static_cast<bf16*>(lo)));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -663,8 +683,8 @@ extern "C" int mtts_bn_tbwd(const float* dout, const float* ddout, const float* 
   a.x = x; a.xdot = xdot; a.dout = dout; a.ddout = ddout; a.o = o; a.odot = odot; a.stats = stats; a.tsums = tsums;
   a.R = R; a.C = C; a.tanh_flag = tanh_flag; a.rows_per_cta = rpc;
   MTTS_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 4 * C, s));
-  bn_reduce_kernel<4><<<grid, block, 0, s>>>(a, ws);
-  bn_tbwd_apply_kernel<<<grid, block, 0, s>>>(a, ws, gamma, gdot, ddx, static_cast<bf16*>(hi), static_cast<bf16*>(lo), ddgamma, ddbeta);
+  MTTS_CHECK_CUDA(mtts_launch(bn_reduce_kernel<4>, dim3(grid), dim3(block), 0, s, a, ws));
+  MTTS_CHECK_CUDA(mtts_launch(bn_tbwd_apply_kernel, dim3(grid), dim3(block), 0, s, a, ws, gamma, gdot, ddx, static_cast<bf16*>(hi), static_cast<bf16*>(lo), ddgamma, ddbeta));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -686,8 +706,8 @@ extern "C" int mtts_loss_fwd(const float* mel, const float* post, const float* m
                "loss_fwd: null argument");
   LossArgs a = make_loss_args(mel, post, mel_tgt, mel_lens, p, p_tgt, e, e_tgt, logd, dur, src_lens, B, T, L, NM);
   MTTS_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 8, s));
-  loss_sums_kernel<<<ew_grid(static_cast<long long>(B) * T * NM, 4), EW_THREADS, 0, s>>>(a, ws);
-  loss_finalize_kernel<<<1, 1, 0, s>>>(a, ws, out6, counts);
+  MTTS_CHECK_CUDA(mtts_launch(loss_sums_kernel, dim3(ew_grid(static_cast<long long>(B) * T * NM, 4)), dim3(EW_THREADS), 0, s, a, ws));
+  MTTS_CHECK_CUDA(mtts_launch(loss_finalize_kernel, dim3(1), dim3(1), 0, s, a, ws, out6, counts));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -699,8 +719,8 @@ extern "C" int mtts_loss_bwd(const float* mel, const float* post, const float* m
   MTTS_REQUIRE(mel_lens && src_lens && p && e && logd && counts && dmel && dpost && dp && de && dlogd, "loss_bwd: null argument");
   MTTS_REQUIRE(tangent || (mel && post && mel_tgt && p_tgt && e_tgt && dur), "loss_bwd: null argument");
   LossArgs a = make_loss_args(mel, post, mel_tgt, mel_lens, p, p_tgt, e, e_tgt, logd, dur, src_lens, B, T, L, NM);
-  loss_bwd_kernel<<<ew_grid(static_cast<long long>(B) * T * NM, 4), EW_THREADS, 0, s>>>(a, counts, scale, tangent, dmel, dpost, dp, de,
-                                                                                      dlogd);
+  MTTS_CHECK_CUDA(mtts_launch(loss_bwd_kernel, dim3(ew_grid(static_cast<long long>(B) * T * NM, 4)), dim3(EW_THREADS), 0, s, a, counts, scale, tangent, dmel, dpost, dp, de,
+                                                                                      dlogd));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -710,7 +730,7 @@ extern "C" int mtts_loss_bwd(const float* mel, const float* post, const float* m
 extern "C" int mtts_split(const float* src, void* hi, void* lo, int64_t n, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   REQ_N4(n, src);
-  split_kernel<<<ew_grid(n / 4, 2), EW_THREADS, 0, s>>>(src, static_cast<bf16*>(hi), static_cast<bf16*>(lo), n / 4);
+  MTTS_CHECK_CUDA(mtts_launch(split_kernel, dim3(ew_grid(n / 4, 2)), dim3(EW_THREADS), 0, s, src, static_cast<bf16*>(hi), static_cast<bf16*>(lo), n / 4));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -718,14 +738,14 @@ extern "C" int mtts_sgd_split(const float* theta, const float* g, float lr, floa
                               mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   REQ_N4(n, theta);
-  sgd_split_kernel<<<ew_grid(n / 4, 2), EW_THREADS, 0, s>>>(theta, g, lr, out, static_cast<bf16*>(hi), static_cast<bf16*>(lo), n / 4);
+  MTTS_CHECK_CUDA(mtts_launch(sgd_split_kernel, dim3(ew_grid(n / 4, 2)), dim3(EW_THREADS), 0, s, theta, g, lr, out, static_cast<bf16*>(hi), static_cast<bf16*>(lo), n / 4));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
 extern "C" int mtts_axpby(float a, const float* x, float b, float* y, int64_t n, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   REQ_N4(n, x);
-  axpby_kernel<<<ew_grid(n / 4, 2), EW_THREADS, 0, s>>>(a, x, b, y, n / 4);
+  MTTS_CHECK_CUDA(mtts_launch(axpby_kernel, dim3(ew_grid(n / 4, 2)), dim3(EW_THREADS), 0, s, a, x, b, y, n / 4));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -733,7 +753,7 @@ extern "C" int mtts_sumsq(const float* x, int64_t n, float* out /* zeroed here *
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   REQ_N4(n, x);
   MTTS_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
-  sumsq_kernel<<<ew_grid(n / 4, 4), EW_THREADS, 0, s>>>(x, n / 4, out);
+  MTTS_CHECK_CUDA(mtts_launch(sumsq_kernel, dim3(ew_grid(n / 4, 4)), dim3(EW_THREADS), 0, s, x, n / 4, out));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -742,8 +762,8 @@ extern "C" int mtts_adam_clip(float* p, const float* g, float* m, float* v, cons
                               mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   REQ_N4(n, p);
-  adam_clip_kernel<<<ew_grid(n / 4, 2), EW_THREADS, 0, s>>>(p, g, m, v, sumsq, gscale, max_norm, hyper, beta1, beta2, eps,
-                                                           static_cast<bf16*>(hi), static_cast<bf16*>(lo), n / 4);
+  MTTS_CHECK_CUDA(mtts_launch(adam_clip_kernel, dim3(ew_grid(n / 4, 2)), dim3(EW_THREADS), 0, s, p, g, m, v, sumsq, gscale, max_norm, hyper, beta1, beta2, eps,
+                                                           static_cast<bf16*>(hi), static_cast<bf16*>(lo), n / 4));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }

@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(const float* __rest
                                                              float* __restrict__ z_out, float* __restrict__ stats,
                                                              float* __restrict__ out, bf16* __restrict__ out_hi,
                                                              bf16* __restrict__ out_lo) {
+  pdl_enter();
   constexpr int C = NV * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   RowVec<NV> g, b;
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(const float* __rest
                                                              int relu_gate, float* __restrict__ dz, bf16* __restrict__ dz_hi,
                                                              bf16* __restrict__ dz_lo, float* __restrict__ dgamma,
                                                              float* __restrict__ dbeta, float* __restrict__ dbias) {
+  pdl_enter();
   constexpr int C = NV * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   RowVec<NV> g;
@@ -224,6 +226,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_tfwd_kernel(const float* __res
                                                               int T, long long R, float* __restrict__ zdot_out,
                                                               float* __restrict__ out, bf16* __restrict__ out_hi,
                                                               bf16* __restrict__ out_lo) {
+  pdl_enter();
   constexpr int C = NV * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   RowVec<NV> g, gd, bd;
@@ -276,6 +279,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_tbwd_kernel(const float* __res
                                                               bf16* __restrict__ ddz_hi, bf16* __restrict__ ddz_lo,
                                                               float* __restrict__ ddgamma, float* __restrict__ ddbeta,
                                                               float* __restrict__ ddbias) {
+  pdl_enter();
   constexpr int C = NV * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   RowVec<NV> g, gdv;
@@ -343,6 +347,7 @@ __global__ void __launch_bounds__(ROW_THREADS) rowdot_fwd_kernel(const float* __
                                                                  const float* __restrict__ b, const float* __restrict__ bdot,
                                                                  const int64_t* __restrict__ lens, int T, long long R,
                                                                  float* __restrict__ out) {
+  pdl_enter();
   constexpr int C = NV * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   RowVec<NV> wv, wd;
@@ -375,6 +380,7 @@ __global__ void __launch_bounds__(ROW_THREADS) rowdot_bwd_kernel(const float* __
                                                                  const int64_t* __restrict__ lens, int T, long long R,
                                                                  float* __restrict__ dh, float* __restrict__ dw,
                                                                  float* __restrict__ db) {
+  pdl_enter();
   constexpr int C = NV * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool tangent = ddout != nullptr;
@@ -454,6 +460,7 @@ __global__ void __launch_bounds__(ROW_THREADS) softmax_kernel(int mode, const fl
                                                               const bf16* __restrict__ pd_hi, const bf16* __restrict__ pd_lo,
                                                               const int64_t* __restrict__ klens, int H, int Lq, int Lk, int ld,
                                                               long long rows, bf16* __restrict__ o_hi, bf16* __restrict__ o_lo) {
+  pdl_enter();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long long r = static_cast<long long>(blockIdx.x) * ROW_WARPS + warp; r < rows; r += static_cast<long long>(gridDim.x) * ROW_WARPS) {
     const long long zidx = r / Lq;
@@ -552,7 +559,7 @@ extern "C" int mtts_ln_fwd(const float* y, const float* res, const float* gamma,
                            void* out_lo, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(y && gamma && beta && R > 0, "ln_fwd: bad args");
-  DISPATCH_NV(C, (ln_fwd_kernel<NV><<<row_grid(R), ROW_THREADS, 0, s>>>(y, res, gamma, beta, lens, T, R, eps, z_out, stats, out,
+  DISPATCH_NV(C, MTTS_CHECK_CUDA(mtts_launch(ln_fwd_kernel<NV>, dim3(row_grid(R)), dim3(ROW_THREADS), 0, s, y, res, gamma, beta, lens, T, R, eps, z_out, stats, out,
                                                                         static_cast<bf16*>(out_hi), static_cast<bf16*>(out_lo))));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
@@ -563,7 +570,7 @@ extern "C" int mtts_ln_bwd(const float* dy, const float* z, const float* stats, 
                            float* dbias, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(dy && z && stats && gamma && R > 0, "ln_bwd: bad args");
-  DISPATCH_NV(C, (ln_bwd_kernel<NV><<<row_grid(R), ROW_THREADS, 0, s>>>(dy, z, stats, gamma, lens, T, R, relu_gate, dz,
+  DISPATCH_NV(C, MTTS_CHECK_CUDA(mtts_launch(ln_bwd_kernel<NV>, dim3(row_grid(R)), dim3(ROW_THREADS), 0, s, dy, z, stats, gamma, lens, T, R, relu_gate, dz,
                                                                         static_cast<bf16*>(dz_hi), static_cast<bf16*>(dz_lo),
                                                                         dgamma, dbeta, dbias)));
   MTTS_CHECK_LAUNCH();
@@ -575,7 +582,7 @@ extern "C" int mtts_ln_tfwd(const float* ydot, const float* resdot, const float*
                             float* zdot_out, float* out, void* out_hi, void* out_lo, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(ydot && z && stats && gamma && R > 0, "ln_tfwd: bad args");
-  DISPATCH_NV(C, (ln_tfwd_kernel<NV><<<row_grid(R), ROW_THREADS, 0, s>>>(ydot, resdot, z, stats, gamma, gdot, bdot, lens, T, R,
+  DISPATCH_NV(C, MTTS_CHECK_CUDA(mtts_launch(ln_tfwd_kernel<NV>, dim3(row_grid(R)), dim3(ROW_THREADS), 0, s, ydot, resdot, z, stats, gamma, gdot, bdot, lens, T, R,
                                                                          zdot_out, out, static_cast<bf16*>(out_hi),
                                                                          static_cast<bf16*>(out_lo))));
   MTTS_CHECK_LAUNCH();
@@ -588,7 +595,7 @@ extern "C" int mtts_ln_tbwd(const float* dy, const float* ddy, const float* z, c
                             mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(dy && ddy && z && zdot && stats && gamma && R > 0, "ln_tbwd: bad args");
-  DISPATCH_NV(C, (ln_tbwd_kernel<NV><<<row_grid(R), ROW_THREADS, 0, s>>>(dy, ddy, z, zdot, stats, gamma, gdot, lens, T, R,
+  DISPATCH_NV(C, MTTS_CHECK_CUDA(mtts_launch(ln_tbwd_kernel<NV>, dim3(row_grid(R)), dim3(ROW_THREADS), 0, s, dy, ddy, z, zdot, stats, gamma, gdot, lens, T, R,
                                                                          relu_gate, ddz, static_cast<bf16*>(ddz_hi),
                                                                          static_cast<bf16*>(ddz_lo), ddgamma, ddbeta, ddbias)));
   MTTS_CHECK_LAUNCH();
@@ -600,7 +607,7 @@ extern "C" int mtts_rowdot_fwd(const float* h, const float* hdot, const float* w
                                mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(h && w && out && R > 0 && (hdot || b), "rowdot_fwd: bad args");
-  DISPATCH_NV(C, (rowdot_fwd_kernel<NV><<<row_grid(R), ROW_THREADS, 0, s>>>(h, hdot, w, wdot, b, bdot, lens, T, R, out)));
+  DISPATCH_NV(C, MTTS_CHECK_CUDA(mtts_launch(rowdot_fwd_kernel<NV>, dim3(row_grid(R)), dim3(ROW_THREADS), 0, s, h, hdot, w, wdot, b, bdot, lens, T, R, out)));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -611,7 +618,7 @@ extern "C" int mtts_rowdot_bwd(const float* dout, const float* ddout, const floa
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(dout && h && w && dh && R > 0, "rowdot_bwd: bad args");
   MTTS_REQUIRE(!ddout || hdot, "rowdot_bwd: tangent mode needs hdot");
-  DISPATCH_NV(C, (rowdot_bwd_kernel<NV><<<row_grid(R), ROW_THREADS, 0, s>>>(dout, ddout, h, hdot, w, wdot, lens, T, R, dh, dw, db)));
+  DISPATCH_NV(C, MTTS_CHECK_CUDA(mtts_launch(rowdot_bwd_kernel<NV>, dim3(row_grid(R)), dim3(ROW_THREADS), 0, s, dout, ddout, h, hdot, w, wdot, lens, T, R, dh, dw, db)));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -626,10 +633,10 @@ extern "C" int mtts_softmax(int mode, const float* A, const float* Bm, const voi
   const long long rows = static_cast<long long>(nz) * Lq;
   MTTS_REQUIRE(ld <= 1024, "softmax: rows longer than 1024 keys are not supported (max_seq_len = 1000)");
 #define SM_LAUNCH(NPL)                                                                                                          \
-  softmax_kernel<NPL><<<row_grid(rows), ROW_THREADS, 0, s>>>(mode, A, Bm, static_cast<const bf16*>(p_hi),                        \
+  MTTS_CHECK_CUDA(mtts_launch(softmax_kernel<NPL>, dim3(row_grid(rows)), dim3(ROW_THREADS), 0, s, mode, A, Bm, static_cast<const bf16*>(p_hi),                        \
                                                               static_cast<const bf16*>(p_lo), static_cast<const bf16*>(pd_hi), \
                                                               static_cast<const bf16*>(pd_lo), klens, H, Lq, Lk, ld, rows,      \
-                                                              static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo))
+                                                              static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo)))
   if (ld <= 128) SM_LAUNCH(4);
   else if (ld <= 256) SM_LAUNCH(8);
   else if (ld <= 512) SM_LAUNCH(16);

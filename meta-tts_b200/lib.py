@@ -78,6 +78,7 @@ def load() -> C.CDLL:
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES: dict[str, list] = {
     "mtts_check_device": [],
+    "mtts_set_pdl": [_i],
     "mtts_gemm": [C.POINTER(GemmDesc), _vp],
     "mtts_length_regulate_index": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "mtts_length_regulate_fwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
