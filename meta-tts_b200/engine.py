@@ -349,6 +349,12 @@ class Gemm:
 
     def __init__(self, be):
         self.be = be
+        self.split_override = None      # engine.hvp() sets 1: the lr-scaled curvature terms run single-pass bf16
+
+    def _gemm(self, *a, **kw):
+        if self.split_override is not None:
+            kw["split"] = self.split_override
+        self.be.gemm(*a, **kw)
 
     # y[b,t,:] = sum_j x[b,t+j-p,:] W_j^T (+bias) [+ sum_j x2[b,t+j-p,:] W2_j^T] ; W: [k, N, Cin]
     def conv_fwd(self, x: Act, w: Wt, bias, out_f32, out_hi, out_lo, relu=False, gate=None, add_c=False,
@@ -366,7 +372,7 @@ class Gemm:
             if x2 is not None:
                 a.hi2, a.lo2 = x2.hi, x2.lo
             bn, pair, _ = _pick_cfg((x.B * x.T + 127) // 128, 1, N, 0, False)
-            self.be.gemm(a, wop, x.B * x.T, N, Cin, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=N, bias=bias,
+            self._gemm(a, wop, x.B * x.T, N, Cin, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=N, bias=bias,
                          gate=gate, flags=flags, block_n=bn, pair=pair)
         else:
             a = Opnd(x.hi, x.lo, L.MAJOR_K, (Cin, x.T, x.B), (1, Cin, x.T * Cin), src2=L.SRC_Z0,
@@ -374,7 +380,7 @@ class Gemm:
             if x2 is not None:
                 a.hi2, a.lo2 = x2.hi, x2.lo
             bn, pair, _ = _pick_cfg((x.T + 127) // 128, x.B, N, 0, False)
-            self.be.gemm(a, wop, x.T, N, Cin, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=N, c_sz0=x.T * N, bias=bias,
+            self._gemm(a, wop, x.T, N, Cin, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=N, c_sz0=x.T * N, bias=bias,
                          gate=gate, flags=flags, ntaps=k, nz0=x.B, block_n=bn, pair=pair)
 
     # dx[b,t,:] = sum_j dy[b,t-j+p,:] W_j  [+ sum_j dy2[b,t-j+p,:] W2_j]
@@ -399,14 +405,14 @@ class Gemm:
             a = Opnd(dy.hi, dy.lo, L.MAJOR_K, (N, dy.B * dy.T), (1, N))
             if dy2 is not None:
                 a.hi2, a.lo2 = dy2.hi, dy2.lo
-            self.be.gemm(a, wop, dy.B * dy.T, Cin, N, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=Cin, gate=gate,
+            self._gemm(a, wop, dy.B * dy.T, Cin, N, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=Cin, gate=gate,
                          flags=flags, block_n=bn, pair=pair, ksplit=ks)
         else:
             a = Opnd(dy.hi, dy.lo, L.MAJOR_K, (N, dy.T, dy.B), (1, N, dy.T * N), src2=L.SRC_Z0,
                      shift_src=L.SRC_TAP, shift_base=p, shift_step=-1)
             if dy2 is not None:
                 a.hi2, a.lo2 = dy2.hi, dy2.lo
-            self.be.gemm(a, wop, dy.T, Cin, N, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=Cin, c_sz0=dy.T * Cin,
+            self._gemm(a, wop, dy.T, Cin, N, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=Cin, c_sz0=dy.T * Cin,
                          gate=gate, flags=flags, ntaps=k, nz0=dy.B, block_n=bn, pair=pair, ksplit=ks)
 
     # dW_j[n,c] += sum_{b,t} dy[b,t,n] x[b,t+j-p,c]  [+ dy2 (x) x2]
@@ -425,7 +431,7 @@ class Gemm:
             b = Opnd(x.hi, x.lo, L.MAJOR_MN, (Cin, R), (1, Cin))
             if dy2 is not None:
                 a.hi2, a.lo2, b.hi2, b.lo2 = dy2.hi, dy2.lo, x2.hi, x2.lo
-            self.be.gemm(a, b, N, Cin, R, c_f32=dw_f32, ldc=Cin, flags=L.EPI_ACCUM, alpha=scale, ksplit=ks, block_n=bn,
+            self._gemm(a, b, N, Cin, R, c_f32=dw_f32, ldc=Cin, flags=L.EPI_ACCUM, alpha=scale, ksplit=ks, block_n=bn,
                          pair=pair)
         else:
             a = Opnd(dy.hi, dy.lo, L.MAJOR_MN, (N, dy.T, dy.B), (1, N, dy.T * N), src2=L.SRC_KB)
@@ -433,7 +439,7 @@ class Gemm:
                      shift_src=L.SRC_Z0, shift_base=-p, shift_step=1)
             if dy2 is not None:
                 a.hi2, a.lo2, b.hi2, b.lo2 = dy2.hi, dy2.lo, x2.hi, x2.lo
-            self.be.gemm(a, b, N, Cin, dy.T, c_f32=dw_f32, ldc=Cin, c_sz0=N * Cin, flags=L.EPI_ACCUM, alpha=scale,
+            self._gemm(a, b, N, Cin, dy.T, c_f32=dw_f32, ldc=Cin, c_sz0=N * Cin, flags=L.EPI_ACCUM, alpha=scale,
                          nkb=dy.B, nz0=k, ksplit=ks, block_n=bn, pair=pair)
 
     # C[b,h] = alpha * ( op(A) op(B)^T [+ op(A2) op(B2)^T] )   (op = identity or transpose, see BMat)
@@ -451,7 +457,7 @@ class Gemm:
             assert (A2.off, A2.sr, A2.sh, A2.sb) == (A.off, A.sr, A.sh, A.sb) and (B2.off, B2.sr, B2.sh, B2.sb) == (Bm.off, Bm.sr, Bm.sh, Bm.sb)
             a.hi2, a.lo2, b.hi2, b.lo2 = A2.hi, A2.lo, B2.hi, B2.lo
         bn, pair, _ = _pick_cfg((M + 127) // 128, nb * nh, N, 0, False)
-        self.be.gemm(a, b, M, N, K, c_f32=Cm.f32, c_hi=Cm.hi, c_lo=Cm.lo, ldc=Cm.sr, c_off=Cm.off, c_sz0=Cm.sh,
+        self._gemm(a, b, M, N, K, c_f32=Cm.f32, c_hi=Cm.hi, c_lo=Cm.lo, ldc=Cm.sr, c_off=Cm.off, c_sz0=Cm.sh,
                      c_sz1=Cm.sb, alpha=alpha, flags=(L.EPI_ADD_C if add_c else 0), nz0=nh, nz1=nb,
                      block_n=bn, pair=pair)
 
@@ -476,6 +482,11 @@ class FS2Engine:
         self.d_inner = tr["conv_filter_size"]
         self.nbins = cfg["variance_embedding"]["n_bins"]
         self.scr = Tape(be, self.split)        # shared scratch (never read across passes)
+        # Precision of the Hessian-vector pass.  Its result enters the outer gradient multiplied by the inner lr
+        # (1e-3); running it single-pass bf16 (hvp_split = 1, operand hi halves only) moves individual gradient
+        # tensors by up to ~3e-3 relative (CPU emulation, tests/test_engine_cpu.py), so the default keeps the
+        # engine's precision and the faster setting is opt-in.
+        self.hvp_split = self.split
         assert self.d % 128 == 0
 
     def new_tape(self) -> Tape:
@@ -1033,6 +1044,13 @@ class FS2Engine:
     # (Pd is non-zero on adapted parameters only; encoder = non-adapted => zero forward tangent.)
     # ---------------------------------------------------------------------------------------------
     def hvp(self, P: ParamSet, Pd: ParamSet, HV: ParamSet, bt: Batch, tp: Tape, tt: Tape, loss_scale: float = 1.0):
+        self.g.split_override = self.hvp_split if self.hvp_split != self.split else None
+        try:
+            self._hvp(P, Pd, HV, bt, tp, tt, loss_scale)
+        finally:
+            self.g.split_override = None
+
+    def _hvp(self, P: ParamSet, Pd: ParamSet, HV: ParamSet, bt: Batch, tp: Tape, tt: Tape, loss_scale: float = 1.0):
         be, g, scr, d = self.be, self.g, self.scr, self.d
         B, Lq, T = bt.B, bt.L, bt.T
         R = B * T
