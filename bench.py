@@ -166,21 +166,43 @@ class ClockSampler:
 # GEMM roofline instrumentation (eager pass, CUDA events around every mtts_gemm launch)
 # ------------------------------------------------------------------------------------------------
 def instrument_gemm(be):
-    """Wrap be.gemm: record (algorithmic flops, start event, end event) per launch."""
+    """Wrap be.gemm: record every launch (arguments + algorithmic FLOPs) of one eager outer step."""
     rec = []
     orig = be.gemm
 
     def wrapped(a, b, M, N, K, **kw):
         nz = kw.get("nz0", 1) * kw.get("nz1", 1)
-        flops = 2.0 * M * N * K * kw.get("ntaps", 1) * kw.get("nkb", 1) * nz
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        terms = 2 if getattr(a, "hi2", None) is not None else 1
+        flops = 2.0 * M * N * K * kw.get("ntaps", 1) * kw.get("nkb", 1) * nz * terms
+        bn, pair = kw.get("block_n", 0), bool(kw.get("pair", False))
+        variant = f"mtts_gemm_{'pair_' if pair else ''}kernel<{bn},{kw.get('split', be.split)}>"
+        rec.append({"variant": variant, "flops": flops, "call": (a, b, M, N, K, dict(kw)),
+                    "shape": (M, N, K, kw.get("ntaps", 1), kw.get("nkb", 1), nz, terms)})
         orig(a, b, M, N, K, **kw)
-        e1.record()
-        rec.append((flops, e0, e1, (M, N, K, kw.get("ntaps", 1), kw.get("nkb", 1), nz)))
 
     be.gemm = wrapped
     return rec, orig
+
+
+def time_variant(orig_gemm, calls, reps=5):
+    """CUDA-event time of one kernel variant's launches of a step, replayed back-to-back from a CUDA graph
+    (same descriptors, same resident operands) on the current stream."""
+    for c in calls[:2]:
+        orig_gemm(*c["call"][:5], **c["call"][5])
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for c in calls:
+            orig_gemm(*c["call"][:5], **c["call"][5])
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps          # ms for all `calls`
 
 
 def load_peaks():
@@ -327,43 +349,56 @@ def run_own_arm(args):
     e2e_value = world * frames_per_task() / (e2e_ms * 1e-3)
     line = None
     if rank == 0:
-        # ---------- (3) roofline of the GEMM kernel: instrumented eager pass ----------
+        # ---------- (3) roofline of the dominant kernel: record one eager step's GEMM launches, then time each
+        #                kernel variant's launches back-to-back from a CUDA graph with CUDA events ----------
         rec, orig = instrument_gemm(sysm.be)
         sysm.use_cuda_graph = False
         sysm.training_step(batches[0], 0)
         torch.cuda.synchronize()
         rec.clear()
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
         sysm.training_step(batches[1], 1)
-        t1.record()
         torch.cuda.synchronize()
         sysm.be.gemm = orig
         sysm.use_cuda_graph = True
-        sysm.be.zero_(sysm.maml.g_outer)
-        gemm_ms = sum(a.elapsed_time(b) for _, a, b, _ in rec)
-        gemm_flops = sum(f for f, _, _, _ in rec)
-        by_shape = {}
-        for f, a, b, shp in rec:
-            d = by_shape.setdefault(shp, [0.0, 0.0, 0])
-            d[0] += f
-            d[1] += a.elapsed_time(b)
-            d[2] += 1
-        top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:5]
+        by_var = {}
+        for r in rec:
+            by_var.setdefault(r["variant"], []).append(r)
         peaks = load_peaks()
-        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
         mma_mult = 3 if split == 3 else 1
-        roofline = {"bound": "tensor", "kernel": "mtts_gemm_kernel (tcgen05 + TMA; all dense contractions of the step)",
-                    "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                    "traffic": None, "peak_source": peaks["source"],
-                    "launches": len(rec), "avg_launch_us": 1e3 * gemm_ms / max(len(rec), 1),
-                    "gemm_share_of_eager_step": gemm_ms / t0.elapsed_time(t1),
-                    "algorithmic_gflop_per_step": gemm_flops / 1e9,
-                    "tensor_pipe_work_multiplier": mma_mult,
-                    "frac_of_issued_mma": mma_mult * achieved / peaks["bf16_tflops"],
-                    "top_shapes_MNK_taps_kb_z": [{"shape": list(k), "launches": v[2], "ms": v[1], "tflops": v[0] / (v[1] * 1e-3) / 1e12}
-                                                 for k, v in top]}
+        vstats = []
+        for v, calls in by_var.items():
+            ms_v = time_variant(orig, calls)
+            fl = sum(c["flops"] for c in calls)
+            vstats.append({"kernel": v, "launches": len(calls), "ms_per_step": ms_v, "algorithmic_gflop": fl / 1e9,
+                           "tflops": fl / (ms_v * 1e-3) / 1e12})
+        sysm.be.zero_(sysm.maml.g_outer)
+        vstats.sort(key=lambda d: -d["ms_per_step"])
+        dom = vstats[0]
+        gemm_ms = sum(v["ms_per_step"] for v in vstats)
+        gemm_flops = sum(v["algorithmic_gflop"] for v in vstats) * 1e9
+        by_shape = {}
+        for c in by_var[dom["kernel"]]:
+            d = by_shape.setdefault(c["shape"], [0.0, 0])
+            d[0] += c["flops"]
+            d[1] += 1
+        top = sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:5]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom["kernel"])
+        roofline = {"bound": "tensor", "kernel": dom["kernel"] + " (tcgen05 2-CTA + TMA GEMM: conv k=9/5/3/1, QKV/out-proj, attention products "
+                                                             "and their dgrad/wgrad/tangent forms)",
+                    "achieved": dom["tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": dom["tflops"] / peaks["bf16_tflops"],
+                    "traffic": traffic, "peak_source": peaks["peak_source"] if "peak_source" in peaks else peaks["source"],
+                    "how": "algorithmic FLOPs (2*M*N*K*taps*kb*z*terms) of this kernel's launches in one outer step / CUDA-event time of "
+                           "those launches replayed back-to-back from a CUDA graph",
+                    "launches_per_step": dom["launches"], "avg_launch_us": 1e3 * dom["ms_per_step"] / dom["launches"],
+                    "share_of_step": dom["ms_per_step"] / ms_per_step,
+                    "tensor_pipe_work_multiplier": mma_mult, "frac_of_issued_mma": mma_mult * dom["tflops"] / peaks["bf16_tflops"],
+                    "top_shapes_MNK_taps_kb_z_terms": [{"shape": list(k), "launches": v[1], "gflop": v[0] / 1e9} for k, v in top],
+                    "all_gemm_kernels": vstats,
+                    "all_gemm": {"ms_per_step": gemm_ms, "algorithmic_gflop_per_step": gemm_flops / 1e9,
+                                 "tflops": gemm_flops / (gemm_ms * 1e-3) / 1e12, "share_of_step": gemm_ms / ms_per_step}}
         # ---------- (4) CPU baseline (bounded sample) ----------
         cb = cpu_arm(steps=2, warmup=1, budget_s=60.0) if not args.no_cpu else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
