@@ -454,8 +454,8 @@ __device__ __forceinline__ void st_split(bf16* hi, bf16* lo, long long i, float 
 // mode 2: ddS = Pd*(dP - d) + P*(ddP - dd),  d = sum(P*dP), dd = sum(Pd*dP + P*ddP)
 //                                                         in: P, Pd (hi/lo), A = dP, Bm = ddP (f32)
 // Single pass over HBM: the row (<= 32*NPL keys) lives in registers, one read + one write per element.
-template <int NPL>
-__global__ void __launch_bounds__(ROW_THREADS) softmax_kernel(int mode, const float* __restrict__ A, const float* __restrict__ Bm,
+template <int NPL, int MODE>     // MODE is a template parameter so that mode 0/1 do not pay mode 2's register footprint
+__global__ void __launch_bounds__(ROW_THREADS) softmax_kernel(int /*mode*/, const float* __restrict__ A, const float* __restrict__ Bm,
                                                               const bf16* __restrict__ p_hi, const bf16* __restrict__ p_lo,
                                                               const bf16* __restrict__ pd_hi, const bf16* __restrict__ pd_lo,
                                                               const int64_t* __restrict__ klens, int H, int Lq, int Lk, int ld,
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(ROW_THREADS) softmax_kernel(int mode, const fl
     const int kl = klens ? static_cast<int>(min(static_cast<long long>(Lk), static_cast<long long>(klens[b]))) : Lk;
     const long long base = r * ld;
     float v[NPL];
-    if (mode == 0) {
+    if (MODE == 0) {
       float m = -INFINITY;
 #pragma unroll
       for (int i = 0; i < NPL; ++i) {
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(ROW_THREADS) softmax_kernel(int mode, const fl
         const int j = lane + 32 * i;
         if (j < ld) st_split(o_hi, o_lo, base + j, v[i] * inv);
       }
-    } else if (mode == 1) {
+    } else if (MODE == 1) {
       float a[NPL];
       float d = 0.f;
 #pragma unroll
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(ROW_THREADS) softmax_kernel(int mode, const fl
         if (j < ld) st_split(o_hi, o_lo, base + j, v[i] * (a[i] - d));
       }
     } else {
-      float a[NPL], pd[NPL], bb[NPL];
+      float pd[NPL], u[NPL];           // u = pd*a + p*b  =>  out = u - pd*d - p*dd  (3 row arrays instead of 4)
       float d = 0.f, dd = 0.f;
 #pragma unroll
       for (int i = 0; i < NPL; ++i) {
@@ -520,20 +520,20 @@ __global__ void __launch_bounds__(ROW_THREADS) softmax_kernel(int mode, const fl
         if (j < kl) {
           v[i] = ld_split(p_hi, p_lo, base + j);
           pd[i] = ld_split(pd_hi, pd_lo, base + j);
-          a[i] = A[base + j];
-          bb[i] = Bm[base + j];
+          const float a = A[base + j], bb = Bm[base + j];
+          d += v[i] * a;
+          u[i] = pd[i] * a + v[i] * bb;
         } else {
-          v[i] = pd[i] = a[i] = bb[i] = 0.f;
+          v[i] = pd[i] = u[i] = 0.f;
         }
-        d += v[i] * a[i];
-        dd += pd[i] * a[i] + v[i] * bb[i];
+        dd += u[i];
       }
       d = warp_sum(d);
       dd = warp_sum(dd);
 #pragma unroll
       for (int i = 0; i < NPL; ++i) {
         const int j = lane + 32 * i;
-        if (j < ld) st_split(o_hi, o_lo, base + j, pd[i] * (a[i] - d) + v[i] * (bb[i] - dd));
+        if (j < ld) st_split(o_hi, o_lo, base + j, u[i] - pd[i] * d - v[i] * dd);
       }
     }
   }
@@ -632,16 +632,23 @@ extern "C" int mtts_softmax(int mode, const float* A, const float* Bm, const voi
   MTTS_REQUIRE(mode != 2 || (pd_hi && Bm), "softmax: mode 2 needs Pdot and ddP");
   const long long rows = static_cast<long long>(nz) * Lq;
   MTTS_REQUIRE(ld <= 1024, "softmax: rows longer than 1024 keys are not supported (max_seq_len = 1000)");
-#define SM_LAUNCH(NPL)                                                                                                          \
-  MTTS_CHECK_CUDA(mtts_launch(softmax_kernel<NPL>, dim3(row_grid(rows)), dim3(ROW_THREADS), 0, s, mode, A, Bm, static_cast<const bf16*>(p_hi),                        \
+#define SM_LAUNCH_M(NPL, MODE)                                                                                                  \
+  MTTS_CHECK_CUDA(mtts_launch(softmax_kernel<NPL, MODE>, dim3(row_grid(rows)), dim3(ROW_THREADS), 0, s, mode, A, Bm, static_cast<const bf16*>(p_hi),                  \
                                                               static_cast<const bf16*>(p_lo), static_cast<const bf16*>(pd_hi), \
                                                               static_cast<const bf16*>(pd_lo), klens, H, Lq, Lk, ld, rows,      \
                                                               static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo)))
+#define SM_LAUNCH(NPL)                   \
+  do {                                   \
+    if (mode == 0) SM_LAUNCH_M(NPL, 0);  \
+    else if (mode == 1) SM_LAUNCH_M(NPL, 1); \
+    else SM_LAUNCH_M(NPL, 2);            \
+  } while (0)
   if (ld <= 128) SM_LAUNCH(4);
   else if (ld <= 256) SM_LAUNCH(8);
   else if (ld <= 512) SM_LAUNCH(16);
   else SM_LAUNCH(32);
 #undef SM_LAUNCH
+#undef SM_LAUNCH_M
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }

@@ -299,11 +299,6 @@ class BMat:
     f32: Optional[torch.Tensor] = None
 
 
-def _wgrad_ksplit(tiles: int, iters: int) -> int:
-    ks = max(1, 148 // max(tiles, 1))
-    return max(1, min(ks, iters // 2 if iters >= 2 else 1, 32))
-
-
 USE_PAIR = True        # 2-CTA (cta_group::2) tiles; set False to fall back to the 1-CTA kernel everywhere
 
 
