@@ -8,10 +8,10 @@
 // products QK^T, PV and their backward / tangent forms.  See include/mtts.h for the reference
 // call sites (SubLayers.py:39-41,54,88; Modules.py:16,23; modules.py:291-296; Layers.py:129-137).
 //
-// Layout of one CTA (192 threads, 1 CTA = 1 output tile of 128 x BN, persistent over its k-range):
+// Layout of one CTA (320 threads, 1 CTA = 1 output tile of 128 x BN over its k-range):
 //   warp 0      TMA producer  (one elected lane)        global -> smem ring (128B-swizzled tiles)
 //   warp 1      MMA issuer    (one elected lane)        tcgen05.mma  smem x smem -> TMEM (fp32)
-//   warps 2..5  epilogue      (128 threads = 128 rows)  tcgen05.ld TMEM -> regs -> bias/act -> global
+//   warps 2..9  epilogue      (2 warps per 32-lane TMEM quarter, each half of the columns)  tcgen05.ld -> regs -> global
 // Pipelines: full[s]/empty[s] mbarriers for the smem ring, one tmem_full mbarrier MMA -> epilogue.
 //
 // bf16x3 mode (SPLIT == 3): operands arrive as hi/lo bf16 pairs; each k-step issues
@@ -24,7 +24,7 @@ namespace {
 constexpr int BM = 128;        // UMMA_M (cta_group::1)
 constexpr int BK = 64;         // bf16 elements per k-block = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
 constexpr int MAX_SMEM = 227 * 1024;
 
 struct OperandParams {
@@ -71,7 +71,7 @@ __device__ __forceinline__ int pick_src(int src, int z0, int z1, int tap, int kb
 // TMEM accumulator tile (128 lanes x BN columns) -> alpha, bias, +C, ReLU, gate -> global (fp32 / bf16 hi,lo / red.add)
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_base, int q, int lane, int m0, int n0, int z0,
-                                              int z1) {
+                                              int z1, int c_begin, int c_end) {
   const int row = m0 + q * 32 + lane;
   const bool row_ok = row < p.M;
   const int64_t c_off = int64_t(z0) * p.c_sz0 + int64_t(z1) * p.c_sz1 + int64_t(row) * p.ldc;
@@ -79,7 +79,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
   const bool vec_ok = ((p.ldc & 7) == 0) && ((p.c_sz0 & 7) == 0) && ((p.c_sz1 & 7) == 0);
   const float bias_row = (bias && (p.flags & MTTS_EPI_BIAS_ROW) && row_ok) ? bias[row] : 0.f;
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     __syncwarp();                       // tcgen05.ld is .sync.aligned: reconverge after guards
     uint32_t r[32];
     tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), r);
@@ -365,7 +365,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
     if (n_iters > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
-      epilogue_tile<BN>(p, tmem_base, q, lane, m0, n0, z0, z1);
+      // two warps share a TMEM lane quarter (warp % 4) and split the BN columns between them
+      constexpr int CH = BN / 32;
+      const int half = (warp - 2) >> 2;
+      const int c_begin = CH >= 2 ? half * (CH / 2) : 0;
+      const int c_end = CH >= 2 ? c_begin + CH / 2 : (half == 0 ? CH : 0);
+      epilogue_tile<BN>(p, tmem_base, q, lane, m0, n0, z0, z1, c_begin, c_end);
     }
   }
 
@@ -560,7 +565,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mtts
     if (n_iters > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
-      epilogue_tile<BN>(p, tmem_base, q, lane, m0, n0, z0, z1);
+      // two warps share a TMEM lane quarter (warp % 4) and split the BN columns between them
+      constexpr int CH = BN / 32;
+      const int half = (warp - 2) >> 2;
+      const int c_begin = CH >= 2 ? half * (CH / 2) : 0;
+      const int c_end = CH >= 2 ? c_begin + CH / 2 : (half == 0 ? CH : 0);
+      epilogue_tile<BN>(p, tmem_base, q, lane, m0, n0, z0, z1, c_begin, c_end);
     }
   }
 
