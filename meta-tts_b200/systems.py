@@ -70,21 +70,54 @@ class _StaticBatch:
         self.h2d_bytes = off
 
     def upload(self, b12, spk_ids=None) -> None:
-        (_, _, spk, texts, src_lens, _, mels, mel_lens, _, pitches, energies, durs) = b12
-        src = {"spk_ids": spk if spk_ids is None else spk_ids, "texts": texts, "src_lens": src_lens, "mels": mels,
-               "mel_lens": mel_lens, "pitches": pitches, "energies": energies, "durations": durs}
         k = self.slot
         self.slot = (k + 1) % self.RING
         if self.events[k] is not None:
             self.events[k].synchronize()                 # the H2D that last used this staging slot has completed
-        for f, _ in self.FIELDS:
-            dst = self.host[k][f]
-            dst.copy_(torch.as_tensor(src[f]).reshape(dst.shape))      # dtype conversion + gather into pinned staging
+        h = self.host[k]
+        # 12-tuple positions (lightning/collate.py:47-60): 2 speaker, 3 texts, 4 text_lens, 6 mels, 7 mel_lens, 9 pitch,
+        # 10 energy, 11 durations
+        for f, i in (("texts", 3), ("src_lens", 4), ("mels", 6), ("mel_lens", 7), ("pitches", 9), ("energies", 10), ("durations", 11)):
+            src = b12[i]
+            dst = h[f]
+            dst.copy_(src if torch.is_tensor(src) else torch.as_tensor(src))      # dtype conversion + gather into pinned staging
+        spk = b12[2] if spk_ids is None else spk_ids
+        h["spk_ids"].copy_(spk if torch.is_tensor(spk) else torch.as_tensor(spk))
         self.dev_buf.copy_(self.host_bufs[k], non_blocking=True)       # ONE H2D per batch
         if self.dev_buf.is_cuda:
-            ev = torch.cuda.Event()
+            ev = self.events[k] or torch.cuda.Event()
             ev.record()
             self.events[k] = ev
+
+
+class _Predictions(tuple):
+    """The reference's 10-tuple of predictions (base_adaptor.py:91-95).  Device tensors; the two boolean masks
+    (entries 6, 7; True = padding) are built on first access so that a training loop that never reads them
+    launches nothing for them."""
+
+    def __new__(cls, out, dev, Lq, T):
+        self = super().__new__(cls, (out["mel"], out["postnet"], out["pitch"], out["energy"], out["logd"], dev.durations,
+                                     None, None, dev.src_lens, out["mel_len"]))
+        self._dev, self._Lq, self._T, self._masks = dev, Lq, T, None
+        return self
+
+    def _get_masks(self):
+        if self._masks is None:
+            d = self._dev
+            ar_l = torch.arange(self._Lq, device=d.src_lens.device)[None, :]
+            ar_t = torch.arange(self._T, device=d.src_lens.device)[None, :]
+            self._masks = (ar_l >= d.src_lens[:, None], ar_t >= d.mel_lens[:, None])
+        return self._masks
+
+    def __getitem__(self, i):
+        if isinstance(i, int) and i in (6, 7, -4, -3):
+            return self._get_masks()[0 if i in (6, -4) else 1]
+        if isinstance(i, slice):
+            return tuple(self[j] for j in range(*i.indices(10)))
+        return super().__getitem__(i)
+
+    def __iter__(self):
+        return iter([self[j] for j in range(10)])
 
 
 class LazyLosses:
@@ -263,13 +296,7 @@ def meta_learn(self, batch, batch_idx, train: bool = True):
         ev.record()
     losses = LazyLosses(hbuf, ev)
     dev = _ent_dev(self, sup12, qry12, steps, first_order)
-    Lq, T = int(qry12[5]), int(qry12[8])
-    ar = self.__dict__.setdefault("_arange", {})
-    if (Lq, T) not in ar:
-        ar[(Lq, T)] = (torch.arange(Lq, device=self.device)[None, :], torch.arange(T, device=self.device)[None, :])
-    ar_l, ar_t = ar[(Lq, T)]
-    preds = (out["mel"], out["postnet"], out["pitch"], out["energy"], out["logd"], dev.durations,
-             ar_l >= dev.src_lens[:, None], ar_t >= dev.mel_lens[:, None], dev.src_lens, out["mel_len"])
+    preds = _Predictions(out, dev, int(qry12[5]), int(qry12[8]))
     return losses, preds
 
 
