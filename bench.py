@@ -40,13 +40,14 @@ METRIC = "mel-frames/sec per outer meta-step"
 UNIT = "mel-frames/s"
 
 
-def workload_config(n_gpus, split):
+def workload_config(n_gpus, split, dropout=True):
     return {
         "workload": f"second-order MAML K={K_INNER}, 1 task/GPU, {SHOTS}-shot support + {QUERIES} queries, "
                     f"{L_PHON} phonemes -> {T_MEL} frames (BASELINE configs[1])",
         "tasks_per_step": n_gpus, "shots": SHOTS, "queries": QUERIES, "phonemes": L_PHON, "frames": T_MEL,
         "inner_steps": K_INNER, "order": "second", "precision": "bf16x3 hi/lo split (fp32-grade)" if split == 3 else "bf16",
-        "dropout": "identity (parity mode; the oracle neutralises it too)", "parallelism": f"dp{n_gpus} (1 task per GPU)",
+        "dropout": ("train mode, ACTIVE (enc/dec 0.2, variance predictors 0.5, postnet 0.5): counter-hash masks fused into the "
+                    "LN/BN kernels, fresh per step" if dropout else "identity (--no-dropout)"), "parallelism": f"dp{n_gpus} (1 task per GPU)",
         "l2": "per-step working set (activation tapes ~GBs + 280 MB weights) >> 126 MB L2: no flush needed",
     }
 
@@ -86,7 +87,7 @@ def cpu_arm(steps, warmup, shots=SHOTS, queries=QUERIES, budget_s=150.0):
     for i in range(total):
         sup, qry = O.synth_task(task=i, shots=sample_shots, queries=sample_q, L=L_PHON, T=T_MEL)
         t0 = time.perf_counter()
-        O.maml_task_step(P, cfg, sup, qry, K_INNER, 0.001, first_order=False)
+        O.maml_task_step(P, cfg, sup, qry, K_INNER, 0.001, first_order=False, drop_seed="torch")
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append((dt, (sample_shots + sample_q) * T_MEL))
@@ -98,7 +99,7 @@ def cpu_arm(steps, warmup, shots=SHOTS, queries=QUERIES, budget_s=150.0):
     secs = sum(t for t, _ in times)
     return {"value": frames / secs, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{len(times)} timed task-step(s) of the same workload (last sample {sample_shots}+{sample_q} utterances), "
-                      f"oracle/fs2_oracle.maml_task_step, fp32 autograd, dropout identity",
+                      f"oracle/fs2_oracle.maml_task_step, fp32 autograd, dropout active (torch's own)",
             "ms_per_step": 1e3 * secs / max(len(times), 1)}
 
 
@@ -238,7 +239,8 @@ def run_own_arm(args):
     algo = copy.deepcopy(DEFAULT_ALGORITHM_CONFIG)
     algo["adapt"]["train"]["steps"] = K_INNER
     algo["adapt"]["test"]["steps"] = K_INNER
-    sysm = MetaSystem(None, DEFAULT_MODEL_CONFIG, DEFAULT_TRAIN_CONFIG, algo, n_speaker=16, device=dev, split=split)
+    sysm = MetaSystem(None, DEFAULT_MODEL_CONFIG, DEFAULT_TRAIN_CONFIG, algo, n_speaker=16, device=dev, split=split,
+                      dropout=not args.no_dropout, seed=rank)
     P = O.init_params(seed=0)
     sysm.load_state_dict({k: v.detach() for k, v in P.items()})
     n_steps_total = args.warmup + args.steps
@@ -413,7 +415,7 @@ def run_own_arm(args):
         cb = cpu_arm(steps=2, warmup=1, budget_s=60.0) if not args.no_cpu else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16x3" if split == 3 else "bf16", "data": "synthetic", "config": workload_config(world, split),
+                "dtype": "bf16x3" if split == 3 else "bf16", "data": "synthetic", "config": workload_config(world, split, not args.no_dropout),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": sysm.h2d_bytes_per_step,
                         "d2h_bytes_per_step": sysm.d2h_bytes_per_step, "api": "MetaSystem.training_step(host batch) + optimizer_step; losses read back on the host one step later",
@@ -439,6 +441,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--split", type=int, default=3, choices=[1, 3], help="3: bf16x3 (parity-grade, default); 1: plain bf16")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-dropout", action="store_true", help="identity dropout (diagnostic; the default runs train-mode dropout)")
     ap.add_argument("--kineto", action="store_true", help="print a per-kernel device-time table of real graph replays")
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager (non-graph) outer step between cudaProfilerStart/Stop and exit (for ncu "

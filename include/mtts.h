@@ -133,23 +133,37 @@ int mtts_length_regulate_bwd(const float* dy /* [B,T,C] */, const int64_t* dur_i
  * together they give exact Hessian-vector products for second-order MAML without autograd.
  * ------------------------------------------------------------------------------------------ */
 
+/* Dropout (train mode): every site is (thr, seed, scale): element idx = row*C + col is KEPT iff
+ * (mix32(idx + seed_eff*0x9E3779B9) >> 8) >= thr with thr = floor(p*2^24) and
+ * seed_eff = seed + (drop_salt ? *drop_salt : 0)*0x632BE5AB (uint32 arithmetic); kept values are multiplied by
+ * scale = 1/(1-p); thr = 0 disables the site.  `seed` is a launch-time scalar naming the site and the pass;
+ * `drop_salt` is a DEVICE word the host refreshes every step, so a captured CUDA graph draws new masks per replay.  mix32 is the murmur3 finaliser — the same integer hash is
+ * evaluated on the host by the oracle (oracle/fs2_oracle.py: drop_mask), so parity holds WITH dropout.
+ * LN kernels have two sites: "pre" on the branch input y before the residual add (nn.Dropout in
+ * SubLayers.py:54,90) and "post" on the LN output (modules.py:223,235); BN kernels have one site on the
+ * (tanh'd) output (F.dropout(..., 0.5) in Layers.py:133-134). */
+
 /* LayerNorm(y + res) then pad-row zeroing.  nn.LayerNorm SubLayers.py:55,91; modules.py:221,233;
  * masked_fill Layers.py:25,28.  z_out = y + res (saved for backward), stats[r] = (mean, rstd). */
 int mtts_ln_fwd(const float* y, const float* res, const float* gamma, const float* beta, const int64_t* lens, int T,
                 int64_t R, int C, float eps, float* z_out, float* stats, float* out, void* out_hi, void* out_lo,
+                uint32_t pre_thr, uint32_t pre_seed, float pre_scale, uint32_t post_thr, uint32_t post_seed, float post_scale, const uint32_t* drop_salt,
                 mtts_stream stream);
 /* relu_gate != 0: the LN input z is a ReLU output and the gradient is also passed through the ReLU
  * (dz *= z > 0) — the Conv->ReLU->LayerNorm order of modules.py:209-235.  dgamma/dbeta/dbias are
  * ACCUMULATED (atomicAdd); dbias = column sum of dz (bias of the producing Linear/Conv). */
 int mtts_ln_bwd(const float* dy, const float* z, const float* stats, const float* gamma, const int64_t* lens, int T, int64_t R,
                 int C, int relu_gate, float* dz, void* dz_hi, void* dz_lo, float* dgamma, float* dbeta, float* dbias,
+                uint32_t pre_thr, uint32_t pre_seed, float pre_scale, uint32_t post_thr, uint32_t post_seed, float post_scale, const uint32_t* drop_salt,
                 mtts_stream stream);
 int mtts_ln_tfwd(const float* ydot, const float* resdot, const float* z, const float* stats, const float* gamma,
                  const float* gdot, const float* bdot, const int64_t* lens, int T, int64_t R, int C, float* zdot_out, float* out,
-                 void* out_hi, void* out_lo, mtts_stream stream);
+                 void* out_hi, void* out_lo,
+                uint32_t pre_thr, uint32_t pre_seed, float pre_scale, uint32_t post_thr, uint32_t post_seed, float post_scale, const uint32_t* drop_salt, mtts_stream stream);
 int mtts_ln_tbwd(const float* dy, const float* ddy, const float* z, const float* zdot, const float* stats, const float* gamma,
                  const float* gdot, const int64_t* lens, int T, int64_t R, int C, int relu_gate, float* ddz, void* ddz_hi,
-                 void* ddz_lo, float* ddgamma, float* ddbeta, float* ddbias, mtts_stream stream);
+                 void* ddz_lo, float* ddgamma, float* ddbeta, float* ddbias,
+                uint32_t pre_thr, uint32_t pre_seed, float pre_scale, uint32_t post_thr, uint32_t post_seed, float post_scale, const uint32_t* drop_salt, mtts_stream stream);
 
 /* VariancePredictor head: Linear(C,1) + masked_fill(mask, 0)  (modules.py:240-250).
  * hdot != NULL selects the tangent form  out = hdot.w + h.wdot + bdot. */
@@ -198,15 +212,15 @@ int mtts_colsum(const float* f32, const void* hi, const void* lo, int nb, int64_
  * ------------------------------------------------------------------------------------------ */
 int mtts_bn_fwd(const float* x, const float* gamma, const float* beta, int64_t R, int C, float eps, float momentum, int tanh_flag,
                 float* running_mean, float* running_var, float* ws /*[2C]*/, float* stats /*[2C]*/, float* out, void* hi,
-                void* lo, mtts_stream stream);
+                void* lo, uint32_t drop_thr, uint32_t drop_seed, float drop_scale, const uint32_t* drop_salt, mtts_stream stream);
 int mtts_bn_bwd(const float* dout, const float* o, const float* x, const float* stats, const float* gamma, int64_t R, int C,
-                int tanh_flag, float* ws /*[2C]*/, float* dx, void* hi, void* lo, float* dgamma, float* dbeta, mtts_stream stream);
+                int tanh_flag, float* ws /*[2C]*/, float* dx, void* hi, void* lo, float* dgamma, float* dbeta, uint32_t drop_thr, uint32_t drop_seed, float drop_scale, const uint32_t* drop_salt, mtts_stream stream);
 int mtts_bn_tfwd(const float* xdot, const float* x, const float* stats, const float* gamma, const float* gdot, const float* bdot,
                  const float* o, int64_t R, int C, int tanh_flag, float* ws /*[2C]*/, float* tsums /*[2C]*/, float* odot, void* hi,
-                 void* lo, mtts_stream stream);
+                 void* lo, uint32_t drop_thr, uint32_t drop_seed, float drop_scale, const uint32_t* drop_salt, mtts_stream stream);
 int mtts_bn_tbwd(const float* dout, const float* ddout, const float* o, const float* odot, const float* x, const float* xdot,
                  const float* stats, const float* tsums, const float* gamma, const float* gdot, int64_t R, int C, int tanh_flag,
-                 float* ws /*[4C]*/, float* ddx, void* hi, void* lo, float* ddgamma, float* ddbeta, mtts_stream stream);
+                 float* ws /*[4C]*/, float* ddx, void* hi, void* lo, float* ddgamma, float* ddbeta, uint32_t drop_thr, uint32_t drop_seed, float drop_scale, const uint32_t* drop_salt, mtts_stream stream);
 
 /* ------------------------------------------------------------------------------------------
  * FastSpeech2Loss (lightning/model/loss.py:19-92): masked L1 (mel, postnet mel) + masked MSE

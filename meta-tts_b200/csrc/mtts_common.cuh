@@ -101,6 +101,30 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// ---- dropout: counter-based hash, reproducible on the host (oracle/fs2_oracle.py: drop_mask) ---------------
+// keep(seed, idx) <=> (mix32(idx + seed_eff*0x9E3779B9) >> 8) >= thr,  thr = floor(p * 2^24);  thr == 0 disables.
+// seed_eff = seed + (*salt) * 0x632BE5AB: `seed` identifies the site and the pass (a launch-time scalar, baked into
+// a captured CUDA graph), `salt` is a device word the host refreshes per step so replays draw fresh masks.
+struct DropSite {
+  uint32_t thr;
+  uint32_t seed;
+  float scale;      // 1 / (1 - p)
+  const uint32_t* salt;
+};
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ float drop_factor(const DropSite& d, uint32_t idx) {   // 0 or scale
+  if (d.thr == 0) return 1.f;
+  const uint32_t seed = d.seed + (d.salt ? __ldg(d.salt) : 0u) * 0x632BE5ABu;
+  return ((mix32(idx + seed * 0x9E3779B9u) >> 8) >= d.thr) ? d.scale : 0.f;
+}
+
 // ---- warp / block reductions -----------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

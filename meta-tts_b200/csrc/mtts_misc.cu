@@ -183,6 +183,7 @@ struct BnArgs {
   const float* tsums;    // [2*C] mean(xdot), mean(xdot*xhat)
   const float* ws_in;    // mode 1
   long long R; int C; int tanh_flag; int rows_per_cta;
+  DropSite drop;       // dropout on the (tanh'd) output; the stored output o is the DROPPED one
 };
 
 template <int MODE>
@@ -204,13 +205,15 @@ __global__ void bn_reduce_kernel(BnArgs a, float* __restrict__ ws) {
     if (MODE == 1) { const float d = x - mean; s0 += d * d; continue; }
     const float xh = (x - mean) * rstd;
     if (MODE == 3) { const float xd = a.xdot[i]; s0 += xd; s1 += xd * xh; continue; }
-    float g = a.dout[i];
+    const float df = drop_factor(a.drop, static_cast<uint32_t>(i));      // 0 or scale
+    const float inv = a.drop.thr ? 1.f / a.drop.scale : 1.f;
+    float g = a.dout[i] * df;
     float t = 1.f, o = 0.f;
-    if (a.tanh_flag) { o = a.o[i]; t = 1.f - o * o; g *= t; }
+    if (a.tanh_flag) { o = a.o[i] * inv; t = 1.f - o * o; g *= t; }
     s0 += g; s1 += g * xh;
     if (MODE == 4) {
-      float gd = a.ddout[i] * t;
-      if (a.tanh_flag) gd -= 2.f * o * a.odot[i] * a.dout[i];
+      float gd = a.ddout[i] * df * t;
+      if (a.tanh_flag) gd -= 2.f * o * (a.odot[i] * inv) * (a.dout[i] * df);
       const float xhd = rstd * (a.xdot[i] - a1 - xh * a2);
       s2 += gd; s3 += gd * xh + g * xhd;
     }
@@ -225,7 +228,7 @@ __global__ void bn_fwd_apply_kernel(const float* __restrict__ x, const float* __
                                     const float* __restrict__ gamma, const float* __restrict__ beta, long long R, int C,
                                     float eps, float momentum, int tanh_flag, float* __restrict__ running_mean,
                                     float* __restrict__ running_var, float* __restrict__ stats, float* __restrict__ out,
-                                    bf16* __restrict__ hi, bf16* __restrict__ lo, int rows_per_cta) {
+                                    bf16* __restrict__ hi, bf16* __restrict__ lo, int rows_per_cta, DropSite drop) {
   pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -248,6 +251,7 @@ __global__ void bn_fwd_apply_kernel(const float* __restrict__ x, const float* __
     const long long i = r * C + c;
     float y = (x[i] - mean) * rstd * g + b;
     if (tanh_flag) y = tanhf(y);
+    y *= drop_factor(drop, static_cast<uint32_t>(i));
     if (out) out[i] = y;
     if (hi) {
       bf16 h, l;
@@ -276,8 +280,8 @@ __global__ void bn_bwd_apply_kernel(BnArgs a, const float* __restrict__ ws, cons
   for (long long r = r0; r < r1; ++r) {
     const long long i = r * a.C + c;
     const float xh = (a.x[i] - mean) * rstd;
-    float g = a.dout[i];
-    if (a.tanh_flag) { const float o = a.o[i]; g *= 1.f - o * o; }
+    float g = a.dout[i] * drop_factor(a.drop, static_cast<uint32_t>(i));
+    if (a.tanh_flag) { const float o = a.o[i] * (a.drop.thr ? 1.f / a.drop.scale : 1.f); g *= 1.f - o * o; }
     const float v = k * (g - m1 - xh * m2);
     if (dx) dx[i] = v;
     if (hi) {
@@ -307,7 +311,8 @@ __global__ void bn_tfwd_apply_kernel(BnArgs a, const float* __restrict__ ws, con
     const float xh = (a.x[i] - mean) * rstd;
     const float xhd = rstd * (a.xdot[i] - a1 - xh * a2);
     float v = xhd * g + xh * gd + bd;
-    if (a.tanh_flag) { const float o = a.o[i]; v *= 1.f - o * o; }
+    if (a.tanh_flag) { const float o = a.o[i] * (a.drop.thr ? 1.f / a.drop.scale : 1.f); v *= 1.f - o * o; }
+    v *= drop_factor(a.drop, static_cast<uint32_t>(i));
     if (od) od[i] = v;
     if (hi) {
       bf16 h, l;
@@ -339,11 +344,13 @@ __global__ void bn_tbwd_apply_kernel(BnArgs a, const float* __restrict__ ws, con
     const long long i = r * a.C + c;
     const float xh = (a.x[i] - mean) * rstd;
     const float xhd = rstd * (a.xdot[i] - a1 - xh * a2);
-    float g = a.dout[i], gd = a.ddout[i];
+    const float df = drop_factor(a.drop, static_cast<uint32_t>(i));
+    const float inv = a.drop.thr ? 1.f / a.drop.scale : 1.f;
+    float g = a.dout[i] * df, gd = a.ddout[i] * df;
     if (a.tanh_flag) {
-      const float o = a.o[i];
+      const float o = a.o[i] * inv;
       const float t = 1.f - o * o;
-      gd = gd * t - 2.f * o * a.odot[i] * g;
+      gd = gd * t - 2.f * o * (a.odot[i] * inv) * g;
       g *= t;
     }
     const float core = g - m1 - xh * m2;
@@ -622,7 +629,7 @@ extern "C" int mtts_colsum(const float* f32, const void* hi, const void* lo, int
 
 extern "C" int mtts_bn_fwd(const float* x, const float* gamma, const float* beta, int64_t R, int C, float eps, float momentum,
                            int tanh_flag, float* running_mean, float* running_var, float* ws /* [2C] */,
-                           float* stats /* [2C] */, float* out, void* hi, void* lo, mtts_stream stream_) {
+                           float* stats /* [2C] */, float* out, void* hi, void* lo, uint32_t drop_thr, uint32_t drop_seed, float drop_scale, const uint32_t* drop_salt, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(x && gamma && beta && ws && stats && R > 0 && C > 0, "bn_fwd: bad args");
   dim3 grid, block;
@@ -630,17 +637,18 @@ extern "C" int mtts_bn_fwd(const float* x, const float* gamma, const float* beta
   bn_launch_dims(R, C, grid, block, rpc);
   BnArgs a{};
   a.x = x; a.R = R; a.C = C; a.tanh_flag = tanh_flag; a.rows_per_cta = rpc; a.ws_in = ws;
+  a.drop = DropSite{drop_thr, drop_seed, drop_scale, drop_salt};
   MTTS_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s));
   MTTS_CHECK_CUDA(mtts_launch(bn_reduce_kernel<0>, dim3(grid), dim3(block), 0, s, a, ws));
   MTTS_CHECK_CUDA(mtts_launch(bn_reduce_kernel<1>, dim3(grid), dim3(block), 0, s, a, ws + C));
   MTTS_CHECK_CUDA(mtts_launch(bn_fwd_apply_kernel, dim3(grid), dim3(block), 0, s, x, ws, gamma, beta, R, C, eps, momentum, tanh_flag, running_mean, running_var, stats,
-                                             out, static_cast<bf16*>(hi), static_cast<bf16*>(lo), rpc));
+                                             out, static_cast<bf16*>(hi), static_cast<bf16*>(lo), rpc, a.drop));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
 extern "C" int mtts_bn_bwd(const float* dout, const float* o, const float* x, const float* stats, const float* gamma, int64_t R,
                            int C, int tanh_flag, float* ws /* [2C] */, float* dx, void* hi, void* lo, float* dgamma,
-                           float* dbeta, mtts_stream stream_) {
+                           float* dbeta, uint32_t drop_thr, uint32_t drop_seed, float drop_scale, const uint32_t* drop_salt, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(dout && x && stats && gamma && ws && (!tanh_flag || o), "bn_bwd: bad args");
   dim3 grid, block;
@@ -648,6 +656,7 @@ extern "C" int mtts_bn_bwd(const float* dout, const float* o, const float* x, co
   bn_launch_dims(R, C, grid, block, rpc);
   BnArgs a{};
   a.x = x; a.dout = dout; a.o = o; a.stats = stats; a.R = R; a.C = C; a.tanh_flag = tanh_flag; a.rows_per_cta = rpc;
+  a.drop = DropSite{drop_thr, drop_seed, drop_scale, drop_salt};
   MTTS_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s));
   MTTS_CHECK_CUDA(mtts_launch(bn_reduce_kernel<2>, dim3(grid), dim3(block), 0, s, a, ws));
   MTTS_CHECK_CUDA(mtts_launch(bn_bwd_apply_kernel, dim3(grid), dim3(block), 0, s, a, ws, gamma, dx, static_cast<bf16*>(hi), static_cast<bf16*>(lo), dgamma, dbeta));
@@ -656,7 +665,7 @@ extern "C" int mtts_bn_bwd(const float* dout, const float* o, const float* x, co
 }
 extern "C" int mtts_bn_tfwd(const float* xdot, const float* x, const float* stats, const float* gamma, const float* gdot,
                             const float* bdot, const float* o, int64_t R, int C, int tanh_flag, float* ws /* [2C] */,
-                            float* tsums /* [2C] */, float* odot, void* hi, void* lo, mtts_stream stream_) {
+                            float* tsums /* [2C] */, float* odot, void* hi, void* lo, uint32_t drop_thr, uint32_t drop_seed, float drop_scale, const uint32_t* drop_salt, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(xdot && x && stats && gamma && ws && tsums && (!tanh_flag || o), "bn_tfwd: bad args");
   dim3 grid, block;
@@ -664,6 +673,7 @@ extern "C" int mtts_bn_tfwd(const float* xdot, const float* x, const float* stat
   bn_launch_dims(R, C, grid, block, rpc);
   BnArgs a{};
   a.x = x; a.xdot = xdot; a.o = o; a.stats = stats; a.R = R; a.C = C; a.tanh_flag = tanh_flag; a.rows_per_cta = rpc;
+  a.drop = DropSite{drop_thr, drop_seed, drop_scale, drop_salt};
   MTTS_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s));
   MTTS_CHECK_CUDA(mtts_launch(bn_reduce_kernel<3>, dim3(grid), dim3(block), 0, s, a, ws));
   MTTS_CHECK_CUDA(mtts_launch(bn_tfwd_apply_kernel, dim3(grid), dim3(block), 0, s, a, ws, gamma, gdot, bdot, tsums, odot, static_cast<bf16*>(hi), static_cast<bf16*>(lo)));
@@ -673,7 +683,7 @@ extern "C" int mtts_bn_tfwd(const float* xdot, const float* x, const float* stat
 extern "C" int mtts_bn_tbwd(const float* dout, const float* ddout, const float* o, const float* odot, const float* x,
                             const float* xdot, const float* stats, const float* tsums, const float* gamma, const float* gdot,
                             int64_t R, int C, int tanh_flag, float* ws /* [4C] */, float* ddx, void* hi, void* lo,
-                            float* ddgamma, float* ddbeta, mtts_stream stream_) {
+                            float* ddgamma, float* ddbeta, uint32_t drop_thr, uint32_t drop_seed, float drop_scale, const uint32_t* drop_salt, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(dout && ddout && x && xdot && stats && tsums && gamma && ws && (!tanh_flag || (o && odot)), "bn_tbwd: bad args");
   dim3 grid, block;
@@ -682,6 +692,7 @@ extern "C" int mtts_bn_tbwd(const float* dout, const float* ddout, const float* 
   BnArgs a{};
   a.x = x; a.xdot = xdot; a.dout = dout; a.ddout = ddout; a.o = o; a.odot = odot; a.stats = stats; a.tsums = tsums;
   a.R = R; a.C = C; a.tanh_flag = tanh_flag; a.rows_per_cta = rpc;
+  a.drop = DropSite{drop_thr, drop_seed, drop_scale, drop_salt};
   MTTS_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 4 * C, s));
   MTTS_CHECK_CUDA(mtts_launch(bn_reduce_kernel<4>, dim3(grid), dim3(block), 0, s, a, ws));
   MTTS_CHECK_CUDA(mtts_launch(bn_tbwd_apply_kernel, dim3(grid), dim3(block), 0, s, a, ws, gamma, gdot, ddx, static_cast<bf16*>(hi), static_cast<bf16*>(lo), ddgamma, ddbeta));

@@ -102,6 +102,20 @@ __device__ __forceinline__ float4 f4_relu_gate(float4 v, float4 z) {
   return make_float4(z.x > 0.f ? v.x : 0.f, z.y > 0.f ? v.y : 0.f, z.z > 0.f ? v.z : 0.f, z.w > 0.f ? v.w : 0.f);
 }
 
+// multiply a row by its dropout keep*scale factors (element index = r*C + column)
+template <int NV>
+__device__ __forceinline__ void drop_row(const DropSite& d, long long r, int lane, RowVec<NV>& v) {
+  if (d.thr == 0) return;
+  const uint32_t base = static_cast<uint32_t>(r * (NV * 128)) + lane * 4;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v.v[i].x *= drop_factor(d, base + i * 128 + 0);
+    v.v[i].y *= drop_factor(d, base + i * 128 + 1);
+    v.v[i].z *= drop_factor(d, base + i * 128 + 2);
+    v.v[i].w *= drop_factor(d, base + i * 128 + 3);
+  }
+}
+
 // per-CTA reduction of per-channel accumulators then one atomicAdd per channel
 template <int NV, int NACC>
 __device__ __forceinline__ void flush_channel_acc(RowVec<NV> (&acc)[NACC], float* const (&dst)[NACC], int lane, int warp) {
@@ -130,7 +144,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(const float* __rest
                                                              const int64_t* __restrict__ lens, int T, long long R, float eps,
                                                              float* __restrict__ z_out, float* __restrict__ stats,
                                                              float* __restrict__ out, bf16* __restrict__ out_hi,
-                                                             bf16* __restrict__ out_lo) {
+                                                             bf16* __restrict__ out_lo, DropSite dpre, DropSite dpost) {
   pdl_enter();
   constexpr int C = NV * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -140,6 +154,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(const float* __rest
   for (long long r = static_cast<long long>(blockIdx.x) * ROW_WARPS + warp; r < R; r += static_cast<long long>(gridDim.x) * ROW_WARPS) {
     RowVec<NV> z;
     load_row<NV>(y + r * C, lane, z);
+    drop_row<NV>(dpre, r, lane, z);                 // dropout on the branch (SubLayers.py:54,90) before the residual add
     if (res) {
       RowVec<NV> rr;
       load_row<NV>(res + r * C, lane, rr);
@@ -159,6 +174,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_fwd_kernel(const float* __rest
     RowVec<NV> o;
     if (valid) {
       ROW_FOREACH(NV, i, o.v[i] = f4_fma(f4_scale(d.v[i], rstd), g.v[i], b.v[i]);)
+      drop_row<NV>(dpost, r, lane, o);              // dropout on the LN output (modules.py:223,235)
     } else {
       zero_row<NV>(o);
     }
@@ -175,7 +191,8 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(const float* __rest
                                                              const int64_t* __restrict__ lens, int T, long long R,
                                                              int relu_gate, float* __restrict__ dz, bf16* __restrict__ dz_hi,
                                                              bf16* __restrict__ dz_lo, float* __restrict__ dgamma,
-                                                             float* __restrict__ dbeta, float* __restrict__ dbias) {
+                                                             float* __restrict__ dbeta, float* __restrict__ dbias, DropSite dpre,
+                                                             DropSite dpost) {
   pdl_enter();
   constexpr int C = NV * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -192,6 +209,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(const float* __rest
       RowVec<NV> zz, d, xh, gg;
       load_row<NV>(z + r * C, lane, zz);
       load_row<NV>(dy + r * C, lane, d);
+      drop_row<NV>(dpost, r, lane, d);              // gradient through the output dropout
       const float mean = stats[2 * r], rstd = stats[2 * r + 1];
       ROW_FOREACH(NV, i, xh.v[i] = f4_scale(make_float4(zz.v[i].x - mean, zz.v[i].y - mean, zz.v[i].z - mean, zz.v[i].w - mean), rstd);)
       ROW_FOREACH(NV, i, gg.v[i] = f4_mul(d.v[i], g.v[i]);)
@@ -204,12 +222,13 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_bwd_kernel(const float* __rest
         if (relu_gate) o.v[i] = f4_relu_gate(o.v[i], zz.v[i]);
         acc[0].v[i] = f4_fma(d.v[i], xh.v[i], acc[0].v[i]);
         acc[1].v[i] = f4_add(acc[1].v[i], d.v[i]);
-        acc[2].v[i] = f4_add(acc[2].v[i], o.v[i]);
       })
     } else {
       zero_row<NV>(o);
     }
-    if (dz) store_row<NV>(dz + r * C, lane, o);
+    if (dz) store_row<NV>(dz + r * C, lane, o);       // residual path: un-dropped
+    drop_row<NV>(dpre, r, lane, o);                   // branch path (and its bias): through the branch dropout
+    ROW_FOREACH(NV, i, acc[2].v[i] = f4_add(acc[2].v[i], o.v[i]);)
     if (dz_hi) store_row_split<NV>(dz_hi + r * C, dz_lo ? dz_lo + r * C : nullptr, lane, o);
   }
   float* const dst[3] = {dgamma, dbeta, dbias};
@@ -225,7 +244,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_tfwd_kernel(const float* __res
                                                               const float* __restrict__ bdot, const int64_t* __restrict__ lens,
                                                               int T, long long R, float* __restrict__ zdot_out,
                                                               float* __restrict__ out, bf16* __restrict__ out_hi,
-                                                              bf16* __restrict__ out_lo) {
+                                                              bf16* __restrict__ out_lo, DropSite dpre, DropSite dpost) {
   pdl_enter();
   constexpr int C = NV * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -236,6 +255,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_tfwd_kernel(const float* __res
   for (long long r = static_cast<long long>(blockIdx.x) * ROW_WARPS + warp; r < R; r += static_cast<long long>(gridDim.x) * ROW_WARPS) {
     RowVec<NV> zd;
     load_row<NV>(ydot + r * C, lane, zd);
+    drop_row<NV>(dpre, r, lane, zd);
     if (resdot) {
       RowVec<NV> rr;
       load_row<NV>(resdot + r * C, lane, rr);
@@ -256,6 +276,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_tfwd_kernel(const float* __res
                                           zd.v[i].z - m1 - xh.v[i].z * m2, zd.v[i].w - m1 - xh.v[i].w * m2), rstd);
         o.v[i] = f4_add(f4_fma(xhd, g.v[i], f4_mul(xh.v[i], gd.v[i])), bd.v[i]);
       })
+      drop_row<NV>(dpost, r, lane, o);
     } else {
       zero_row<NV>(o);
     }
@@ -278,7 +299,7 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_tbwd_kernel(const float* __res
                                                               int T, long long R, int relu_gate, float* __restrict__ ddz,
                                                               bf16* __restrict__ ddz_hi, bf16* __restrict__ ddz_lo,
                                                               float* __restrict__ ddgamma, float* __restrict__ ddbeta,
-                                                              float* __restrict__ ddbias) {
+                                                              float* __restrict__ ddbias, DropSite dpre, DropSite dpost) {
   pdl_enter();
   constexpr int C = NV * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -298,6 +319,8 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_tbwd_kernel(const float* __res
       load_row<NV>(zdot + r * C, lane, zd);
       load_row<NV>(dy + r * C, lane, d);
       load_row<NV>(ddy + r * C, lane, dd);
+      drop_row<NV>(dpost, r, lane, d);
+      drop_row<NV>(dpost, r, lane, dd);
       const float mean = stats[2 * r], rstd = stats[2 * r + 1];
       ROW_FOREACH(NV, i, xh.v[i] = f4_scale(make_float4(zz.v[i].x - mean, zz.v[i].y - mean, zz.v[i].z - mean, zz.v[i].w - mean), rstd);)
       const float a1 = row_sum<NV>(zd) * (1.f / C);
@@ -324,12 +347,13 @@ __global__ void __launch_bounds__(ROW_THREADS) ln_tbwd_kernel(const float* __res
         o.v[i] = t;
         acc[0].v[i] = f4_fma(dd.v[i], X, f4_fma(d.v[i], XD, acc[0].v[i]));
         acc[1].v[i] = f4_add(acc[1].v[i], dd.v[i]);
-        acc[2].v[i] = f4_add(acc[2].v[i], t);
       })
     } else {
       zero_row<NV>(o);
     }
     if (ddz) store_row<NV>(ddz + r * C, lane, o);
+    drop_row<NV>(dpre, r, lane, o);
+    ROW_FOREACH(NV, i, acc[2].v[i] = f4_add(acc[2].v[i], o.v[i]);)
     if (ddz_hi) store_row_split<NV>(ddz_hi + r * C, ddz_lo ? ddz_lo + r * C : nullptr, lane, o);
   }
   float* const dst[3] = {ddgamma, ddbeta, ddbias};
@@ -556,48 +580,48 @@ __global__ void __launch_bounds__(ROW_THREADS) softmax_kernel(int /*mode*/, cons
 
 extern "C" int mtts_ln_fwd(const float* y, const float* res, const float* gamma, const float* beta, const int64_t* lens,
                            int T, int64_t R, int C, float eps, float* z_out, float* stats, float* out, void* out_hi,
-                           void* out_lo, mtts_stream stream_) {
+                           void* out_lo, uint32_t pre_thr, uint32_t pre_seed, float pre_scale, uint32_t post_thr, uint32_t post_seed, float post_scale, const uint32_t* drop_salt, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(y && gamma && beta && R > 0, "ln_fwd: bad args");
   DISPATCH_NV(C, MTTS_CHECK_CUDA(mtts_launch(ln_fwd_kernel<NV>, dim3(row_grid(R)), dim3(ROW_THREADS), 0, s, y, res, gamma, beta, lens, T, R, eps, z_out, stats, out,
-                                                                        static_cast<bf16*>(out_hi), static_cast<bf16*>(out_lo))));
+                                                                        static_cast<bf16*>(out_hi), static_cast<bf16*>(out_lo), DropSite{pre_thr, pre_seed, pre_scale, drop_salt}, DropSite{post_thr, post_seed, post_scale, drop_salt})));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
 
 extern "C" int mtts_ln_bwd(const float* dy, const float* z, const float* stats, const float* gamma, const int64_t* lens, int T,
                            int64_t R, int C, int relu_gate, float* dz, void* dz_hi, void* dz_lo, float* dgamma, float* dbeta,
-                           float* dbias, mtts_stream stream_) {
+                           float* dbias, uint32_t pre_thr, uint32_t pre_seed, float pre_scale, uint32_t post_thr, uint32_t post_seed, float post_scale, const uint32_t* drop_salt, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(dy && z && stats && gamma && R > 0, "ln_bwd: bad args");
   DISPATCH_NV(C, MTTS_CHECK_CUDA(mtts_launch(ln_bwd_kernel<NV>, dim3(row_grid(R)), dim3(ROW_THREADS), 0, s, dy, z, stats, gamma, lens, T, R, relu_gate, dz,
                                                                         static_cast<bf16*>(dz_hi), static_cast<bf16*>(dz_lo),
-                                                                        dgamma, dbeta, dbias)));
+                                                                        dgamma, dbeta, dbias, DropSite{pre_thr, pre_seed, pre_scale, drop_salt}, DropSite{post_thr, post_seed, post_scale, drop_salt})));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
 
 extern "C" int mtts_ln_tfwd(const float* ydot, const float* resdot, const float* z, const float* stats, const float* gamma,
                             const float* gdot, const float* bdot, const int64_t* lens, int T, int64_t R, int C,
-                            float* zdot_out, float* out, void* out_hi, void* out_lo, mtts_stream stream_) {
+                            float* zdot_out, float* out, void* out_hi, void* out_lo, uint32_t pre_thr, uint32_t pre_seed, float pre_scale, uint32_t post_thr, uint32_t post_seed, float post_scale, const uint32_t* drop_salt, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(ydot && z && stats && gamma && R > 0, "ln_tfwd: bad args");
   DISPATCH_NV(C, MTTS_CHECK_CUDA(mtts_launch(ln_tfwd_kernel<NV>, dim3(row_grid(R)), dim3(ROW_THREADS), 0, s, ydot, resdot, z, stats, gamma, gdot, bdot, lens, T, R,
                                                                          zdot_out, out, static_cast<bf16*>(out_hi),
-                                                                         static_cast<bf16*>(out_lo))));
+                                                                         static_cast<bf16*>(out_lo), DropSite{pre_thr, pre_seed, pre_scale, drop_salt}, DropSite{post_thr, post_seed, post_scale, drop_salt})));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
 
 extern "C" int mtts_ln_tbwd(const float* dy, const float* ddy, const float* z, const float* zdot, const float* stats,
                             const float* gamma, const float* gdot, const int64_t* lens, int T, int64_t R, int C, int relu_gate,
-                            float* ddz, void* ddz_hi, void* ddz_lo, float* ddgamma, float* ddbeta, float* ddbias,
+                            float* ddz, void* ddz_hi, void* ddz_lo, float* ddgamma, float* ddbeta, float* ddbias, uint32_t pre_thr, uint32_t pre_seed, float pre_scale, uint32_t post_thr, uint32_t post_seed, float post_scale, const uint32_t* drop_salt,
                             mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(dy && ddy && z && zdot && stats && gamma && R > 0, "ln_tbwd: bad args");
   DISPATCH_NV(C, MTTS_CHECK_CUDA(mtts_launch(ln_tbwd_kernel<NV>, dim3(row_grid(R)), dim3(ROW_THREADS), 0, s, dy, ddy, z, zdot, stats, gamma, gdot, lens, T, R,
                                                                          relu_gate, ddz, static_cast<bf16*>(ddz_hi),
-                                                                         static_cast<bf16*>(ddz_lo), ddgamma, ddbeta, ddbias)));
+                                                                         static_cast<bf16*>(ddz_lo), ddgamma, ddbeta, ddbias, DropSite{pre_thr, pre_seed, pre_scale, drop_salt}, DropSite{post_thr, post_seed, post_scale, drop_salt})));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }

@@ -22,13 +22,14 @@ state_dict (same keys, Conv1d [out, in, k]).
 from __future__ import annotations
 
 import math
+import zlib
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
 from . import lib as L
-from .ops import Opnd
+from .ops import NO_DROP, Opnd
 
 N_SYMBOLS = 360      # len(text.symbols.symbols), text/symbols.py:21-29
 N_MEL = 80
@@ -500,6 +501,23 @@ class FS2Engine:
         om = lambda hi, lo, f32=None: BMat(hi, lo, 0, T * d, dk, d, T, dk, f32)  # noqa: E731
         return dk, Tp, q, pm, om
 
+    # ---- dropout sites (include/mtts.h): launch scalar = crc32(site) ^ (pass_index * 2654435761); the device adds the
+    #      per-step salt.  The pass index lives on the primal tape, so every pass over it draws the same mask. ----
+    def _site(self, tp: Tape, site: str, p: float):
+        idx = getattr(tp, "drop_pass", None)
+        if idx is None or p <= 0.0:
+            return NO_DROP
+        scalar = (zlib.crc32(site.encode()) ^ ((int(idx) * 2654435761) & 0xFFFFFFFF)) & 0xFFFFFFFF
+        return (int(p * (1 << 24)), scalar, 1.0 / (1.0 - p))
+
+    def _fft_drop(self, tp: Tape, pf: str):
+        p = self.cfg["transformer"]["encoder_dropout" if pf.startswith("encoder") else "decoder_dropout"]
+        return self._site(tp, f"{pf}.slf_attn", p), self._site(tp, f"{pf}.pos_ffn", p)
+
+    def _vp_drop(self, tp: Tape, pf: str):
+        p = self.cfg["variance_predictor"]["dropout"]
+        return self._site(tp, f"{pf}.1", p), self._site(tp, f"{pf}.2", p)
+
     def _fft_names(self, pf):
         a, f = f"{pf}.slf_attn", f"{pf}.pos_ffn"
         return a, f
@@ -530,14 +548,16 @@ class FS2Engine:
         g.conv_fwd(o, P.get(f"{a_}.fc.weight"), P.get(f"{a_}.fc.bias").f32, y0, None, None)
         y1 = tp.act(f"{pf}.y1", B, T, d)
         be.ln_fwd(y0, x.f32, P.get(f"{a_}.layer_norm.weight").f32, P.get(f"{a_}.layer_norm.bias").f32, lens, T, R, d,
-                  tp.f32(f"{pf}.z1", (B, T, d)), tp.f32(f"{pf}.st1", (R, 2)), y1.f32, y1.hi, y1.lo)
+                  tp.f32(f"{pf}.z1", (B, T, d)), tp.f32(f"{pf}.st1", (R, 2)), y1.f32, y1.hi, y1.lo,
+                  pre=self._fft_drop(tp, pf)[0])
         h = tp.act(f"{pf}.h", B, T, self.d_inner, f32=False)
         g.conv_fwd(y1, P.get(f"{f_}.w_1.weight"), P.get(f"{f_}.w_1.bias").f32, None, h.hi, h.lo, relu=True)
         y2 = scr.scratch("y0", (B, T, d))
         g.conv_fwd(h, P.get(f"{f_}.w_2.weight"), P.get(f"{f_}.w_2.bias").f32, y2, None, None)
         out = tp.act(f"{pf}.out", B, T, d)
         be.ln_fwd(y2, y1.f32, P.get(f"{f_}.layer_norm.weight").f32, P.get(f"{f_}.layer_norm.bias").f32, lens, T, R, d,
-                  tp.f32(f"{pf}.z2", (B, T, d)), tp.f32(f"{pf}.st2", (R, 2)), out.f32, out.hi, out.lo)
+                  tp.f32(f"{pf}.z2", (B, T, d)), tp.f32(f"{pf}.st2", (R, 2)), out.f32, out.hi, out.lo,
+                  pre=self._fft_drop(tp, pf)[1])
         return out
 
     def fft_bwd(self, P: ParamSet, G: ParamSet, pf: str, tp: Tape, x: Act, lens, H: int, dout: torch.Tensor,
@@ -560,7 +580,7 @@ class FS2Engine:
         dz2 = tp.act(f"{pf}.dz2", B, T, d)          # f32 part becomes dL/dy1 (total) after the ADD_C below
         be.ln_bwd(dout, tp.f32(f"{pf}.z2", (B, T, d)), tp.f32(f"{pf}.st2", (R, 2)), P.get(f"{f_}.layer_norm.weight").f32,
                   lens, T, R, d, 0, dz2.f32, dz2.hi, dz2.lo, G.get(f"{f_}.layer_norm.weight").f32,
-                  G.get(f"{f_}.layer_norm.bias").f32, G.get(f"{f_}.w_2.bias").f32)
+                  G.get(f"{f_}.layer_norm.bias").f32, G.get(f"{f_}.w_2.bias").f32, pre=self._fft_drop(tp, pf)[1])
         # conv k=1 (w_2), ReLU gate, conv k=9 (w_1)
         dh = tp.act(f"{pf}.dh", B, T, self.d_inner, f32=False)
         g.conv_dgrad(dz2, P.get(f"{f_}.w_2.weight"), None, dh.hi, dh.lo, gate=h.hi)
@@ -573,7 +593,7 @@ class FS2Engine:
         dz1 = Act(dx_out, *tp.bf(f"{pf}.dz1", (B, T, d)), B, T, d)
         be.ln_bwd(dz2.f32, tp.f32(f"{pf}.z1", (B, T, d)), tp.f32(f"{pf}.st1", (R, 2)), P.get(f"{a_}.layer_norm.weight").f32,
                   lens, T, R, d, 0, dz1.f32, dz1.hi, dz1.lo, G.get(f"{a_}.layer_norm.weight").f32,
-                  G.get(f"{a_}.layer_norm.bias").f32, G.get(f"{a_}.fc.bias").f32)
+                  G.get(f"{a_}.layer_norm.bias").f32, G.get(f"{a_}.fc.bias").f32, pre=self._fft_drop(tp, pf)[0])
         do = tp.act(f"{pf}.do", B, T, d, f32=False)
         g.conv_dgrad(dz1, P.get(f"{a_}.fc.weight"), None, do.hi, do.lo)
         with be.side():
@@ -655,7 +675,7 @@ class FS2Engine:
         y1d = tt.act(f"{pf}.y1d", B, T, d)
         be.ln_tfwd(y0d, xd.f32 if xd is not None else None, tp.f32(f"{pf}.z1", (B, T, d)), tp.f32(f"{pf}.st1", (R, 2)),
                    P.get(f"{a_}.layer_norm.weight").f32, gd(f"{a_}.layer_norm.weight"), gd(f"{a_}.layer_norm.bias"), lens, T,
-                   R, d, tt.f32(f"{pf}.z1d", (B, T, d)), y1d.f32, y1d.hi, y1d.lo)
+                   R, d, tt.f32(f"{pf}.z1d", (B, T, d)), y1d.f32, y1d.hi, y1d.lo, pre=self._fft_drop(tp, pf)[0])
         # conv9 + relu gate, conv1, LN2
         hd = tt.act(f"{pf}.hd", B, T, self.d_inner, f32=False)
         hd_f = scr.scratch("h_f", (B, T, self.d_inner))
@@ -666,7 +686,7 @@ class FS2Engine:
         outd = tt.act(f"{pf}.outd", B, T, d)
         be.ln_tfwd(y2d, y1d.f32, tp.f32(f"{pf}.z2", (B, T, d)), tp.f32(f"{pf}.st2", (R, 2)),
                    P.get(f"{f_}.layer_norm.weight").f32, gd(f"{f_}.layer_norm.weight"), gd(f"{f_}.layer_norm.bias"), lens, T,
-                   R, d, tt.f32(f"{pf}.z2d", (B, T, d)), outd.f32, outd.hi, outd.lo)
+                   R, d, tt.f32(f"{pf}.z2d", (B, T, d)), outd.f32, outd.hi, outd.lo, pre=self._fft_drop(tp, pf)[1])
         return outd
 
     def fft_tbwd(self, P: ParamSet, Pd: ParamSet, HV: ParamSet, pf: str, tp: Tape, tt: Tape, x: Act, xd: Optional[Act],
@@ -705,7 +725,8 @@ class FS2Engine:
         ddz2 = tt.act(f"{pf}.ddz2", B, T, d)
         be.ln_tbwd(dout, ddout, tp.f32(f"{pf}.z2", (B, T, d)), tt.f32(f"{pf}.z2d", (B, T, d)), tp.f32(f"{pf}.st2", (R, 2)),
                    P.get(f"{f_}.layer_norm.weight").f32, gd(f"{f_}.layer_norm.weight"), lens, T, R, d, 0, ddz2.f32, ddz2.hi,
-                   ddz2.lo, hv(f"{f_}.layer_norm.weight"), hv(f"{f_}.layer_norm.bias"), hv(f"{f_}.w_2.bias"))
+                   ddz2.lo, hv(f"{f_}.layer_norm.weight"), hv(f"{f_}.layer_norm.bias"), hv(f"{f_}.w_2.bias"),
+                   pre=self._fft_drop(tp, pf)[1])
         # ---- w_2 (k=1) with ReLU gate ----
         ddh = tt.act(f"{pf}.ddh", B, T, self.d_inner, f32=False)
         ddh_f = scr.scratch("h_f", (B, T, self.d_inner))
@@ -721,7 +742,7 @@ class FS2Engine:
         be.ln_tbwd(dz2.f32, ddz2.f32, tp.f32(f"{pf}.z1", (B, T, d)), tt.f32(f"{pf}.z1d", (B, T, d)),
                    tp.f32(f"{pf}.st1", (R, 2)), P.get(f"{a_}.layer_norm.weight").f32, gd(f"{a_}.layer_norm.weight"), lens, T,
                    R, d, 0, ddz1.f32, ddz1.hi, ddz1.lo, hv(f"{a_}.layer_norm.weight"), hv(f"{a_}.layer_norm.bias"),
-                   hv(f"{a_}.fc.bias"))
+                   hv(f"{a_}.fc.bias"), pre=self._fft_drop(tp, pf)[0])
         # ---- fc ----
         ddo = tt.act(f"{pf}.ddo", B, T, d, f32=False)
         ddo_f = scr.scratch("o_f", (B, T, d))
@@ -763,12 +784,12 @@ class FS2Engine:
         g.conv_fwd(x, P.get(f"{c}.conv1d_1.conv.weight"), P.get(f"{c}.conv1d_1.conv.bias").f32, h1, None, None, relu=True)
         a1 = tp.act(f"{pf}.a1", B, Lq, d)
         be.ln_fwd(h1, None, P.get(f"{c}.layer_norm_1.weight").f32, P.get(f"{c}.layer_norm_1.bias").f32, None, Lq, R, d, None,
-                  tp.f32(f"{pf}.st1", (R, 2)), a1.f32, a1.hi, a1.lo)
+                  tp.f32(f"{pf}.st1", (R, 2)), a1.f32, a1.hi, a1.lo, post=self._vp_drop(tp, pf)[0])
         h2 = tp.f32(f"{pf}.h2", (B, Lq, d))
         g.conv_fwd(a1, P.get(f"{c}.conv1d_2.conv.weight"), P.get(f"{c}.conv1d_2.conv.bias").f32, h2, None, None, relu=True)
         a2 = tp.f32(f"{pf}.a2", (B, Lq, d))
         be.ln_fwd(h2, None, P.get(f"{c}.layer_norm_2.weight").f32, P.get(f"{c}.layer_norm_2.bias").f32, None, Lq, R, d, None,
-                  tp.f32(f"{pf}.st2", (R, 2)), a2, None, None)
+                  tp.f32(f"{pf}.st2", (R, 2)), a2, None, None, post=self._vp_drop(tp, pf)[1])
         be.rowdot_fwd(a2, None, P.get(f"{pf}.linear_layer.weight").f32, None, P.get(f"{pf}.linear_layer.bias").f32, None, lens,
                       Lq, R, d, out)
 
@@ -785,7 +806,7 @@ class FS2Engine:
         dc2 = tp.act(f"{pf}.dc2", B, Lq, d, f32=False)
         be.ln_bwd(da2, tp.f32(f"{pf}.h2", (B, Lq, d)), tp.f32(f"{pf}.st2", (R, 2)), P.get(f"{c}.layer_norm_2.weight").f32,
                   None, Lq, R, d, 1, None, dc2.hi, dc2.lo, G.get(f"{c}.layer_norm_2.weight").f32,
-                  G.get(f"{c}.layer_norm_2.bias").f32, G.get(f"{c}.conv1d_2.conv.bias").f32)
+                  G.get(f"{c}.layer_norm_2.bias").f32, G.get(f"{c}.conv1d_2.conv.bias").f32, post=self._vp_drop(tp, pf)[1])
         with be.side():
             g.conv_wgrad(dc2, a1, G.get(f"{c}.conv1d_2.conv.weight").f32)
         da1 = tp.f32(f"{pf}.da1", (B, Lq, d))
@@ -793,7 +814,7 @@ class FS2Engine:
         dc1 = tp.act(f"{pf}.dc1", B, Lq, d, f32=False)
         be.ln_bwd(da1, tp.f32(f"{pf}.h1", (B, Lq, d)), tp.f32(f"{pf}.st1", (R, 2)), P.get(f"{c}.layer_norm_1.weight").f32,
                   None, Lq, R, d, 1, None, dc1.hi, dc1.lo, G.get(f"{c}.layer_norm_1.weight").f32,
-                  G.get(f"{c}.layer_norm_1.bias").f32, G.get(f"{c}.conv1d_1.conv.bias").f32)
+                  G.get(f"{c}.layer_norm_1.bias").f32, G.get(f"{c}.conv1d_1.conv.bias").f32, post=self._vp_drop(tp, pf)[0])
         with be.side():
             g.conv_wgrad(dc1, x, G.get(f"{c}.conv1d_1.conv.weight").f32)
         g.conv_dgrad(dc1, P.get(f"{c}.conv1d_1.conv.weight"), dx_acc, None, None, add_c=True)
@@ -818,13 +839,15 @@ class FS2Engine:
                     h1d, None, None, relu_gate=h1g)
         a1d = tt.act(f"{pf}.a1d", B, Lq, d)
         be.ln_tfwd(h1d, None, h1, tp.f32(f"{pf}.st1", (R, 2)), P.get(f"{c}.layer_norm_1.weight").f32,
-                   gd(f"{c}.layer_norm_1.weight"), gd(f"{c}.layer_norm_1.bias"), None, Lq, R, d, None, a1d.f32, a1d.hi, a1d.lo)
+                   gd(f"{c}.layer_norm_1.weight"), gd(f"{c}.layer_norm_1.bias"), None, Lq, R, d, None, a1d.f32, a1d.hi, a1d.lo,
+                   post=self._vp_drop(tp, pf)[0])
         h2d = tt.f32(f"{pf}.h2d", (B, Lq, d))
         self._lin_t(a1, a1d, P.get(f"{c}.conv1d_2.conv.weight"), wdt(f"{c}.conv1d_2.conv.weight"), gd(f"{c}.conv1d_2.conv.bias"),
                     h2d, None, None, relu_gate=h2g)
         a2d = tt.f32(f"{pf}.a2d", (B, Lq, d))
         be.ln_tfwd(h2d, None, h2, tp.f32(f"{pf}.st2", (R, 2)), P.get(f"{c}.layer_norm_2.weight").f32,
-                   gd(f"{c}.layer_norm_2.weight"), gd(f"{c}.layer_norm_2.bias"), None, Lq, R, d, None, a2d, None, None)
+                   gd(f"{c}.layer_norm_2.weight"), gd(f"{c}.layer_norm_2.bias"), None, Lq, R, d, None, a2d, None, None,
+                   post=self._vp_drop(tp, pf)[1])
         be.rowdot_fwd(tp.f32(f"{pf}.a2", (B, Lq, d)), a2d, P.get(f"{pf}.linear_layer.weight").f32, gd(f"{pf}.linear_layer.weight"),
                       None, gd(f"{pf}.linear_layer.bias"), lens, Lq, R, d, outd)
 
@@ -848,7 +871,7 @@ class FS2Engine:
         be.ln_tbwd(tp.f32(f"{pf}.da2", (B, Lq, d)), dda2, tp.f32(f"{pf}.h2", (B, Lq, d)), tt.f32(f"{pf}.h2d", (B, Lq, d)),
                    tp.f32(f"{pf}.st2", (R, 2)), P.get(f"{c}.layer_norm_2.weight").f32, gd(f"{c}.layer_norm_2.weight"), None, Lq,
                    R, d, 1, None, ddc2.hi, ddc2.lo, hv(f"{c}.layer_norm_2.weight"), hv(f"{c}.layer_norm_2.bias"),
-                   hv(f"{c}.conv1d_2.conv.bias"))
+                   hv(f"{c}.conv1d_2.conv.bias"), post=self._vp_drop(tp, pf)[1])
         with be.side():
             self._wgrad_t(dc2, ddc2, a1, a1d, hv(f"{c}.conv1d_2.conv.weight"))
         dda1 = tt.f32(f"{pf}.dda1", (B, Lq, d))
@@ -857,7 +880,7 @@ class FS2Engine:
         be.ln_tbwd(tp.f32(f"{pf}.da1", (B, Lq, d)), dda1, tp.f32(f"{pf}.h1", (B, Lq, d)), tt.f32(f"{pf}.h1d", (B, Lq, d)),
                    tp.f32(f"{pf}.st1", (R, 2)), P.get(f"{c}.layer_norm_1.weight").f32, gd(f"{c}.layer_norm_1.weight"), None, Lq,
                    R, d, 1, None, ddc1.hi, ddc1.lo, hv(f"{c}.layer_norm_1.weight"), hv(f"{c}.layer_norm_1.bias"),
-                   hv(f"{c}.conv1d_1.conv.bias"))
+                   hv(f"{c}.conv1d_1.conv.bias"), post=self._vp_drop(tp, pf)[0])
         with be.side():
             self._wgrad_t(dc1, ddc1, x, xd, hv(f"{c}.conv1d_1.conv.weight"))
         self._dgrad_t(dc1, ddc1, P.get(f"{c}.conv1d_1.conv.weight"), wdt(f"{c}.conv1d_1.conv.weight"), ddx_acc, None, None,
@@ -901,13 +924,17 @@ class FS2Engine:
             rm = self.consts[f"{pre}.1.running_mean"] if update_bn else None
             rv = self.consts[f"{pre}.1.running_var"] if update_bn else None
             be.bn_fwd(c, P.get(f"{pre}.1.weight").f32, P.get(f"{pre}.1.bias").f32, R, co, i < 4, rm, rv,
-                      scr.scratch("bn.ws", (4 * 512,)), tp.f32(f"post.{i}.st", (2 * co,)), o.f32, o.hi, o.lo)
+                      scr.scratch("bn.ws", (4 * 512,)), tp.f32(f"post.{i}.st", (2 * co,)), o.f32, o.hi, o.lo,
+                      drop=self._site(tp, f"postnet.{i}", 0.5))
             xin = o
         return xin
 
-    def forward(self, P: ParamSet, bt: Batch, tp: Tape, update_bn: bool = True):
-        """Teacher-forced forward + loss.  Returns dict with the reference's prediction tensors."""
+    def forward(self, P: ParamSet, bt: Batch, tp: Tape, update_bn: bool = True, drop_pass: Optional[int] = None):
+        """Teacher-forced forward + loss.  Returns dict with the reference's prediction tensors.
+        drop_pass: None = dropout off (eval / parity-with-identity); an int = train-mode dropout, pass index mixed
+        into every site seed (backward / tangent passes over `tp` reuse it)."""
         be, g, scr, d = self.be, self.g, self.scr, self.d
+        tp.drop_pass = drop_pass
         B, Lq, T = bt.B, bt.L, bt.T
         assert T <= self.cfg["max_seq_len"] and Lq <= self.cfg["max_seq_len"], "sequence longer than max_seq_len"
         # ---- encoder (Models.py:73-100) ----
@@ -977,7 +1004,7 @@ class FS2Engine:
             be.bn_bwd(dout, tp.f32(f"post.{i}.o", (B, T, co)) if i < 4 else None, tp.f32(f"post.{i}.c", (B, T, co)),
                       tp.f32(f"post.{i}.st", (2 * co,)), P.get(f"{pre}.1.weight").f32, R, co, i < 4, scr.scratch("bn.ws", (4 * 512,)),
                       dc.f32, dc.hi, dc.lo, G.get(f"{pre}.1.weight").f32, G.get(f"{pre}.1.bias").f32,
-                      beta=P.get(f"{pre}.1.bias").f32)
+                      beta=P.get(f"{pre}.1.bias").f32, drop=self._site(tp, f"postnet.{i}", 0.5))
             with be.side():
                 be.colsum(dc.f32, None, None, 1, R, co, G.get(f"{pre}.0.conv.bias").f32)
                 g.conv_wgrad(dc, xin, G.get(f"{pre}.0.conv.weight").f32)
@@ -1102,7 +1129,7 @@ class FS2Engine:
             be.bn_tfwd(cd, tp.f32(f"post.{i}.c", (B, T, co)), tp.f32(f"post.{i}.st", (2 * co,)), P.get(f"{pre}.1.weight").f32,
                        gd(f"{pre}.1.weight"), gd(f"{pre}.1.bias"), tp.f32(f"post.{i}.o", (B, T, co)) if i < 4 else None, R, co,
                        i < 4, scr.scratch("bn.ws", (4 * 512,)), tt.f32(f"post.{i}.ts", (2 * co,)), od.f32, od.hi, od.lo,
-                       beta=P.get(f"{pre}.1.bias").f32)
+                       beta=P.get(f"{pre}.1.bias").f32, drop=self._site(tp, f"postnet.{i}", 0.5))
             xin = tp.act(f"post.{i}.o", B, T, co, bf=(i < 4))
             xind = od
         # (postnet_output tangent = od4 + meld, but the L1 losses have zero curvature: not needed)
@@ -1125,7 +1152,7 @@ class FS2Engine:
                        tp.f32(f"post.{i}.c", (B, T, co)), tt.f32(f"post.{i}.cd", (B, T, co)), tp.f32(f"post.{i}.st", (2 * co,)),
                        tt.f32(f"post.{i}.ts", (2 * co,)), P.get(f"{pre}.1.weight").f32, gd(f"{pre}.1.weight"), R, co, i < 4,
                        scr.scratch("bn.ws", (4 * 512,)), ddc.f32, ddc.hi, ddc.lo, hv(f"{pre}.1.weight"), hv(f"{pre}.1.bias"),
-                       beta=P.get(f"{pre}.1.bias").f32, bdot=gd(f"{pre}.1.bias"))
+                       beta=P.get(f"{pre}.1.bias").f32, bdot=gd(f"{pre}.1.bias"), drop=self._site(tp, f"postnet.{i}", 0.5))
             with be.side():
                 be.colsum(ddc.f32, None, None, 1, R, co, hv(f"{pre}.0.conv.bias"))
                 self._wgrad_t(dc, ddc, xin, xind, hv(f"{pre}.0.conv.weight"))

@@ -76,6 +76,9 @@ def load() -> C.CDLL:
 
 # name -> argtypes; every function returns int (0 = ok)
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_u32 = C.c_uint32
+_D2 = [_u32, _u32, _f, _u32, _u32, _f, _vp]      # (thr, seed, scale) x {pre, post}, salt*
+_D1 = [_u32, _u32, _f, _vp]
 SIGNATURES: dict[str, list] = {
     "mtts_check_device": [],
     "mtts_set_pdl": [_i],
@@ -83,10 +86,10 @@ SIGNATURES: dict[str, list] = {
     "mtts_length_regulate_index": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "mtts_length_regulate_fwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "mtts_length_regulate_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],
-    "mtts_ln_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp],
-    "mtts_ln_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "mtts_ln_tfwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp],
-    "mtts_ln_tbwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mtts_ln_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _f, _vp, _vp, _vp, _vp, _vp] + _D2 + [_vp],
+    "mtts_ln_bwd": [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp] + _D2 + [_vp],
+    "mtts_ln_tfwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp] + _D2 + [_vp],
+    "mtts_ln_tbwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp] + _D2 + [_vp],
     "mtts_rowdot_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp],
     "mtts_rowdot_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp],
     "mtts_softmax": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
@@ -97,10 +100,10 @@ SIGNATURES: dict[str, list] = {
     "mtts_spk_embed": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "mtts_spk_embed_bwd": [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp],
     "mtts_colsum": [_vp, _vp, _vp, _i, _i64, _i, _vp, _vp],
-    "mtts_bn_fwd": [_vp, _vp, _vp, _i64, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "mtts_bn_bwd": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "mtts_bn_tfwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
-    "mtts_bn_tbwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mtts_bn_fwd": [_vp, _vp, _vp, _i64, _i, _f, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp] + _D1 + [_vp],
+    "mtts_bn_bwd": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp] + _D1 + [_vp],
+    "mtts_bn_tfwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp] + _D1 + [_vp],
+    "mtts_bn_tbwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp] + _D1 + [_vp],
     "mtts_loss_fwd": [_vp] * 11 + [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "mtts_loss_bwd": [_vp] * 11 + [_i, _i, _i, _i, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "mtts_split": [_vp, _vp, _vp, _i64, _vp],

@@ -127,13 +127,15 @@ class MamlEngine:
         return {n: sd[n] for n, e in self.layout.entries.items() if e.adapted}
 
     # ---- one task ---------------------------------------------------------------------------------
-    def adapt(self, sup: Batch, steps: int, start: int = 0) -> None:
-        """Inner loop (base_adaptor.py:98-112): fast weights theta_{start+1..start+steps}."""
+    def adapt(self, sup: Batch, steps: int, start: int = 0, drop_base: Optional[int] = None) -> None:
+        """Inner loop (base_adaptor.py:98-112): fast weights theta_{start+1..start+steps}.
+        drop_base: None = dropout off; else support pass k uses dropout pass index drop_base + k (learner.train(),
+        base_adaptor.py:103)."""
         be, eng, lay = self.be, self.engine, self.layout
         a0 = lay.adapt_begin
         for k in range(start, start + steps):
             P = self.params(k)
-            eng.forward(P, sup, self.tapes[k])
+            eng.forward(P, sup, self.tapes[k], drop_pass=None if drop_base is None else drop_base + k)
             g_ad = self.g_inner[a0:]
             be.zero_(g_ad)
             eng.backward(P, self.grads(self.g_inner), sup, self.tapes[k], 1.0, into_encoder=False)
@@ -142,15 +144,16 @@ class MamlEngine:
             be.sgd_split(src, g_ad, self.lr, dst[0], dst[1], dst[2])      # l2l maml_update fused with operand prep
         self.bn_batches += steps
 
-    def task_step(self, sup: Batch, qry: Batch, steps: int, first_order: bool, accumulate_scale: Optional[float] = None):
+    def task_step(self, sup: Batch, qry: Batch, steps: int, first_order: bool, accumulate_scale: Optional[float] = None,
+                  drop_base: Optional[int] = None):
         """meta_learn (base_adaptor.py:114-124) + the task's outer gradient into self.g_task.
         Returns the query loss 6-vector tensor (device) and the query predictions dict."""
         assert steps <= self.K_max
         be, eng, lay = self.be, self.engine, self.layout
         a0 = lay.adapt_begin
-        self.adapt(sup, steps)
+        self.adapt(sup, steps, drop_base=drop_base)
         PK = self.params(steps)
-        out = eng.forward(PK, qry, self.tape_q)
+        out = eng.forward(PK, qry, self.tape_q, drop_pass=None if drop_base is None else drop_base + steps)
         self.bn_batches += 1
         be.zero_(self.g_task)
         eng.backward(PK, self.grads(self.g_task), qry, self.tape_q, 1.0, into_encoder=True)

@@ -164,6 +164,16 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+NO_DROP = (0, 0, 1.0)
+
+
+def drop_site(p: float, seed: int):
+    """(thr, seed, scale) of one dropout site (include/mtts.h): thr = floor(p * 2^24), scale = 1/(1-p)."""
+    if p is None or p <= 0.0 or seed is None:
+        return NO_DROP
+    return (int(p * (1 << 24)), int(seed) & 0xFFFFFFFF, 1.0 / (1.0 - p))
+
+
 class _SideCtx:
     """Fork: everything issued so far on the current stream happens-before the side work."""
 
@@ -204,6 +214,7 @@ class CudaOps:
         self._side = torch.cuda.Stream(device=self.device)      # weight-gradient GEMMs / bias column sums (off the critical path)
         self._side_used = False
         self.use_side_stream = True
+        self.drop_salt = None          # device int32[1] (uint32 bits) mixed into every dropout seed; None = 0
 
     # ---- side stream: work that nothing on the critical path waits for (captured as a parallel graph branch) ----
     def side(self):
@@ -250,22 +261,24 @@ class CudaOps:
         return length_regulate_bwd(dy, dur, Lp, out)
 
     # ---- row ops ----
-    def ln_fwd(self, y, res, gamma, beta, lens, T, R, C, z_out, stats, out, out_hi, out_lo, eps=1e-5):
+    def ln_fwd(self, y, res, gamma, beta, lens, T, R, C, z_out, stats, out, out_hi, out_lo, eps=1e-5, pre=NO_DROP, post=NO_DROP):
         self._call("mtts_ln_fwd", _p(y), _p(res), _p(gamma), _p(beta), _p(lens), T, R, C, eps, _p(z_out), _p(stats),
-                   _p(out), _p(out_hi), _p(out_lo))
+                   _p(out), _p(out_hi), _p(out_lo), *pre, *post, _p(self.drop_salt))
 
-    def ln_bwd(self, dy, z, stats, gamma, lens, T, R, C, relu_gate, dz, dz_hi, dz_lo, dgamma, dbeta, dbias):
+    def ln_bwd(self, dy, z, stats, gamma, lens, T, R, C, relu_gate, dz, dz_hi, dz_lo, dgamma, dbeta, dbias, pre=NO_DROP,
+               post=NO_DROP):
         self._call("mtts_ln_bwd", _p(dy), _p(z), _p(stats), _p(gamma), _p(lens), T, R, C, int(relu_gate), _p(dz),
-                   _p(dz_hi), _p(dz_lo), _p(dgamma), _p(dbeta), _p(dbias))
+                   _p(dz_hi), _p(dz_lo), _p(dgamma), _p(dbeta), _p(dbias), *pre, *post, _p(self.drop_salt))
 
-    def ln_tfwd(self, ydot, resdot, z, stats, gamma, gdot, bdot, lens, T, R, C, zdot_out, out, out_hi, out_lo):
+    def ln_tfwd(self, ydot, resdot, z, stats, gamma, gdot, bdot, lens, T, R, C, zdot_out, out, out_hi, out_lo, pre=NO_DROP,
+                post=NO_DROP):
         self._call("mtts_ln_tfwd", _p(ydot), _p(resdot), _p(z), _p(stats), _p(gamma), _p(gdot), _p(bdot), _p(lens),
-                   T, R, C, _p(zdot_out), _p(out), _p(out_hi), _p(out_lo))
+                   T, R, C, _p(zdot_out), _p(out), _p(out_hi), _p(out_lo), *pre, *post, _p(self.drop_salt))
 
     def ln_tbwd(self, dy, ddy, z, zdot, stats, gamma, gdot, lens, T, R, C, relu_gate, ddz, ddz_hi, ddz_lo,
-                ddgamma, ddbeta, ddbias):
+                ddgamma, ddbeta, ddbias, pre=NO_DROP, post=NO_DROP):
         self._call("mtts_ln_tbwd", _p(dy), _p(ddy), _p(z), _p(zdot), _p(stats), _p(gamma), _p(gdot), _p(lens), T, R, C,
-                   int(relu_gate), _p(ddz), _p(ddz_hi), _p(ddz_lo), _p(ddgamma), _p(ddbeta), _p(ddbias))
+                   int(relu_gate), _p(ddz), _p(ddz_hi), _p(ddz_lo), _p(ddgamma), _p(ddbeta), _p(ddbias), *pre, *post, _p(self.drop_salt))
 
     def rowdot_fwd(self, h, hdot, w, wdot, b, bdot, lens, T, R, C, out):
         self._call("mtts_rowdot_fwd", _p(h), _p(hdot), _p(w), _p(wdot), _p(b), _p(bdot), _p(lens), T, R, C, _p(out))
@@ -302,23 +315,25 @@ class CudaOps:
 
     # ---- batch norm ----
     def bn_fwd(self, x, gamma, beta, R, C, tanh_flag, running_mean, running_var, ws, stats, out, hi, lo,
-               eps=1e-5, momentum=0.1):
+               eps=1e-5, momentum=0.1, drop=NO_DROP):
         self._call("mtts_bn_fwd", _p(x), _p(gamma), _p(beta), R, C, eps, momentum, int(tanh_flag), _p(running_mean),
-                   _p(running_var), _p(ws), _p(stats), _p(out), _p(hi), _p(lo))
+                   _p(running_var), _p(ws), _p(stats), _p(out), _p(hi), _p(lo), *drop, _p(self.drop_salt))
 
-    def bn_bwd(self, dout, o, x, stats, gamma, R, C, tanh_flag, ws, dx, hi, lo, dgamma, dbeta, beta=None):
+    def bn_bwd(self, dout, o, x, stats, gamma, R, C, tanh_flag, ws, dx, hi, lo, dgamma, dbeta, beta=None, drop=NO_DROP):
         self._call("mtts_bn_bwd", _p(dout), _p(o), _p(x), _p(stats), _p(gamma), R, C, int(tanh_flag), _p(ws), _p(dx),
-                   _p(hi), _p(lo), _p(dgamma), _p(dbeta))
+                   _p(hi), _p(lo), _p(dgamma), _p(dbeta), *drop, _p(self.drop_salt))
 
-    def bn_tfwd(self, xdot, x, stats, gamma, gdot, bdot, o, R, C, tanh_flag, ws, tsums, odot, hi, lo, beta=None):
+    def bn_tfwd(self, xdot, x, stats, gamma, gdot, bdot, o, R, C, tanh_flag, ws, tsums, odot, hi, lo, beta=None,
+                drop=NO_DROP):
         self._call("mtts_bn_tfwd", _p(xdot), _p(x), _p(stats), _p(gamma), _p(gdot), _p(bdot), _p(o), R, C,
-                   int(tanh_flag), _p(ws), _p(tsums), _p(odot), _p(hi), _p(lo))
+                   int(tanh_flag), _p(ws), _p(tsums), _p(odot), _p(hi), _p(lo), *drop, _p(self.drop_salt))
 
     def bn_tbwd(self, dout, ddout, o, odot, x, xdot, stats, tsums, gamma, gdot, R, C, tanh_flag, ws, ddx, hi, lo,
-                ddgamma, ddbeta, beta=None, bdot=None):
+                ddgamma, ddbeta, beta=None, bdot=None, drop=NO_DROP):
         # beta / bdot are only used by the CPU restatement (the kernels use the saved tanh output o / odot)
         self._call("mtts_bn_tbwd", _p(dout), _p(ddout), _p(o), _p(odot), _p(x), _p(xdot), _p(stats), _p(tsums),
-                   _p(gamma), _p(gdot), R, C, int(tanh_flag), _p(ws), _p(ddx), _p(hi), _p(lo), _p(ddgamma), _p(ddbeta))
+                   _p(gamma), _p(gdot), R, C, int(tanh_flag), _p(ws), _p(ddx), _p(hi), _p(lo), _p(ddgamma), _p(ddbeta),
+                   *drop, _p(self.drop_salt))
 
     # ---- loss ----
     def loss_fwd(self, mel, post, mel_tgt, mel_lens, p, p_tgt, e, e_tgt, logd, dur, src_lens, B, T, Lp, NM, ws, out6,

@@ -45,12 +45,13 @@ class _StaticBatch:
     All tensor fields live in ONE contiguous byte buffer: one cudaMemcpyAsync per batch; the host may run
     one step ahead of the device (ring of 2, guarded by events)."""
     FIELDS = (("spk_ids", torch.int64), ("texts", torch.int64), ("src_lens", torch.int64), ("mels", torch.float32),
-              ("mel_lens", torch.int64), ("pitches", torch.float32), ("energies", torch.float32), ("durations", torch.int64))
+              ("mel_lens", torch.int64), ("pitches", torch.float32), ("energies", torch.float32), ("durations", torch.int64),
+              ("salt", torch.int32))        # per-step dropout salt (uint32 bits): rides in the same H2D copy
     RING = 2
 
     def __init__(self, device, n: int, L: int, T: int, n_spk_ids: int, average_spk: bool):
         shapes = {"spk_ids": (n_spk_ids,), "texts": (n, L), "src_lens": (n,), "mels": (n, T, N_MEL), "mel_lens": (n,),
-                  "pitches": (n, L), "energies": (n, L), "durations": (n, L)}
+                  "pitches": (n, L), "energies": (n, L), "durations": (n, L), "salt": (1,)}
         offs, off = {}, 0
         for f, dt in self.FIELDS:
             nbytes = int(torch.tensor([], dtype=dt).element_size()) * int(torch.Size(shapes[f]).numel())
@@ -60,6 +61,7 @@ class _StaticBatch:
         self.dev_buf = torch.zeros(off, dtype=torch.uint8, device=device)
         view = lambda buf, f, dt: buf[offs[f][0]:offs[f][0] + offs[f][1]].view(dt).view(shapes[f])  # noqa: E731
         d = {f: view(self.dev_buf, f, dt) for f, dt in self.FIELDS}
+        self.salt = d.pop("salt")
         self.dev = Batch(average_spk=average_spk, B=n, L=L, T=T, **d)
         pin = torch.cuda.is_available() and self.dev_buf.is_cuda
         self.host_bufs = [torch.zeros(off, dtype=torch.uint8).pin_memory() if pin else torch.zeros(off, dtype=torch.uint8)
@@ -69,7 +71,7 @@ class _StaticBatch:
         self.slot = 0
         self.h2d_bytes = off
 
-    def upload(self, b12, spk_ids=None) -> None:
+    def upload(self, b12, spk_ids=None, salt: int = 0) -> None:
         k = self.slot
         self.slot = (k + 1) % self.RING
         if self.events[k] is not None:
@@ -83,6 +85,8 @@ class _StaticBatch:
             dst.copy_(src if torch.is_tensor(src) else torch.as_tensor(src))      # dtype conversion + gather into pinned staging
         spk = b12[2] if spk_ids is None else spk_ids
         h["spk_ids"].copy_(spk if torch.is_tensor(spk) else torch.as_tensor(spk))
+        salt &= 0xFFFFFFFF
+        h["salt"][0] = salt - (1 << 32) if salt >= (1 << 31) else salt
         self.dev_buf.copy_(self.host_bufs[k], non_blocking=True)       # ONE H2D per batch
         if self.dev_buf.is_cuda:
             ev = self.events[k] or torch.cuda.Event()
@@ -168,7 +172,8 @@ DEFAULT_TRAIN_CONFIG = {
 
 def _metasystem_init(self, preprocess_config=None, model_config=None, train_config=None, algorithm_config=None,
                      log_dir=None, result_dir=None, *, n_speaker: int = 16, device: str = "cuda:0", split: int = 3,
-                     use_cuda_graph: bool = True, second_order: bool = True, process_group=None, backend=None):
+                     use_cuda_graph: bool = True, second_order: bool = True, process_group=None, backend=None,
+                     dropout: bool = True, seed: int = 0):
     self.preprocess_config = preprocess_config
     self.model_config = model_config or DEFAULT_MODEL_CONFIG
     self.train_config = train_config or DEFAULT_TRAIN_CONFIG
@@ -180,6 +185,11 @@ def _metasystem_init(self, preprocess_config=None, model_config=None, train_conf
     assert ad.get("speaker_emb", "table") == "table", "only the table speaker embedding is on the hot path"
     self.device = torch.device(device)
     self.second_order = second_order       # reference: first_order = not train  (base_adaptor.py:107)
+    # learner.train() (base_adaptor.py:103): dropout is active in every meta_learn forward.  Masks come from a counter
+    # hash of (site, pass, element, salt); salt = seed + step * world + rank rides in the support batch's H2D copy.
+    self.dropout = dropout
+    self.seed = seed
+    self._drop_steps = 0
     # `backend` exists for host-logic tests (tests inject the CPU restatement); the product path is CudaOps,
     # which raises without a B200 — there is no fallback.
     self.be = backend if backend is not None else CudaOps(split=split, device=device)
@@ -225,11 +235,13 @@ def _run_task(self, sup12, qry12, steps: int, first_order: bool, accumulate_scal
     key, ent = _get_task(self, sup12, qry12, steps, first_order)
     sb, qb, graph, result, tapes = ent
     self.maml.use_tapes(tapes)
-    sb.upload(sup12)
+    drop_base = 0 if self.dropout else None
+    self.be.drop_salt = sb.salt
+    sb.upload(sup12, salt=self.next_salt() if self.dropout else 0)
     qb.upload(qry12, spk_ids=sup12[2])            # query uses the SUPPORT speaker ids, averaged (base_adaptor.py:122)
     if not self.use_cuda_graph:
         n0 = _ops.launch_count
-        result = self.maml.task_step(sb.dev, qb.dev, steps, first_order, accumulate_scale)
+        result = self.maml.task_step(sb.dev, qb.dev, steps, first_order, accumulate_scale, drop_base)
         self.launches_per_task_step = _ops.launch_count - n0
         return result
     if graph is None:
@@ -237,7 +249,7 @@ def _run_task(self, sup12, qry12, steps: int, first_order: bool, accumulate_scal
         bn0 = self.maml.bn_batches
         saved = {k: v.clone() for k, v in self.maml.consts.items() if k.endswith(("running_mean", "running_var"))}
         g_outer_saved = self.maml.g_outer.clone()
-        self.maml.task_step(sb.dev, qb.dev, steps, first_order, accumulate_scale)
+        self.maml.task_step(sb.dev, qb.dev, steps, first_order, accumulate_scale, drop_base)
         torch.cuda.synchronize()
         for k, v in saved.items():
             self.maml.consts[k].copy_(v)           # the warm-up must not advance BatchNorm running statistics
@@ -246,13 +258,24 @@ def _run_task(self, sup12, qry12, steps: int, first_order: bool, accumulate_scal
         graph = torch.cuda.CUDAGraph()
         n0 = _ops.launch_count
         with torch.cuda.graph(graph):
-            result = self.maml.task_step(sb.dev, qb.dev, steps, first_order, accumulate_scale)
+            result = self.maml.task_step(sb.dev, qb.dev, steps, first_order, accumulate_scale, drop_base)
         self.launches_per_task_step = _ops.launch_count - n0
         self.maml.bn_batches = bn0
         ent[2], ent[3] = graph, result
     graph.replay()
     self.maml.bn_batches += steps + 1
     return ent[3]
+
+
+def next_salt(self) -> int:
+    """Dropout salt of the next task step: distinct per step and per rank (uint32)."""
+    dist = torch.distributed.is_initialized()
+    world = torch.distributed.get_world_size(self.process_group) if dist else 1
+    rank = torch.distributed.get_rank(self.process_group) if dist else 0
+    salt = (self.seed * 0x9E3779B1 + self._drop_steps * world + rank) & 0xFFFFFFFF
+    self.last_salt = salt
+    self._drop_steps += 1
+    return salt
 
 
 def _scale(self) -> float:
@@ -268,8 +291,9 @@ def adapt(self, batch, adaptation_steps: int = 5, learner=None, train: bool = Tr
     sup12 = batch[0][0][0]
     start = int(learner) if learner is not None else 0
     sb = _StaticBatch(self.device, sup12[3].shape[0], int(sup12[5]), int(sup12[8]), sup12[3].shape[0], False)
-    sb.upload(sup12)
-    self.maml.adapt(sb.dev, adaptation_steps, start=start)
+    self.be.drop_salt = sb.salt
+    sb.upload(sup12, salt=self.next_salt() if self.dropout else 0)
+    self.maml.adapt(sb.dev, adaptation_steps, start=start, drop_base=start if self.dropout else None)
     return start + adaptation_steps
 
 
@@ -344,6 +368,7 @@ class MetaSystem:
     training_step = training_step
     validation_step = validation_step
     optimizer_step = optimizer_step
+    next_salt = next_salt
     _on_meta_batch_start = staticmethod(_assert_meta_batch)
 
 

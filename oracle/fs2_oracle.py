@@ -14,9 +14,14 @@ lives in learn2learn (requirements.txt:2, unpinned, absent): its published algor
 call sites lightning/systems/base_adaptor.py:98-124 and lightning/systems/utils.py:17-77.
 
 Every function cites the reference file:line it follows (paths relative to /root/reference).
-Dropout is the identity everywhere (torch's CPU Philox stream cannot be matched by a CUDA kernel;
-SURVEY.md §8c) while BatchNorm keeps train-mode batch statistics, as in `learner.train()`
-(base_adaptor.py:103).
+Dropout: `learner.train()` (base_adaptor.py:103) keeps every nn.Dropout / F.dropout active.  torch's CPU
+Philox stream cannot be matched by a CUDA kernel, so the masks are defined by a counter
+hash instead (`drop_keep`: murmur3 finaliser of element index + site/pass seed + per-step salt; spec in
+include/mtts.h) which this file evaluates with exact integer arithmetic and the kernels evaluate on the
+device — same sites, same rates, same 1/(1-p) scaling as the reference, and parity holds WITH dropout.
+`drop_seed=None` gives identity dropout (used for the goldens from the real reference modules, which were
+generated with the Dropout modules neutralised); `drop_seed="torch"` uses torch's own dropout (timing only).
+BatchNorm keeps train-mode batch statistics.
 """
 from __future__ import annotations
 
@@ -175,6 +180,55 @@ def adapted_names(P: Params, modules: Sequence[str] = ADAPT_MODULES) -> List[str
 
 
 # ------------------------------------------------------------------------------------------------
+# dropout: the counter-based hash of include/mtts.h evaluated on the host (exact integer arithmetic), so the
+# oracle and the kernels drop the SAME elements and parity holds in train mode with dropout active
+# ------------------------------------------------------------------------------------------------
+def _mul32(h: torch.Tensor, c: int) -> torch.Tensor:
+    lo = (h * (c & 0xFFFF)) & 0xFFFFFFFF
+    hi = ((h * (c >> 16)) & 0xFFFF) << 16
+    return (lo + hi) & 0xFFFFFFFF
+
+
+def drop_keep(thr: int, seed: int, numel: int) -> torch.Tensor:
+    """bool [numel]: element i kept iff (mix32(i + seed*0x9E3779B9) >> 8) >= thr  (seed = the EFFECTIVE seed)."""
+    c = ((int(seed) & 0xFFFFFFFF) * 0x9E3779B9) & 0xFFFFFFFF
+    h = (torch.arange(numel, dtype=torch.int64) + c) & 0xFFFFFFFF
+    h = h ^ (h >> 16)
+    h = _mul32(h, 0x85EBCA6B)
+    h = h ^ (h >> 13)
+    h = _mul32(h, 0xC2B2AE35)
+    h = h ^ (h >> 16)
+    return (h >> 8) >= int(thr)
+
+
+def drop_mask(p: float, seed: int, numel: int) -> torch.Tensor:
+    """float32 [numel]: 1/(1-p) where kept, 0 where dropped; thr = floor(p*2^24)."""
+    if p is None or p <= 0.0 or seed is None:
+        return torch.ones(numel)
+    return drop_keep(int(p * (1 << 24)), seed, numel).float() * (1.0 / (1.0 - p))
+
+
+def site_seed(pass_seed, site: str) -> Optional[int]:
+    """Effective seed of one dropout site of one forward pass.  pass_seed = (pass_index, salt) or None:
+    the launch-time scalar is crc32(site) ^ (pass_index * 2654435761) and the device adds salt * 0x632BE5AB
+    (include/mtts.h); an int pass_seed means salt 0."""
+    if pass_seed is None:
+        return None
+    import zlib
+    idx, salt = pass_seed if isinstance(pass_seed, tuple) else (pass_seed, 0)
+    scalar = (zlib.crc32(site.encode()) ^ ((int(idx) * 2654435761) & 0xFFFFFFFF)) & 0xFFFFFFFF
+    return (scalar + (int(salt) & 0xFFFFFFFF) * 0x632BE5AB) & 0xFFFFFFFF
+
+
+def _drop(x: torch.Tensor, p: float, pass_seed: Optional[int], site: str) -> torch.Tensor:
+    if pass_seed is None:
+        return x
+    if pass_seed == "torch":          # the reference's own nn.Dropout / F.dropout (Philox): used only when TIMING the CPU arm
+        return F.dropout(x, p, True)
+    return x * drop_mask(p, site_seed(pass_seed, site), x.numel()).reshape(x.shape).to(x.dtype)
+
+
+# ------------------------------------------------------------------------------------------------
 # model forward
 # ------------------------------------------------------------------------------------------------
 def get_mask_from_lengths(lengths: torch.Tensor, max_len: Optional[int] = None) -> torch.Tensor:
@@ -185,7 +239,7 @@ def get_mask_from_lengths(lengths: torch.Tensor, max_len: Optional[int] = None) 
     return ids >= lengths.unsqueeze(1).expand(-1, int(max_len))
 
 
-def fft_block(P: Params, prefix: str, x, mask, n_head: int):
+def fft_block(P: Params, prefix: str, x, mask, n_head: int, p_drop: float = 0.0, drop_seed: Optional[int] = None):
     """transformer/Layers.py:21-30 -> SubLayers.py:29-57 -> Modules.py:14-25 ; SubLayers.py:85-93."""
     B, Lq, d_model = x.shape
     d_k = d_model // n_head
@@ -202,7 +256,8 @@ def fft_block(P: Params, prefix: str, x, mask, n_head: int):
     attn = torch.softmax(attn, dim=2)
     out = torch.bmm(attn, v)
     out = out.view(n_head, B, Lq, d_k).permute(1, 2, 0, 3).contiguous().view(B, Lq, -1)
-    out = F.linear(out, P[f"{prefix}.slf_attn.fc.weight"], P[f"{prefix}.slf_attn.fc.bias"])     # dropout = id
+    out = F.linear(out, P[f"{prefix}.slf_attn.fc.weight"], P[f"{prefix}.slf_attn.fc.bias"])
+    out = _drop(out, p_drop, drop_seed, f"{prefix}.slf_attn")                                  # SubLayers.py:54
     out = F.layer_norm(out + residual, (d_model,), P[f"{prefix}.slf_attn.layer_norm.weight"],
                        P[f"{prefix}.slf_attn.layer_norm.bias"])
     out = out.masked_fill(mask.unsqueeze(-1), 0)
@@ -211,37 +266,42 @@ def fft_block(P: Params, prefix: str, x, mask, n_head: int):
     w2, b2 = P[f"{prefix}.pos_ffn.w_2.weight"], P[f"{prefix}.pos_ffn.w_2.bias"]
     h = F.conv1d(out.transpose(1, 2), w1, b1, padding=(w1.shape[2] - 1) // 2)
     h = F.conv1d(F.relu(h), w2, b2, padding=(w2.shape[2] - 1) // 2).transpose(1, 2)
+    h = _drop(h.contiguous(), p_drop, drop_seed, f"{prefix}.pos_ffn")                          # SubLayers.py:90
     out = F.layer_norm(h + residual, (d_model,), P[f"{prefix}.pos_ffn.layer_norm.weight"],
                        P[f"{prefix}.pos_ffn.layer_norm.bias"])
     return out.masked_fill(mask.unsqueeze(-1), 0)
 
 
-def encoder(P: Params, cfg, src_seq, mask):
+def encoder(P: Params, cfg, src_seq, mask, drop_seed: Optional[int] = None):
     """transformer/Models.py:73-100 (training branch)."""
     L = src_seq.shape[1]
     x = F.embedding(src_seq, P["encoder.src_word_emb.weight"], padding_idx=0) + P["encoder.position_enc"][:, :L, :]
     for i in range(cfg["transformer"]["encoder_layer"]):
-        x = fft_block(P, f"encoder.layer_stack.{i}", x, mask, cfg["transformer"]["encoder_head"])
+        x = fft_block(P, f"encoder.layer_stack.{i}", x, mask, cfg["transformer"]["encoder_head"],
+                      cfg["transformer"]["encoder_dropout"], drop_seed)
     return x
 
 
-def decoder(P: Params, cfg, enc_seq, mask):
+def decoder(P: Params, cfg, enc_seq, mask, drop_seed: Optional[int] = None):
     """transformer/Models.py:139-171 (training branch: truncate to max_seq_len)."""
     max_len = min(enc_seq.shape[1], cfg["max_seq_len"])
     x = enc_seq[:, :max_len, :] + P["decoder.position_enc"][:, :max_len, :]
     mask = mask[:, :max_len]
     for i in range(cfg["transformer"]["decoder_layer"]):
-        x = fft_block(P, f"decoder.layer_stack.{i}", x, mask, cfg["transformer"]["decoder_head"])
+        x = fft_block(P, f"decoder.layer_stack.{i}", x, mask, cfg["transformer"]["decoder_head"],
+                      cfg["transformer"]["decoder_dropout"], drop_seed)
     return x, mask
 
 
-def variance_predictor(P: Params, prefix: str, x, mask):
+def variance_predictor(P: Params, prefix: str, x, mask, p_drop: float = 0.0, drop_seed: Optional[int] = None):
     """lightning/model/modules.py:242-250 (+ Conv 291-296)."""
     c = f"{prefix}.conv_layer"
     h = F.conv1d(x.transpose(1, 2), P[f"{c}.conv1d_1.conv.weight"], P[f"{c}.conv1d_1.conv.bias"], padding=1).transpose(1, 2)
     h = F.layer_norm(F.relu(h), (h.shape[-1],), P[f"{c}.layer_norm_1.weight"], P[f"{c}.layer_norm_1.bias"])
+    h = _drop(h.contiguous(), p_drop, drop_seed, f"{prefix}.1")                                # modules.py:223
     h = F.conv1d(h.transpose(1, 2), P[f"{c}.conv1d_2.conv.weight"], P[f"{c}.conv1d_2.conv.bias"], padding=1).transpose(1, 2)
     h = F.layer_norm(F.relu(h), (h.shape[-1],), P[f"{c}.layer_norm_2.weight"], P[f"{c}.layer_norm_2.bias"])
+    h = _drop(h.contiguous(), p_drop, drop_seed, f"{prefix}.2")                                # modules.py:235
     out = F.linear(h, P[f"{prefix}.linear_layer.weight"], P[f"{prefix}.linear_layer.bias"]).squeeze(-1)
     if mask is not None:
         out = out.masked_fill(mask, 0.0)
@@ -265,18 +325,18 @@ def length_regulator_ref(x, duration, max_len):
 
 
 def variance_adaptor(P: Params, x, src_mask, mel_mask, max_len, pitch_target, energy_target, duration_target,
-                     p_control=1.0, e_control=1.0, d_control=1.0):
+                     p_control=1.0, e_control=1.0, d_control=1.0, p_drop: float = 0.0, drop_seed: Optional[int] = None):
     """lightning/model/modules.py:102-158, phoneme-level pitch/energy (preprocess/LibriTTS.yaml:37,40)."""
     va = "variance_adaptor"
-    log_d = variance_predictor(P, f"{va}.duration_predictor", x, src_mask)
-    p_pred = variance_predictor(P, f"{va}.pitch_predictor", x, src_mask)
+    log_d = variance_predictor(P, f"{va}.duration_predictor", x, src_mask, p_drop, drop_seed)
+    p_pred = variance_predictor(P, f"{va}.pitch_predictor", x, src_mask, p_drop, drop_seed)
     if pitch_target is not None:
         p_emb = F.embedding(torch.bucketize(pitch_target, P[f"{va}.pitch_bins"]), P[f"{va}.pitch_embedding.weight"])
     else:
         p_pred = p_pred * p_control
         p_emb = F.embedding(torch.bucketize(p_pred, P[f"{va}.pitch_bins"]), P[f"{va}.pitch_embedding.weight"])
     x = x + p_emb
-    e_pred = variance_predictor(P, f"{va}.energy_predictor", x, src_mask)
+    e_pred = variance_predictor(P, f"{va}.energy_predictor", x, src_mask, p_drop, drop_seed)
     if energy_target is not None:
         e_emb = F.embedding(torch.bucketize(energy_target, P[f"{va}.energy_bins"]), P[f"{va}.energy_embedding.weight"])
     else:
@@ -293,7 +353,7 @@ def variance_adaptor(P: Params, x, src_mask, mel_mask, max_len, pitch_target, en
     return x, p_pred, e_pred, log_d, d_rounded, mel_len, mel_mask
 
 
-def postnet(P: Params, x, training: bool = True):
+def postnet(P: Params, x, training: bool = True, drop_seed: Optional[int] = None):
     """transformer/Layers.py:129-137: 4x tanh(BN(conv5)) + BN(conv5); dropout = id.
     BatchNorm1d in train mode: batch statistics over all B*T positions (padded frames included),
     running stats updated in place (momentum 0.1, unbiased variance)."""
@@ -307,28 +367,32 @@ def postnet(P: Params, x, training: bool = True):
                          P[f"{pre}.1.bias"], training, 0.1, 1e-5)
         if i < 4:
             h = torch.tanh(h)
+        # F.dropout(..., 0.5, self.training) Layers.py:133-134; the kernels index elements token-major [B, T, C]
+        h = _drop(h.transpose(1, 2).contiguous(), 0.5, drop_seed, f"postnet.{i}").transpose(1, 2)
     return h.contiguous().transpose(1, 2)
 
 
 def fs2_forward(P: Params, cfg, speaker_args, texts, src_lens, max_src_len, mels=None, mel_lens=None,
                 max_mel_len=None, p_targets=None, e_targets=None, d_targets=None,
-                p_control=1.0, e_control=1.0, d_control=1.0, average_spk_emb=False, training=True):
+                p_control=1.0, e_control=1.0, d_control=1.0, average_spk_emb=False, training=True,
+                drop_seed: Optional[int] = None):
     """lightning/systems/base_adaptor.py:41-95 (`forward_learner`; maths identical to
     lightning/model/fastspeech2.py:40-112).  Returns the reference's 10-tuple."""
     max_src_len = int(max_src_len)
     src_masks = get_mask_from_lengths(src_lens, max_src_len)
-    output = encoder(P, cfg, texts, src_masks)
+    output = encoder(P, cfg, texts, src_masks, drop_seed)
     mel_masks = get_mask_from_lengths(mel_lens, int(max_mel_len)) if mel_lens is not None else None
     spk_emb = F.embedding(speaker_args, P["speaker_emb.model.weight"])            # speaker_encoder.py:62-65
     if average_spk_emb:
         spk_emb = spk_emb.mean(dim=0, keepdim=True).expand(output.shape[0], -1)   # base_adaptor.py:66-67
     output = output + spk_emb.unsqueeze(1).expand(-1, max_src_len, -1)
     (output, p_pred, e_pred, log_d_pred, d_rounded, mel_lens_out, mel_masks) = variance_adaptor(
-        P, output, src_masks, mel_masks, max_mel_len, p_targets, e_targets, d_targets, p_control, e_control, d_control)
+        P, output, src_masks, mel_masks, max_mel_len, p_targets, e_targets, d_targets, p_control, e_control, d_control,
+        cfg["variance_predictor"]["dropout"], drop_seed)
     output = output + spk_emb.unsqueeze(1).expand(-1, int(max(mel_lens_out)), -1)   # base_adaptor.py:80-84
-    output, mel_masks = decoder(P, cfg, output, mel_masks)
+    output, mel_masks = decoder(P, cfg, output, mel_masks, drop_seed)
     output = F.linear(output, P["mel_linear.weight"], P["mel_linear.bias"])
-    postnet_output = postnet(P, output, training) + output
+    postnet_output = postnet(P, output, training, drop_seed) + output
     return (output, postnet_output, p_pred, e_pred, log_d_pred, d_rounded, src_masks, mel_masks, src_lens, mel_lens_out)
 
 
@@ -363,7 +427,7 @@ def fs2_loss(inputs, predictions):
 # ------------------------------------------------------------------------------------------------
 def maml_task_step(P: Params, cfg, sup_batch, qry_batch, adaptation_steps: int, lr: float = 0.001,
                    first_order: bool = False, adapt_modules: Sequence[str] = ADAPT_MODULES,
-                   return_fast_weights: bool = False):
+                   return_fast_weights: bool = False, drop_seed: Optional[int] = None):
     """One task of one outer meta-step.
 
     learner = self.learner.clone()          l2l clone_module: theta_0[k] = P[k].clone()  (differentiable)
@@ -391,14 +455,20 @@ def maml_task_step(P: Params, cfg, sup_batch, qry_batch, adaptation_steps: int, 
         m.update(theta)
         return m
 
-    for _ in range(adaptation_steps):
-        preds = fs2_forward(merged(), cfg, *sup_batch[2:])
+    # dropout: forward pass k of the task uses pass seed drop_seed + k (query pass: + adaptation_steps); None = identity
+    if drop_seed is None or drop_seed == "torch":
+        ds = lambda k: drop_seed
+    else:
+        d_base, d_salt = drop_seed if isinstance(drop_seed, tuple) else (drop_seed, 0)
+        ds = lambda k: (d_base + k, d_salt)
+    for step_i in range(adaptation_steps):
+        preds = fs2_forward(merged(), cfg, *sup_batch[2:], drop_seed=ds(step_i))
         loss = fs2_loss(sup_batch, preds)[0]
         keys = list(theta.keys())
         grads = torch.autograd.grad(loss, [theta[k] for k in keys], retain_graph=second_order,
                                     create_graph=second_order, allow_unused=False)
         theta = {k: theta[k] + (-lr * g) for k, g in zip(keys, grads)}
-    predictions = fs2_forward(merged(), cfg, sup_batch[2], *qry_batch[3:], average_spk_emb=True)
+    predictions = fs2_forward(merged(), cfg, sup_batch[2], *qry_batch[3:], average_spk_emb=True, drop_seed=ds(adaptation_steps))
     valid = fs2_loss(qry_batch, predictions)
     outer = torch.autograd.grad(valid[0], [leaves[k] for k in names_tr], allow_unused=True)
     grads = {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(names_tr, outer)}

@@ -56,6 +56,9 @@ def _row_mask(lens, T, R):
     return (r % T) < lens[(r // T)]
 
 
+NO_DROP = (0, 0, 1.0)
+
+
 class RefOps:
     name = "ref"
 
@@ -201,11 +204,24 @@ class RefOps:
     def _ln(z, gamma, beta, mask, eps=1e-5):
         return F.layer_norm(z, (z.shape[-1],), gamma, beta, eps) * mask[:, None]
 
-    def ln_fwd(self, y, res, gamma, beta, lens, T, R, C, z_out, stats, out, out_hi, out_lo, eps=1e-5):
+    # dropout sites: (thr, seed, scale) as in include/mtts.h; the same integer hash evaluated on the host
+    drop_salt = None
+
+    def _dm(self, site, R, C):
+        thr, seed, scale = site
+        if thr == 0:
+            return 1.0
+        from oracle.fs2_oracle import drop_keep
+        salt = (int(self.drop_salt.reshape(-1)[0].item()) & 0xFFFFFFFF) if self.drop_salt is not None else 0
+        eff = (int(seed) + salt * 0x632BE5AB) & 0xFFFFFFFF
+        return drop_keep(thr, eff, R * C).reshape(R, C).double() * float(torch.tensor(scale, dtype=torch.float32))
+
+    def ln_fwd(self, y, res, gamma, beta, lens, T, R, C, z_out, stats, out, out_hi, out_lo, eps=1e-5, pre=NO_DROP,
+               post=NO_DROP):
         self.n_calls += 1
-        z = y.reshape(R, C).double() + (res.reshape(R, C).double() if res is not None else 0)
+        z = y.reshape(R, C).double() * self._dm(pre, R, C) + (res.reshape(R, C).double() if res is not None else 0)
         mask = _row_mask(lens, T, R).double()
-        o = self._ln(z, gamma.double(), beta.double(), mask, eps)
+        o = self._ln(z, gamma.double(), beta.double(), mask, eps) * self._dm(post, R, C)
         if stats is not None:
             mean = z.mean(1)
             rstd = 1.0 / torch.sqrt(z.var(1, unbiased=False) + eps)
@@ -214,17 +230,19 @@ class RefOps:
         _put(out, o)
         _put_split(out_hi, out_lo, o)
 
-    def ln_bwd(self, dy, z, stats, gamma, lens, T, R, C, relu_gate, dz, dz_hi, dz_lo, dgamma, dbeta, dbias):
+    def ln_bwd(self, dy, z, stats, gamma, lens, T, R, C, relu_gate, dz, dz_hi, dz_lo, dgamma, dbeta, dbias, pre=NO_DROP,
+               post=NO_DROP):
         self.n_calls += 1
         zz = z.reshape(R, C).double()
         mask = _row_mask(lens, T, R).double()
         g = gamma.double()
         beta0 = torch.zeros(C, dtype=torch.float64)
         _, fn = vjp(lambda a, b, c: self._ln(a, b, c, mask), zz, g, beta0)
-        dzz, dg, db = fn(dy.reshape(R, C).double())
+        dzz, dg, db = fn(dy.reshape(R, C).double() * self._dm(post, R, C))
         if relu_gate:
             dzz = dzz * (zz > 0)
-        _put(dz, dzz)
+        _put(dz, dzz)                               # residual path
+        dzz = dzz * self._dm(pre, R, C)             # branch path
         _put_split(dz_hi, dz_lo, dzz)
         if dgamma is not None:
             dgamma += dg.float()
@@ -233,24 +251,27 @@ class RefOps:
         if dbias is not None:
             dbias += dzz.sum(0).float()
 
-    def ln_tfwd(self, ydot, resdot, z, stats, gamma, gdot, bdot, lens, T, R, C, zdot_out, out, out_hi, out_lo):
+    def ln_tfwd(self, ydot, resdot, z, stats, gamma, gdot, bdot, lens, T, R, C, zdot_out, out, out_hi, out_lo, pre=NO_DROP,
+                post=NO_DROP):
         self.n_calls += 1
         zz = z.reshape(R, C).double()
-        zd = ydot.reshape(R, C).double() + (resdot.reshape(R, C).double() if resdot is not None else 0)
+        zd = ydot.reshape(R, C).double() * self._dm(pre, R, C) + (resdot.reshape(R, C).double() if resdot is not None else 0)
         mask = _row_mask(lens, T, R).double()
         g = gamma.double()
         gd = gdot.double() if gdot is not None else torch.zeros_like(g)
         bd = bdot.double() if bdot is not None else torch.zeros_like(g)
         _, od = jvp(lambda a, b, c: self._ln(a, b, c, mask), (zz, g, torch.zeros_like(g)), (zd, gd, bd))
+        od = od * self._dm(post, R, C)
         _put(zdot_out, zd)
         _put(out, od)
         _put_split(out_hi, out_lo, od)
 
     def ln_tbwd(self, dy, ddy, z, zdot, stats, gamma, gdot, lens, T, R, C, relu_gate, ddz, ddz_hi, ddz_lo, ddgamma,
-                ddbeta, ddbias):
+                ddbeta, ddbias, pre=NO_DROP, post=NO_DROP):
         self.n_calls += 1
         zz, zd = z.reshape(R, C).double(), zdot.reshape(R, C).double()
-        d, dd = dy.reshape(R, C).double(), ddy.reshape(R, C).double()
+        mpost = self._dm(post, R, C)
+        d, dd = dy.reshape(R, C).double() * mpost, ddy.reshape(R, C).double() * mpost
         mask = _row_mask(lens, T, R).double()
         g = gamma.double()
         gd = gdot.double() if gdot is not None else torch.zeros_like(g)
@@ -264,6 +285,7 @@ class RefOps:
         if relu_gate:
             tz = tz * (zz > 0)
         _put(ddz, tz)
+        tz = tz * self._dm(pre, R, C)
         _put_split(ddz_hi, ddz_lo, tz)
         if ddgamma is not None:
             ddgamma += tg.float()
@@ -399,17 +421,17 @@ class RefOps:
     # BatchNorm (train) + tanh
     # ------------------------------------------------------------------------------------------
     @staticmethod
-    def _bn(x, gamma, beta, tanh_flag, eps=1e-5):
+    def _bn(x, gamma, beta, tanh_flag, eps=1e-5, m=1.0):
         mean = x.mean(0)
         var = x.var(0, unbiased=False)
         y = (x - mean) / torch.sqrt(var + eps) * gamma + beta
-        return torch.tanh(y) if tanh_flag else y
+        return (torch.tanh(y) if tanh_flag else y) * m
 
     def bn_fwd(self, x, gamma, beta, R, C, tanh_flag, running_mean, running_var, ws, stats, out, hi, lo, eps=1e-5,
-               momentum=0.1):
+               momentum=0.1, drop=NO_DROP):
         self.n_calls += 1
         xx = x.reshape(R, C).double()
-        o = self._bn(xx, gamma.double(), beta.double(), tanh_flag, eps)
+        o = self._bn(xx, gamma.double(), beta.double(), tanh_flag, eps, self._dm(drop, R, C))
         mean, var = xx.mean(0), xx.var(0, unbiased=False)
         stats.copy_(torch.cat([mean, 1.0 / torch.sqrt(var + eps)]).float().reshape(stats.shape))
         if running_mean is not None:
@@ -418,12 +440,13 @@ class RefOps:
         _put(out, o)
         _put_split(hi, lo, o)
 
-    def bn_bwd(self, dout, o, x, stats, gamma, R, C, tanh_flag, ws, dx, hi, lo, dgamma, dbeta, beta=None):
+    def bn_bwd(self, dout, o, x, stats, gamma, R, C, tanh_flag, ws, dx, hi, lo, dgamma, dbeta, beta=None, drop=NO_DROP):
         self.n_calls += 1
         xx, g = x.reshape(R, C).double(), gamma.double()
         bt = beta.double() if beta is not None else torch.zeros_like(g)
         assert beta is not None or not tanh_flag, "RefOps needs beta for the tanh layers"
-        _, fn = vjp(lambda a, b, c: self._bn(a, b, c, tanh_flag), xx, g, bt)
+        m = self._dm(drop, R, C)
+        _, fn = vjp(lambda a, b, c: self._bn(a, b, c, tanh_flag, m=m), xx, g, bt)
         dxx, dg, db = fn(dout.reshape(R, C).double())
         _put(dx, dxx)
         _put_split(hi, lo, dxx)
@@ -432,14 +455,16 @@ class RefOps:
         if dbeta is not None:
             dbeta += db.float()
 
-    def bn_tfwd(self, xdot, x, stats, gamma, gdot, bdot, o, R, C, tanh_flag, ws, tsums, odot, hi, lo, beta=None):
+    def bn_tfwd(self, xdot, x, stats, gamma, gdot, bdot, o, R, C, tanh_flag, ws, tsums, odot, hi, lo, beta=None,
+                drop=NO_DROP):
         self.n_calls += 1
         xx, xd, g = x.reshape(R, C).double(), xdot.reshape(R, C).double(), gamma.double()
         gd = gdot.double() if gdot is not None else torch.zeros_like(g)
         bd = bdot.double() if bdot is not None else torch.zeros_like(g)
         bt = beta.double() if beta is not None else torch.zeros_like(g)
         assert beta is not None or not tanh_flag
-        _, od = jvp(lambda a, b, c: self._bn(a, b, c, tanh_flag), (xx, g, bt), (xd, gd, bd))
+        m = self._dm(drop, R, C)
+        _, od = jvp(lambda a, b, c: self._bn(a, b, c, tanh_flag, m=m), (xx, g, bt), (xd, gd, bd))
         mean, rstd = stats.reshape(2, C)[0].double(), stats.reshape(2, C)[1].double()
         xh = (xx - mean) * rstd
         tsums.copy_(torch.cat([xd.mean(0), (xd * xh).mean(0)]).float().reshape(tsums.shape))
@@ -447,8 +472,9 @@ class RefOps:
         _put_split(hi, lo, od)
 
     def bn_tbwd(self, dout, ddout, o, odot, x, xdot, stats, tsums, gamma, gdot, R, C, tanh_flag, ws, ddx, hi, lo,
-                ddgamma, ddbeta, beta=None, bdot=None):
+                ddgamma, ddbeta, beta=None, bdot=None, drop=NO_DROP):
         self.n_calls += 1
+        m = self._dm(drop, R, C)
         xx, xd, g = x.reshape(R, C).double(), xdot.reshape(R, C).double(), gamma.double()
         gd = gdot.double() if gdot is not None else torch.zeros_like(g)
         assert beta is not None or not tanh_flag
@@ -456,7 +482,7 @@ class RefOps:
         bd = bdot.double() if bdot is not None else torch.zeros_like(g)
 
         def bwd(a, gg, bb, cot):
-            _, fn = vjp(lambda p, q, r: self._bn(p, q, r, tanh_flag), a, gg, bb)
+            _, fn = vjp(lambda p, q, r: self._bn(p, q, r, tanh_flag, m=m), a, gg, bb)
             return fn(cot)
 
         _, (tx, tg, tb) = jvp(bwd, (xx, g, b0, dout.reshape(R, C).double()),

@@ -31,13 +31,18 @@ def _engine(P, cfg, split=3, K=2):
     return m
 
 
-def _check_task(m, P, cfg, sup, qry, steps, first_order, grad_tol, label, fast_tol=3e-3):
+def _check_task(m, P, cfg, sup, qry, steps, first_order, grad_tol, label, fast_tol=3e-3, salt=None):
+    """salt = None: dropout off (identity) on both sides.  salt = uint32: train-mode dropout ON; the oracle applies the
+    masks of the same counter hash (oracle/fs2_oracle.py drop_keep) the kernels evaluate on the device."""
     Pc = {k: v.detach().clone() for k, v in P.items()}
-    losses, preds, grads, fast = O.maml_task_step(Pc, cfg, sup, qry, steps, 0.001, first_order, return_fast_weights=True)
+    losses, preds, grads, fast = O.maml_task_step(Pc, cfg, sup, qry, steps, 0.001, first_order, return_fast_weights=True,
+                                                  drop_seed=None if salt is None else (0, salt))
     dev = m.theta.device
     bs = batch_from_tuple(sup, dev)
     bq = batch_from_tuple(qry, dev, spk_ids=sup[2], average_spk=True)
-    loss6, out = m.task_step(bs, bq, steps, first_order)
+    if salt is not None:
+        m.be.drop_salt = torch.tensor([salt - (1 << 32) if salt >= (1 << 31) else salt], dtype=torch.int32, device=dev)
+    loss6, out = m.task_step(bs, bq, steps, first_order, drop_base=None if salt is None else 0)
     torch.cuda.synchronize()
     r_loss = _rel(loss6, torch.stack(losses))
     r_mel = _rel(out["mel"].reshape(preds[0].shape), preds[0])
@@ -71,6 +76,38 @@ def test_small_model_all_modes(cuda_device):
     for steps, fo in ((1, True), (1, False), (2, False)):
         m.load_state_dict({k: v.detach().clone() for k, v in P.items()})
         _check_task(m, P, cfg, sup, qry, steps, fo, 1e-3, f"small K={steps} fo={fo}")
+
+
+def test_dropout_on_parity(cuda_device):
+    """Train-mode dropout ACTIVE (encoder/decoder 0.2, variance predictors 0.5, postnet 0.5 — the reference's
+    learner.train(), base_adaptor.py:103): outputs, fast weights and second-order gradients still match the oracle,
+    because both sides drop the same elements."""
+    cfg = O.small_model_config(1, 1)
+    P = O.init_params(seed=0, model_config=cfg)
+    m = _engine(P, cfg)
+    sup, qry = O.synth_task(task=3, shots=2, queries=2, L=6, T=18, ragged=True)
+    for steps, fo, salt in ((1, True, 7), (2, False, 0xF00DFACE)):
+        m.load_state_dict({k: v.detach().clone() for k, v in P.items()})
+        _check_task(m, P, cfg, sup, qry, steps, fo, 2e-3, f"small dropout K={steps} fo={fo}", salt=salt, fast_tol=1e-2)
+    # masks really are active and salt-dependent: same task, two salts -> different losses
+    dev = m.theta.device
+    bs, bq = batch_from_tuple(sup, dev), batch_from_tuple(qry, dev, spk_ids=sup[2], average_spk=True)
+    vals = []
+    for salt in (1, 2, 2):
+        m.load_state_dict({k: v.detach().clone() for k, v in P.items()})
+        m.be.drop_salt = torch.tensor([salt], dtype=torch.int32, device=dev)
+        vals.append(m.task_step(bs, bq, 1, True, drop_base=0)[0].cpu().clone())
+    # (not bit-equal: split-K / channel-sum atomics reorder fp32 additions run to run)
+    assert not torch.allclose(vals[0], vals[1], rtol=1e-2) and torch.allclose(vals[1], vals[2], rtol=1e-5)
+
+
+def test_config2_full_size_dropout_parity(cuda_device):
+    """BASELINE configs[1] with dropout ON (what bench.py times)."""
+    cfg = O.BASE_MODEL_CONFIG
+    P = O.init_params(seed=0)
+    m = _engine(P, cfg, K=1)
+    sup, qry = O.synth_task(task=0, shots=4, queries=4, L=128, T=864)
+    _check_task(m, P, cfg, sup, qry, 1, False, 4e-3, "config2 full size second-order, dropout ON", salt=20260925, fast_tol=2e-2)
 
 
 def test_base_model_ragged_second_order(cuda_device):

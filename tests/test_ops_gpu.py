@@ -12,10 +12,16 @@ from oracle.ops_reference import RefOps  # noqa: E402
 TOL = 2e-5
 
 
-def _both(cuda_device, name, args, kwargs=None, tol=TOL, split=3, skip=()):
+SALT = 0x9ABCDEF1          # > 2^31: exercises the uint32 wrap of the host-side hash
+
+
+def _both(cuda_device, name, args, kwargs=None, tol=TOL, split=3, skip=(), salt=None):
     """Run op `name` on RefOps (CPU) and CudaOps (GPU); compare every tensor argument afterwards."""
     kwargs = kwargs or {}
     ref, cu = RefOps(split=split), CudaOps(split=split)
+    if salt is not None:
+        ref.drop_salt = torch.tensor([salt - (1 << 32) if salt >= (1 << 31) else salt], dtype=torch.int32)
+        cu.drop_salt = ref.drop_salt.to(cuda_device)
     cargs = [a.clone() if torch.is_tensor(a) else a for a in args]
     gargs = [a.to(cuda_device) if torch.is_tensor(a) else a for a in args]
     ckw = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in kwargs.items()}
@@ -68,34 +74,46 @@ def bf(*s):
     return torch.zeros(*s, dtype=torch.bfloat16)
 
 
+def _site(p, seed):
+    return (int(p * (1 << 24)), seed, 1.0 / (1.0 - p))
+
+
+@pytest.mark.parametrize("drop", [False, True])
 @pytest.mark.parametrize("with_res,with_lens", [(True, True), (False, False)])
-def test_layernorm_family(cuda_device, with_res, with_lens):
+def test_layernorm_family(cuda_device, with_res, with_lens, drop):
+    """drop=True: both dropout sites active (pre 0.2 on the branch, post 0.5 on the output); the kernels' counter hash
+    must select exactly the elements the host hash selects, else the errors are O(1)."""
     B, T, C = 3, 37, 256
     R = B * T
+    kw = {"pre": _site(0.2, 0xDEADBEEF), "post": _site(0.5, 12345)} if drop else {}
+    salt = SALT if drop else None
     lens = torch.tensor([37, 20, 5]) if with_lens else None
     y, res = R_(R, C, seed=1), (R_(R, C, seed=2) if with_res else None)
     gamma, beta = 1 + 0.1 * R_(C, seed=3), 0.1 * R_(C, seed=4)
     z, st, out, oh, ol = torch.zeros(R, C), torch.zeros(R, 2), torch.zeros(R, C), bf(R, C), bf(R, C)
-    c, g = _both(cuda_device, "ln_fwd", [y, res, gamma, beta, lens, T, R, C, z, st, out, oh, ol])
+    c, g = _both(cuda_device, "ln_fwd", [y, res, gamma, beta, lens, T, R, C, z, st, out, oh, ol], kw, salt=salt)
+    if drop:
+        keep = (c[10][:lens[0] if with_lens else T] != 0).float().mean().item()
+        assert 0.45 < keep < 0.55                       # post site, p = 0.5
     _hl_check(c[11], c[12], g[11], g[12])
     z, st = c[8], c[9]
     dy = R_(R, C, seed=5)
     for gate in (0, 1):
         dz, dh, dl = torch.zeros(R, C), bf(R, C), bf(R, C)
         dg, db, dbias = torch.zeros(C), torch.zeros(C), torch.zeros(C)
-        c2, g2 = _both(cuda_device, "ln_bwd", [dy, z, st, gamma, lens, T, R, C, gate, dz, dh, dl, dg, db, dbias])
+        c2, g2 = _both(cuda_device, "ln_bwd", [dy, z, st, gamma, lens, T, R, C, gate, dz, dh, dl, dg, db, dbias], kw, salt=salt)
         _hl_check(c2[10], c2[11], g2[10], g2[11])
     ydot, resdot = R_(R, C, seed=6), (R_(R, C, seed=7) if with_res else None)
     gdot, bdot = R_(C, seed=8), R_(C, seed=9)
     zd, od, odh, odl = torch.zeros(R, C), torch.zeros(R, C), bf(R, C), bf(R, C)
-    c3, _ = _both(cuda_device, "ln_tfwd", [ydot, resdot, z, st, gamma, gdot, bdot, lens, T, R, C, zd, od, odh, odl])
+    c3, _ = _both(cuda_device, "ln_tfwd", [ydot, resdot, z, st, gamma, gdot, bdot, lens, T, R, C, zd, od, odh, odl], kw, salt=salt)
     zd = c3[11]
     ddy = R_(R, C, seed=10)
     for gate in (0, 1):
         ddz, dh, dl = torch.zeros(R, C), bf(R, C), bf(R, C)
         dg, db, dbias = torch.zeros(C), torch.zeros(C), torch.zeros(C)
         _both(cuda_device, "ln_tbwd", [dy, ddy, z, zd, st, gamma, gdot, lens, T, R, C, gate, ddz, dh, dl, dg, db, dbias],
-              tol=5e-5)
+              kw, tol=5e-5, salt=salt)
 
 
 def test_rowdot(cuda_device):
@@ -157,25 +175,28 @@ def test_gathers_and_sums(cuda_device):
     _both(cuda_device, "colsum", [None, xh, xl, 1, R, C, torch.zeros(C)], tol=5e-5)
 
 
+@pytest.mark.parametrize("drop", [False, True])
 @pytest.mark.parametrize("C,tanh", [(512, True), (80, False)])
-def test_batchnorm_family(cuda_device, C, tanh):
+def test_batchnorm_family(cuda_device, C, tanh, drop):
     R = 4 * 53
+    kw = {"drop": _site(0.5, 0xC0FFEE)} if drop else {}
+    salt = SALT if drop else None
     x, xd = 2 * R_(R, C, seed=1) + 0.5, R_(R, C, seed=2)
     gamma, beta, gd, bd = 1 + 0.1 * R_(C, seed=3), 0.1 * R_(C, seed=4), R_(C, seed=5), R_(C, seed=6)
     rm, rv = torch.zeros(C), torch.ones(C)
     ws, st, out, oh, ol = torch.zeros(4 * 512), torch.zeros(2 * C), torch.zeros(R, C), bf(R, C), bf(R, C)
-    c, g = _both(cuda_device, "bn_fwd", [x, gamma, beta, R, C, tanh, rm, rv, ws, st, out, oh, ol], tol=5e-5, skip=(8,))
+    c, g = _both(cuda_device, "bn_fwd", [x, gamma, beta, R, C, tanh, rm, rv, ws, st, out, oh, ol], kw, tol=5e-5, skip=(8,), salt=salt)
     st, o = c[9], c[10]
     dout, ddout = R_(R, C, seed=7), R_(R, C, seed=8)
     _both(cuda_device, "bn_bwd", [dout, o if tanh else None, x, st, gamma, R, C, tanh, ws, torch.zeros(R, C), bf(R, C), bf(R, C),
-                                  torch.zeros(C), torch.zeros(C)], {"beta": beta}, tol=1e-4, skip=(8,))
+                                  torch.zeros(C), torch.zeros(C)], {"beta": beta, **kw}, tol=1e-4, skip=(8,), salt=salt)
     ts, od = torch.zeros(2 * C), torch.zeros(R, C)
     c2, _ = _both(cuda_device, "bn_tfwd", [xd, x, st, gamma, gd, bd, o if tanh else None, R, C, tanh, ws, ts, od, bf(R, C), bf(R, C)],
-                  {"beta": beta}, tol=1e-4, skip=(10,))
+                  {"beta": beta, **kw}, tol=1e-4, skip=(10,), salt=salt)
     ts, od = c2[11], c2[12]
     _both(cuda_device, "bn_tbwd", [dout, ddout, o if tanh else None, od if tanh else None, x, xd, st, ts, gamma, gd, R, C, tanh, ws,
                                    torch.zeros(R, C), bf(R, C), bf(R, C), torch.zeros(C), torch.zeros(C)],
-          {"beta": beta, "bdot": bd}, tol=2e-4, skip=(13,))
+          {"beta": beta, "bdot": bd, **kw}, tol=2e-4, skip=(13,), salt=salt)
 
 
 def test_loss_family(cuda_device):

@@ -24,11 +24,11 @@ def test_training_step_and_optimizer_step_match_torch_adam():
     names = O.trainable_names(P)
     acc = {k: torch.zeros_like(P[k]) for k in names}
     for t in range(2):                                     # two micro-steps (grad_acc_step = 2), then one optimizer step
-        sup, qry = O.synth_task(task=t, shots=2, queries=2, L=5, T=12, ragged=True)
+        sup, qry = O.synth_task(task=t + 2, shots=2, queries=2, L=5, T=12, ragged=True)   # (task 1 sits on a ReLU kink with dropout on)
         out = sysm.training_step([([sup], [qry])], t)
         assert set(out) == {"loss", "losses", "output", "_batch"} and len(out["losses"]) == 6 and len(out["output"]) == 10
         Pc = {k: v.detach().clone() for k, v in P.items()}
-        losses, preds, grads = O.maml_task_step(Pc, CFG, sup, qry, 1, 0.001, False)
+        losses, preds, grads = O.maml_task_step(Pc, CFG, sup, qry, 1, 0.001, False, drop_seed=(0, sysm.last_salt))   # dropout ON
         assert abs(float(out["loss"]) - float(losses[0])) < 1e-4 * abs(float(losses[0]))
         assert torch.equal(out["output"][6], preds[6]) and torch.equal(out["output"][7], preds[7])   # masks
         for k in names:
