@@ -383,6 +383,26 @@ def run_own_arm(args):
             fl = sum(c["flops"] for c in calls)
             vstats.append({"kernel": v, "launches": len(calls), "ms_per_step": ms_v, "algorithmic_gflop": fl / 1e9,
                            "tflops": fl / (ms_v * 1e-3) / 1e12})
+        if args.gemm_table:
+            # diagnostic: time per (variant, shape, epilogue) group, each group's launches replayed back-to-back
+            groups = {}
+            for r in rec:
+                kw = r["call"][5]
+                out = "f32" if kw.get("c_f32") is not None and kw.get("c_hi") is None else ("hilo" if kw.get("c_f32") is None else "f32+hilo")
+                key = (r["variant"], r["shape"], kw.get("flags", 0), kw.get("ksplit", 1), out,
+                       "A" + ("mn" if r["call"][0].major else "k") + "/B" + ("mn" if r["call"][1].major else "k"))
+                groups.setdefault(key, []).append(r)
+            rows = []
+            for key, calls in groups.items():
+                ms_g = time_variant(orig, calls * max(1, 24 // len(calls)), reps=3) / max(1, 24 // len(calls))
+                fl = sum(c["flops"] for c in calls)
+                rows.append((ms_g, key, len(calls), fl))
+            rows.sort(key=lambda r: -r[0])
+            tot = sum(r[0] for r in rows)
+            print(f"# gemm table: {len(rows)} groups, {tot:.3f} ms/step summed", file=sys.stderr)
+            for ms_g, key, n, fl in rows:
+                print(f"{ms_g:7.3f} ms {100 * ms_g / tot:5.1f}%  n={n:3d}  {1e3 * ms_g / n:6.1f} us/launch  {fl / ms_g / 1e9:6.1f} TF/s(alg)  "
+                      f"{key[0]:28s} MNK/taps/kb/z/terms={key[1]} flags={key[2]} ksplit={key[3]} out={key[4]} {key[5]}", file=sys.stderr)
         sysm.be.zero_(sysm.maml.g_outer)
         vstats.sort(key=lambda d: -d["ms_per_step"])
         dom = vstats[0]
@@ -441,6 +461,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--split", type=int, default=3, choices=[1, 3], help="3: bf16x3 (parity-grade, default); 1: plain bf16")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gemm-table", action="store_true", help="diagnostic: per-shape GEMM time table on stderr")
     ap.add_argument("--no-dropout", action="store_true", help="identity dropout (diagnostic; the default runs train-mode dropout)")
     ap.add_argument("--kineto", action="store_true", help="print a per-kernel device-time table of real graph replays")
     ap.add_argument("--profile-step", action="store_true",

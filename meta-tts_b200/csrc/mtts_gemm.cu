@@ -17,6 +17,7 @@
 // bf16x3 mode (SPLIT == 3): operands arrive as hi/lo bf16 pairs; each k-step issues
 // hi*hi + hi*lo + lo*hi into the same TMEM accumulator (error ~2^-17, i.e. fp32-grade), which is
 // how the 1e-3 (fp32 relative) parity bar is met on bf16 tensor cores.
+#include <stdlib.h>
 #include "mtts_common.cuh"
 
 namespace {
@@ -50,6 +51,7 @@ struct alignas(64) GemmParams {
   const float* bias;
   int64_t bias_sz0;
   const bf16* gate;
+  int32_t dbg;               // MTTS_GEMM_DBG (diagnostics only): bits 0-3 stage cap, 16 skip MMA, 32 skip TMA, 64 epilogue sleeps, 128 no stores
 };
 
 template <int BN, int SPLIT>
@@ -76,7 +78,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
   const bool row_ok = row < p.M;
   const int64_t c_off = int64_t(z0) * p.c_sz0 + int64_t(z1) * p.c_sz1 + int64_t(row) * p.ldc;
   const float* bias = p.bias ? p.bias + int64_t(z0) * p.bias_sz0 : nullptr;
-  const bool vec_ok = ((p.ldc & 7) == 0) && ((p.c_sz0 & 7) == 0) && ((p.c_sz1 & 7) == 0);
+  const bool vec_ok = ((p.ldc & 7) == 0) && ((p.c_sz0 & 7) == 0) && ((p.c_sz1 & 7) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.c_f32) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.c_hi) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.c_lo) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.gate) & 15) == 0);
   const float bias_row = (bias && (p.flags & MTTS_EPI_BIAS_ROW) && row_ok) ? bias[row] : 0.f;
 #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
@@ -85,7 +89,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
     tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), r);
     tmem_ld_wait();
     const int col0 = n0 + c * 32;
-    if (!row_ok || col0 >= p.N) continue;
+    if (!row_ok || col0 >= p.N || (p.dbg & 128)) continue;
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
@@ -148,9 +152,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
     if (p.c_f32) {
       float* dst = p.c_f32 + c_off + col0;
       if (p.flags & MTTS_EPI_ACCUM) {
+        if (full) {
+          // 128-bit vector reductions (REDG.E.ADD.F32x4): the scalar form is bound by the SM's atomic issue rate
+          // (~1 lane-op / clk: 20 us for one 256 x 256 tile)
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.N) atomicAdd(dst + j, v[j]);
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]),
+                         "f"(v[j + 3])
+                         : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) atomicAdd(dst + j, v[j]);
+        }
       } else if (full) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
@@ -253,6 +267,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int nstages = (p.dbg & 15) ? min(p.dbg & 15, C::STAGES) : C::STAGES;
   pdl_wait();                                    // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
@@ -260,19 +275,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
     if (lane == 0 && n_iters > 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = it_begin; it < it_end; ++it) {
-        const int kc = it % kchunks;
-        const int rest = it / kchunks;
-        const int kb = rest % p.nkb;
-        const int rest2 = rest / p.nkb;
-        const int tap = rest2 % p.ntaps;
-        const bool t2 = rest2 >= p.ntaps;                 // second product term (tangent passes)
+      // (term, tap, kb, kc) odometer: no integer divisions on the per-k-iteration critical path
+      int kc = it_begin % kchunks, kb, tap, term;
+      {
+        int rest = it_begin / kchunks;
+        kb = rest % p.nkb;
+        rest /= p.nkb;
+        tap = rest % p.ntaps;
+        term = rest / p.ntaps;
+      }
+      auto advance = [&]() {
+        if (++kc == kchunks) {
+          kc = 0;
+          if (++kb == p.nkb) {
+            kb = 0;
+            if (++tap == p.ntaps) {
+              tap = 0;
+              ++term;
+            }
+          }
+        }
+      };
+      for (int it = it_begin; it < it_end; ++it, advance()) {
+        const bool t2 = term > 0;                         // second product term (tangent passes)
         const CUtensorMap* ma_hi = t2 ? &p.map_a2_hi : &p.map_a_hi;
         const CUtensorMap* ma_lo = t2 ? &p.map_a2_lo : &p.map_a_lo;
         const CUtensorMap* mb_hi = t2 ? &p.map_b2_hi : &p.map_b_hi;
         const CUtensorMap* mb_lo = t2 ? &p.map_b2_lo : &p.map_b_lo;
 
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (p.dbg & 32) {                                  // diagnostics: no loads, just hand the slot over
+          mbar_arrive(&full_bar[stage]);
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+          continue;
+        }
         mbar_arrive_expect_tx(&full_bar[stage], C::STAGE);
 
         uint8_t* sa = smem + stage * C::STAGE;
@@ -284,7 +320,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
           const int shift = p.a.shift_base + p.a.shift_step * pick_src(p.a.shift_src, z0, z1, tap, kb);
           const int c2 = pick_src(p.a.src2, z0, z1, tap, kb);
           const int c3 = pick_src(p.a.src3, z0, z1, tap, kb);
-          if (p.a.major == MTTS_MAJOR_K) {
+          if (p.dbg & 256) {
+            tma_load_2d(sa, ma_hi, &full_bar[stage], kc * BK, m0 + shift);
+            if (SPLIT == 3) tma_load_2d(sa_lo, ma_lo, &full_bar[stage], kc * BK, m0 + shift);
+          } else if (p.a.major == MTTS_MAJOR_K) {
             tma_load_4d(sa, ma_hi, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
             if (SPLIT == 3) tma_load_4d(sa_lo, ma_lo, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
           } else {
@@ -300,7 +339,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
           const int shift = p.b.shift_base + p.b.shift_step * pick_src(p.b.shift_src, z0, z1, tap, kb);
           const int c2 = pick_src(p.b.src2, z0, z1, tap, kb);
           const int c3 = pick_src(p.b.src3, z0, z1, tap, kb);
-          if (p.b.major == MTTS_MAJOR_K) {
+          if (p.dbg & 256) {
+            tma_load_2d(sb, mb_hi, &full_bar[stage], kc * BK, n0 + shift);
+            if (SPLIT == 3) tma_load_2d(sb_lo, mb_lo, &full_bar[stage], kc * BK, n0 + shift);
+          } else if (p.b.major == MTTS_MAJOR_K) {
             tma_load_4d(sb, mb_hi, &full_bar[stage], kc * BK, n0 + shift, c2, c3);
             if (SPLIT == 3) tma_load_4d(sb_lo, mb_lo, &full_bar[stage], kc * BK, n0 + shift, c2, c3);
           } else {
@@ -312,7 +354,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
             }
           }
         }
-        if (++stage == C::STAGES) {
+        if (++stage == nstages) {
           stage = 0;
           phase ^= 1;
         }
@@ -337,6 +379,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
         const uint32_t sa_lo = sa + C::A_TILE;
         const uint32_t sb = sa + C::A_TILE * (SPLIT == 3 ? 2 : 1);
         const uint32_t sb_lo = sb + C::B_TILE;
+        if (!(p.dbg & 16))
 #pragma unroll
         for (int kk = 0; kk < BK / UMMA_K; ++kk) {
           const uint64_t da = make_umma_desc(sa + kk * a_step, a_lbo, 1024);
@@ -351,7 +394,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
           }
         }
         umma_commit(&empty_bar[stage]);   // frees this smem slot once the MMAs above have read it
-        if (++stage == C::STAGES) {
+        if (++stage == nstages) {
           stage = 0;
           phase ^= 1;
         }
@@ -363,7 +406,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
     // TMEM lane quarter accessible to a warp is (warp_id % 4); warps 2,3,4,5 -> quarters 2,3,0,1.
     const int q = warp & 3;
     if (n_iters > 0) {
-      mbar_wait(tmem_full_bar, 0);
+      if (p.dbg & 64) mbar_wait_sleep(tmem_full_bar, 0); else mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
       // two warps share a TMEM lane quarter (warp % 4) and split the BN columns between them
       constexpr int CH = BN / 32;
@@ -464,13 +507,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mtts
     if (lane == 0 && n_iters > 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = it_begin; it < it_end; ++it) {
-        const int kc = it % kchunks;
-        const int rest = it / kchunks;
-        const int kb = rest % p.nkb;
-        const int rest2 = rest / p.nkb;
-        const int tap = rest2 % p.ntaps;
-        const bool t2 = rest2 >= p.ntaps;
+      // (term, tap, kb, kc) odometer: no integer divisions on the per-k-iteration critical path
+      int kc = it_begin % kchunks, kb, tap, term;
+      {
+        int rest = it_begin / kchunks;
+        kb = rest % p.nkb;
+        rest /= p.nkb;
+        tap = rest % p.ntaps;
+        term = rest / p.ntaps;
+      }
+      auto advance = [&]() {
+        if (++kc == kchunks) {
+          kc = 0;
+          if (++kb == p.nkb) {
+            kb = 0;
+            if (++tap == p.ntaps) {
+              tap = 0;
+              ++term;
+            }
+          }
+        }
+      };
+      for (int it = it_begin; it < it_end; ++it, advance()) {
+        const bool t2 = term > 0;                         // second product term (tangent passes)
         const CUtensorMap* ma_hi = t2 ? &p.map_a2_hi : &p.map_a_hi;
         const CUtensorMap* ma_lo = t2 ? &p.map_a2_lo : &p.map_a_lo;
         const CUtensorMap* mb_hi = t2 ? &p.map_b2_hi : &p.map_b_hi;
@@ -539,6 +598,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mtts
         const uint32_t sa_lo = sa + C::A_TILE;
         const uint32_t sb = sa + C::A_TILE * (SPLIT == 3 ? 2 : 1);
         const uint32_t sb_lo = sb + C::B_TILE;
+        if (!(p.dbg & 16))
 #pragma unroll
         for (int kk = 0; kk < BK / UMMA_K; ++kk) {
           const uint64_t da = make_umma_desc(sa + kk * a_step, a_lbo, 1024);
@@ -601,7 +661,7 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-int encode_operand_map(CUtensorMap* map, const void* ptr, const mtts_operand& op, int block_mn, const char* name) {
+int encode_operand_map(CUtensorMap* map, const void* ptr, const mtts_operand& op, int block_mn, const char* name, int rank = 4) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) {
     mtts_set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -624,7 +684,7 @@ int encode_operand_map(CUtensorMap* map, const void* ptr, const mtts_operand& op
   }
   cuuint32_t box[4] = {64u, op.major == MTTS_MAJOR_K ? static_cast<cuuint32_t>(block_mn) : 64u, 1u, 1u};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -698,12 +758,17 @@ extern "C" int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream_) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
   int rc;
-  if ((rc = encode_operand_map(&p.map_a_hi, d->a.hi, d->a, BM, "A.hi")) != MTTS_OK) return rc;
+  {
+    const char* e = getenv("MTTS_GEMM_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
+  const int rank = (p.dbg & 256) ? 2 : 4;          // diagnostics: rank-2 tensor maps for plain 2-D problems
+  if ((rc = encode_operand_map(&p.map_a_hi, d->a.hi, d->a, BM, "A.hi", rank)) != MTTS_OK) return rc;
   const int b_rows = pair ? bn / 2 : bn;         // 2-CTA: each CTA stages half of the B tile
-  if ((rc = encode_operand_map(&p.map_b_hi, d->b.hi, d->b, b_rows, "B.hi")) != MTTS_OK) return rc;
+  if ((rc = encode_operand_map(&p.map_b_hi, d->b.hi, d->b, b_rows, "B.hi", rank)) != MTTS_OK) return rc;
   if (d->split == 3) {
-    if ((rc = encode_operand_map(&p.map_a_lo, d->a.lo, d->a, BM, "A.lo")) != MTTS_OK) return rc;
-    if ((rc = encode_operand_map(&p.map_b_lo, d->b.lo, d->b, b_rows, "B.lo")) != MTTS_OK) return rc;
+    if ((rc = encode_operand_map(&p.map_a_lo, d->a.lo, d->a, BM, "A.lo", rank)) != MTTS_OK) return rc;
+    if ((rc = encode_operand_map(&p.map_b_lo, d->b.lo, d->b, b_rows, "B.lo", rank)) != MTTS_OK) return rc;
   }
   const bool two = d->a2_hi != nullptr || d->b2_hi != nullptr;
   if (two) {

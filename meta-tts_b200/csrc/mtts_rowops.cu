@@ -563,6 +563,143 @@ __global__ void __launch_bounds__(ROW_THREADS) softmax_kernel(int /*mode*/, cons
   }
 }
 
+// ---- vectorised variant (ld % 4 == 0, 16-byte aligned bases): lane l owns keys [128*i + 4*l, +4) for i < NQ -------------
+// 128-bit loads of the fp32 input and 64-bit loads / stores of the bf16 halves (the scalar kernel issued 2-byte stores:
+// 64 B per warp instruction).
+__device__ __forceinline__ float4 ld4_split(const bf16* hi, const bf16* lo, long long i) {
+  const uint2 h = *reinterpret_cast<const uint2*>(hi + i);
+  float4 v = make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xFFFF0000u), __uint_as_float(h.y << 16),
+                         __uint_as_float(h.y & 0xFFFF0000u));
+  if (lo) {
+    const uint2 l = *reinterpret_cast<const uint2*>(lo + i);
+    v.x += __uint_as_float(l.x << 16); v.y += __uint_as_float(l.x & 0xFFFF0000u);
+    v.z += __uint_as_float(l.y << 16); v.w += __uint_as_float(l.y & 0xFFFF0000u);
+  }
+  return v;
+}
+__device__ __forceinline__ void st4_split(bf16* hi, bf16* lo, long long i, float4 v) {
+  bf16 h0, h1, h2, h3, l0, l1, l2, l3;
+  split_bf16(v.x, h0, l0); split_bf16(v.y, h1, l1); split_bf16(v.z, h2, l2); split_bf16(v.w, h3, l3);
+  uint2 h, l;
+  h.x = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
+  h.y = uint32_t(__bfloat16_as_ushort(h2)) | (uint32_t(__bfloat16_as_ushort(h3)) << 16);
+  *reinterpret_cast<uint2*>(hi + i) = h;
+  if (lo) {
+    l.x = uint32_t(__bfloat16_as_ushort(l0)) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
+    l.y = uint32_t(__bfloat16_as_ushort(l2)) | (uint32_t(__bfloat16_as_ushort(l3)) << 16);
+    *reinterpret_cast<uint2*>(lo + i) = l;
+  }
+}
+#define F4_EACH(v, EXPR_X, EXPR_Y, EXPR_Z, EXPR_W) { (v).x = EXPR_X; (v).y = EXPR_Y; (v).z = EXPR_Z; (v).w = EXPR_W; }
+
+template <int NQ, int MODE>
+__global__ void __launch_bounds__(ROW_THREADS) softmax_vec_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                                  const bf16* __restrict__ p_hi, const bf16* __restrict__ p_lo,
+                                                                  const bf16* __restrict__ pd_hi, const bf16* __restrict__ pd_lo,
+                                                                  const int64_t* __restrict__ klens, int H, int Lq, int Lk, int ld,
+                                                                  long long rows, bf16* __restrict__ o_hi, bf16* __restrict__ o_lo) {
+  pdl_enter();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long r = static_cast<long long>(blockIdx.x) * ROW_WARPS + warp; r < rows; r += static_cast<long long>(gridDim.x) * ROW_WARPS) {
+    const long long zidx = r / Lq;
+    const int b = static_cast<int>(zidx / H);
+    const int kl = klens ? static_cast<int>(min(static_cast<long long>(Lk), static_cast<long long>(klens[b]))) : Lk;
+    const long long base = r * ld;
+    float4 v[NQ];
+    if (MODE == 0) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const int j = 128 * i + 4 * lane;
+        float4 t = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (j < ld) t = *reinterpret_cast<const float4*>(A + base + j);
+        if (j + 0 >= kl) t.x = -INFINITY;
+        if (j + 1 >= kl) t.y = -INFINITY;
+        if (j + 2 >= kl) t.z = -INFINITY;
+        if (j + 3 >= kl) t.w = -INFINITY;
+        v[i] = t;
+        m = fmaxf(fmaxf(m, fmaxf(t.x, t.y)), fmaxf(t.z, t.w));
+      }
+      m = warp_max(m);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const int j = 128 * i + 4 * lane;
+        F4_EACH(v[i], (j + 0 < kl ? __expf(v[i].x - m) : 0.f), (j + 1 < kl ? __expf(v[i].y - m) : 0.f),
+                (j + 2 < kl ? __expf(v[i].z - m) : 0.f), (j + 3 < kl ? __expf(v[i].w - m) : 0.f));
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+      s = warp_sum(s);
+      const float inv = 1.f / s;
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const int j = 128 * i + 4 * lane;
+        if (j < ld) st4_split(o_hi, o_lo, base + j, make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv));
+      }
+    } else if (MODE == 1) {
+      float4 a[NQ];
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const int j = 128 * i + 4 * lane;
+        v[i] = z4;
+        a[i] = z4;
+        if (j < kl) {          // groups straddling kl: P is exactly 0 beyond kl (written so by mode 0), so no per-element mask
+          v[i] = ld4_split(p_hi, p_lo, base + j);
+          a[i] = *reinterpret_cast<const float4*>(A + base + j);
+          if (j + 1 >= kl) { v[i].y = 0.f; a[i].y = 0.f; }   // (columns past Lk are never written by the GEMM: may hold NaN)
+          if (j + 2 >= kl) { v[i].z = 0.f; a[i].z = 0.f; }
+          if (j + 3 >= kl) { v[i].w = 0.f; a[i].w = 0.f; }
+        }
+        d += (v[i].x * a[i].x + v[i].y * a[i].y) + (v[i].z * a[i].z + v[i].w * a[i].w);
+      }
+      d = warp_sum(d);
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const int j = 128 * i + 4 * lane;
+        if (j < ld)
+          st4_split(o_hi, o_lo, base + j, make_float4(v[i].x * (a[i].x - d), v[i].y * (a[i].y - d), v[i].z * (a[i].z - d),
+                                                       v[i].w * (a[i].w - d)));
+      }
+    } else {
+      float4 pd[NQ], u[NQ];
+      float d = 0.f, dd = 0.f;
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const int j = 128 * i + 4 * lane;
+        v[i] = pd[i] = u[i] = z4;
+        if (j < kl) {
+          v[i] = ld4_split(p_hi, p_lo, base + j);
+          pd[i] = ld4_split(pd_hi, pd_lo, base + j);
+          if (j + 1 >= kl) { v[i].y = 0.f; pd[i].y = 0.f; }
+          if (j + 2 >= kl) { v[i].z = 0.f; pd[i].z = 0.f; }
+          if (j + 3 >= kl) { v[i].w = 0.f; pd[i].w = 0.f; }
+          float4 a = *reinterpret_cast<const float4*>(A + base + j);
+          float4 bb = *reinterpret_cast<const float4*>(Bm + base + j);
+          if (j + 1 >= kl) { a.y = 0.f; bb.y = 0.f; }
+          if (j + 2 >= kl) { a.z = 0.f; bb.z = 0.f; }
+          if (j + 3 >= kl) { a.w = 0.f; bb.w = 0.f; }
+          d += (v[i].x * a.x + v[i].y * a.y) + (v[i].z * a.z + v[i].w * a.w);
+          F4_EACH(u[i], pd[i].x * a.x + v[i].x * bb.x, pd[i].y * a.y + v[i].y * bb.y, pd[i].z * a.z + v[i].z * bb.z,
+                  pd[i].w * a.w + v[i].w * bb.w);
+        }
+        dd += (u[i].x + u[i].y) + (u[i].z + u[i].w);
+      }
+      d = warp_sum(d);
+      dd = warp_sum(dd);
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        const int j = 128 * i + 4 * lane;
+        if (j < ld)
+          st4_split(o_hi, o_lo, base + j,
+                    make_float4(u[i].x - pd[i].x * d - v[i].x * dd, u[i].y - pd[i].y * d - v[i].y * dd,
+                                u[i].z - pd[i].z * d - v[i].z * dd, u[i].w - pd[i].w * d - v[i].w * dd));
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -667,6 +804,33 @@ extern "C" int mtts_softmax(int mode, const float* A, const float* Bm, const voi
     else if (mode == 1) SM_LAUNCH_M(NPL, 1); \
     else SM_LAUNCH_M(NPL, 2);            \
   } while (0)
+  // vector path: rows a multiple of 4 keys long with 16-byte aligned bases (the engine pads keys to a multiple of 32)
+  const uintptr_t al = reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bm) | reinterpret_cast<uintptr_t>(p_hi) |
+                       reinterpret_cast<uintptr_t>(p_lo) | reinterpret_cast<uintptr_t>(pd_hi) | reinterpret_cast<uintptr_t>(pd_lo) |
+                       reinterpret_cast<uintptr_t>(o_hi) | reinterpret_cast<uintptr_t>(o_lo);
+  if ((ld & 3) == 0 && (al & 15) == 0) {
+#define SMV_LAUNCH_M(NQ, MODE)                                                                                                   \
+  MTTS_CHECK_CUDA(mtts_launch(softmax_vec_kernel<NQ, MODE>, dim3(row_grid(rows)), dim3(ROW_THREADS), 0, s, A, Bm, static_cast<const bf16*>(p_hi), \
+                              static_cast<const bf16*>(p_lo), static_cast<const bf16*>(pd_hi), static_cast<const bf16*>(pd_lo), klens, H, Lq, \
+                              Lk, ld, rows, static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo)))
+#define SMV_LAUNCH(NQ)                        \
+  do {                                        \
+    if (mode == 0) SMV_LAUNCH_M(NQ, 0);       \
+    else if (mode == 1) SMV_LAUNCH_M(NQ, 1);  \
+    else SMV_LAUNCH_M(NQ, 2);                 \
+  } while (0)
+    const int nq = (ld + 127) / 128;
+    if (nq <= 1) SMV_LAUNCH(1);
+    else if (nq <= 2) SMV_LAUNCH(2);
+    else if (nq <= 4) SMV_LAUNCH(4);
+    else if (nq <= 6) SMV_LAUNCH(6);
+    else if (nq <= 7) SMV_LAUNCH(7);
+    else SMV_LAUNCH(8);
+#undef SMV_LAUNCH
+#undef SMV_LAUNCH_M
+    MTTS_CHECK_LAUNCH();
+    return MTTS_OK;
+  }
   if (ld <= 128) SM_LAUNCH(4);
   else if (ld <= 256) SM_LAUNCH(8);
   else if (ld <= 512) SM_LAUNCH(16);

@@ -328,14 +328,16 @@ def _pick_cfg(mt: int, nz: int, N: int, k_iters: int, can_splitk: bool):
         o = opts[0]                      # widest tile; fill the machine along the contraction instead
         ks = max(1, min(148 // max(ctas(o), 1), max(1, k_iters // 6), 16))
         return o[0], o[1], ks
-    for o in opts:
-        if ctas(o) >= 96:
-            return o[0], o[1], 1
-    # no split-K possible: widest tile that still yields >= 48 CTAs, else the most CTAs
-    for o in opts:
-        if ctas(o) >= 48:
-            return o[0], o[1], 1
-    o = max(opts, key=ctas)
+    # no split-K: in-graph launch-time model fitted to tools/gemm_floor.py on B200 (profiles/r01_gemm_floor_in_graph.txt):
+    # a wave costs  fixed(tile) + k_iters * per_iter(tile)  and a launch runs ceil(ctas / 148) waves.  (The former
+    # ">= 96 CTAs" rule picked 128-wide pairs for the QKV projection: 23.9 us where the 256-wide pair takes 16.2.)
+    fixed = {(64, False): 5.9, (128, False): 7.2, (128, True): 7.8, (256, False): 11.0, (256, True): 11.0}
+    per_it = {(64, False): 0.78, (128, False): 0.80, (128, True): 0.76, (256, False): 1.5, (256, True): 0.87}     # 1-CTA 256: 2 smem stages only
+
+    def cost(o):
+        return -(-ctas(o) // 148) * (fixed[o] + k_iters * per_it[o])
+
+    o = min(opts, key=cost)
     return o[0], o[1], 1
 
 

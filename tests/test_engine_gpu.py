@@ -66,6 +66,10 @@ def _check_task(m, P, cfg, sup, qry, steps, first_order, grad_tol, label, fast_t
     # pre-activation is ~1e-6 from 0 gates differently in two fp32 implementations; seen 1 in 20k on CPU too).
     assert r_fast < fast_tol
     assert r_grad < grad_tol
+    # robust to ReLU-kink flips: the MEDIAN per-tensor relative error (a flipped unit moves a handful of tensors, not most)
+    per = sorted(((got[k].double() - grads[k].double()).norm() / grads[k].double().norm()).item() for k in grads
+                 if grads[k].double().norm() > 1e-4 * tot_ref)
+    assert per[len(per) // 2] < 1e-3, f"median per-tensor gradient rel err {per[len(per) // 2]:.2e}"
 
 
 def test_small_model_all_modes(cuda_device):
@@ -151,6 +155,24 @@ def test_config2_full_size_parity(cuda_device):
     m = _engine(P, cfg, K=1)
     sup, qry = O.synth_task(task=0, shots=4, queries=4, L=128, T=864)
     _check_task(m, P, cfg, sup, qry, 1, False, 1e-3, "config2 full size second-order")
+
+
+@pytest.mark.parametrize("first_order,salt", [(False, None), (False, 77), (True, 78)])
+def test_config3_config4_k5_structure(cuda_device, first_order, salt):
+    """BASELINE configs[2] / configs[3] structure: S = Q = 5, K = 5 inner steps (meta_emb_vad.yaml:23-29), second-order
+    (config 3) and first-order (config 4), base model, ragged batch — at reduced sequence length so the oracle's
+    5-step double backward finishes in seconds.  Exercises all five fast-weight arenas and the 5-deep adjoint recursion."""
+    cfg = O.BASE_MODEL_CONFIG
+    P = O.init_params(seed=0)
+    m = _engine(P, cfg, K=5)
+    sup, qry = O.synth_task(task=5, shots=5, queries=5, L=16, T=64, ragged=True)
+    # Tolerance: this task step evaluates 14.5 M ReLU inputs, ~25 of them within 1e-6 of zero and ~950 within 1e-5
+    # (counted in the oracle); bf16x3 products carry ~4e-6 relative error, so a few units gate differently than in the
+    # fp32 oracle.  A flip changes the forward by ~1e-6 but switches that unit's whole gradient on or off; in the small
+    # variance predictors (80 rows here) one flip moves a conv weight gradient by ~1e-2 of the total norm (the CPU
+    # restatement with exact products matches to 4e-5 on the same inputs).  Hence total < 2e-2 + the median criterion.
+    _check_task(m, P, cfg, sup, qry, 5, first_order, 2e-2, f"config{'4' if first_order else '3'} structure K=5 salt={salt}",
+                fast_tol=2e-2, salt=salt)
 
 
 def test_bf16_single_pass_mode_runs(cuda_device):
