@@ -337,18 +337,25 @@ def run_own_arm(args):
     last_loss = float("nan")
     for rep in range(3):                                             # the host side is noisy on shared boxes: best of 3
         barrier()
+        for k_ in sysm.host_prof:
+            sysm.host_prof[k_] = 0.0
+        sysm.trace_events = [] if args.trace_e2e else None
         t_host = 0.0
         e0.record()
-        prev = None
+        pending = []
+        wait_ms = []
         for i in range(args.steps):
             t0 = time.perf_counter()
             out = sysm.training_step(batches[i % len(batches)], i)   # H2D of this step's batch + async D2H of its 6 losses
             sysm.optimizer_step()
             t_host += time.perf_counter() - t0
-            if prev is not None:
-                last_loss = float(prev["loss"])                       # host reads the previous step's result (logging pattern)
-            prev = out
-        last_loss = float(prev["loss"])                               # ... and the last one before the clock stops
+            pending.append(out)
+            if len(pending) > args.lag:                                # the host reads results `lag` steps behind (logging pattern)
+                t1 = time.perf_counter()
+                last_loss = float(pending.pop(0)["loss"])
+                wait_ms.append(round(1e3 * (time.perf_counter() - t1), 2))
+        for out in pending:
+            last_loss = float(out["loss"])                            # ... and every outstanding one before the clock stops
         e1.record()
         barrier()
         ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -356,6 +363,17 @@ def run_own_arm(args):
             dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
         e2e_runs.append(ms2.item() / args.steps)
         host_ms.append(1e3 * t_host / args.steps)
+        if rank == 0 and sysm.trace_events:
+            tr = sysm.trace_events
+            g_ms = [a_.elapsed_time(b_) for a_, b_ in tr]
+            gaps = [tr[j][1].elapsed_time(tr[j + 1][0]) for j in range(len(tr) - 1)]
+            print("# e2e gaps ms:", [round(g_, 2) for g_ in gaps], "host wait ms:", wait_ms, file=sys.stderr)
+            print(f"# e2e trace: graph replay on device {statistics.mean(g_ms):.3f} ms (min {min(g_ms):.3f} max {max(g_ms):.3f}); "
+                  f"between graphs (D2H + optimizer + H2D + idle) {statistics.mean(gaps):.3f} ms (min {min(gaps):.3f} max {max(gaps):.3f})",
+                  file=sys.stderr)
+        if rank == 0:
+            print("# e2e rep", rep, f"{e2e_runs[-1]:.3f} ms/step; host ms/step:",
+                  {k_: round(1e3 * v_ / args.steps, 3) for k_, v_ in sysm.host_prof.items()}, file=sys.stderr)
     ms2 = torch.tensor([min(e2e_runs) * args.steps], device=dev)
     e2e_ms = ms2.item() / args.steps
     e2e_value = world * frames_per_task() / (e2e_ms * 1e-3)
@@ -438,7 +456,7 @@ def run_own_arm(args):
                 "dtype": "bf16x3" if split == 3 else "bf16", "data": "synthetic", "config": workload_config(world, split, not args.no_dropout),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": sysm.h2d_bytes_per_step,
-                        "d2h_bytes_per_step": sysm.d2h_bytes_per_step, "api": "MetaSystem.training_step(host batch) + optimizer_step; losses read back on the host one step later",
+                        "d2h_bytes_per_step": sysm.d2h_bytes_per_step, "api": f"MetaSystem.training_step(host batch) + optimizer_step; losses read back on the host {args.lag} step(s) later",
                         "runs_ms_per_step": e2e_runs, "host_enqueue_ms_per_step": host_ms},
                 "gpu_launches": launches_step * args.steps, "gpu_launches_per_step": launches_step,
                 "roofline": roofline, "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),
@@ -461,6 +479,8 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--split", type=int, default=3, choices=[1, 3], help="3: bf16x3 (parity-grade, default); 1: plain bf16")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--lag", type=int, default=2, help="e2e: the host reads step i-lag's losses after enqueueing step i (1..2)")
+    ap.add_argument("--trace-e2e", action="store_true", help="diagnostic: CUDA events around every graph replay of the e2e loop")
     ap.add_argument("--gemm-table", action="store_true", help="diagnostic: per-shape GEMM time table on stderr")
     ap.add_argument("--no-dropout", action="store_true", help="identity dropout (diagnostic; the default runs train-mode dropout)")
     ap.add_argument("--kineto", action="store_true", help="print a per-kernel device-time table of real graph replays")

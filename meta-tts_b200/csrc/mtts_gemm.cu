@@ -32,6 +32,7 @@ struct OperandParams {
   int32_t major;
   int32_t src2, src3;
   int32_t shift_src, shift_base, shift_step;
+  int32_t rank;              // rank of this operand's tensor maps (2, 3 or 4)
 };
 
 struct alignas(64) GemmParams {
@@ -54,11 +55,15 @@ struct alignas(64) GemmParams {
   int32_t dbg;               // MTTS_GEMM_DBG (diagnostics only): bits 0-3 stage cap, 16 skip MMA, 32 skip TMA, 64 epilogue sleeps, 128 no stores
 };
 
-template <int BN, int SPLIT>
+// KD = k-blocks (of BK = 64) per pipeline stage.  One stage fill costs ~0.3 us of fixed TMA / barrier time on top of
+// its bytes and more than two fills in flight buy nothing (tools/gemm_probe2.py), so narrow tiles — whose MMAs take
+// only ~0.25 us per k-block — use KD = 2: half the fills per unit of K.
+template <int BN, int SPLIT, int KD = 1>
 struct Cfg {
   static constexpr int A_TILE = BM * BK * 2;                  // 16 KB
   static constexpr int B_TILE = BN * BK * 2;
-  static constexpr int STAGE = (A_TILE + B_TILE) * (SPLIT == 3 ? 2 : 1);
+  static constexpr int SUB = (A_TILE + B_TILE) * (SPLIT == 3 ? 2 : 1);   // one k-block of A (hi, lo) and B (hi, lo)
+  static constexpr int STAGE = SUB * KD;
   static constexpr int BAR_BYTES = 1024;
   static constexpr int STAGES_RAW = (MAX_SMEM - BAR_BYTES - 1024 /*align slack*/) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
@@ -207,9 +212,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
   }
 }
 
-template <int BN, int SPLIT>
+template <int BN, int SPLIT, int KD>
 __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<BN, SPLIT>;
+  using C = Cfg<BN, SPLIT, KD>;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -231,7 +236,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
   const int z1 = blockIdx.z / p.nz0;
 
   // this CTA's slice of the (tap, kb, kc) iteration space
-  const int kchunks = (p.K + BK - 1) / BK;
+  const int kchunks = ((p.K + BK - 1) / BK + KD - 1) / KD;     // stage fills along K (KD k-blocks each; the tail block is OOB zero-filled)
   const int total_iters = p.nterms * p.ntaps * p.nkb * kchunks;
   const int per_split = (total_iters + p.ksplit - 1) / p.ksplit;
   const int it_begin = blockIdx.y * per_split;
@@ -311,7 +316,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
         }
         mbar_arrive_expect_tx(&full_bar[stage], C::STAGE);
 
-        uint8_t* sa = smem + stage * C::STAGE;
+#pragma unroll
+        for (int sub = 0; sub < KD; ++sub) {
+        const int kcb = (kc * KD + sub) * BK;             // element offset of this k-block along K
+        uint8_t* sa = smem + stage * C::STAGE + sub * C::SUB;
         uint8_t* sa_lo = sa + C::A_TILE;
         uint8_t* sb = sa + C::A_TILE * (SPLIT == 3 ? 2 : 1);
         uint8_t* sb_lo = sb + C::B_TILE;
@@ -320,18 +328,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
           const int shift = p.a.shift_base + p.a.shift_step * pick_src(p.a.shift_src, z0, z1, tap, kb);
           const int c2 = pick_src(p.a.src2, z0, z1, tap, kb);
           const int c3 = pick_src(p.a.src3, z0, z1, tap, kb);
-          if (p.dbg & 256) {
-            tma_load_2d(sa, ma_hi, &full_bar[stage], kc * BK, m0 + shift);
-            if (SPLIT == 3) tma_load_2d(sa_lo, ma_lo, &full_bar[stage], kc * BK, m0 + shift);
-          } else if (p.a.major == MTTS_MAJOR_K) {
-            tma_load_4d(sa, ma_hi, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
-            if (SPLIT == 3) tma_load_4d(sa_lo, ma_lo, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
+          if (p.a.major == MTTS_MAJOR_K) {
+            tma_load_nd(p.a.rank, sa, ma_hi, &full_bar[stage], kcb, m0 + shift, c2, c3);
+            if (SPLIT == 3) tma_load_nd(p.a.rank, sa_lo, ma_lo, &full_bar[stage], kcb, m0 + shift, c2, c3);
           } else {
 #pragma unroll
             for (int i = 0; i < BM / 64; ++i) {
-              tma_load_4d(sa + i * (BK * 128), ma_hi, &full_bar[stage], m0 + 64 * i, kc * BK + shift, c2, c3);
+              tma_load_nd(p.a.rank, sa + i * (BK * 128), ma_hi, &full_bar[stage], m0 + 64 * i, kcb + shift, c2, c3);
               if (SPLIT == 3)
-                tma_load_4d(sa_lo + i * (BK * 128), ma_lo, &full_bar[stage], m0 + 64 * i, kc * BK + shift, c2, c3);
+                tma_load_nd(p.a.rank, sa_lo + i * (BK * 128), ma_lo, &full_bar[stage], m0 + 64 * i, kcb + shift, c2, c3);
             }
           }
         }
@@ -339,21 +344,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
           const int shift = p.b.shift_base + p.b.shift_step * pick_src(p.b.shift_src, z0, z1, tap, kb);
           const int c2 = pick_src(p.b.src2, z0, z1, tap, kb);
           const int c3 = pick_src(p.b.src3, z0, z1, tap, kb);
-          if (p.dbg & 256) {
-            tma_load_2d(sb, mb_hi, &full_bar[stage], kc * BK, n0 + shift);
-            if (SPLIT == 3) tma_load_2d(sb_lo, mb_lo, &full_bar[stage], kc * BK, n0 + shift);
-          } else if (p.b.major == MTTS_MAJOR_K) {
-            tma_load_4d(sb, mb_hi, &full_bar[stage], kc * BK, n0 + shift, c2, c3);
-            if (SPLIT == 3) tma_load_4d(sb_lo, mb_lo, &full_bar[stage], kc * BK, n0 + shift, c2, c3);
+          if (p.b.major == MTTS_MAJOR_K) {
+            tma_load_nd(p.b.rank, sb, mb_hi, &full_bar[stage], kcb, n0 + shift, c2, c3);
+            if (SPLIT == 3) tma_load_nd(p.b.rank, sb_lo, mb_lo, &full_bar[stage], kcb, n0 + shift, c2, c3);
           } else {
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i) {
-              tma_load_4d(sb + i * (BK * 128), mb_hi, &full_bar[stage], n0 + 64 * i, kc * BK + shift, c2, c3);
+              tma_load_nd(p.b.rank, sb + i * (BK * 128), mb_hi, &full_bar[stage], n0 + 64 * i, kcb + shift, c2, c3);
               if (SPLIT == 3)
-                tma_load_4d(sb_lo + i * (BK * 128), mb_lo, &full_bar[stage], n0 + 64 * i, kc * BK + shift, c2, c3);
+                tma_load_nd(p.b.rank, sb_lo + i * (BK * 128), mb_lo, &full_bar[stage], n0 + 64 * i, kcb + shift, c2, c3);
             }
           }
         }
+        }   // sub
         if (++stage == nstages) {
           stage = 0;
           phase ^= 1;
@@ -375,11 +378,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
       for (int it = 0; it < n_iters; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * C::STAGE);
+        if (!(p.dbg & 16))
+#pragma unroll
+        for (int sub = 0; sub < KD; ++sub) {
+        const uint32_t sa = smem_u32(smem + stage * C::STAGE + sub * C::SUB);
         const uint32_t sa_lo = sa + C::A_TILE;
         const uint32_t sb = sa + C::A_TILE * (SPLIT == 3 ? 2 : 1);
         const uint32_t sb_lo = sb + C::B_TILE;
-        if (!(p.dbg & 16))
 #pragma unroll
         for (int kk = 0; kk < BK / UMMA_K; ++kk) {
           const uint64_t da = make_umma_desc(sa + kk * a_step, a_lbo, 1024);
@@ -393,6 +398,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
             umma_bf16(tmem_base, da_lo, db, idesc, 1);
           }
         }
+        }   // sub
         umma_commit(&empty_bar[stage]);   // frees this smem slot once the MMAs above have read it
         if (++stage == nstages) {
           stage = 0;
@@ -547,14 +553,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mtts
           const int c2 = pick_src(p.a.src2, z0, z1, tap, kb);
           const int c3 = pick_src(p.a.src3, z0, z1, tap, kb);
           if (p.a.major == MTTS_MAJOR_K) {
-            tma_load_4d_2cta(sa, ma_hi, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
-            if (SPLIT == 3) tma_load_4d_2cta(sa_lo, ma_lo, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
+            tma_load_nd_2cta(p.a.rank, sa, ma_hi, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
+            if (SPLIT == 3) tma_load_nd_2cta(p.a.rank, sa_lo, ma_lo, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
           } else {
 #pragma unroll
             for (int i = 0; i < BM / 64; ++i) {
-              tma_load_4d_2cta(sa + i * (BK * 128), ma_hi, &full_bar[stage], m0 + 64 * i, kc * BK + shift, c2, c3);
+              tma_load_nd_2cta(p.a.rank, sa + i * (BK * 128), ma_hi, &full_bar[stage], m0 + 64 * i, kc * BK + shift, c2, c3);
               if (SPLIT == 3)
-                tma_load_4d_2cta(sa_lo + i * (BK * 128), ma_lo, &full_bar[stage], m0 + 64 * i, kc * BK + shift, c2, c3);
+                tma_load_nd_2cta(p.a.rank, sa_lo + i * (BK * 128), ma_lo, &full_bar[stage], m0 + 64 * i, kc * BK + shift, c2, c3);
             }
           }
         }
@@ -563,14 +569,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mtts
           const int c2 = pick_src(p.b.src2, z0, z1, tap, kb);
           const int c3 = pick_src(p.b.src3, z0, z1, tap, kb);
           if (p.b.major == MTTS_MAJOR_K) {
-            tma_load_4d_2cta(sb, mb_hi, &full_bar[stage], kc * BK, nb0 + shift, c2, c3);
-            if (SPLIT == 3) tma_load_4d_2cta(sb_lo, mb_lo, &full_bar[stage], kc * BK, nb0 + shift, c2, c3);
+            tma_load_nd_2cta(p.b.rank, sb, mb_hi, &full_bar[stage], kc * BK, nb0 + shift, c2, c3);
+            if (SPLIT == 3) tma_load_nd_2cta(p.b.rank, sb_lo, mb_lo, &full_bar[stage], kc * BK, nb0 + shift, c2, c3);
           } else {
 #pragma unroll
             for (int i = 0; i < BN / 128; ++i) {
-              tma_load_4d_2cta(sb + i * (BK * 128), mb_hi, &full_bar[stage], nb0 + 64 * i, kc * BK + shift, c2, c3);
+              tma_load_nd_2cta(p.b.rank, sb + i * (BK * 128), mb_hi, &full_bar[stage], nb0 + 64 * i, kc * BK + shift, c2, c3);
               if (SPLIT == 3)
-                tma_load_4d_2cta(sb_lo + i * (BK * 128), mb_lo, &full_bar[stage], nb0 + 64 * i, kc * BK + shift, c2, c3);
+                tma_load_nd_2cta(p.b.rank, sb_lo + i * (BK * 128), mb_lo, &full_bar[stage], nb0 + 64 * i, kc * BK + shift, c2, c3);
             }
           }
         }
@@ -711,16 +717,16 @@ int launch_pair(const GemmParams& p, dim3 grid, cudaStream_t stream) {
   return MTTS_OK;
 }
 
-template <int BN, int SPLIT>
+template <int BN, int SPLIT, int KD = 1>
 int launch(const GemmParams& p, dim3 grid, cudaStream_t stream) {
-  using C = Cfg<BN, SPLIT>;
+  using C = Cfg<BN, SPLIT, KD>;
   static bool configured = false;
   if (!configured) {
-    MTTS_CHECK_CUDA(cudaFuncSetAttribute(mtts_gemm_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MTTS_CHECK_CUDA(cudaFuncSetAttribute(mtts_gemm_kernel<BN, SPLIT, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM));
     configured = true;
   }
-  MTTS_CHECK_CUDA(mtts_launch(mtts_gemm_kernel<BN, SPLIT>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, p));
+  MTTS_CHECK_CUDA(mtts_launch(mtts_gemm_kernel<BN, SPLIT, KD>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, p));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -762,30 +768,39 @@ extern "C" int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream_) {
     const char* e = getenv("MTTS_GEMM_DBG");
     p.dbg = e ? atoi(e) : 0;
   }
-  const int rank = (p.dbg & 256) ? 2 : 4;          // diagnostics: rank-2 tensor maps for plain 2-D problems
-  if ((rc = encode_operand_map(&p.map_a_hi, d->a.hi, d->a, BM, "A.hi", rank)) != MTTS_OK) return rc;
+  // smallest tensor-map rank that covers each operand's geometry (MTTS_GEMM_DBG bit 256 forces rank 4)
+  auto op_rank = [&](const mtts_operand& o) {
+    if (p.dbg & 256) return 4;
+    if (o.dims[3] > 1 || o.src3 != MTTS_SRC_ZERO) return 4;
+    if (o.dims[2] > 1 || o.src2 != MTTS_SRC_ZERO) return 3;
+    return 2;
+  };
+  const int ra = op_rank(d->a), rb = op_rank(d->b);
+  if ((rc = encode_operand_map(&p.map_a_hi, d->a.hi, d->a, BM, "A.hi", ra)) != MTTS_OK) return rc;
   const int b_rows = pair ? bn / 2 : bn;         // 2-CTA: each CTA stages half of the B tile
-  if ((rc = encode_operand_map(&p.map_b_hi, d->b.hi, d->b, b_rows, "B.hi", rank)) != MTTS_OK) return rc;
+  if ((rc = encode_operand_map(&p.map_b_hi, d->b.hi, d->b, b_rows, "B.hi", rb)) != MTTS_OK) return rc;
   if (d->split == 3) {
-    if ((rc = encode_operand_map(&p.map_a_lo, d->a.lo, d->a, BM, "A.lo", rank)) != MTTS_OK) return rc;
-    if ((rc = encode_operand_map(&p.map_b_lo, d->b.lo, d->b, b_rows, "B.lo", rank)) != MTTS_OK) return rc;
+    if ((rc = encode_operand_map(&p.map_a_lo, d->a.lo, d->a, BM, "A.lo", ra)) != MTTS_OK) return rc;
+    if ((rc = encode_operand_map(&p.map_b_lo, d->b.lo, d->b, b_rows, "B.lo", rb)) != MTTS_OK) return rc;
   }
   const bool two = d->a2_hi != nullptr || d->b2_hi != nullptr;
   if (two) {
     MTTS_REQUIRE(d->a2_hi && d->b2_hi && (d->split == 1 || (d->a2_lo && d->b2_lo)), "gemm: incomplete second term");
-    if ((rc = encode_operand_map(&p.map_a2_hi, d->a2_hi, d->a, BM, "A2.hi")) != MTTS_OK) return rc;
-    if ((rc = encode_operand_map(&p.map_b2_hi, d->b2_hi, d->b, b_rows, "B2.hi")) != MTTS_OK) return rc;
+    if ((rc = encode_operand_map(&p.map_a2_hi, d->a2_hi, d->a, BM, "A2.hi", ra)) != MTTS_OK) return rc;
+    if ((rc = encode_operand_map(&p.map_b2_hi, d->b2_hi, d->b, b_rows, "B2.hi", rb)) != MTTS_OK) return rc;
     if (d->split == 3) {
-      if ((rc = encode_operand_map(&p.map_a2_lo, d->a2_lo, d->a, BM, "A2.lo")) != MTTS_OK) return rc;
-      if ((rc = encode_operand_map(&p.map_b2_lo, d->b2_lo, d->b, b_rows, "B2.lo")) != MTTS_OK) return rc;
+      if ((rc = encode_operand_map(&p.map_a2_lo, d->a2_lo, d->a, BM, "A2.lo", ra)) != MTTS_OK) return rc;
+      if ((rc = encode_operand_map(&p.map_b2_lo, d->b2_lo, d->b, b_rows, "B2.lo", rb)) != MTTS_OK) return rc;
     }
   }
   p.nterms = two ? 2 : 1;
-  p.a = {d->a.major, d->a.src2, d->a.src3, d->a.shift_src, d->a.shift_base, d->a.shift_step};
-  p.b = {d->b.major, d->b.src2, d->b.src3, d->b.shift_src, d->b.shift_base, d->b.shift_step};
+  p.a = {d->a.major, d->a.src2, d->a.src3, d->a.shift_src, d->a.shift_base, d->a.shift_step, ra};
+  p.b = {d->b.major, d->b.src2, d->b.src3, d->b.shift_src, d->b.shift_base, d->b.shift_step, rb};
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.ntaps = d->ntaps; p.nkb = d->nkb; p.nz0 = d->nz0; p.nz1 = d->nz1;
-  const int kchunks = mtts_cdiv(d->K, BK);
+  // narrow 1-CTA tiles run two k-blocks per stage fill (Cfg::KD)
+  const int kd = (!pair && bn == 64 && mtts_cdiv(d->K, BK) >= 2 && !(p.dbg & 512)) ? 2 : 1;
+  const int kchunks = mtts_cdiv(mtts_cdiv(d->K, BK), kd);
   const int total_iters = p.nterms * d->ntaps * d->nkb * kchunks;
   p.ksplit = ksplit > total_iters ? total_iters : ksplit;
   // every split must own >= 1 iteration
@@ -810,11 +825,11 @@ extern "C" int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream_) {
   }
 
   if (d->split == 1) {
-    if (bn == 64) return launch<64, 1>(p, grid, stream);
+    if (bn == 64) return kd == 2 ? launch<64, 1, 2>(p, grid, stream) : launch<64, 1>(p, grid, stream);
     if (bn == 128) return launch<128, 1>(p, grid, stream);
     return launch<256, 1>(p, grid, stream);
   } else {
-    if (bn == 64) return launch<64, 3>(p, grid, stream);
+    if (bn == 64) return kd == 2 ? launch<64, 3, 2>(p, grid, stream) : launch<64, 3>(p, grid, stream);
     if (bn == 128) return launch<128, 3>(p, grid, stream);
     return launch<256, 3>(p, grid, stream);
   }

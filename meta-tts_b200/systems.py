@@ -24,6 +24,8 @@ from __future__ import annotations
 import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import time
+
 import torch
 
 from . import ops as _ops
@@ -47,7 +49,7 @@ class _StaticBatch:
     FIELDS = (("spk_ids", torch.int64), ("texts", torch.int64), ("src_lens", torch.int64), ("mels", torch.float32),
               ("mel_lens", torch.int64), ("pitches", torch.float32), ("energies", torch.float32), ("durations", torch.int64),
               ("salt", torch.int32))        # per-step dropout salt (uint32 bits): rides in the same H2D copy
-    RING = 2
+    RING = 4        # the host may enqueue up to RING - 1 steps ahead of the device
 
     def __init__(self, device, n: int, L: int, T: int, n_spk_ids: int, average_spk: bool):
         shapes = {"spk_ids": (n_spk_ids,), "texts": (n, L), "src_lens": (n,), "mels": (n, T, N_MEL), "mel_lens": (n,),
@@ -149,6 +151,46 @@ class LazyLosses:
         return iter([h[i] for i in range(6)])
 
 
+class LazyScalar:
+    """One entry of a LazyLosses 6-tuple that has not been waited for yet: `float(x)` / `x.item()` / formatting /
+    arithmetic wait for the step's asynchronous device-to-host copy.  (The reference returns a CUDA tensor from
+    training_step and only synchronises when it logs — meta.py:76-80; returning a Python float here would force a
+    full device sync inside every training_step and forbid the host from running ahead.)"""
+
+    def __init__(self, losses: "LazyLosses", i: int):
+        self._l, self._i = losses, i
+
+    def item(self) -> float:
+        return float(self._l.wait()[self._i])
+
+    __float__ = item
+
+    def __repr__(self):
+        return f"{self.item():.6f}"
+
+    def __format__(self, spec):
+        return format(self.item(), spec)
+
+    def __add__(self, o):
+        return self.item() + float(o)
+
+    __radd__ = __add__
+
+    def __mul__(self, o):
+        return self.item() * float(o)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        return self.item() / float(o)
+
+    def __lt__(self, o):
+        return self.item() < float(o)
+
+    def __gt__(self, o):
+        return self.item() > float(o)
+
+
 DEFAULT_MODEL_CONFIG = {
     "transformer": {"encoder_layer": 4, "encoder_head": 2, "encoder_hidden": 256, "decoder_layer": 6, "decoder_head": 2,
                     "decoder_hidden": 256, "conv_filter_size": 1024, "conv_kernel_size": [9, 1],
@@ -198,6 +240,7 @@ def _metasystem_init(self, preprocess_config=None, model_config=None, train_conf
     self.use_cuda_graph = use_cuda_graph
     self.process_group = process_group
     self._graphs: Dict[Tuple, Tuple] = {}
+    self.host_prof = {"upload": 0.0, "replay": 0.0, "optimizer": 0.0, "d2h": 0.0, "step": 0.0}      # host seconds spent enqueueing (diagnostics)
     self._pending_tasks = 0
     self.launches_per_task_step: Optional[int] = None
     self.h2d_bytes_per_step = 0
@@ -237,8 +280,10 @@ def _run_task(self, sup12, qry12, steps: int, first_order: bool, accumulate_scal
     self.maml.use_tapes(tapes)
     drop_base = 0 if self.dropout else None
     self.be.drop_salt = sb.salt
+    t0 = time.perf_counter()
     sb.upload(sup12, salt=self.next_salt() if self.dropout else 0)
     qb.upload(qry12, spk_ids=sup12[2])            # query uses the SUPPORT speaker ids, averaged (base_adaptor.py:122)
+    self.host_prof["upload"] += time.perf_counter() - t0
     if not self.use_cuda_graph:
         n0 = _ops.launch_count
         result = self.maml.task_step(sb.dev, qb.dev, steps, first_order, accumulate_scale, drop_base)
@@ -262,7 +307,16 @@ def _run_task(self, sup12, qry12, steps: int, first_order: bool, accumulate_scal
         self.launches_per_task_step = _ops.launch_count - n0
         self.maml.bn_batches = bn0
         ent[2], ent[3] = graph, result
+    t0 = time.perf_counter()
+    tr = getattr(self, "trace_events", None)
+    if tr is not None:
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
     graph.replay()
+    if tr is not None:
+        eb.record()
+        tr.append((ea, eb))
+    self.host_prof["replay"] += time.perf_counter() - t0
     self.maml.bn_batches += steps + 1
     return ent[3]
 
@@ -309,15 +363,17 @@ def meta_learn(self, batch, batch_idx, train: bool = True):
     # D2H read of the 6 losses (the step's result): asynchronous copy into a pinned ring, waited on access
     if not hasattr(self, "_loss_ring"):
         pin = loss6.is_cuda
-        self._loss_ring = [torch.zeros(6).pin_memory() if pin else torch.zeros(6) for _ in range(4)]
+        self._loss_ring = [torch.zeros(6).pin_memory() if pin else torch.zeros(6) for _ in range(8)]
         self._loss_slot = 0
     hbuf = self._loss_ring[self._loss_slot]
     self._loss_slot = (self._loss_slot + 1) % len(self._loss_ring)
+    t0 = time.perf_counter()
     hbuf.copy_(loss6, non_blocking=True)
     ev = None
     if loss6.is_cuda:
         ev = torch.cuda.Event()
         ev.record()
+    self.host_prof["d2h"] += time.perf_counter() - t0
     losses = LazyLosses(hbuf, ev)
     dev = _ent_dev(self, sup12, qry12, steps, first_order)
     preds = _Predictions(out, dev, int(qry12[5]), int(qry12[8]))
@@ -331,9 +387,11 @@ def _ent_dev(self, sup12, qry12, steps, first_order):
 
 def training_step(self, batch, batch_idx):
     """meta.py:68-80"""
+    t0 = time.perf_counter()
     train_loss, predictions = self.meta_learn(batch, batch_idx, train=True)
+    self.host_prof["step"] += time.perf_counter() - t0
     qry_batch = batch[0][1][0]
-    return {"loss": train_loss[0], "losses": train_loss, "output": predictions, "_batch": qry_batch}
+    return {"loss": LazyScalar(train_loss, 0), "losses": train_loss, "output": predictions, "_batch": qry_batch}
 
 
 def validation_step(self, batch, batch_idx):
@@ -347,6 +405,7 @@ def optimizer_step(self):
     outer gradient (one flat buffer, summed; the 1/(acc*world) scale was folded in at accumulation),
     clip_grad_norm_(grad_clip_thresh), Adam, LambdaLR; then zero the accumulation buffer."""
     m = self.maml
+    t0 = time.perf_counter()
     if torch.distributed.is_initialized() and torch.distributed.get_world_size(self.process_group) > 1:
         torch.distributed.all_reduce(m.g_outer, group=self.process_group)
     opt = self.train_config["optimizer"]
@@ -355,6 +414,7 @@ def optimizer_step(self):
                    anneal_rate=float(opt.get("anneal_rate", 0.3)))
     self.be.zero_(m.g_outer)
     self._pending_tasks = 0
+    self.host_prof["optimizer"] += time.perf_counter() - t0
 
 
 class MetaSystem:
