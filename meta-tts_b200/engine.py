@@ -480,6 +480,8 @@ class FS2Engine:
         self.d_inner = tr["conv_filter_size"]
         self.nbins = cfg["variance_embedding"]["n_bins"]
         self.scr = Tape(be, self.split)        # shared scratch (never read across passes)
+        self._scr_main = self.scr
+        self._scr_branch = Tape(be, self.split)   # scratch of work issued on an auxiliary stream (may run concurrently)
         # Precision of the Hessian-vector pass.  Its result enters the outer gradient multiplied by the inner lr
         # (1e-3); running it single-pass bf16 (hvp_split = 1, operand hi halves only) moves individual gradient
         # tensors by up to ~3e-3 relative (CPU emulation, tests/test_engine_cpu.py), so the default keeps the
@@ -891,6 +893,26 @@ class FS2Engine:
     # ---------------------------------------------------------------------------------------------
     # whole model
     # ---------------------------------------------------------------------------------------------
+    class _BranchScratch:
+        """While issuing work for an auxiliary stream, bind the branch's own scratch buffers."""
+
+        def __init__(self, eng):
+            self.eng = eng
+
+        def __enter__(self):
+            self.eng.scr = self.eng._scr_branch
+
+        def __exit__(self, *a):
+            self.eng.scr = self.eng._scr_main
+            return False
+
+    def encoder_early(self, P: ParamSet, bt: Batch, tp: Tape, drop_pass: Optional[int] = None) -> Act:
+        """The encoder of a pass whose other inputs are not ready yet (the query pass: the encoder is not adapted, so it
+        does not depend on the inner loop).  Issued on the 'enc' branch; `forward(..., enc=...)` joins it."""
+        tp.drop_pass = drop_pass
+        with self.be.branch("enc"), FS2Engine._BranchScratch(self):
+            return self.encoder_fwd(P, bt.texts, bt.src_lens, bt.B, bt.L, tp)
+
     def encoder_fwd(self, P: ParamSet, texts, src_lens, B: int, Lq: int, tp: Tape) -> Act:
         """Encoder.forward (Models.py:73-100): embedding + position_enc, then the FFT blocks."""
         d = self.d
@@ -931,7 +953,8 @@ class FS2Engine:
             xin = o
         return xin
 
-    def forward(self, P: ParamSet, bt: Batch, tp: Tape, update_bn: bool = True, drop_pass: Optional[int] = None):
+    def forward(self, P: ParamSet, bt: Batch, tp: Tape, update_bn: bool = True, drop_pass: Optional[int] = None,
+                enc: Optional[Act] = None):
         """Teacher-forced forward + loss.  Returns dict with the reference's prediction tensors.
         drop_pass: None = dropout off (eval / parity-with-identity); an int = train-mode dropout, pass index mixed
         into every site seed (backward / tangent passes over `tp` reuse it)."""
@@ -940,7 +963,11 @@ class FS2Engine:
         B, Lq, T = bt.B, bt.L, bt.T
         assert T <= self.cfg["max_seq_len"] and Lq <= self.cfg["max_seq_len"], "sequence longer than max_seq_len"
         # ---- encoder (Models.py:73-100) ----
-        x = self.encoder_fwd(P, bt.texts, bt.src_lens, B, Lq, tp)
+        if enc is None:
+            x = self.encoder_fwd(P, bt.texts, bt.src_lens, B, Lq, tp)
+        else:
+            be.join("enc")                                    # computed ahead of time by encoder_early (same tape)
+            x = enc
         # ---- speaker embedding (base_adaptor.py:64-70) ----
         spk = tp.f32("spk", (B, d))
         be.spk_embed(bt.spk_ids, P.get("speaker_emb.model.weight").f32, bt.spk_ids.numel(), d, bt.average_spk, B, spk)
@@ -951,15 +978,19 @@ class FS2Engine:
         logd = tp.f32("logd", (B, Lq))
         ppred = tp.f32("ppred", (B, Lq))
         epred = tp.f32("epred", (B, Lq))
-        self.vp_fwd(P, f"{va}.duration_predictor", tp, x0, bt.src_lens, logd)
-        self.vp_fwd(P, f"{va}.pitch_predictor", tp, x0, bt.src_lens, ppred)
+        # The three predictor chains only feed the loss: they run on the 'vp' branch while this stream goes on through
+        # the length regulator, decoder and postnet (15 small launches off the critical path); joined before the loss.
+        with be.branch("vp"):
+            self.vp_fwd(P, f"{va}.duration_predictor", tp, x0, bt.src_lens, logd)
+            self.vp_fwd(P, f"{va}.pitch_predictor", tp, x0, bt.src_lens, ppred)
         idx_p = tp.buf("va.idx_p", (B, Lq), torch.int64)
         idx_e = tp.buf("va.idx_e", (B, Lq), torch.int64)
         be.bucketize(bt.pitches, self.consts[f"{va}.pitch_bins"], self.nbins - 1, B * Lq, idx_p)
         be.bucketize(bt.energies, self.consts[f"{va}.energy_bins"], self.nbins - 1, B * Lq, idx_e)
         x1 = tp.act("va.x1", B, Lq, d)
         be.embed_fwd(idx_p, P.get(f"{va}.pitch_embedding.weight").f32, x0.f32, None, Lq, B * Lq, d, x1.f32, x1.hi, x1.lo)
-        self.vp_fwd(P, f"{va}.energy_predictor", tp, x1, bt.src_lens, epred)
+        with be.branch("vp"):
+            self.vp_fwd(P, f"{va}.energy_predictor", tp, x1, bt.src_lens, epred)
         x2 = scr.scratch("va.x2", (B, Lq, d))
         be.embed_fwd(idx_e, P.get(f"{va}.energy_embedding.weight").f32, x1.f32, None, Lq, B * Lq, d, x2, None, None)
         lr_idx = tp.buf("lr.idx", (B, T), torch.int32)
@@ -976,12 +1007,14 @@ class FS2Engine:
         post = xin.f32
         be.axpby(1.0, mel.f32, 1.0, post)                    # postnet(output) + output
         loss6 = tp.f32("loss6", (6,))
+        be.join("vp")
         be.loss_fwd(mel.f32, post, bt.mels, bt.mel_lens, ppred, bt.pitches, epred, bt.energies, logd, bt.durations,
                     bt.src_lens, B, T, Lq, N_MEL, scr.scratch("loss.ws", (8,)), loss6, tp.f32("loss.counts", (2,)))
         return {"mel": mel.f32, "postnet": post, "pitch": ppred, "energy": epred, "logd": logd, "loss6": loss6,
                 "mel_len": lr_len}
 
-    def backward(self, P: ParamSet, G: ParamSet, bt: Batch, tp: Tape, loss_scale: float = 1.0, into_encoder: bool = True):
+    def backward(self, P: ParamSet, G: ParamSet, bt: Batch, tp: Tape, loss_scale: float = 1.0, into_encoder: bool = True,
+                 enc_G: Optional[ParamSet] = None):
         """dL*loss_scale/dparams accumulated into G (G must be zeroed by the caller when needed)."""
         be, g, scr, d = self.be, self.g, self.scr, self.d
         B, Lq, T = bt.B, bt.L, bt.T
@@ -996,6 +1029,17 @@ class FS2Engine:
                     bt.energies, tp.f32("logd", (B, Lq)), bt.durations, bt.src_lens, B, T, Lq, N_MEL,
                     tp.f32("loss.counts", (2,)), loss_scale, 0, dmel.f32, dpost, dp, de, dlogd)
         be.axpby(1.0, dpost, 1.0, dmel.f32)                  # residual: postnet_output = postnet(mel) + mel
+        # ---- variance predictors: they need only the loss gradients -> 'vp' branch, concurrently with the postnet /
+        #      decoder backward; their input gradients land in separate buffers that are folded into dx after the join ----
+        x0 = tp.act("va.x0", B, Lq, d)
+        x1 = tp.act("va.x1", B, Lq, d)
+        dxe, dx0 = tp.f32("va.dxe", (B, Lq, d)), tp.f32("va.dx0", (B, Lq, d))
+        with be.branch("vp"):
+            be.zero_(dxe)
+            be.zero_(dx0)
+            self.vp_bwd(P, G, f"{va}.energy_predictor", tp, x1, bt.src_lens, de, dxe)
+            self.vp_bwd(P, G, f"{va}.pitch_predictor", tp, x0, bt.src_lens, dp, dx0)
+            self.vp_bwd(P, G, f"{va}.duration_predictor", tp, x0, bt.src_lens, dlogd, dx0)
         # ---- postnet ----
         for i in range(4, -1, -1):
             pre = f"postnet.convolutions.{i}"
@@ -1036,17 +1080,20 @@ class FS2Engine:
         dx = tp.f32("va.dx", (B, Lq, d))
         be.lr_bwd(dcur, bt.durations, Lq, dx)
         # ---- variance adaptor ----
-        x0 = tp.act("va.x0", B, Lq, d)
-        x1 = tp.act("va.x1", B, Lq, d)
         be.embed_bwd(tp.buf("va.idx_e", (B, Lq), torch.int64), dx, B * Lq, d, -1, 1.0, G.get(f"{va}.energy_embedding.weight").f32)
-        self.vp_bwd(P, G, f"{va}.energy_predictor", tp, x1, bt.src_lens, de, dx)
+        be.join("vp")
+        be.axpby(1.0, dxe, 1.0, dx)                          # + energy predictor (input x1 = x0 + pitch embedding)
         be.embed_bwd(tp.buf("va.idx_p", (B, Lq), torch.int64), dx, B * Lq, d, -1, 1.0, G.get(f"{va}.pitch_embedding.weight").f32)
-        self.vp_bwd(P, G, f"{va}.pitch_predictor", tp, x0, bt.src_lens, dp, dx)
-        self.vp_bwd(P, G, f"{va}.duration_predictor", tp, x0, bt.src_lens, dlogd, dx)
+        be.axpby(1.0, dx0, 1.0, dx)                          # + pitch and duration predictors (input x0)
         be.colsum(dx, None, None, B, Lq, d, dspk)
         be.spk_embed_bwd(bt.spk_ids, dspk, bt.spk_ids.numel(), d, bt.average_spk, B, 1.0, G.get("speaker_emb.model.weight").f32)
         # ---- encoder ----
-        if into_encoder:
+        if into_encoder and enc_G is not None:
+            # nothing downstream on this stream needs the encoder gradient soon (the Hessian-vector passes follow):
+            # run the encoder backward on the 'enc' branch into its own accumulation arena; the caller joins
+            with be.branch("enc"), FS2Engine._BranchScratch(self):
+                self._encoder_bwd(P, enc_G, bt, tp, dx)
+        elif into_encoder:
             self._encoder_bwd(P, G, bt, tp, dx)
         be.join_side()                                      # weight-gradient branch joins before anyone reads G
 
@@ -1099,13 +1146,15 @@ class FS2Engine:
         va_adapted = lay.is_adapted_module(va)
         assert va_adapted and spkd is not None, "HVP expects speaker_emb and variance_adaptor in adapt.modules"
         logdd, ppd, epd = tt.f32("logdd", (B, Lq)), tt.f32("ppredd", (B, Lq)), tt.f32("epredd", (B, Lq))
-        self.vp_tfwd(P, Pd, f"{va}.duration_predictor", tp, tt, x0, x0d, bt.src_lens, logdd)
-        self.vp_tfwd(P, Pd, f"{va}.pitch_predictor", tp, tt, x0, x0d, bt.src_lens, ppd)
+        with be.branch("vp"):
+            self.vp_tfwd(P, Pd, f"{va}.duration_predictor", tp, tt, x0, x0d, bt.src_lens, logdd)
+            self.vp_tfwd(P, Pd, f"{va}.pitch_predictor", tp, tt, x0, x0d, bt.src_lens, ppd)
         idx_p = tp.buf("va.idx_p", (B, Lq), torch.int64)
         idx_e = tp.buf("va.idx_e", (B, Lq), torch.int64)
         x1d = tt.act("va.x1d", B, Lq, d)
         be.embed_fwd(idx_p, Pd.get(f"{va}.pitch_embedding.weight").f32, x0d.f32, None, Lq, B * Lq, d, x1d.f32, x1d.hi, x1d.lo)
-        self.vp_tfwd(P, Pd, f"{va}.energy_predictor", tp, tt, x1, x1d, bt.src_lens, epd)
+        with be.branch("vp"):
+            self.vp_tfwd(P, Pd, f"{va}.energy_predictor", tp, tt, x1, x1d, bt.src_lens, epd)
         x2d = scr.scratch("va.x2", (B, Lq, d))
         be.embed_fwd(idx_e, Pd.get(f"{va}.energy_embedding.weight").f32, x1d.f32, None, Lq, B * Lq, d, x2d, None, None)
         xrd = scr.scratch("lr.out", (B, T, d))
@@ -1139,8 +1188,16 @@ class FS2Engine:
         ddmel = tt.act("ddmel", B, T, N_MEL)
         ddpost = tt.f32("post.4.ddout", (B, T, N_MEL))
         ddp, dde, ddlogd = tt.f32("ddp", (B, Lq)), tt.f32("dde", (B, Lq)), tt.f32("ddlogd", (B, Lq))
+        be.join("vp")
         be.loss_bwd(None, None, None, bt.mel_lens, ppd, None, epd, None, logdd, None, bt.src_lens, B, T, Lq, N_MEL,
                     tp.f32("loss.counts", (2,)), loss_scale, 1, ddmel.f32, ddpost, ddp, dde, ddlogd)
+        ddxe, ddx0 = tt.f32("va.ddxe", (B, Lq, d)), tt.f32("va.ddx0", (B, Lq, d))
+        with be.branch("vp"):                                # predictor tangent-backward chains, folded into ddx below
+            be.zero_(ddxe)
+            be.zero_(ddx0)
+            self.vp_tbwd(P, Pd, HV, f"{va}.energy_predictor", tp, tt, x1, x1d, bt.src_lens, tp.f32("de", (B, Lq)), dde, ddxe)
+            self.vp_tbwd(P, Pd, HV, f"{va}.pitch_predictor", tp, tt, x0, x0d, bt.src_lens, tp.f32("dp", (B, Lq)), ddp, ddx0)
+            self.vp_tbwd(P, Pd, HV, f"{va}.duration_predictor", tp, tt, x0, x0d, bt.src_lens, tp.f32("dlogd", (B, Lq)), ddlogd, ddx0)
         # ddmel = 0 + ddpost(=0) so far; postnet chain
         for i in range(4, -1, -1):
             pre = f"postnet.convolutions.{i}"
@@ -1188,10 +1245,10 @@ class FS2Engine:
         ddx = tt.f32("va.ddx", (B, Lq, d))
         be.lr_bwd(ddcur, bt.durations, Lq, ddx)
         be.embed_bwd(idx_e, ddx, B * Lq, d, -1, 1.0, hv(f"{va}.energy_embedding.weight"))
-        self.vp_tbwd(P, Pd, HV, f"{va}.energy_predictor", tp, tt, x1, x1d, bt.src_lens, tp.f32("de", (B, Lq)), dde, ddx)
+        be.join("vp")
+        be.axpby(1.0, ddxe, 1.0, ddx)
         be.embed_bwd(idx_p, ddx, B * Lq, d, -1, 1.0, hv(f"{va}.pitch_embedding.weight"))
-        self.vp_tbwd(P, Pd, HV, f"{va}.pitch_predictor", tp, tt, x0, x0d, bt.src_lens, tp.f32("dp", (B, Lq)), ddp, ddx)
-        self.vp_tbwd(P, Pd, HV, f"{va}.duration_predictor", tp, tt, x0, x0d, bt.src_lens, tp.f32("dlogd", (B, Lq)), ddlogd, ddx)
+        be.axpby(1.0, ddx0, 1.0, ddx)
         be.colsum(ddx, None, None, B, Lq, d, ddspk)
         be.spk_embed_bwd(bt.spk_ids, ddspk, bt.spk_ids.numel(), d, bt.average_spk, B, 1.0, hv("speaker_emb.model.weight"))
         # encoder: zero forward tangent => the tangent backward is a plain backward of ddx (mixed partials)

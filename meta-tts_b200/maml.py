@@ -59,6 +59,7 @@ class MamlEngine:
         self.g_task = z((n,))            # this task's outer gradient (lambda | gphi)
         self.g_outer = z((n,))           # accumulated over tasks (allreduce buffer)
         self.hv = z((n,))
+        self.g_enc = z((lay.adapt_begin,))   # query-pass gradient of the (non-adapted) prefix, accumulated on the 'enc' branch
         self.lam_hi = z((na,), bf)
         self.lam_lo = z((na,), bf) if be.split == 3 else None
         self.consts: Dict[str, torch.Tensor] = {}
@@ -151,12 +152,21 @@ class MamlEngine:
         assert steps <= self.K_max
         be, eng, lay = self.be, self.engine, self.layout
         a0 = lay.adapt_begin
+        dq = None if drop_base is None else drop_base + steps
+        # the encoder is not adapted: the query's encoder pass does not depend on the inner loop -> 'enc' branch
+        xq = eng.encoder_early(self.params(0), qry, self.tape_q, drop_pass=dq)
         self.adapt(sup, steps, drop_base=drop_base)
         PK = self.params(steps)
-        out = eng.forward(PK, qry, self.tape_q, drop_pass=None if drop_base is None else drop_base + steps)
+        out = eng.forward(PK, qry, self.tape_q, drop_pass=dq, enc=xq)
         self.bn_batches += 1
         be.zero_(self.g_task)
-        eng.backward(PK, self.grads(self.g_task), qry, self.tape_q, 1.0, into_encoder=True)
+        overlap_enc = (not first_order) and steps > 0 and not lay.entries["encoder.src_word_emb.weight"].adapted
+        if overlap_enc:
+            # the query's encoder backward overlaps the Hessian-vector passes; it accumulates into its own arena
+            # (the adjoint recursion below rewrites all of g_task) and is folded in after the join
+            be.zero_(self.g_enc)
+        eng.backward(PK, self.grads(self.g_task), qry, self.tape_q, 1.0, into_encoder=True,
+                     enc_G=self.grads(self.g_enc) if overlap_enc else None)
         if not first_order:
             for k in range(steps - 1, -1, -1):
                 be.split_(self.g_task[a0:], self.lam_hi, self.lam_lo)
@@ -164,6 +174,9 @@ class MamlEngine:
                 be.zero_(self.hv)
                 eng.hvp(self.params(k), Pd, self.grads(self.hv), sup, self.tapes[k], self.tape_t)
                 be.axpby(-self.lr, self.hv, 1.0, self.g_task)              # lambda_k | gphi update in one pass
+        if overlap_enc:
+            be.join("enc")
+            be.axpby(1.0, self.g_enc, 1.0, self.g_task[:a0])
         if accumulate_scale is not None:
             be.axpby(accumulate_scale, self.g_task, 1.0, self.g_outer)
         return out["loss6"], out

@@ -6,6 +6,7 @@ hand-written sm_100a kernels through ctypes; nothing falls back to torch ops.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Optional, Sequence
 
@@ -199,6 +200,37 @@ class _SideCtx:
         return False
 
 
+class _BranchCtx:
+    """Fork a named auxiliary stream from the current stream (work issued so far happens-before the branch).  Inside the
+    branch the weight-gradient side stream is not used (its join on the main stream would otherwise wait for the branch)."""
+
+    def __init__(self, be, name):
+        self.be, self.name, self.ctx, self.saved = be, name, None, None
+
+    def __enter__(self):
+        be = self.be
+        if not be.use_branches:
+            return self
+        st = be._branches.get(self.name)
+        if st is None:
+            st = be._branches[self.name] = torch.cuda.Stream(device=be.device)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        st.wait_event(ev)
+        be._branch_used.add(self.name)
+        self.saved = be.use_side_stream
+        be.use_side_stream = False
+        self.ctx = torch.cuda.stream(st)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+            self.be.use_side_stream = self.saved
+        return False
+
+
 class CudaOps:
     """sm_100a backend.  `split` = 1 (bf16) or 3 (bf16x3 hi/lo, fp32-grade)."""
 
@@ -214,11 +246,25 @@ class CudaOps:
         self._side = torch.cuda.Stream(device=self.device)      # weight-gradient GEMMs / bias column sums (off the critical path)
         self._side_used = False
         self.use_side_stream = True
+        self._branches = {}            # named auxiliary streams (encoder work that nothing on the main chain waits for)
+        self._branch_used = set()
+        self.use_branches = os.environ.get("MTTS_NO_BRANCH", "0") != "1"
         self.drop_salt = None          # device int32[1] (uint32 bits) mixed into every dropout seed; None = 0
 
     # ---- side stream: work that nothing on the critical path waits for (captured as a parallel graph branch) ----
     def side(self):
         return _SideCtx(self)
+
+    def branch(self, name: str):
+        return _BranchCtx(self, name)
+
+    def join(self, name: str):
+        """The current stream waits for everything issued on branch `name`."""
+        if name in self._branch_used:
+            ev = torch.cuda.Event()
+            ev.record(self._branches[name])
+            torch.cuda.current_stream().wait_event(ev)
+            self._branch_used.discard(name)
 
     def join_side(self):
         if self._side_used:

@@ -84,6 +84,13 @@ class RefOps:
     def join_side(self):
         pass
 
+    def branch(self, name):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def join(self, name):
+        pass
+
     # ------------------------------------------------------------------------------------------
     # GEMM descriptor emulator (semantics of mtts_gemm: TMA coordinates, OOB zero fill, epilogue)
     # ------------------------------------------------------------------------------------------
