@@ -76,12 +76,19 @@ __device__ __forceinline__ int pick_src(int src, int z0, int z1, int tap, int kb
 }
 
 // TMEM accumulator tile (128 lanes x BN columns) -> alpha, bias, +C, ReLU, gate -> global (fp32 / bf16 hi,lo / red.add)
+//
+// Stores are COALESCED through a per-warp 4 KB staging buffer (`stage`, carved out of the pipeline's shared memory,
+// which is idle once the accumulator is complete): tcgen05.ld hands every thread 32 consecutive columns of ITS row,
+// so direct stores make each warp instruction touch 32 different rows (16 B of each).  The warp instead writes its
+// 32 x 32 chunk to shared memory (XOR-swizzled float4 slots: conflict-free both ways) and reads it back with lane
+// l -> (row l / 8 of 4, float4 l % 8): every global instruction then covers 4 rows x 128 contiguous bytes.
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_base, int q, int lane, int m0, int n0, int z0,
-                                              int z1, int c_begin, int c_end) {
+                                              int z1, int c_begin, int c_end, float4* stage) {
   const int row = m0 + q * 32 + lane;
   const bool row_ok = row < p.M;
-  const int64_t c_off = int64_t(z0) * p.c_sz0 + int64_t(z1) * p.c_sz1 + int64_t(row) * p.ldc;
+  const int64_t z_off = int64_t(z0) * p.c_sz0 + int64_t(z1) * p.c_sz1;
+  const int64_t c_off = z_off + int64_t(row) * p.ldc;
   const float* bias = p.bias ? p.bias + int64_t(z0) * p.bias_sz0 : nullptr;
   const bool vec_ok = ((p.ldc & 7) == 0) && ((p.c_sz0 & 7) == 0) && ((p.c_sz1 & 7) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.c_f32) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.c_hi) & 15) == 0) &&
@@ -94,72 +101,112 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
     tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), r);
     tmem_ld_wait();
     const int col0 = n0 + c * 32;
-    if (!row_ok || col0 >= p.N || (p.dbg & 128)) continue;
+    if (col0 >= p.N || (p.dbg & 128)) continue;          // warp-uniform
+    const bool full = (col0 + 32 <= p.N) && vec_ok;      // warp-uniform
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-    if (bias) {
-      if (p.flags & MTTS_EPI_BIAS_ROW) {
+    if (row_ok) {
+      if (bias) {
+        if (p.flags & MTTS_EPI_BIAS_ROW) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += bias_row;
-      } else if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0)) {
+          for (int j = 0; j < 32; ++j) v[j] += bias_row;
+        } else if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0)) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
-          v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+            v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) v[j] += __ldg(bias + col0 + j);
         }
-      } else {
+      }
+      if (p.flags & MTTS_EPI_ADD_C) {
+        const float* src = p.c_f32 + c_off + col0;
+        if (full) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.N) v[j] += __ldg(bias + col0 + j);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 cc = *reinterpret_cast<const float4*>(src + j);
+            v[j] += cc.x; v[j + 1] += cc.y; v[j + 2] += cc.z; v[j + 3] += cc.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) v[j] += src[j];
+        }
+      }
+      if (p.flags & MTTS_EPI_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (p.flags & MTTS_EPI_GATE) {
+        const bf16* g = p.gate + c_off + col0;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 gg = *reinterpret_cast<const uint4*>(g + j);
+            const uint32_t w[4] = {gg.x, gg.y, gg.z, gg.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+              const uint32_t lo16 = w[t] & 0xFFFFu, hi16 = w[t] >> 16;
+              if (!((lo16 & 0x8000u) == 0 && (lo16 & 0x7FFFu) != 0)) v[j + 2 * t] = 0.f;
+              if (!((hi16 & 0x8000u) == 0 && (hi16 & 0x7FFFu) != 0)) v[j + 2 * t + 1] = 0.f;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N && !(__bfloat162float(g[j]) > 0.f)) v[j] = 0.f;
+        }
       }
     }
-    const bool full = (col0 + 32 <= p.N) && vec_ok;
-    if (p.flags & MTTS_EPI_ADD_C) {
-      const float* src = p.c_f32 + c_off + col0;
-      if (full) {
+    if (full && !(p.dbg & 1024)) {
+      // ---- coalesced path: transpose the warp's 32 x 32 chunk through shared memory ----
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 cc = *reinterpret_cast<const float4*>(src + j);
-          v[j] += cc.x; v[j + 1] += cc.y; v[j + 2] += cc.z; v[j + 3] += cc.w;
-        }
-      } else {
+      for (int j = 0; j < 8; ++j) stage[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      __syncwarp();
+      const int jj = lane & 7;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.N) v[j] += src[j];
-      }
-    }
-    if (p.flags & MTTS_EPI_RELU) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-    }
-    if (p.flags & MTTS_EPI_GATE) {
-      const bf16* g = p.gate + c_off + col0;
-      if (full) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const uint4 gg = *reinterpret_cast<const uint4*>(g + j);
-          const uint32_t w[4] = {gg.x, gg.y, gg.z, gg.w};
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-            const uint32_t lo16 = w[t] & 0xFFFFu, hi16 = w[t] >> 16;
-            if (!((lo16 & 0x8000u) == 0 && (lo16 & 0x7FFFu) != 0)) v[j + 2 * t] = 0.f;
-            if (!((hi16 & 0x8000u) == 0 && (hi16 & 0x7FFFu) != 0)) v[j + 2 * t + 1] = 0.f;
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + (lane >> 3);
+        const float4 t = stage[rr * 8 + (jj ^ (rr & 7))];
+        const int grow = m0 + q * 32 + rr;
+        if (grow < p.M) {
+          const int64_t off = z_off + int64_t(grow) * p.ldc + col0 + jj * 4;
+          if (p.c_f32) {
+            float* dst = p.c_f32 + off;
+            if (p.flags & MTTS_EPI_ACCUM)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+            else
+              *reinterpret_cast<float4*>(dst) = t;
+          }
+          if (p.c_hi) {
+            bf16 h0, h1, h2, h3, l0, l1, l2, l3;
+            split_bf16(t.x, h0, l0); split_bf16(t.y, h1, l1); split_bf16(t.z, h2, l2); split_bf16(t.w, h3, l3);
+            uint2 h;
+            h.x = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
+            h.y = uint32_t(__bfloat16_as_ushort(h2)) | (uint32_t(__bfloat16_as_ushort(h3)) << 16);
+            *reinterpret_cast<uint2*>(p.c_hi + off) = h;
+            if (p.c_lo) {
+              uint2 l;
+              l.x = uint32_t(__bfloat16_as_ushort(l0)) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
+              l.y = uint32_t(__bfloat16_as_ushort(l2)) | (uint32_t(__bfloat16_as_ushort(l3)) << 16);
+              *reinterpret_cast<uint2*>(p.c_lo + off) = l;
+            }
           }
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < p.N && !(__bfloat162float(g[j]) > 0.f)) v[j] = 0.f;
       }
+      __syncwarp();                     // the staging buffer is rewritten by the next chunk
+      continue;
     }
+    if (!row_ok) continue;
     if (p.c_f32) {
       float* dst = p.c_f32 + c_off + col0;
       if (p.flags & MTTS_EPI_ACCUM) {
         if (full) {
-          // 128-bit vector reductions (REDG.E.ADD.F32x4): the scalar form is bound by the SM's atomic issue rate
-          // (~1 lane-op / clk: 20 us for one 256 x 256 tile)
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]),
@@ -212,6 +259,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
   }
 }
 
+// ================================================================================================
 template <int BN, int SPLIT, int KD>
 __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN, SPLIT, KD>;
@@ -419,7 +467,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
       const int half = (warp - 2) >> 2;
       const int c_begin = CH >= 2 ? half * (CH / 2) : 0;
       const int c_end = CH >= 2 ? c_begin + CH / 2 : (half == 0 ? CH : 0);
-      epilogue_tile<BN>(p, tmem_base, q, lane, m0, n0, z0, z1, c_begin, c_end);
+      epilogue_tile<BN>(p, tmem_base, q, lane, m0, n0, z0, z1, c_begin, c_end,
+                        reinterpret_cast<float4*>(smem) + (warp - 2) * 256);
     }
   }
 
@@ -636,7 +685,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mtts
       const int half = (warp - 2) >> 2;
       const int c_begin = CH >= 2 ? half * (CH / 2) : 0;
       const int c_end = CH >= 2 ? c_begin + CH / 2 : (half == 0 ? CH : 0);
-      epilogue_tile<BN>(p, tmem_base, q, lane, m0, n0, z0, z1, c_begin, c_end);
+      epilogue_tile<BN>(p, tmem_base, q, lane, m0, n0, z0, z1, c_begin, c_end,
+                        reinterpret_cast<float4*>(smem) + (warp - 2) * 256);
     }
   }
 
