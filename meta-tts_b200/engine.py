@@ -604,14 +604,17 @@ class FS2Engine:
             g.conv_wgrad(dz1, o, G.get(f"{a_}.fc.weight").f32)
         # attention
         dP = tp.f32(f"{pf}.dP", (B, H, T, Tp))
+        dq_h, dq_l = tp.bf(f"{pf}.dqkv", (R, 3 * d))
+        with be.branch("att", local=True):                  # dV needs only dO and P: beside dP -> softmax-bwd -> dQ
+            g.bmm(pm(p_h, p_l), True, om(do.hi, do.lo), True, qm(dq_h, dq_l, 2), B, H)                  # dV = P^T dO
         g.bmm(om(do.hi, do.lo), False, qm(qkv_h, qkv_l, 2), False, pm(None, None, dP), B, H)
         ds_h, ds_l = tp.bf(f"{pf}.dS", (B, H, T, Tp))
         be.softmax(1, dP, None, p_h, p_l, None, None, lens, B * H, H, T, T, Tp, ds_h, ds_l)
-        dq_h, dq_l = tp.bf(f"{pf}.dqkv", (R, 3 * d))
         sc = 1.0 / math.sqrt(dk)
-        g.bmm(pm(p_h, p_l), True, om(do.hi, do.lo), True, qm(dq_h, dq_l, 2), B, H)                      # dV = P^T dO
         g.bmm(pm(ds_h, ds_l), False, qm(qkv_h, qkv_l, 1), True, qm(dq_h, dq_l, 0), B, H, alpha=sc)       # dQ = dS K
-        g.bmm(pm(ds_h, ds_l), True, qm(qkv_h, qkv_l, 0), True, qm(dq_h, dq_l, 1), B, H, alpha=sc)        # dK = dS^T Q
+        with be.branch("att", local=True):                  # dK runs beside dQ (disjoint column blocks of dqkv)
+            g.bmm(pm(ds_h, ds_l), True, qm(qkv_h, qkv_l, 0), True, qm(dq_h, dq_l, 1), B, H, alpha=sc)    # dK = dS^T Q
+        be.join("att", local=True)
         dqkv = Act(None, dq_h, dq_l, B, T, 3 * d)
         with be.side():
             g.conv_wgrad(dqkv, x, gwqkv.f32)
@@ -761,14 +764,16 @@ class FS2Engine:
         dds_h, dds_l = tt.bf(f"{pf}.ddS", (B, H, T, Tp))
         be.softmax(2, dP, ddP, p_h, p_l, pd_h, pd_l, lens, B * H, H, T, T, Tp, dds_h, dds_l)
         ddq_h, ddq_l = tt.bf(f"{pf}.ddqkv", (R, 3 * d))
-        # ddV = Pd^T dO + P^T ddO
-        g.bmm(pm(pd_h, pd_l), True, om(do.hi, do.lo), True, qm(ddq_h, ddq_l, 2), B, H, A2=pm(p_h, p_l), B2=om(ddo.hi, ddo.lo))
+        with be.branch("att", local=True):
+            # ddV = Pd^T dO + P^T ddO
+            g.bmm(pm(pd_h, pd_l), True, om(do.hi, do.lo), True, qm(ddq_h, ddq_l, 2), B, H, A2=pm(p_h, p_l), B2=om(ddo.hi, ddo.lo))
+            # ddK = scale (ddS^T Q + dS^T Qd)
+            g.bmm(pm(dds_h, dds_l), True, qm(qkv_h, qkv_l, 0), True, qm(ddq_h, ddq_l, 1), B, H, alpha=sc,
+                  A2=pm(ds_h, ds_l), B2=qm(qd_h, qd_l, 0))
         # ddQ = scale (ddS K + dS Kd)
         g.bmm(pm(dds_h, dds_l), False, qm(qkv_h, qkv_l, 1), True, qm(ddq_h, ddq_l, 0), B, H, alpha=sc,
               A2=pm(ds_h, ds_l), B2=qm(qd_h, qd_l, 1))
-        # ddK = scale (ddS^T Q + dS^T Qd)
-        g.bmm(pm(dds_h, dds_l), True, qm(qkv_h, qkv_l, 0), True, qm(ddq_h, ddq_l, 1), B, H, alpha=sc,
-              A2=pm(ds_h, ds_l), B2=qm(qd_h, qd_l, 0))
+        be.join("att", local=True)
         dqkv = Act(None, dq_h, dq_l, B, T, 3 * d)
         ddqkv = Act(None, ddq_h, ddq_l, B, T, 3 * d)
         with be.side():

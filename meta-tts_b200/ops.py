@@ -204,13 +204,15 @@ class _BranchCtx:
     """Fork a named auxiliary stream from the current stream (work issued so far happens-before the branch).  Inside the
     branch the weight-gradient side stream is not used (its join on the main stream would otherwise wait for the branch)."""
 
-    def __init__(self, be, name):
-        self.be, self.name, self.ctx, self.saved = be, name, None, None
+    def __init__(self, be, name, local=False):
+        self.be, self.name, self.ctx, self.saved, self.local = be, name, None, None, local
 
     def __enter__(self):
         be = self.be
-        if not be.use_branches:
+        if not be.use_branches or (self.local and not be.use_local_branches):
             return self
+        if self.local:                         # a branch private to the chain (main or another branch) that forks it
+            self.name = f"{self.name}@{be._cur_branch or 'main'}"
         st = be._branches.get(self.name)
         if st is None:
             st = be._branches[self.name] = torch.cuda.Stream(device=be.device)
@@ -218,8 +220,9 @@ class _BranchCtx:
         ev.record(torch.cuda.current_stream())
         st.wait_event(ev)
         be._branch_used.add(self.name)
-        self.saved = be.use_side_stream
+        self.saved = (be.use_side_stream, be._cur_branch)
         be.use_side_stream = False
+        be._cur_branch = self.name
         self.ctx = torch.cuda.stream(st)
         self.ctx.__enter__()
         return self
@@ -227,7 +230,7 @@ class _BranchCtx:
     def __exit__(self, *a):
         if self.ctx is not None:
             self.ctx.__exit__(*a)
-            self.be.use_side_stream = self.saved
+            self.be.use_side_stream, self.be._cur_branch = self.saved
         return False
 
 
@@ -248,6 +251,8 @@ class CudaOps:
         self.use_side_stream = True
         self._branches = {}            # named auxiliary streams (encoder work that nothing on the main chain waits for)
         self._branch_used = set()
+        self._cur_branch = None
+        self.use_local_branches = os.environ.get("MTTS_NO_ATT", "0") != "1"
         self.use_branches = os.environ.get("MTTS_NO_BRANCH", "0") != "1"
         self.drop_salt = None          # device int32[1] (uint32 bits) mixed into every dropout seed; None = 0
 
@@ -255,11 +260,13 @@ class CudaOps:
     def side(self):
         return _SideCtx(self)
 
-    def branch(self, name: str):
-        return _BranchCtx(self, name)
+    def branch(self, name: str, local: bool = False):
+        return _BranchCtx(self, name, local)
 
-    def join(self, name: str):
+    def join(self, name: str, local: bool = False):
         """The current stream waits for everything issued on branch `name`."""
+        if local:
+            name = f"{name}@{self._cur_branch or 'main'}"
         if name in self._branch_used:
             ev = torch.cuda.Event()
             ev.record(self._branches[name])

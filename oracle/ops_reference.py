@@ -84,11 +84,11 @@ class RefOps:
     def join_side(self):
         pass
 
-    def branch(self, name):
+    def branch(self, name, local=False):
         import contextlib
         return contextlib.nullcontext()
 
-    def join(self, name):
+    def join(self, name, local=False):
         pass
 
     # ------------------------------------------------------------------------------------------
