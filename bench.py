@@ -206,6 +206,68 @@ def time_variant(orig_gemm, calls, reps=5):
     return e0.elapsed_time(e1) / reps          # ms for all `calls`
 
 
+def fft_block_roofline(sysm, peak_tflops, B=SHOTS, T=T_MEL, reps=5):
+    """BASELINE's second metric: the decoder FFT block (MHA + conv k=9 / k=1 + 2 x (residual, LayerNorm)) against its
+    arithmetic roofline.  Six blocks' forward (then backward) are captured in one CUDA graph on a [B, T, 256] input and
+    timed with CUDA events; FLOPs from SURVEY.md 8(a8): F_fft(T) = 5 767 168 T + 1 024 T^2 per sequence (backward = 2x)."""
+    from meta_tts_b200.engine import Act
+    m = sysm.maml
+    eng, be = m.engine, sysm.be
+    P = m.params(0)
+    d = eng.d
+    tp = eng.new_tape()
+    tp.drop_pass = 0                                       # dropout active, like the step
+    x = tp.act("x", B, T, d)
+    x.f32.normal_()
+    be.split_(x.f32, x.hi, x.lo)
+    lens = torch.full((B,), T, dtype=torch.int64, device=x.f32.device)
+    G = m.grads(torch.zeros_like(m.g_task))
+    dout = torch.randn(B, T, d, device=x.f32.device) * 1e-3
+    dxs = [torch.empty(B, T, d, device=x.f32.device) for _ in range(eng.n_dec)]
+    names = [f"decoder.layer_stack.{i}" for i in range(eng.n_dec)]
+
+    def fwd():
+        y = x
+        for pf in names:
+            y = eng.fft_fwd(P, pf, tp, y, lens, eng.h_dec)
+
+    def bwd():
+        dcur = dout
+        for i in range(eng.n_dec - 1, -1, -1):
+            xin = tp.act(f"{names[i - 1]}.out", B, T, d) if i > 0 else x
+            eng.fft_bwd(P, G, names[i], tp, xin, lens, eng.h_dec, dcur, dxs[i])
+            dcur = dxs[i]
+        be.join_side()
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps / eng.n_dec          # ms per block
+
+    f_fft = (5767168.0 * T + 1024.0 * T * T) * B
+    t_f = timed(fwd)
+    t_b = timed(bwd)
+    tf_f, tf_b = f_fft / (t_f * 1e-3) / 1e12, 2 * f_fft / (t_b * 1e-3) / 1e12
+    tf_fb = 3 * f_fft / ((t_f + t_b) * 1e-3) / 1e12
+    mult = 3 if be.split == 3 else 1
+    return {"what": f"decoder FFT block, B={B} x T={T}, d=256, 2 heads, conv 1024 k=9/1, dropout on; 6 blocks per graph",
+            "gflop_fwd": f_fft / 1e9, "fwd_ms": t_f, "bwd_ms": t_b, "fwd_tflops": tf_f, "bwd_tflops": tf_b,
+            "fwd_bwd_tflops": tf_fb, "peak_tflops": peak_tflops, "frac_fwd": tf_f / peak_tflops, "frac_bwd": tf_b / peak_tflops,
+            "frac_fwd_bwd": tf_fb / peak_tflops, "frac_fwd_bwd_as_issued_mma": mult * tf_fb / peak_tflops,
+            "flops": "F_fft(T) = 5767168 T + 1024 T^2 per sequence (SURVEY 8 a8); backward = 2 F_fft"}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -422,6 +484,7 @@ def run_own_arm(args):
                 print(f"{ms_g:7.3f} ms {100 * ms_g / tot:5.1f}%  n={n:3d}  {1e3 * ms_g / n:6.1f} us/launch  {fl / ms_g / 1e9:6.1f} TF/s(alg)  "
                       f"{key[0]:28s} MNK/taps/kb/z/terms={key[1]} flags={key[2]} ksplit={key[3]} out={key[4]} {key[5]}", file=sys.stderr)
         sysm.be.zero_(sysm.maml.g_outer)
+        fft_block = fft_block_roofline(sysm, peaks["bf16_tflops"])
         vstats.sort(key=lambda d: -d["ms_per_step"])
         dom = vstats[0]
         gemm_ms = sum(v["ms_per_step"] for v in vstats)
@@ -459,7 +522,7 @@ def run_own_arm(args):
                         "d2h_bytes_per_step": sysm.d2h_bytes_per_step, "api": f"MetaSystem.training_step(host batch) + optimizer_step; losses read back on the host {args.lag} step(s) later",
                         "runs_ms_per_step": e2e_runs, "host_enqueue_ms_per_step": host_ms},
                 "gpu_launches": launches_step * args.steps, "gpu_launches_per_step": launches_step,
-                "roofline": roofline, "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),
+                "roofline": roofline, "fft_block": fft_block, "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),
                 "last_query_loss": last_loss, "hbm_bytes_resident": sysm.maml.memory_bytes()}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:

@@ -490,11 +490,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
 // and its own epilogue over its 128 TMEM lanes.  The two CTAs' row tiles are consecutive m-tiles of the
 // same z; an odd tail gets a dummy partner (all-OOB A rows, nothing stored).
 // ================================================================================================
-template <int BN, int SPLIT>
+template <int BN, int SPLIT, int KD = 1>
 struct Cfg2 {
   static constexpr int A_TILE = BM * BK * 2;                  // this CTA's 128 rows
   static constexpr int B_TILE = (BN / 2) * BK * 2;            // this CTA's half of the B tile
-  static constexpr int STAGE = (A_TILE + B_TILE) * (SPLIT == 3 ? 2 : 1);
+  static constexpr int SUB = (A_TILE + B_TILE) * (SPLIT == 3 ? 2 : 1);
+  static constexpr int STAGE = SUB * KD;                      // KD k-blocks per stage fill (see Cfg)
   static constexpr int BAR_BYTES = 1024;
   static constexpr int STAGES_RAW = (MAX_SMEM - BAR_BYTES - 1024) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
@@ -502,9 +503,9 @@ struct Cfg2 {
   static_assert(STAGES >= 2, "need at least a double buffer");
 };
 
-template <int BN, int SPLIT>
+template <int BN, int SPLIT, int KD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mtts_gemm_pair_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg2<BN, SPLIT>;
+  using C = Cfg2<BN, SPLIT, KD>;
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -527,7 +528,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mtts
   const int z0 = blockIdx.z % p.nz0;
   const int z1 = blockIdx.z / p.nz0;
 
-  const int kchunks = (p.K + BK - 1) / BK;
+  const int kchunks = ((p.K + BK - 1) / BK + KD - 1) / KD;     // stage fills along K
   const int total_iters = p.nterms * p.ntaps * p.nkb * kchunks;
   const int per_split = (total_iters + p.ksplit - 1) / p.ksplit;
   const int it_begin = blockIdx.y * per_split;
@@ -593,7 +594,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mtts
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE);   // bytes of both CTAs
 
-        uint8_t* sa = smem + stage * C::STAGE;
+#pragma unroll
+        for (int sub = 0; sub < KD; ++sub) {
+        const int kcb = (kc * KD + sub) * BK;
+        uint8_t* sa = smem + stage * C::STAGE + sub * C::SUB;
         uint8_t* sa_lo = sa + C::A_TILE;
         uint8_t* sb = sa + C::A_TILE * (SPLIT == 3 ? 2 : 1);
         uint8_t* sb_lo = sb + C::B_TILE;
@@ -602,14 +606,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mtts
           const int c2 = pick_src(p.a.src2, z0, z1, tap, kb);
           const int c3 = pick_src(p.a.src3, z0, z1, tap, kb);
           if (p.a.major == MTTS_MAJOR_K) {
-            tma_load_nd_2cta(p.a.rank, sa, ma_hi, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
-            if (SPLIT == 3) tma_load_nd_2cta(p.a.rank, sa_lo, ma_lo, &full_bar[stage], kc * BK, m0 + shift, c2, c3);
+            tma_load_nd_2cta(p.a.rank, sa, ma_hi, &full_bar[stage], kcb, m0 + shift, c2, c3);
+            if (SPLIT == 3) tma_load_nd_2cta(p.a.rank, sa_lo, ma_lo, &full_bar[stage], kcb, m0 + shift, c2, c3);
           } else {
 #pragma unroll
             for (int i = 0; i < BM / 64; ++i) {
-              tma_load_nd_2cta(p.a.rank, sa + i * (BK * 128), ma_hi, &full_bar[stage], m0 + 64 * i, kc * BK + shift, c2, c3);
+              tma_load_nd_2cta(p.a.rank, sa + i * (BK * 128), ma_hi, &full_bar[stage], m0 + 64 * i, kcb + shift, c2, c3);
               if (SPLIT == 3)
-                tma_load_nd_2cta(p.a.rank, sa_lo + i * (BK * 128), ma_lo, &full_bar[stage], m0 + 64 * i, kc * BK + shift, c2, c3);
+                tma_load_nd_2cta(p.a.rank, sa_lo + i * (BK * 128), ma_lo, &full_bar[stage], m0 + 64 * i, kcb + shift, c2, c3);
             }
           }
         }
@@ -618,17 +622,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mtts
           const int c2 = pick_src(p.b.src2, z0, z1, tap, kb);
           const int c3 = pick_src(p.b.src3, z0, z1, tap, kb);
           if (p.b.major == MTTS_MAJOR_K) {
-            tma_load_nd_2cta(p.b.rank, sb, mb_hi, &full_bar[stage], kc * BK, nb0 + shift, c2, c3);
-            if (SPLIT == 3) tma_load_nd_2cta(p.b.rank, sb_lo, mb_lo, &full_bar[stage], kc * BK, nb0 + shift, c2, c3);
+            tma_load_nd_2cta(p.b.rank, sb, mb_hi, &full_bar[stage], kcb, nb0 + shift, c2, c3);
+            if (SPLIT == 3) tma_load_nd_2cta(p.b.rank, sb_lo, mb_lo, &full_bar[stage], kcb, nb0 + shift, c2, c3);
           } else {
 #pragma unroll
             for (int i = 0; i < BN / 128; ++i) {
-              tma_load_nd_2cta(p.b.rank, sb + i * (BK * 128), mb_hi, &full_bar[stage], nb0 + 64 * i, kc * BK + shift, c2, c3);
+              tma_load_nd_2cta(p.b.rank, sb + i * (BK * 128), mb_hi, &full_bar[stage], nb0 + 64 * i, kcb + shift, c2, c3);
               if (SPLIT == 3)
-                tma_load_nd_2cta(p.b.rank, sb_lo + i * (BK * 128), mb_lo, &full_bar[stage], nb0 + 64 * i, kc * BK + shift, c2, c3);
+                tma_load_nd_2cta(p.b.rank, sb_lo + i * (BK * 128), mb_lo, &full_bar[stage], nb0 + 64 * i, kcb + shift, c2, c3);
             }
           }
         }
+        }   // sub
         if (++stage == C::STAGES) {
           stage = 0;
           phase ^= 1;
@@ -649,11 +654,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mtts
       for (int it = 0; it < n_iters; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * C::STAGE);
+        if (!(p.dbg & 16))
+#pragma unroll
+        for (int sub = 0; sub < KD; ++sub) {
+        const uint32_t sa = smem_u32(smem + stage * C::STAGE + sub * C::SUB);
         const uint32_t sa_lo = sa + C::A_TILE;
         const uint32_t sb = sa + C::A_TILE * (SPLIT == 3 ? 2 : 1);
         const uint32_t sb_lo = sb + C::B_TILE;
-        if (!(p.dbg & 16))
 #pragma unroll
         for (int kk = 0; kk < BK / UMMA_K; ++kk) {
           const uint64_t da = make_umma_desc(sa + kk * a_step, a_lbo, 1024);
@@ -667,6 +674,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) mtts
             umma_bf16_2cta(tmem_base, da_lo, db, idesc, 1);
           }
         }
+        }   // sub
         umma_commit_2cta(&empty_bar[stage], 3);   // both CTAs may refill this slot
         if (++stage == C::STAGES) {
           stage = 0;
@@ -753,16 +761,16 @@ int encode_operand_map(CUtensorMap* map, const void* ptr, const mtts_operand& op
   return MTTS_OK;
 }
 
-template <int BN, int SPLIT>
+template <int BN, int SPLIT, int KD = 1>
 int launch_pair(const GemmParams& p, dim3 grid, cudaStream_t stream) {
-  using C = Cfg2<BN, SPLIT>;
+  using C = Cfg2<BN, SPLIT, KD>;
   static bool configured = false;
   if (!configured) {
-    MTTS_CHECK_CUDA(cudaFuncSetAttribute(mtts_gemm_pair_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MTTS_CHECK_CUDA(cudaFuncSetAttribute(mtts_gemm_pair_kernel<BN, SPLIT, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM));
     configured = true;
   }
-  MTTS_CHECK_CUDA(mtts_launch(mtts_gemm_pair_kernel<BN, SPLIT>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, p));   // __cluster_dims__(2,1,1)
+  MTTS_CHECK_CUDA(mtts_launch(mtts_gemm_pair_kernel<BN, SPLIT, KD>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, p));   // __cluster_dims__(2,1,1)
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -849,7 +857,7 @@ extern "C" int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream_) {
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.ntaps = d->ntaps; p.nkb = d->nkb; p.nz0 = d->nz0; p.nz1 = d->nz1;
   // narrow 1-CTA tiles run two k-blocks per stage fill (Cfg::KD)
-  const int kd = (!pair && bn == 64 && mtts_cdiv(d->K, BK) >= 2 && !(p.dbg & 512)) ? 2 : 1;
+  const int kd = (((!pair && bn == 64) || (pair && bn == 128)) && mtts_cdiv(d->K, BK) >= 2 && !(p.dbg & 512)) ? 2 : 1;
   const int kchunks = mtts_cdiv(mtts_cdiv(d->K, BK), kd);
   const int total_iters = p.nterms * d->ntaps * d->nkb * kchunks;
   p.ksplit = ksplit > total_iters ? total_iters : ksplit;
@@ -870,6 +878,7 @@ extern "C" int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream_) {
   MTTS_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "gemm: grid too large");
   if (pair) {
     grid.x = 2 * mtts_cdiv(m_tiles, 2) * p.n_tiles;
+    if (bn == 128 && kd == 2) return d->split == 1 ? launch_pair<128, 1, 2>(p, grid, stream) : launch_pair<128, 3, 2>(p, grid, stream);
     if (d->split == 1) return bn == 128 ? launch_pair<128, 1>(p, grid, stream) : launch_pair<256, 1>(p, grid, stream);
     return bn == 128 ? launch_pair<128, 3>(p, grid, stream) : launch_pair<256, 3>(p, grid, stream);
   }

@@ -332,10 +332,12 @@ def _pick_cfg(mt: int, nz: int, N: int, k_iters: int, can_splitk: bool):
     # a wave costs  fixed(tile) + k_iters * per_iter(tile)  and a launch runs ceil(ctas / 148) waves.  (The former
     # ">= 96 CTAs" rule picked 128-wide pairs for the QKV projection: 23.9 us where the 256-wide pair takes 16.2.)
     fixed = {(64, False): 5.9, (128, False): 7.2, (128, True): 7.8, (256, False): 11.0, (256, True): 11.0}
-    per_it = {(64, False): 0.78, (128, False): 0.80, (128, True): 0.76, (256, False): 1.5, (256, True): 0.87}     # 1-CTA 256: 2 smem stages only
+    # us per k-block: narrow tiles and the 128-wide pair run two k-blocks per stage fill (KD = 2)
+    per_it = {(64, False): 0.59, (128, False): 0.80, (128, True): 0.55, (256, False): 1.5, (256, True): 0.87}
 
     def cost(o):
-        return -(-ctas(o) // 148) * (fixed[o] + k_iters * per_it[o])
+        waves = -(-ctas(o) // 148)
+        return (fixed[o] + k_iters * per_it[o]) * (1.0 + 0.7 * (waves - 1))   # later waves overlap the previous one's tail
 
     o = min(opts, key=cost)
     return o[0], o[1], 1
