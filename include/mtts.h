@@ -108,6 +108,12 @@ typedef struct {
 
 int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream);
 
+/* Ragged -> padded pack = the padding half of collate on the device.  Replaces utils/tools.py:270-301 (pad_1D / pad_2D:
+ * np.pad per utterance + np.stack) as used by lightning/collate.py:22-26: dst[b, t, :] = src[row_off[b] + t, :] for
+ * t < row_off[b+1] - row_off[b], else 0; rows are copied as bytes (row_bytes a multiple of 4), so every dtype is exact.
+ * src holds the B utterances back to back (sum of lengths rows), row_off is int64[B + 1] on the device. */
+int mtts_pack_rows(const void* src, const int64_t* row_off, int B, int Lmax, int row_bytes, void* dst, mtts_stream stream);
+
 /* ------------------------------------------------------------------------------------------
  * LengthRegulator  (reference: lightning/model/modules.py:167-194 + utils/tools.py:304-322)
  *   idx[b,t]  = #{ j : cumsum(max(d[b,:],0))[j] <= t }   (searchsorted right)   -- integer, bit-exact

@@ -8,6 +8,7 @@
 //
 // HBM-bound: forward moves B*(L_touched + T)*C*4 bytes.  One warp per output row, 128-bit
 // vectorised loads/stores, no host sync, shapes static => CUDA-graph capturable.
+#include <algorithm>
 #include "mtts_common.cuh"
 
 namespace {
@@ -139,7 +140,54 @@ __global__ void lr_segsum_kernel(const float* __restrict__ dy, const int64_t* __
   }
 }
 
+// Ragged -> padded pack (collate on the device): dst[b, t, :] = t < len_b ? src[row_off[b] + t, :] : 0, bytes copied
+// unchanged (bit-exact for every dtype).  One thread per CHUNK-byte piece of the padded output.
+template <typename V>
+__global__ void pack_rows_kernel(const V* __restrict__ src, const int64_t* __restrict__ row_off, int Lmax, int vec_per_row,
+                                 long long total, V* __restrict__ dst) {
+  pdl_enter();
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / vec_per_row;                 // padded row index b * Lmax + t
+    const int v = static_cast<int>(i - row * vec_per_row);
+    const int b = static_cast<int>(row / Lmax);
+    const int t = static_cast<int>(row - static_cast<long long>(b) * Lmax);
+    const long long r0 = row_off[b], r1 = row_off[b + 1];
+    V out{};
+    if (t < r1 - r0) out = src[(r0 + t) * vec_per_row + v];
+    dst[i] = out;
+  }
+}
+
 }  // namespace
+
+extern "C" int mtts_pack_rows(const void* src, const int64_t* row_off, int B, int Lmax, int row_bytes, void* dst,
+                              mtts_stream stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(src && row_off && dst && B > 0 && Lmax > 0 && row_bytes > 0, "pack_rows: bad args");
+  const uintptr_t al = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | static_cast<uintptr_t>(row_bytes);
+  const int threads = 256;
+  auto blocks = [&](long long total) { return static_cast<unsigned>(std::min<long long>(mtts_cdiv64(total, threads), 148 * 16)); };
+  if ((al & 15) == 0) {
+    const int vpr = row_bytes / 16;
+    const long long total = static_cast<long long>(B) * Lmax * vpr;
+    MTTS_CHECK_CUDA(mtts_launch(pack_rows_kernel<uint4>, dim3(blocks(total)), dim3(threads), 0, stream, static_cast<const uint4*>(src),
+                                row_off, Lmax, vpr, total, static_cast<uint4*>(dst)));
+  } else if ((al & 7) == 0) {
+    const int vpr = row_bytes / 8;
+    const long long total = static_cast<long long>(B) * Lmax * vpr;
+    MTTS_CHECK_CUDA(mtts_launch(pack_rows_kernel<uint2>, dim3(blocks(total)), dim3(threads), 0, stream, static_cast<const uint2*>(src),
+                                row_off, Lmax, vpr, total, static_cast<uint2*>(dst)));
+  } else {
+    MTTS_REQUIRE((al & 3) == 0, "pack_rows: rows must be a multiple of 4 bytes and 4-byte aligned");
+    const int vpr = row_bytes / 4;
+    const long long total = static_cast<long long>(B) * Lmax * vpr;
+    MTTS_CHECK_CUDA(mtts_launch(pack_rows_kernel<uint32_t>, dim3(blocks(total)), dim3(threads), 0, stream,
+                                static_cast<const uint32_t*>(src), row_off, Lmax, vpr, total, static_cast<uint32_t*>(dst)));
+  }
+  MTTS_CHECK_LAUNCH();
+  return MTTS_OK;
+}
 
 extern "C" int mtts_length_regulate_index(const int64_t* dur_i64, const float* dur_f32, int B, int L, int T,
                                           int32_t* idx, int64_t* mel_len, mtts_stream stream_) {

@@ -83,6 +83,7 @@ SIGNATURES: dict[str, list] = {
     "mtts_check_device": [],
     "mtts_set_pdl": [_i],
     "mtts_gemm": [C.POINTER(GemmDesc), _vp],
+    "mtts_pack_rows": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "mtts_length_regulate_index": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "mtts_length_regulate_fwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],
     "mtts_length_regulate_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp],

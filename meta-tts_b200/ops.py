@@ -303,6 +303,11 @@ class CudaOps:
         kw.setdefault("split", self.split)
         gemm(a, b, M, N, K, **kw)
 
+    # ---- collate on the device: ragged -> padded ----
+    def pack_rows(self, src, row_off, B, Lmax, row_bytes, dst):
+        """dst[b, t] = src[row_off[b] + t] (t < len_b) else 0; byte-exact (include/mtts.h: mtts_pack_rows)."""
+        self._call("mtts_pack_rows", _p(src), _p(row_off), B, Lmax, row_bytes, _p(dst))
+
     # ---- length regulator ----
     def lr_index(self, dur, T, idx=None, mel_len=None):
         return length_regulate_index(dur, T, idx, mel_len)

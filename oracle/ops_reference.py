@@ -175,6 +175,18 @@ class RefOps:
                         c_lo.reshape(-1)[idx] = l.reshape(-1)
 
     # ------------------------------------------------------------------------------------------
+    # ragged -> padded pack (utils/tools.py:270-301 pad_1D / pad_2D semantics, bytes copied unchanged)
+    # ------------------------------------------------------------------------------------------
+    def pack_rows(self, src, row_off, B, Lmax, row_bytes, dst):
+        self.n_calls += 1
+        s8 = src.contiguous().view(torch.uint8).reshape(-1, row_bytes)
+        d8 = dst.view(torch.uint8).reshape(B, Lmax, row_bytes)
+        d8.zero_()
+        for b in range(B):
+            r0, r1 = int(row_off[b]), int(row_off[b + 1])
+            d8[b, :r1 - r0] = s8[r0:r1]
+
+    # ------------------------------------------------------------------------------------------
     # LengthRegulator
     # ------------------------------------------------------------------------------------------
     def lr_index(self, dur, T, idx_out=None, len_out=None):
