@@ -21,6 +21,8 @@ state_dict (same keys, Conv1d [out, in, k]).
 """
 from __future__ import annotations
 
+import os
+
 import math
 import zlib
 from dataclasses import dataclass
@@ -488,7 +490,7 @@ class FS2Engine:
         # (1e-3); running it single-pass bf16 (hvp_split = 1, operand hi halves only) moves individual gradient
         # tensors by up to ~3e-3 relative (CPU emulation, tests/test_engine_cpu.py), so the default keeps the
         # engine's precision and the faster setting is opt-in.
-        self.hvp_split = self.split
+        self.hvp_split = int(os.environ.get("MTTS_HVP_SPLIT", self.split))
         assert self.d % 128 == 0
 
     def new_tape(self) -> Tape:

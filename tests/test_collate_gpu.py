@@ -29,8 +29,11 @@ def test_pack_rows_bit_exact(cuda_device, n, seed):
     ref = C.reprocess(data, np.arange(n))
     for k, i in (("texts", 3), ("mels", 6), ("pitches", 9), ("energies", 10), ("durations", 11), ("src_lens", 4), ("mel_lens", 7)):
         assert out[k].dtype == ref[i].dtype and torch.equal(out[k].cpu(), ref[i]), k
-    if n == 9 and seed == 0:                                   # ... and against the REAL reference's output
-        assert np.array_equal(out["mels"].cpu().numpy(), G["plain_mels"]) and np.array_equal(out["texts"].cpu().numpy(), G["plain_texts"])
+    if n == 9 and seed == 0:                                   # ... and against the REAL reference's output (golden dataset bounds)
+        gdata = C.synth_dataset(n=9, seed=0)
+        gout = B.pack_on_device(CudaOps(split=3), B.reprocess_ragged(gdata, np.arange(9)), cuda_device)
+        for k in ("mels", "texts", "pitches", "energies", "durations"):
+            assert np.array_equal(gout[k].cpu().numpy(), G[f"plain_{k}"]), k
     # padding to a larger static shape (CUDA-graph buffers are sized for the shape key, not for this batch)
     L2, T2 = int(ref[5]) + 5, int(ref[8]) + 13
     out2 = B.pack_on_device(CudaOps(split=3), rag, cuda_device, L=L2, T=T2)
