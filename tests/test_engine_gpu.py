@@ -31,7 +31,7 @@ def _engine(P, cfg, split=3, K=2):
     return m
 
 
-def _check_task(m, P, cfg, sup, qry, steps, first_order, grad_tol, label, fast_tol=3e-3, salt=None):
+def _check_task(m, P, cfg, sup, qry, steps, first_order, grad_tol, label, fast_tol=3e-3, salt=None, median_tol=2e-3):
     """salt = None: dropout off (identity) on both sides.  salt = uint32: train-mode dropout ON; the oracle applies the
     masks of the same counter hash (oracle/fs2_oracle.py drop_keep) the kernels evaluate on the device."""
     Pc = {k: v.detach().clone() for k, v in P.items()}
@@ -70,7 +70,7 @@ def _check_task(m, P, cfg, sup, qry, steps, first_order, grad_tol, label, fast_t
     per = sorted(((got[k].double() - grads[k].double()).norm() / grads[k].double().norm()).item() for k in grads
                  if grads[k].double().norm() > 1e-4 * tot_ref)
     print(f"[engine]   per-tensor gradient rel err: median {per[len(per) // 2]:.2e}, p90 {per[int(0.9 * len(per))]:.2e}")
-    assert per[len(per) // 2] < 2e-3, f"median per-tensor gradient rel err {per[len(per) // 2]:.2e}"
+    assert per[len(per) // 2] < median_tol, f"median per-tensor gradient rel err {per[len(per) // 2]:.2e}"
 
 
 def test_small_model_all_modes(cuda_device):
@@ -172,8 +172,11 @@ def test_config3_config4_k5_structure(cuda_device, first_order, salt):
     # fp32 oracle.  A flip changes the forward by ~1e-6 but switches that unit's whole gradient on or off; in the small
     # variance predictors (80 rows here) one flip moves a conv weight gradient by ~1e-2 of the total norm (the CPU
     # restatement with exact products matches to 4e-5 on the same inputs).  Hence total < 2e-2 + the median criterion.
+    # Which units flip varies run to run (split-K / channel-sum atomics reorder fp32 additions): 9 repeats on one B200
+    # gave total 1.5e-4 ... 1.3e-2 and median 3e-5 ... 5.6e-3 for the same inputs (profiles/r01_s2_k5_repeats.log), a flip
+    # early in the decoder moving every upstream tensor a little — so the median bar here is 1e-2, not 2e-3.
     _check_task(m, P, cfg, sup, qry, 5, first_order, 2e-2, f"config{'4' if first_order else '3'} structure K=5 salt={salt}",
-                fast_tol=2e-2, salt=salt)
+                fast_tol=2e-2, salt=salt, median_tol=1e-2)
 
 
 def test_bf16_single_pass_mode_runs(cuda_device):
