@@ -257,6 +257,44 @@ int mtts_sumsq(const float* x, int64_t n, float* out, mtts_stream stream);
 int mtts_adam_clip(float* p, const float* g, float* m, float* v, const float* sumsq, float gscale, float max_norm,
                    const float* hyper, float beta1, float beta2, float eps, void* hi, void* lo, int64_t n, mtts_stream stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Free-running synthesis (BASELINE configs[4]; lightning/systems/base_adaptor.py:160-186 calls
+ * forward_learner without targets) and eval-mode PostNet.
+ * ------------------------------------------------------------------------------------------ */
+/* duration_rounded = clamp(round(exp(log_d) - 1) * d_control, min=0)   modules.py:133-137 (round half to even). */
+int mtts_duration_round(const float* logd, float d_control, int64_t n, float* out, mtts_stream stream);
+/* BatchNorm1d under model.eval(): y = (x - running_mean) / sqrt(running_var + eps) * gamma + beta (+ tanh); no update. */
+int mtts_bn_eval(const float* x, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                 int64_t R, int C, float eps, int tanh_flag, float* out, void* hi, void* lo, mtts_stream stream);
+/* op 0: log(max(x, a) * b)  (dynamic_range_compression, audio/audio_processing.py:85-91)
+ * op 1: exp(x) * a          (dynamic_range_decompression :94-100, a = scale / C)
+ * op 2: x * a               (p_control / e_control, modules.py:86,97).  Any of out / hi(+lo) may be NULL. */
+enum { MTTS_UN_LOGCLAMP = 0, MTTS_UN_EXP = 1, MTTS_UN_SCALE = 2 };
+int mtts_unary(int op, const float* x, int64_t n, float a, float b, float* out, void* hi, void* lo, mtts_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * STFT / iSTFT / Griffin-Lim (audio/stft.py:15-127, audio/audio_processing.py:7-82, audio/tools.py:18-34).
+ * The Fourier- and mel-basis products run through mtts_gemm (the stride-hop conv1d of STFT.transform is a
+ * (n_fft/hop)-tap conv over the hop-reshaped signal [rows, hop]; conv_transpose1d of STFT.inverse is the
+ * matching dgrad form, so the overlap-add happens in the accumulator).  Frame-major layouts:
+ * ri[r, c] = real part of bin c of frame r, ri[r, im_off + c] = imaginary part; row stride ld.
+ * ------------------------------------------------------------------------------------------ */
+/* F.pad(mode="reflect") by `pad` on both sides (stft.py:60-65) fused with the operand split; columns
+ * [N + 2*pad, ld) are zero-filled (ld = rows * hop of the hop-reshaped view; ld may cut the padded tail short). */
+int mtts_reflect_pad(const float* x /* [B,N] */, int B, int64_t N, int pad, int64_t ld, float* out /* [B,ld] or NULL */,
+                     void* hi, void* lo, mtts_stream stream);
+/* magnitude = sqrt(re^2 + im^2), phase = atan2(im, re) (stft.py:78-79), energy[r] = ||magnitude[r,:]||_2 (stft.py:175).
+ * mag / phase / mag_hi / mag_lo rows have stride ldm >= nb, columns [nb, ldm) zero-filled (GEMM-operand ready). */
+int mtts_stft_polar(const float* ri, int64_t R, int nb, int ld, int im_off, int ldm, float* mag /* [R,ldm] */,
+                    float* phase /* [R,ldm] */, float* energy /* [R] */, void* mag_hi, void* mag_lo, mtts_stream stream);
+/* X = [mag*cos(ph) | mag*sin(ph)] (stft.py:86-88) as bf16 hi/lo GEMM operand; ph = phase, or the angles of `ri`
+ * when phase == NULL (one Griffin-Lim iteration, audio_processing.py:79-81). */
+int mtts_stft_recombine(const float* mag /* [R,ldm] */, const float* phase /* [R,ldm] */, const float* ri, int64_t R, int nb,
+                        int ld, int im_off, int ldm, void* hi, void* lo, mtts_stream stream);
+/* out[b, i] = ola[b, i + trim] / (wsum[i + trim] > tiny ? wsum[i + trim] : 1) * scale   (stft.py:96-122). */
+int mtts_istft_finish(const float* ola /* [B,n] */, const float* wsum /* [n] */, float tiny, float scale, int B, int64_t n,
+                      int trim, float* out /* [B, n - 2*trim] */, mtts_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libmtts.so")
 SRC_ZERO, SRC_Z0, SRC_Z1, SRC_TAP, SRC_KB = 0, 1, 2, 3, 4
 MAJOR_K, MAJOR_MN = 0, 1
 EPI_RELU, EPI_ACCUM, EPI_GATE, EPI_BIAS_ROW, EPI_ADD_C = 1, 2, 4, 8, 16
+UN_LOGCLAMP, UN_EXP, UN_SCALE = 0, 1, 2
 
 
 class Operand(C.Structure):
@@ -111,6 +112,13 @@ SIGNATURES: dict[str, list] = {
     "mtts_sgd_split": [_vp, _vp, _f, _vp, _vp, _vp, _i64, _vp],
     "mtts_axpby": [_f, _vp, _f, _vp, _i64, _vp],
     "mtts_sumsq": [_vp, _i64, _vp, _vp],
+    "mtts_duration_round": [_vp, _f, _i64, _vp, _vp],
+    "mtts_bn_eval": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _i, _vp, _vp, _vp, _vp],
+    "mtts_unary": [_i, _vp, _i64, _f, _f, _vp, _vp, _vp, _vp],
+    "mtts_reflect_pad": [_vp, _i, _i64, _i, _i64, _vp, _vp, _vp, _vp],
+    "mtts_stft_polar": [_vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "mtts_stft_recombine": [_vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _vp],
+    "mtts_istft_finish": [_vp, _vp, _f, _f, _i, _i64, _i, _vp, _vp],
     "mtts_adam_clip": [_vp, _vp, _vp, _vp, _vp, _f, _f, _vp, _f, _f, _f, _vp, _vp, _i64, _vp],
 }
 

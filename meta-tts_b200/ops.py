@@ -393,6 +393,30 @@ class CudaOps:
                    _p(gamma), _p(gdot), R, C, int(tanh_flag), _p(ws), _p(ddx), _p(hi), _p(lo), _p(ddgamma), _p(ddbeta),
                    *drop, _p(self.drop_salt))
 
+    def bn_eval(self, x, gamma, beta, running_mean, running_var, R, C, tanh_flag, out, hi, lo, eps=1e-5):
+        self._call("mtts_bn_eval", _p(x), _p(gamma), _p(beta), _p(running_mean), _p(running_var), R, C, eps, int(tanh_flag),
+                   _p(out), _p(hi), _p(lo))
+
+    # ---- free-running synthesis / vocoder-side decode ----
+    def duration_round(self, logd, d_control, out):
+        self._call("mtts_duration_round", _p(logd), float(d_control), logd.numel(), _p(out))
+
+    def unary(self, op, x, a, b, out, hi=None, lo=None):
+        """op 0: log(max(x,a)*b); 1: exp(x)*a; 2: x*a (include/mtts.h MTTS_UN_*)."""
+        self._call("mtts_unary", int(op), _p(x), x.numel(), float(a), float(b), _p(out), _p(hi), _p(lo))
+
+    def reflect_pad(self, x, B, N, pad, ld, out, hi, lo):
+        self._call("mtts_reflect_pad", _p(x), B, N, pad, ld, _p(out), _p(hi), _p(lo))
+
+    def stft_polar(self, ri, R, nb, ld, im_off, ldm, mag, phase, energy, mag_hi=None, mag_lo=None):
+        self._call("mtts_stft_polar", _p(ri), R, nb, ld, im_off, ldm, _p(mag), _p(phase), _p(energy), _p(mag_hi), _p(mag_lo))
+
+    def stft_recombine(self, mag, phase, ri, R, nb, ld, im_off, ldm, hi, lo):
+        self._call("mtts_stft_recombine", _p(mag), _p(phase), _p(ri), R, nb, ld, im_off, ldm, _p(hi), _p(lo))
+
+    def istft_finish(self, ola, wsum, tiny, scale, B, n, trim, out):
+        self._call("mtts_istft_finish", _p(ola), _p(wsum), float(tiny), float(scale), B, n, trim, _p(out))
+
     # ---- loss ----
     def loss_fwd(self, mel, post, mel_tgt, mel_lens, p, p_tgt, e, e_tgt, logd, dur, src_lens, B, T, Lp, NM, ws, out6,
                  counts):

@@ -557,6 +557,71 @@ class RefOps:
             _put(dst, g)
 
     # ------------------------------------------------------------------------------------------
+    # free-running synthesis / vocoder-side decode (include/mtts.h: mtts_duration_round ... mtts_istft_finish)
+    # ------------------------------------------------------------------------------------------
+    def bn_eval(self, x, gamma, beta, running_mean, running_var, R, C, tanh_flag, out, hi, lo, eps=1e-5):
+        self.n_calls += 1
+        xx = x.reshape(R, C).double()
+        y = (xx - running_mean.double()) / torch.sqrt(running_var.double() + eps) * gamma.double() + beta.double()
+        o = torch.tanh(y) if tanh_flag else y
+        _put(out, o)
+        _put_split(hi, lo, o)
+
+    def duration_round(self, logd, d_control, out):
+        self.n_calls += 1
+        out.copy_(torch.clamp(torch.round(torch.exp(logd) - 1) * d_control, min=0).reshape(out.shape))
+
+    def unary(self, op, x, a, b, out, hi=None, lo=None):
+        self.n_calls += 1
+        v = x.float()
+        v = torch.log(torch.clamp(v, min=a) * b) if op == 0 else (torch.exp(v) * a if op == 1 else v * a)
+        _put(out, v)
+        _put_split(hi, lo, v)
+
+    def reflect_pad(self, x, B, N, pad, ld, out, hi, lo):
+        self.n_calls += 1
+        xp = F.pad(x.reshape(B, 1, N).float(), (pad, pad), mode="reflect").reshape(B, N + 2 * pad)
+        v = torch.zeros(B, ld)
+        n = min(ld, N + 2 * pad)
+        v[:, :n] = xp[:, :n]
+        _put(out, v)
+        _put_split(hi, lo, v)
+
+    def stft_polar(self, ri, R, nb, ld, im_off, ldm, mag, phase, energy, mag_hi=None, mag_lo=None):
+        self.n_calls += 1
+        r = ri.reshape(R, ld).float()
+        re, im = r[:, :nb], r[:, im_off:im_off + nb]
+        m = torch.zeros(R, ldm)
+        ph = torch.zeros(R, ldm)
+        m[:, :nb] = torch.sqrt(re ** 2 + im ** 2)
+        ph[:, :nb] = torch.atan2(im, re)
+        _put(mag, m)
+        _put(phase, ph)
+        _put_split(mag_hi, mag_lo, m)
+        if energy is not None:
+            energy.copy_(torch.norm(m[:, :nb], dim=1).reshape(energy.shape))
+
+    def stft_recombine(self, mag, phase, ri, R, nb, ld, im_off, ldm, hi, lo):
+        self.n_calls += 1
+        m = mag.reshape(R, ldm)[:, :nb].float()
+        if phase is not None:
+            ph = phase.reshape(R, ldm)[:, :nb].float()
+        else:
+            r = ri.reshape(R, ld).float()
+            ph = torch.atan2(r[:, im_off:im_off + nb], r[:, :nb])
+        v = torch.zeros(R, ld)
+        v[:, :nb] = m * torch.cos(ph)
+        v[:, im_off:im_off + nb] = m * torch.sin(ph)
+        _put_split(hi, lo, v)
+
+    def istft_finish(self, ola, wsum, tiny, scale, B, n, trim, out):
+        self.n_calls += 1
+        v = ola.reshape(B, n).float().clone()
+        nz = wsum > tiny
+        v[:, nz] = v[:, nz] / wsum[nz]
+        out.copy_((v * scale)[:, trim:n - trim].reshape(out.shape))
+
+    # ------------------------------------------------------------------------------------------
     # flat elementwise
     # ------------------------------------------------------------------------------------------
     def split_(self, src, hi, lo):
