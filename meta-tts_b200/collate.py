@@ -169,3 +169,16 @@ class SpeakerTaskCollate:
             qry_idx = ~sup_idx
             return ([reprocess(data, idx) for idx in idx_arr[:, sup_idx]], [reprocess(data, idx) for idx in idx_arr[:, qry_idx]])
         return [reprocess(data, idx) for idx in idx_arr]
+
+
+def split_reprocess(batch, idxs):
+    """lightning/collate.py:63-125 (table speaker ids): the rows `idxs` of a collated 12-tuple, re-trimmed to their own
+    maximum lengths (used by the 1-shot test protocol, base_adaptor.py:144-151)."""
+    (ids, raw_texts, speaker_args, texts, text_lens, max_text_lens, mels, mel_lens, max_mel_lens, pitches, energies,
+     durations) = batch
+    idxs = np.asarray(idxs)
+    sub_text_lens, sub_mel_lens = text_lens[idxs], mel_lens[idxs]
+    Ls, Ts = sub_text_lens.max(), sub_mel_lens.max()
+    cut = lambda t: t[idxs][:, :Ls] if t.shape[1] == max_text_lens else t[idxs][:, :Ts]  # noqa: E731
+    return ([ids[i] for i in idxs], [raw_texts[i] for i in idxs], speaker_args[idxs], texts[idxs][:, :Ls], sub_text_lens, Ls,
+            mels[idxs][:, :Ts], sub_mel_lens, Ts, cut(pitches), cut(energies), durations[idxs][:, :Ls])

@@ -932,18 +932,39 @@ class FS2Engine:
             x = self.fft_fwd(P, f"encoder.layer_stack.{i}", tp, x, src_lens, self.h_enc)
         return x
 
-    def decoder_fwd(self, P: ParamSet, xin_f32, spk, mel_lens, B: int, T: int, tp: Tape) -> Act:
+    def _position_table(self, name: str, T: int, eval_mode: bool):
+        """Models.py:82-91 / 148-160: the stored table covers max_seq_len + 1 positions; under model.eval() a longer
+        sequence gets a freshly computed sinusoid table (float64 on the host -> fp32, as get_sinusoid_encoding_table),
+        in train mode the reference truncates the sequence instead (not supported here: refuse loudly)."""
+        tab = self.consts[name]
+        if T <= self.cfg["max_seq_len"]:
+            return tab
+        if not eval_mode:
+            raise ValueError(f"sequence of {T} positions > max_seq_len={self.cfg['max_seq_len']} in train mode: the "
+                             "reference truncates the decoder input (Models.py:161-166); not supported")
+        key = (name, T)
+        cache = self.__dict__.setdefault("_long_tables", {})
+        if key not in cache:
+            pos = torch.arange(T, dtype=torch.float64)[:, None]
+            j = torch.arange(self.d, dtype=torch.float64)[None, :]
+            ang = pos / torch.pow(torch.tensor(10000.0, dtype=torch.float64), 2 * torch.div(j, 2, rounding_mode="floor") / self.d)
+            t = torch.where((torch.arange(self.d) % 2 == 0)[None, :], torch.sin(ang), torch.cos(ang)).to(torch.float32)
+            cache[key] = t.contiguous().to(tab.device)
+        return cache[key]
+
+    def decoder_fwd(self, P: ParamSet, xin_f32, spk, mel_lens, B: int, T: int, tp: Tape, eval_mode: bool = False) -> Act:
         """Decoder.forward (Models.py:139-171) on (x + spk_emb): + position_enc, then the FFT blocks.
         `spk` may be None (plain Decoder module)."""
         d = self.d
         y = tp.act("dec.x0", B, T, d)
-        self.be.add_rowvec(xin_f32, spk, d, self.consts["decoder.position_enc"], B, T, d, y.f32, y.hi, y.lo)
+        self.be.add_rowvec(xin_f32, spk, d, self._position_table("decoder.position_enc", T, eval_mode), B, T, d, y.f32, y.hi, y.lo)
         for i in range(self.n_dec):
             y = self.fft_fwd(P, f"decoder.layer_stack.{i}", tp, y, mel_lens, self.h_dec)
         return y
 
-    def postnet_fwd(self, P: ParamSet, mel: Act, tp: Tape, update_bn: bool = True) -> Act:
-        """PostNet.forward (Layers.py:129-137): 4 x tanh(BN(conv5)) + BN(conv5), batch statistics."""
+    def postnet_fwd(self, P: ParamSet, mel: Act, tp: Tape, update_bn: bool = True, eval_mode: bool = False) -> Act:
+        """PostNet.forward (Layers.py:129-137): 4 x tanh(BN(conv5)) + BN(conv5); batch statistics in train mode,
+        running statistics (no update, no dropout) under model.eval()."""
         be, g, scr = self.be, self.g, self.scr
         B, T = mel.B, mel.T
         R = B * T
@@ -954,6 +975,11 @@ class FS2Engine:
             c = tp.f32(f"post.{i}.c", (B, T, co))
             g.conv_fwd(xin, P.get(f"{pre}.0.conv.weight"), P.get(f"{pre}.0.conv.bias").f32, c, None, None)
             o = tp.act(f"post.{i}.o", B, T, co, bf=(i < 4))
+            if eval_mode:
+                be.bn_eval(c, P.get(f"{pre}.1.weight").f32, P.get(f"{pre}.1.bias").f32, self.consts[f"{pre}.1.running_mean"],
+                           self.consts[f"{pre}.1.running_var"], R, co, i < 4, o.f32, o.hi, o.lo)
+                xin = o
+                continue
             rm = self.consts[f"{pre}.1.running_mean"] if update_bn else None
             rv = self.consts[f"{pre}.1.running_var"] if update_bn else None
             be.bn_fwd(c, P.get(f"{pre}.1.weight").f32, P.get(f"{pre}.1.bias").f32, R, co, i < 4, rm, rv,
@@ -963,14 +989,16 @@ class FS2Engine:
         return xin
 
     def forward(self, P: ParamSet, bt: Batch, tp: Tape, update_bn: bool = True, drop_pass: Optional[int] = None,
-                enc: Optional[Act] = None):
+                enc: Optional[Act] = None, eval_mode: bool = False):
         """Teacher-forced forward + loss.  Returns dict with the reference's prediction tensors.
         drop_pass: None = dropout off (eval / parity-with-identity); an int = train-mode dropout, pass index mixed
-        into every site seed (backward / tangent passes over `tp` reuse it)."""
+        into every site seed (backward / tangent passes over `tp` reuse it).
+        eval_mode: model.eval() semantics (PostNet BatchNorm uses running statistics; drop_pass must be None)."""
         be, g, scr, d = self.be, self.g, self.scr, self.d
+        assert not (eval_mode and drop_pass is not None), "eval mode has no dropout"
         tp.drop_pass = drop_pass
         B, Lq, T = bt.B, bt.L, bt.T
-        assert T <= self.cfg["max_seq_len"] and Lq <= self.cfg["max_seq_len"], "sequence longer than max_seq_len"
+        assert Lq <= self.cfg["max_seq_len"], "phoneme sequence longer than max_seq_len"
         # ---- encoder (Models.py:73-100) ----
         if enc is None:
             x = self.encoder_fwd(P, bt.texts, bt.src_lens, B, Lq, tp)
@@ -1008,11 +1036,11 @@ class FS2Engine:
         xr = scr.scratch("lr.out", (B, T, d))
         be.lr_fwd(x2, lr_idx, xr)
         # ---- decoder (Models.py:139-171) ----
-        y = self.decoder_fwd(P, xr, spk, bt.mel_lens, B, T, tp)
+        y = self.decoder_fwd(P, xr, spk, bt.mel_lens, B, T, tp, eval_mode)
         # ---- mel_linear + postnet (fastspeech2.py:97-99, Layers.py:129-137) ----
         mel = tp.act("mel", B, T, N_MEL)
         g.conv_fwd(y, P.get("mel_linear.weight"), P.get("mel_linear.bias").f32, mel.f32, mel.hi, mel.lo)
-        xin = self.postnet_fwd(P, mel, tp, update_bn)
+        xin = self.postnet_fwd(P, mel, tp, update_bn, eval_mode)
         post = xin.f32
         be.axpby(1.0, mel.f32, 1.0, post)                    # postnet(output) + output
         loss6 = tp.f32("loss6", (6,))
@@ -1021,6 +1049,62 @@ class FS2Engine:
                     bt.src_lens, B, T, Lq, N_MEL, scr.scratch("loss.ws", (8,)), loss6, tp.f32("loss.counts", (2,)))
         return {"mel": mel.f32, "postnet": post, "pitch": ppred, "energy": epred, "logd": logd, "loss6": loss6,
                 "mel_len": lr_len}
+
+    def synthesize(self, P: ParamSet, bt: Batch, tp: Tape, p_control: float = 1.0, e_control: float = 1.0,
+                   d_control: float = 1.0, update_bn: bool = True, drop_pass: Optional[int] = None, eval_mode: bool = False):
+        """Free-running forward: `forward_learner(learner, spk, texts, src_lens, max_src_len)` with every target None
+        (base_adaptor.py:160-162,183-185 -> modules.py:85-99,132-139): pitch / energy embeddings come from the
+        (control-scaled) PREDICTIONS, durations are clamp(round(exp(log_d) - 1) * d_control, 0), and the output length is
+        data dependent.  ONE host synchronisation reads the B*L rounded durations (the reference syncs B*L times,
+        modules.py:186); everything else is the training path's kernels.  `bt` needs spk_ids / texts / src_lens only.
+        Returns the prediction dict (mel / postnet: [B, T, 80] with T = max(mel_len); d_rounded float as the reference)."""
+        be, g, scr, d = self.be, self.g, self.scr, self.d
+        assert not (eval_mode and drop_pass is not None), "eval mode has no dropout"
+        tp.drop_pass = drop_pass
+        B, Lq = bt.B, bt.L
+        va = "variance_adaptor"
+        x = self.encoder_fwd(P, bt.texts, bt.src_lens, B, Lq, tp)
+        spk = tp.f32("spk", (B, d))
+        be.spk_embed(bt.spk_ids, P.get("speaker_emb.model.weight").f32, bt.spk_ids.numel(), d, bt.average_spk, B, spk)
+        x0 = tp.act("va.x0", B, Lq, d)
+        be.add_rowvec(x.f32, spk, d, None, B, Lq, d, x0.f32, x0.hi, x0.lo)
+        logd, ppred, epred = tp.f32("logd", (B, Lq)), tp.f32("ppred", (B, Lq)), tp.f32("epred", (B, Lq))
+        self.vp_fwd(P, f"{va}.duration_predictor", tp, x0, bt.src_lens, logd)
+        self.vp_fwd(P, f"{va}.pitch_predictor", tp, x0, bt.src_lens, ppred)
+        if p_control != 1.0:
+            be.unary(L.UN_SCALE, ppred, p_control, 0.0, ppred)              # prediction * control (modules.py:86)
+        idx_p = tp.buf("va.idx_p", (B, Lq), torch.int64)
+        be.bucketize(ppred, self.consts[f"{va}.pitch_bins"], self.nbins - 1, B * Lq, idx_p)
+        x1 = tp.act("va.x1", B, Lq, d)
+        be.embed_fwd(idx_p, P.get(f"{va}.pitch_embedding.weight").f32, x0.f32, None, Lq, B * Lq, d, x1.f32, x1.hi, x1.lo)
+        self.vp_fwd(P, f"{va}.energy_predictor", tp, x1, bt.src_lens, epred)
+        if e_control != 1.0:
+            be.unary(L.UN_SCALE, epred, e_control, 0.0, epred)
+        idx_e = tp.buf("va.idx_e", (B, Lq), torch.int64)
+        be.bucketize(epred, self.consts[f"{va}.energy_bins"], self.nbins - 1, B * Lq, idx_e)
+        x2 = scr.scratch("va.x2", (B, Lq, d))
+        be.embed_fwd(idx_e, P.get(f"{va}.energy_embedding.weight").f32, x1.f32, None, Lq, B * Lq, d, x2, None, None)
+        drnd = tp.f32("d_rounded", (B, Lq))
+        be.duration_round(logd, d_control, drnd)
+        # the output length is data dependent: one D2H of B*L floats (plumbing); int() truncation as modules.py:186-187
+        T = int(drnd.detach().to("cpu").to(torch.int64).clamp_(min=0).sum(dim=1).max())
+        if T <= 0:
+            raise ValueError("free-running synthesis predicted zero frames for every utterance")
+        if T > (1 << 20):
+            raise ValueError(f"free-running synthesis predicted {T} frames (diverged duration predictor?)")
+        lr_idx = tp.buf("lr.idx", (B, T), torch.int32)
+        lr_len = tp.buf("lr.mel_len", (B,), torch.int64)
+        be.lr_index(drnd, T, lr_idx, lr_len)
+        xr = scr.scratch("lr.out", (B, T, d))
+        be.lr_fwd(x2, lr_idx, xr)
+        y = self.decoder_fwd(P, xr, spk, lr_len, B, T, tp, eval_mode)
+        mel = tp.act("mel", B, T, N_MEL)
+        g.conv_fwd(y, P.get("mel_linear.weight"), P.get("mel_linear.bias").f32, mel.f32, mel.hi, mel.lo)
+        xin = self.postnet_fwd(P, mel, tp, update_bn, eval_mode)
+        post = xin.f32
+        be.axpby(1.0, mel.f32, 1.0, post)
+        return {"mel": mel.f32, "postnet": post, "pitch": ppred, "energy": epred, "logd": logd, "d_rounded": drnd,
+                "mel_len": lr_len, "T": T}
 
     def backward(self, P: ParamSet, G: ParamSet, bt: Batch, tp: Tape, loss_scale: float = 1.0, into_encoder: bool = True,
                  enc_G: Optional[ParamSet] = None):

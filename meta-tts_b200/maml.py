@@ -26,10 +26,15 @@ import torch
 from .engine import Batch, FS2Engine, N_MEL, ParamLayout, ParamSet, Tape, const_names
 
 
-def batch_from_tuple(b12, device, spk_ids=None, average_spk=False) -> Batch:
-    """Reference 12-tuple (lightning/collate.py:47-60) -> device Batch (plumbing: H2D copies)."""
+def batch_from_tuple(b12, device, spk_ids=None, average_spk=False, targets: bool = True) -> Batch:
+    """Reference 12-tuple (lightning/collate.py:47-60) -> device Batch (plumbing: H2D copies).
+    targets=False keeps only what free-running synthesis reads (`*qry_batch[3:6]`, base_adaptor.py:161)."""
     (_, _, spk, texts, src_lens, max_src, mels, mel_lens, max_mel, pitches, energies, durs) = b12
     to = lambda t, dt: torch.as_tensor(t).to(device=device, dtype=dt).contiguous()  # noqa: E731
+    if not targets:
+        return Batch(spk_ids=to(spk if spk_ids is None else spk_ids, torch.int64), average_spk=average_spk,
+                     texts=to(texts, torch.int64), src_lens=to(src_lens, torch.int64), mels=None, mel_lens=None, pitches=None,
+                     energies=None, durations=None, B=int(texts.shape[0]), L=int(max_src), T=0)
     return Batch(spk_ids=to(spk if spk_ids is None else spk_ids, torch.int64), average_spk=average_spk,
                  texts=to(texts, torch.int64), src_lens=to(src_lens, torch.int64), mels=to(mels, torch.float32),
                  mel_lens=to(mel_lens, torch.int64), pitches=to(pitches, torch.float32),
@@ -144,6 +149,41 @@ class MamlEngine:
             dst = self.fast[k]
             be.sgd_split(src, g_ad, self.lr, dst[0], dst[1], dst[2])      # l2l maml_update fused with operand prep
         self.bn_batches += steps
+
+    def adapt_rolling(self, sup: Batch, steps: int, tape: Tape, fresh: bool, drop_base: Optional[int] = None) -> None:
+        """FIRST-ORDER inner steps that keep no history (test-time adaptation, base_adaptor.py:98-112 with train=False ->
+        first_order=True, called repeatedly with `learner=learner`, base_adaptor.py:172-174): the fast weights live in arena 0
+        and are updated in place, one activation tape is reused for every step.  fresh = start from the meta parameters
+        (the reference's `self.learner.clone()`), else continue from the current fast weights."""
+        be, eng, lay = self.be, self.engine, self.layout
+        a0 = lay.adapt_begin
+        dst = self.fast[0]
+        for s in range(steps):
+            first = fresh and s == 0
+            P = self.params(0) if first else self.params(1)
+            eng.forward(P, sup, tape, drop_pass=None if drop_base is None else drop_base + s)
+            g_ad = self.g_inner[a0:]
+            be.zero_(g_ad)
+            eng.backward(P, self.grads(self.g_inner), sup, tape, 1.0, into_encoder=False)
+            be.sgd_split(self.theta[a0:] if first else dst[0], g_ad, self.lr, dst[0], dst[1], dst[2])
+        self.bn_batches += steps
+
+    def predict(self, bt: Batch, adapted: bool, free_running: bool = False, eval_mode: bool = False,
+                drop_pass: Optional[int] = None, p_control: float = 1.0, e_control: float = 1.0, d_control: float = 1.0):
+        """One forward_learner call outside the training step (base_adaptor.py:160-186): meta parameters (adapted=False) or
+        the rolling fast weights of `adapt_rolling`; teacher forced (+ loss) or free running; eval or train mode.
+        Shapes differ call to call, so the activations go to a throw-away tape."""
+        eng = self.engine
+        P = self.params(1) if adapted else self.params(0)
+        tape = eng.new_tape()
+        if free_running:
+            out = eng.synthesize(P, bt, tape, p_control, e_control, d_control, update_bn=not eval_mode, drop_pass=drop_pass,
+                                 eval_mode=eval_mode)
+        else:
+            out = eng.forward(P, bt, tape, update_bn=not eval_mode, drop_pass=drop_pass, eval_mode=eval_mode)
+        if not eval_mode:
+            self.bn_batches += 1
+        return out
 
     def task_step(self, sup: Batch, qry: Batch, steps: int, first_order: bool, accumulate_scale: Optional[float] = None,
                   drop_base: Optional[int] = None):

@@ -415,6 +415,86 @@ def validation_step(self, batch, batch_idx):
     return {"losses": val_loss, "output": predictions, "_batch": batch[0][1][0]}
 
 
+# dropout pass indices of a test step (shared with oracle/fs2_oracle.py: test_time_adaptation)
+TEST_RECON_PASS, TEST_SYNTH_PASS = 10000, 20000
+
+
+def _pred10(out, bt: Batch, free_running: bool):
+    """Engine prediction dict -> the reference's 10-tuple (base_adaptor.py:91-95); masks True = padding (tools.py:91-99)."""
+    Lq, T = bt.L, int(out["mel"].shape[1])
+    dev = bt.src_lens.device
+    src_masks = torch.arange(Lq, device=dev)[None, :] >= bt.src_lens[:, None]
+    mel_masks = torch.arange(T, device=dev)[None, :] >= out["mel_len"][:, None]
+    d_rounded = out["d_rounded"] if free_running else bt.durations
+    return (out["mel"], out["postnet"], out["pitch"], out["energy"], out["logd"], d_rounded, src_masks, mel_masks,
+            bt.src_lens, out["mel_len"])
+
+
+def _set_salt(self, salt: int) -> None:
+    salt &= 0xFFFFFFFF
+    self.be.drop_salt = torch.tensor([salt - (1 << 32) if salt >= (1 << 31) else salt], dtype=torch.int32, device=self.device)
+
+
+def _test_step(self, batch, batch_idx):
+    """base_adaptor.py:153-189 — few-shot adaptation inference (BASELINE configs[4]): evaluate the un-adapted learner
+    (eval mode), then `test.steps / train.steps` rounds of first-order adaptation on the support set, after each of which the
+    query is reconstructed (teacher forced, with losses) and — at `saving_steps` — synthesised free-running.  The adapted
+    learner is in train mode (the reference's adapt() calls `learner.train()` and nothing switches it back), so those
+    forwards run with dropout and BatchNorm batch statistics."""
+    _assert_meta_batch(batch)
+    outputs = {}
+    test_cfg = self.algorithm_config["adapt"]["test"]
+    saving_steps = test_cfg.get("saving_steps", [5, 10, 20, 50, 100])
+    sup12, qry12 = batch[0][0][0], batch[0][1][0]
+    outputs["_batch"] = qry12
+    m, dev = self.maml, self.device
+    sup = batch_from_tuple(sup12, dev)
+    qry_tf = batch_from_tuple(qry12, dev, spk_ids=sup12[2], average_spk=True)              # *qry_batch[3:]
+    qry_fr = batch_from_tuple(qry12, dev, spk_ids=sup12[2], average_spk=True, targets=False)   # *qry_batch[3:6]
+    drop = self.dropout
+    if drop:
+        _set_salt(self, self.next_salt())
+
+    def recon(adapted, eval_mode, drop_pass):
+        out = m.predict(qry_tf, adapted, False, eval_mode, drop_pass)
+        loss6 = out["loss6"].clone()
+        return {"losses": tuple(loss6[i] for i in range(6)), "output": _pred10(out, qry_tf, False)}
+
+    def synth(adapted, eval_mode, drop_pass):
+        return {"output": _pred10(m.predict(qry_fr, adapted, True, eval_mode, drop_pass), qry_fr, True)}
+
+    # the initial model: Lightning's test loop runs the module in eval mode (dropout off, BN running statistics)
+    outputs["step_0"] = {"recon": recon(False, True, None)}
+    outputs["step_0"].update({"synth": synth(False, True, None)})
+    tape = m.engine.new_tape()
+    done = 0
+    for ft_step in range(self.adaptation_steps, self.test_adaptation_steps + 1, self.adaptation_steps):
+        m.adapt_rolling(sup, self.adaptation_steps, tape, fresh=(done == 0), drop_base=done if drop else None)
+        done += self.adaptation_steps
+        outputs[f"step_{ft_step}"] = {"recon": recon(True, False, TEST_RECON_PASS + ft_step if drop else None)}
+        if ft_step in saving_steps:
+            outputs[f"step_{ft_step}"].update({"synth": synth(True, False, TEST_SYNTH_PASS + ft_step if drop else None)})
+    return outputs
+
+
+def test_step(self, batch, batch_idx):
+    """base_adaptor.py:139-151: one outputs dict per evaluation (one per support utterance in the "1-shot" protocol)."""
+    _assert_meta_batch(batch)
+    all_outputs = []
+    qry12 = batch[0][1][0]
+    if self.algorithm_config["adapt"]["test"].get("1-shot", False):
+        from .collate import split_reprocess
+
+        sup12 = batch[0][0][0]
+        for i in range(len(sup12[0])):                       # Task(batch_size=1, shuffle=False)
+            all_outputs.append(_test_step(self, [([split_reprocess(sup12, [i])], [qry12])], batch_idx))
+    else:
+        all_outputs.append(_test_step(self, batch, batch_idx))
+    if torch.distributed.is_initialized():
+        torch.distributed.barrier(group=self.process_group)
+    return all_outputs
+
+
 def optimizer_step(self):
     """What Lightning does after `accumulate_grad_batches` training_steps: DDP mean-allreduce of the
     outer gradient (one flat buffer, summed; the 1/(acc*world) scale was folded in at accumulation),
@@ -442,6 +522,8 @@ class MetaSystem:
     meta_learn = meta_learn
     training_step = training_step
     validation_step = validation_step
+    test_step = test_step
+    _test_step = _test_step
     optimizer_step = optimizer_step
     next_salt = next_salt
     _on_meta_batch_start = staticmethod(_assert_meta_batch)

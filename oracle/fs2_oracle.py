@@ -479,6 +479,71 @@ def maml_task_step(P: Params, cfg, sup_batch, qry_batch, adaptation_steps: int, 
     return losses, preds_d, grads
 
 
+# pass indices of the counter-hash dropout during a test step (shared with meta-tts_b200/systems.py: test_step):
+# adaptation step s (0-based, counted across the adapt() rounds) -> s; the teacher-forced "recon" forward after ft_step
+# inner steps -> TEST_RECON_PASS + ft_step; the free-running "synth" forward -> TEST_SYNTH_PASS + ft_step.
+TEST_RECON_PASS, TEST_SYNTH_PASS = 10000, 20000
+
+
+def test_time_adaptation(P: Params, cfg, sup_batch, qry_batch, adaptation_steps: int, test_adaptation_steps: int,
+                         saving_steps=(5, 10, 20, 50, 100), lr: float = 0.001, adapt_modules: Sequence[str] = ADAPT_MODULES,
+                         drop_seed=None):
+    """`BaseAdaptorSystem._test_step` (lightning/systems/base_adaptor.py:160-189) — few-shot adaptation inference
+    (BASELINE configs[4]).
+
+    step_0: the un-adapted learner.  Under `trainer.test` Lightning puts the module in eval mode and `self.learner` wraps
+    the model's own submodules, so these two forwards run with dropout off and BatchNorm running statistics:
+        recon = forward_learner(self.learner, sup[2], *qry[3:], average_spk_emb=True) + loss    (teacher forced)
+        synth = forward_learner(self.learner, sup[2], *qry[3:6], average_spk_emb=True)          (free running)
+    then for ft_step = adaptation_steps, 2*adaptation_steps, ..., test_adaptation_steps:
+        learner = self.adapt(batch, adaptation_steps, learner=learner, train=False)   first call: clone() + .train()
+            -> FIRST-ORDER inner steps (first_order = not train, base_adaptor.py:107), continuing from the previous
+               learner (base_adaptor.py:101-103): theta <- theta - lr * grad, no graph kept
+        recon (+ synth when ft_step in saving_steps) with the adapted learner, which is in TRAIN mode: dropout active
+        (drop_seed) and BatchNorm batch statistics; l2l's clone_module shares buffers that do not require grad, so every
+        one of these forwards also advances the model's running statistics (P is updated in place, as the reference).
+    Returns {f"step_{k}": {"recon": {"losses": 6-tuple, "output": 10-tuple}, "synth": {"output": 10-tuple}}}.
+    """
+    assert test_adaptation_steps % adaptation_steps == 0                         # base_adaptor.py:39
+    names_ad = [k for k in trainable_names(P) if k.split(".")[0] in adapt_modules]
+    if drop_seed is None:
+        ds = lambda k: None  # noqa: E731
+    else:
+        d_base, d_salt = drop_seed if isinstance(drop_seed, tuple) else (drop_seed, 0)
+        ds = lambda k: (d_base + k, d_salt)  # noqa: E731
+    det = lambda tup: tuple(t.detach() if torch.is_tensor(t) and t.is_floating_point() else t for t in tup)  # noqa: E731
+    out = {}
+    with torch.no_grad():
+        preds = fs2_forward(P, cfg, sup_batch[2], *qry_batch[3:], average_spk_emb=True, training=False)
+        out["step_0"] = {"recon": {"losses": tuple(v.detach() for v in fs2_loss(qry_batch, preds)), "output": det(preds)}}
+        preds = fs2_forward(P, cfg, sup_batch[2], *qry_batch[3:6], average_spk_emb=True, training=False)
+        out["step_0"]["synth"] = {"output": det(preds)}
+    theta = {k: P[k].detach().clone() for k in names_ad}                         # clone_module
+    done = 0
+    for ft_step in range(adaptation_steps, test_adaptation_steps + 1, adaptation_steps):
+        for _ in range(adaptation_steps):
+            leaves = {k: v.detach().requires_grad_(True) for k, v in theta.items()}
+            m = dict(P)
+            m.update(leaves)
+            preds = fs2_forward(m, cfg, *sup_batch[2:], drop_seed=ds(done))
+            loss = fs2_loss(sup_batch, preds)[0]
+            keys = list(leaves.keys())
+            grads = torch.autograd.grad(loss, [leaves[k] for k in keys])
+            theta = {k: (leaves[k] + (-lr * g)).detach() for k, g in zip(keys, grads)}
+            done += 1
+        m = dict(P)
+        m.update(theta)
+        with torch.no_grad():
+            preds = fs2_forward(m, cfg, sup_batch[2], *qry_batch[3:], average_spk_emb=True, drop_seed=ds(TEST_RECON_PASS + ft_step))
+            out[f"step_{ft_step}"] = {"recon": {"losses": tuple(v.detach() for v in fs2_loss(qry_batch, preds)),
+                                                "output": det(preds)}}
+            if ft_step in saving_steps:
+                preds = fs2_forward(m, cfg, sup_batch[2], *qry_batch[3:6], average_spk_emb=True,
+                                    drop_seed=ds(TEST_SYNTH_PASS + ft_step))
+                out[f"step_{ft_step}"]["synth"] = {"output": det(preds)}
+    return out, theta
+
+
 # ------------------------------------------------------------------------------------------------
 # synthetic LibriTTS-shaped tasks (SURVEY.md §8d) — shared by tests, smoke and bench
 # ------------------------------------------------------------------------------------------------

@@ -1,0 +1,102 @@
+"""SURVEY §8 rows f3/f5 on the B200: `MetaSystem.test_step` (few-shot adaptation inference, BASELINE configs[4]) through the
+C ABI against `oracle.fs2_oracle.test_time_adaptation` — eval-mode step_0, rolling first-order adaptation, train-mode
+teacher-forced recon and free-running synthesis (dropout off and on).  Outputs within 1e-3 relative fp32 (north_star);
+rounded durations / mel lengths / masks bit-exact; plus the full configs[4] size (16-shot, 20 steps, 128 phonemes) with
+size-independent properties."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from meta_tts_b200.systems import DEFAULT_ALGORITHM_CONFIG, DEFAULT_TRAIN_CONFIG, MetaSystem  # noqa: E402
+from oracle import fs2_oracle as O  # noqa: E402
+from tests_helpers_adapt import check_outputs, rel, talkative_params  # noqa: E402
+
+
+def _system(cfg, steps, test_steps, saving, dropout, one_shot=False):
+    algo = copy.deepcopy(DEFAULT_ALGORITHM_CONFIG)
+    algo["adapt"]["train"]["steps"] = steps
+    algo["adapt"]["test"] = {"steps": test_steps, "saving_steps": list(saving), "1-shot": one_shot}
+    return MetaSystem(None, cfg, DEFAULT_TRAIN_CONFIG, algo, n_speaker=16, device="cuda:0", use_cuda_graph=False, dropout=dropout, seed=3)
+
+
+@pytest.mark.parametrize("dropout", [False, True])
+def test_small_model_test_step(cuda_device, dropout):
+    cfg = O.small_model_config(1, 1)
+    P = talkative_params(cfg)
+    sysm = _system(cfg, 2, 6, (2, 6), dropout)
+    sysm.load_state_dict({k: v.detach().clone() for k, v in P.items()})
+    sup, qry = O.synth_task(task=2, shots=3, queries=1, L=7, T=20, ragged=True)
+    outs = sysm.test_step([([sup], [qry])], 0)
+    torch.cuda.synchronize()
+    Pc = {k: v.detach().clone() for k, v in P.items()}
+    ref, theta = O.test_time_adaptation(Pc, cfg, sup, qry, 2, 6, saving_steps=(2, 6), drop_seed=(0, sysm.last_salt) if dropout else None)
+    check_outputs(outs[0], ref, verbose=f"small dropout={dropout}")
+    fw = sysm.maml.fast_weights(1)
+    assert sorted(rel(fw[k], theta[k]) for k in theta)[len(theta) // 2] < 1e-4
+    for i in range(5):
+        assert rel(sysm.maml.consts[f"postnet.convolutions.{i}.1.running_var"], Pc[f"postnet.convolutions.{i}.1.running_var"]) < 1e-4
+
+
+def test_base_model_test_step_ragged(cuda_device):
+    """Base model (4 + 6 layers), 4-shot ragged support, 10 first-order steps in 2 rounds, dropout on."""
+    cfg = O.BASE_MODEL_CONFIG
+    P = talkative_params(cfg)
+    sysm = _system(cfg, 5, 10, (5, 10), True)
+    sysm.load_state_dict({k: v.detach().clone() for k, v in P.items()})
+    sup, qry = O.synth_task(task=6, shots=4, queries=1, L=24, T=90, ragged=True)
+    outs = sysm.test_step([([sup], [qry])], 0)
+    torch.cuda.synchronize()
+    Pc = {k: v.detach().clone() for k, v in P.items()}
+    ref, _ = O.test_time_adaptation(Pc, cfg, sup, qry, 5, 10, saving_steps=(5, 10), drop_seed=(0, sysm.last_salt))
+    check_outputs(outs[0], ref, verbose="base ragged K=10 dropout")
+
+
+def test_config5_full_size(cuda_device):
+    """BASELINE configs[4]: 20 first-order inner steps on a 16-shot support set (128 phonemes -> 864 frames), then free-running
+    synthesis of the query and Griffin-Lim decode.  The oracle's 20 full-size steps take minutes on the host, so the step_0
+    forwards are compared against the oracle and the adapted ones are checked through properties: the support-driven query
+    loss goes down, mel_len == sum(d_rounded), padded frames are zero, the waveform has hop * (T - 2) samples."""
+    from meta_tts_b200 import audio as PA
+    from meta_tts_b200 import ops as _ops
+
+    cfg = O.BASE_MODEL_CONFIG
+    P = talkative_params(cfg)
+    sysm = _system(cfg, 5, 20, (5, 10, 20), True)
+    sysm.load_state_dict({k: v.detach().clone() for k, v in P.items()})
+    sup, qry = O.synth_task(task=9, shots=16, queries=1, L=128, T=864)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = _ops.launch_count
+    ev0.record()
+    out = sysm.test_step([([sup], [qry])], 0)[0]
+    ev1.record()
+    torch.cuda.synchronize()
+    print(f"[config5] test_step (20 first-order steps on 16 x 864 frames + 5 recon + 4 synth forwards): {ev0.elapsed_time(ev1):.1f} ms, "
+          f"{_ops.launch_count - n0} launches")
+    with torch.no_grad():
+        Pc = {k: v.detach().clone() for k, v in P.items()}
+        r0 = O.fs2_forward(Pc, cfg, sup[2], *qry[3:], average_spk_emb=True, training=False)
+        s0 = O.fs2_forward(Pc, cfg, sup[2], *qry[3:6], average_spk_emb=True, training=False)
+    g = out["step_0"]
+    assert rel(g["recon"]["output"][1], r0[1]) < 1e-3 and rel(g["recon"]["output"][0], r0[0]) < 1e-3
+    assert torch.equal(g["synth"]["output"][5].cpu(), s0[5]) and torch.equal(g["synth"]["output"][9].cpu(), s0[9])
+    assert g["synth"]["output"][1].shape == s0[1].shape and rel(g["synth"]["output"][1], s0[1]) < 1e-3
+    losses = [float(out[f"step_{k}"]["recon"]["losses"][0]) for k in (0, 5, 10, 15, 20)]
+    print("[config5] query loss after 0/5/10/15/20 steps:", [f"{v:.4f}" for v in losses])
+    assert losses[-1] < losses[1]            # (step_0 is eval mode, the others train mode: compare like with like)
+    for k in (5, 10, 20):
+        o = out[f"step_{k}"]["synth"]["output"]
+        mel_len, d_r = o[9].cpu(), o[5].cpu()
+        assert torch.equal(mel_len, d_r.to(torch.int64).clamp(min=0).sum(1)) and o[1].shape[1] == int(mel_len.max())
+    # vocoder-side decode of the step-20 synthesis (tools.py:18-34)
+    mel = out["step_20"]["synth"]["output"][1][0]                      # [T, 80] postnet mel
+    T = mel.shape[0]
+    stft = PA.TacotronSTFT(1024, 256, 1024, 80, 22050, 0, 8000, device="cuda:0")
+    ev0.record()
+    wav = PA.inv_mel_spec(mel.t(), None, stft, 60)
+    ev1.record()
+    torch.cuda.synchronize()
+    print(f"[config5] Griffin-Lim x60 on {T} frames: {ev0.elapsed_time(ev1):.1f} ms")
+    assert wav.shape == (256 * (T - 2),) and bool(torch.isfinite(torch.from_numpy(wav)).all())

@@ -231,3 +231,59 @@ def test_elementwise(cuda_device):
     ss = (g.double() ** 2).sum().float().reshape(1)
     _both(cuda_device, "adam_clip", [x.clone(), g, 0.1 * R_(n, seed=3), R_(n, seed=4).abs(), ss, 0.5, 1.0, hyper, 0.9, 0.98, 1e-9,
                                      bf(n), bf(n)], tol=5e-5)
+
+
+# ---- free-running synthesis / vocoder-side elementwise kernels (csrc/mtts_audio.cu) ----------------------------------
+def test_duration_round_exact(cuda_device):
+    """Integer path: clamp(round(exp(log_d) - 1) * d_control, 0) with round-half-to-even, incl. exact .5 cases."""
+    g = torch.Generator().manual_seed(0)
+    logd = torch.cat([torch.randn(4000, generator=g) * 1.5 + 1.0, torch.log(torch.tensor([1.5, 2.5, 3.5, 4.5, 1.0, 0.5])),
+                      torch.tensor([-3.0, 0.0, 6.0])])
+    for dc in (1.0, 1.3, 0.5):
+        ref, got = _both(cuda_device, "duration_round", [logd, dc, torch.zeros_like(logd)], skip=(2,))
+        # exp() differs by an ulp between libm and the device: only inputs whose exp(log_d) - 1 sits within 1e-5 (relative)
+        # of a rounding boundary may legitimately differ; everything else must be identical
+        v = torch.exp(logd.double()) - 1
+        safe = ((v % 1.0) - 0.5).abs() > 1e-5 * v.abs().clamp_min(1.0)
+        assert int(safe.sum()) > 3900 and torch.equal(ref[2][safe], got[2][safe])
+        assert float(got[2].min()) >= 0.0 and torch.equal(got[2], got[2].round())
+
+
+def test_bn_eval_and_unary(cuda_device):
+    g = torch.Generator().manual_seed(1)
+    R, C = 333, 80
+    x = torch.randn(R, C, generator=g) * 2 + 0.3
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    rm, rv = torch.randn(C, generator=g) * 0.2, torch.rand(C, generator=g) + 0.2
+    bf = lambda: torch.zeros(R, C, dtype=torch.bfloat16)  # noqa: E731
+    for tanh in (True, False):
+        _both(cuda_device, "bn_eval", [x, gamma, beta, rm, rv, R, C, tanh, torch.zeros(R, C), bf(), bf()])
+    v = torch.rand(1000, generator=g) * 3
+    _both(cuda_device, "unary", [0, v - 0.5, 1e-5, 1.0, torch.zeros(1000)])                 # log(clamp)
+    _both(cuda_device, "unary", [1, v - 1.5, 0.25, 0.0, torch.zeros(1000), torch.zeros(1000, dtype=torch.bfloat16),
+                                 torch.zeros(1000, dtype=torch.bfloat16)])                    # exp * a, + operand split
+    _both(cuda_device, "unary", [2, v, 1.7, 0.0, torch.zeros(1000)])
+
+
+def test_stft_elementwise_kernels(cuda_device):
+    g = torch.Generator().manual_seed(2)
+    B, N, pad, ld = 3, 700, 512, 1792
+    x = torch.randn(B, N, generator=g)
+    bf = lambda *s: torch.zeros(*s, dtype=torch.bfloat16)  # noqa: E731
+    _both(cuda_device, "reflect_pad", [x, B, N, pad, ld, torch.zeros(B, ld), bf(B, ld), bf(B, ld)])
+    _both(cuda_device, "reflect_pad", [x, B, N, pad, 1500, torch.zeros(B, 1500), bf(B, 1500), bf(B, 1500)])   # ld cuts the tail
+    R, nb, io = 77, 513, 520
+    ri = torch.randn(R, 2 * io, generator=g)
+    mag, ph, en = torch.zeros(R, io), torch.zeros(R, io), torch.zeros(R)
+    ref, got = _both(cuda_device, "stft_polar", [ri, R, nb, 2 * io, io, io, mag, ph, en, bf(R, io), bf(R, io)], tol=1e-5)
+    assert float(got[6][:, nb:].abs().max()) == 0.0 and float(got[7][:, nb:].abs().max()) == 0.0      # pad columns zeroed
+    _both(cuda_device, "stft_recombine", [ref[6], ref[7], None, R, nb, 2 * io, io, io, bf(R, 2 * io), bf(R, 2 * io)], tol=1e-5)
+    _both(cuda_device, "stft_recombine", [ref[6], None, ri, R, nb, 2 * io, io, io, bf(R, 2 * io), bf(R, 2 * io)], tol=1e-5)
+    n, trim = 2048, 512
+    ola = torch.randn(2, n, generator=g)
+    ws = torch.rand(n, generator=g)
+    ws[:7] = 0.0                                                         # below `tiny`: left un-normalised
+    _both(cuda_device, "istft_finish", [ola, ws, 1.1754944e-38, 4.0, 2, n, trim, torch.zeros(2, n - 2 * trim)])
+    ws2 = ws.clone()
+    ws2[600:620] = 0.0
+    _both(cuda_device, "istft_finish", [ola, ws2, 1.1754944e-38, 4.0, 2, n, trim, torch.zeros(2, n - 2 * trim)])
