@@ -1092,6 +1092,9 @@ class FS2Engine:
             raise ValueError("free-running synthesis predicted zero frames for every utterance")
         if T > (1 << 20):
             raise ValueError(f"free-running synthesis predicted {T} frames (diverged duration predictor?)")
+        if not eval_mode:
+            T = min(T, self.cfg["max_seq_len"])      # train mode: the decoder keeps the first max_seq_len frames (Models.py:161-166);
+                                                     # mel_len stays the full sum of durations, as the reference returns it
         lr_idx = tp.buf("lr.idx", (B, T), torch.int32)
         lr_len = tp.buf("lr.mel_len", (B,), torch.int64)
         be.lr_index(drnd, T, lr_idx, lr_len)

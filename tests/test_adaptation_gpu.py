@@ -79,17 +79,16 @@ def test_config5_full_size(cuda_device):
         Pc = {k: v.detach().clone() for k, v in P.items()}
         r0 = O.fs2_forward(Pc, cfg, sup[2], *qry[3:], average_spk_emb=True, training=False)
         s0 = O.fs2_forward(Pc, cfg, sup[2], *qry[3:6], average_spk_emb=True, training=False)
-    g = out["step_0"]
-    assert rel(g["recon"]["output"][1], r0[1]) < 1e-3 and rel(g["recon"]["output"][0], r0[0]) < 1e-3
-    assert torch.equal(g["synth"]["output"][5].cpu(), s0[5]) and torch.equal(g["synth"]["output"][9].cpu(), s0[9])
-    assert g["synth"]["output"][1].shape == s0[1].shape and rel(g["synth"]["output"][1], s0[1]) < 1e-3
+    ref0 = {"step_0": {"recon": {"losses": tuple(O.fs2_loss(qry, r0)), "output": r0}, "synth": {"output": s0}}}
+    check_outputs({"step_0": out["step_0"]}, ref0, verbose="config5 full size")
     losses = [float(out[f"step_{k}"]["recon"]["losses"][0]) for k in (0, 5, 10, 15, 20)]
     print("[config5] query loss after 0/5/10/15/20 steps:", [f"{v:.4f}" for v in losses])
     assert losses[-1] < losses[1]            # (step_0 is eval mode, the others train mode: compare like with like)
     for k in (5, 10, 20):
         o = out[f"step_{k}"]["synth"]["output"]
         mel_len, d_r = o[9].cpu(), o[5].cpu()
-        assert torch.equal(mel_len, d_r.to(torch.int64).clamp(min=0).sum(1)) and o[1].shape[1] == int(mel_len.max())
+        assert torch.equal(mel_len, d_r.to(torch.int64).clamp(min=0).sum(1))
+        assert o[1].shape[1] == min(int(mel_len.max()), 1000)          # train mode: decoder truncates at max_seq_len (Models.py:161-166)
     # vocoder-side decode of the step-20 synthesis (tools.py:18-34)
     mel = out["step_20"]["synth"]["output"][1][0]                      # [T, 80] postnet mel
     T = mel.shape[0]
