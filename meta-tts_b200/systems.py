@@ -512,6 +512,65 @@ def optimizer_step(self):
     self.host_prof["optimizer"] += time.perf_counter() - t0
 
 
+def _prefixed_state_dict(self):
+    return {("model." + k): v for k, v in self.maml.state_dict().items()}
+
+
+def on_load_checkpoint(self, checkpoint: dict) -> None:
+    """system.py:115-194: make a reference (Lightning) checkpoint loadable — rename the old speaker-table key, reconcile a
+    speaker table of another size, drop unknown keys, report missing ones; a changed checkpoint loses its optimizer state."""
+    from .checkpoint import adapt_checkpoint
+
+    self.test_global_step = checkpoint.get("global_step", 0)
+    self.checkpoint_changes = adapt_checkpoint(checkpoint, _prefixed_state_dict(self), self.preprocess_config,
+                                               self.algorithm_config, verbose=getattr(self, "local_rank", 0) == 0 and
+                                               getattr(self, "verbose_checkpoint", False))
+
+
+def load_checkpoint(self, checkpoint: dict) -> None:
+    """What Lightning's `Trainer(resume_from_checkpoint=...)` / `trainer.test(ckpt_path=...)` do with a checkpoint dict
+    (`torch.load(path)`): on_load_checkpoint, load_state_dict (missing keys keep the current values), optimizer + scheduler
+    state (torch.optim.Adam layout over `model.parameters()`), global step."""
+    from .checkpoint import import_adam_state
+
+    self.on_load_checkpoint(checkpoint)
+    sd = _prefixed_state_dict(self)
+    sd.update(checkpoint["state_dict"])
+    self.load_state_dict(sd)
+    opt = checkpoint.get("optimizer_states")
+    if opt:
+        import_adam_state(self.maml, opt[0])
+    sch = checkpoint.get("lr_schedulers")
+    if sch and not opt:
+        self.maml.opt_step = int(sch[0].get("last_epoch", 0))
+    self.global_step = int(checkpoint.get("global_step", self.maml.opt_step))
+
+
+def save_checkpoint(self) -> dict:
+    """A Lightning-format checkpoint dict the reference can load (`torch.save` it): `state_dict` with the `model.` prefix,
+    `global_step`, `optimizer_states` (torch Adam layout), `lr_schedulers` (LambdaLR last_epoch)."""
+    from .checkpoint import export_adam_state
+
+    opt = self.train_config["optimizer"]
+    return {"global_step": self.maml.opt_step, "epoch": 0, "state_dict": _prefixed_state_dict(self),
+            "optimizer_states": [export_adam_state(self.maml, tuple(opt["betas"]), float(opt["eps"]),
+                                                   float(opt.get("weight_decay", 0.0)))],
+            "lr_schedulers": [{"last_epoch": self.maml.opt_step, "_step_count": self.maml.opt_step + 1}]}
+
+
+def on_test_start(self) -> None:
+    """system.py:197-212: with `adapt.test.avg_train_spk_emb` on LibriTTS the 39 test speakers' table rows are replaced by the
+    mean of the 247 train-clean-100 rows before testing."""
+    ad = self.algorithm_config["adapt"]
+    if ad.get("speaker_emb", "table") != "table":
+        return
+    if (self.preprocess_config or {}).get("dataset") == "LibriTTS" and ad.get("test", {}).get("avg_train_spk_emb", False):
+        sd = self.maml.state_dict()
+        w = sd["speaker_emb.model.weight"]
+        w[-39:] = w[:247].mean(dim=0)
+        self.load_state_dict(sd)
+
+
 class MetaSystem:
     """B200-native counterpart of `lightning.systems.meta.MetaSystem` (hot path only)."""
 
@@ -524,6 +583,11 @@ class MetaSystem:
     validation_step = validation_step
     test_step = test_step
     _test_step = _test_step
+    on_load_checkpoint = on_load_checkpoint
+    load_checkpoint = load_checkpoint
+    save_checkpoint = save_checkpoint
+    on_save_checkpoint = staticmethod(lambda checkpoint: checkpoint)       # system.py:111-113
+    on_test_start = on_test_start
     optimizer_step = optimizer_step
     next_salt = next_salt
     _on_meta_batch_start = staticmethod(_assert_meta_batch)
