@@ -252,6 +252,8 @@ int mtts_split(const float* src, void* hi, void* lo, int64_t n, mtts_stream stre
 int mtts_sgd_split(const float* theta, const float* g, float lr, float* out, void* hi, void* lo, int64_t n, mtts_stream stream);
 int mtts_axpby(float a, const float* x, float b, float* y, int64_t n, mtts_stream stream);
 int mtts_sumsq(const float* x, int64_t n, float* out, mtts_stream stream);
+/* out = <x, y>  (conjugate-gradient scalars of the iMAML hypergradient, hypertorch/hypergrad/CG_torch.py:21-35). */
+int mtts_dot(const float* x, const float* y, int64_t n, float* out, mtts_stream stream);
 /* clip_grad_norm_(max_norm) + Adam (lightning/optimizer.py:6-16, main.py:61).  sumsq = sum g^2 of
  * the UNSCALED buffer, gscale multiplies g first (1/(n_tasks)); hyper = device (lr, 1-b1^t, 1-b2^t). */
 int mtts_adam_clip(float* p, const float* g, float* m, float* v, const float* sumsq, float gscale, float max_norm,

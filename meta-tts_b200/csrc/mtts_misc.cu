@@ -519,6 +519,17 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n4, float* _
   s = block_sum(s);
   if (threadIdx.x == 0) atomicAdd(out, s);
 }
+__global__ void dot_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n4, float* __restrict__ out) {
+  pdl_enter();
+  float s = 0.f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 u = *reinterpret_cast<const float4*>(x + i * 4);
+    const float4 w = *reinterpret_cast<const float4*>(y + i * 4);
+    s += (u.x * w.x + u.y * w.y) + (u.z * w.z + u.w * w.w);
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
 // clip-by-global-norm (torch clip_grad_norm_: coef = min(1, max_norm/(norm+1e-6))) + Adam (no weight decay)
 // hyper[0] = lr, hyper[1] = bias_correction1 = 1-beta1^t, hyper[2] = bias_correction2 = 1-beta2^t  (device, so graphs replay)
 __global__ void adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -765,6 +776,15 @@ extern "C" int mtts_sumsq(const float* x, int64_t n, float* out /* zeroed here *
   REQ_N4(n, x);
   MTTS_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
   MTTS_CHECK_CUDA(mtts_launch(sumsq_kernel, dim3(ew_grid(n / 4, 4)), dim3(EW_THREADS), 0, s, x, n / 4, out));
+  MTTS_CHECK_LAUNCH();
+  return MTTS_OK;
+}
+extern "C" int mtts_dot(const float* x, const float* y, int64_t n, float* out /* zeroed here */, mtts_stream stream_) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  REQ_N4(n, x);
+  MTTS_REQUIRE(y != nullptr && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "dot: bad second operand");
+  MTTS_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
+  MTTS_CHECK_CUDA(mtts_launch(dot_kernel, dim3(ew_grid(n / 4, 4)), dim3(EW_THREADS), 0, s, x, y, n / 4, out));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }

@@ -112,6 +112,7 @@ SIGNATURES: dict[str, list] = {
     "mtts_sgd_split": [_vp, _vp, _f, _vp, _vp, _vp, _i64, _vp],
     "mtts_axpby": [_f, _vp, _f, _vp, _i64, _vp],
     "mtts_sumsq": [_vp, _i64, _vp, _vp],
+    "mtts_dot": [_vp, _vp, _i64, _vp, _vp],
     "mtts_duration_round": [_vp, _f, _i64, _vp, _vp],
     "mtts_bn_eval": [_vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _i, _vp, _vp, _vp, _vp],
     "mtts_unary": [_i, _vp, _i64, _f, _f, _vp, _vp, _vp, _vp],

@@ -442,6 +442,9 @@ class CudaOps:
     def sumsq(self, x, out):
         self._call("mtts_sumsq", _p(x), x.numel(), _p(out))
 
+    def dot(self, x, y, out):
+        self._call("mtts_dot", _p(x), _p(y), x.numel(), _p(out))
+
     def adam_clip(self, p, g, m, v, sumsq, gscale, max_norm, hyper, beta1, beta2, eps, hi, lo):
         self._call("mtts_adam_clip", _p(p), _p(g), _p(m), _p(v), _p(sumsq), gscale, max_norm, _p(hyper), beta1, beta2,
                    eps, _p(hi), _p(lo), p.numel())

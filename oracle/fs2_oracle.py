@@ -545,6 +545,128 @@ def test_time_adaptation(P: Params, cfg, sup_batch, qry_batch, adaptation_steps:
 
 
 # ------------------------------------------------------------------------------------------------
+# iMAML: lightning/systems/imaml.py:51-150, lightning/systems/utils.py:78-189,
+# hypertorch/hypergrad/CG_torch.py:6-41
+# ------------------------------------------------------------------------------------------------
+def split_batch(batch, idxs):
+    """lightning/collate.py:63-125 (`split_reprocess`, table speaker ids): rows `idxs` of a 12-tuple, re-trimmed."""
+    import numpy as np
+    (ids, raw, spk, texts, tl, mtl, mels, ml, mml, pit, ene, dur) = batch
+    idxs = np.asarray(idxs)
+    stl, sml = tl[idxs], ml[idxs]
+    Ls, Ts = stl.max(), sml.max()
+    cut = lambda t: t[idxs][:, :Ls] if t.shape[1] == mtl else t[idxs][:, :Ts]  # noqa: E731
+    return ([ids[i] for i in idxs], [raw[i] for i in idxs], spk[idxs], texts[idxs][:, :Ls], stl, Ls, mels[idxs][:, :Ts], sml, Ts,
+            cut(pit), cut(ene), dur[idxs][:, :Ls])
+
+
+class SupportTask:
+    """lightning/systems/utils.py:78-116 (`Task`): mini-batches of the support set drawn by
+    BatchSampler(RandomSampler(range(n)), batch_size, drop_last=True); the iterator restarts (reshuffles) when exhausted."""
+
+    def __init__(self, sup_data, batch_size, shuffle=True):
+        from torch.utils.data import BatchSampler, RandomSampler
+        self.sup = sup_data
+        n = len(sup_data[0])
+        self.sampler = BatchSampler(RandomSampler(range(n)) if shuffle else range(n), batch_size=batch_size, drop_last=True)
+        self.it = iter(self.sampler)
+
+    def reset_iterator(self):
+        self.it = iter(self.sampler)
+
+    def next_batch(self):
+        try:
+            idxs = next(self.it)
+        except StopIteration:
+            self.reset_iterator()
+            idxs = next(self.it)
+        return split_batch(self.sup, idxs)
+
+
+def cg_solve(Ax, b, max_iter, epsilon):
+    """hypertorch/hypergrad/CG_torch.py:6-41, statement for statement (NB: on early exit the last update of x is NOT
+    applied — `x_last` is returned)."""
+    cat = lambda ts: torch.cat([t.reshape(-1) for t in ts])  # noqa: E731
+    x_last = [torch.zeros_like(bb) for bb in b]
+    r_last = [bb.clone() for bb in b]
+    p_last = [rr.clone() for rr in r_last]
+    for _ in range(max_iter):
+        Ap = Ax(p_last)
+        rTr = torch.sum(cat(r_last) * cat(r_last))
+        pAp = torch.sum(cat(p_last) * cat(Ap))
+        alpha = rTr / pAp
+        x = [xx + alpha * pp for xx, pp in zip(x_last, p_last)]
+        r = [rr - alpha * pp for rr, pp in zip(r_last, Ap)]
+        r_vec = cat(r)
+        if float(torch.norm(r_vec)) < epsilon:
+            break
+        beta = torch.sum(r_vec * r_vec) / rTr
+        p = [rr + beta * pp for rr, pp in zip(r, p_last)]
+        x_last, p_last, r_last = x, p, r
+    return x_last
+
+
+def imaml_task_step(P: Params, cfg, sup_batch, qry_batch, adaptation_steps: int, lr: float, reg_param: float, cg_iters: int,
+                    batch_size: int, stochastic: bool = True, adapt_modules: Sequence[str] = ADAPT_MODULES, drop_seed=None,
+                    cg_eps: float = 1e-10):
+    """One iMAML task (imaml.py:51-133 + systems/utils.py:120-189 `CG`), up to the hypergradient (clip / reduce / Adam excluded).
+
+    adapt():   K first-order steps on support MINI-batches of  L(w) + 0.5 * reg * ||theta0 - w||^2   (imaml.py:68-75)
+    CG():      b = d L_query(w) / d w;   A v = v - J_fp^T v with fp_map(w) = w - lr * grad[L_mb(w) + 0.5 reg ||theta0 - w||^2]
+               (a fresh mini-batch per product when stochastic), i.e. A = lr * (H_mb + reg I);  v = cg(A, b, K iterations)
+               hypergradient = (d fp_map / d theta0)^T v + d L_query / d theta0 = lr * reg * v      (theta0 enters fp_map only
+               through the proximal term; the query loss is evaluated at w, so its direct term is zero)
+    The reference then writes the gradients with `update_tensor_grads(hparams, grads)` where `hparams` are ALL trainable
+    model parameters but `grads` only the adapted ones (imaml.py:140-141) — positionally misaligned unless every module is
+    adapted; the evident intent (adapted parameters receive their hypergradient, the rest none) is what is returned here.
+    Dropout pass indices: inner step s -> s, the query forward -> K, CG product j -> K + 1 + j.
+    Returns (query losses, query predictions, {adapted name: hypergradient}, adapted weights w)."""
+    names_ad = [k for k in trainable_names(P) if k.split(".")[0] in adapt_modules]
+    if drop_seed is None:
+        ds = lambda k: None  # noqa: E731
+    else:
+        d_base, d_salt = drop_seed if isinstance(drop_seed, tuple) else (drop_seed, 0)
+        ds = lambda k: (d_base + k, d_salt)  # noqa: E731
+    theta0 = {k: P[k].detach() for k in names_ad}
+    w = {k: P[k].detach().clone() for k in names_ad}
+    task = SupportTask(sup_batch, batch_size)
+
+    def reg_loss(mb, leaves, seed):
+        m = dict(P)
+        m.update(leaves)
+        loss = fs2_loss(mb, fs2_forward(m, cfg, *mb[2:], drop_seed=seed))[0]
+        return loss + 0.5 * reg_param * sum(((theta0[k] - leaves[k]) ** 2).sum() for k in names_ad)
+
+    for s in range(adaptation_steps):
+        leaves = {k: v.detach().requires_grad_(True) for k, v in w.items()}
+        g = torch.autograd.grad(reg_loss(task.next_batch(), leaves, ds(s)), [leaves[k] for k in names_ad])
+        w = {k: (leaves[k] - lr * gi).detach() for k, gi in zip(names_ad, g)}
+    task.reset_iterator()                                                       # imaml.py:116
+    params = {k: v.detach().requires_grad_(True) for k, v in w.items()}
+    m = dict(P)
+    m.update(params)
+    preds = fs2_forward(m, cfg, sup_batch[2], *qry_batch[3:], average_spk_emb=True, drop_seed=ds(adaptation_steps))
+    valid = fs2_loss(qry_batch, preds)
+    b = list(torch.autograd.grad(valid[0], [params[k] for k in names_ad]))
+    counter = [0]
+
+    def Ax(xs):
+        mb = task.next_batch() if stochastic else sup_batch
+        loss = reg_loss(mb, params, ds(adaptation_steps + 1 + counter[0]))
+        counter[0] += 1
+        g = torch.autograd.grad(loss, [params[k] for k in names_ad], create_graph=True)
+        mapped = [params[k] - lr * gi for k, gi in zip(names_ad, g)]
+        J = torch.autograd.grad(mapped, [params[k] for k in names_ad], grad_outputs=xs)
+        return [v - j for v, j in zip(xs, J)]
+
+    vs = cg_solve(Ax, b, cg_iters, cg_eps)
+    grads = {k: (lr * reg_param * v).detach() for k, v in zip(names_ad, vs)}
+    losses = tuple(v.detach() for v in valid)
+    preds_d = tuple(t.detach() if torch.is_tensor(t) and t.is_floating_point() else t for t in preds)
+    return losses, preds_d, grads, {k: v.detach() for k, v in w.items()}
+
+
+# ------------------------------------------------------------------------------------------------
 # synthetic LibriTTS-shaped tasks (SURVEY.md §8d) — shared by tests, smoke and bench
 # ------------------------------------------------------------------------------------------------
 def synth_batch(n: int, L: int, T: int, seed: int, speaker: int = 0, ragged: bool = False, n_speaker: int = 16):

@@ -642,6 +642,10 @@ class RefOps:
         self.n_calls += 1
         out.copy_((x.double() ** 2).sum().float().reshape(out.shape))
 
+    def dot(self, x, y, out):
+        self.n_calls += 1
+        out.copy_((x.double() * y.double()).sum().float().reshape(out.shape))
+
     def adam_clip(self, p, g, m, v, sumsq, gscale, max_norm, hyper, beta1, beta2, eps, hi, lo):
         self.n_calls += 1
         norm = torch.sqrt(sumsq.double()).item() * gscale
