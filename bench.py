@@ -35,6 +35,19 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 SHOTS, QUERIES, L_PHON, T_MEL, K_INNER = 4, 4, 128, 864, 1
+FIRST_ORDER, GRAD_ACC, WORKLOAD = False, 1, "config2"
+# BASELINE.json configs: the driver's default line is configs[1]; the others are extra lines for profiles/ (--workload)
+WORKLOADS = {
+    "config2": dict(shots=4, queries=4, k=1, first_order=False, acc=1, tag="BASELINE configs[1]"),
+    "config3": dict(shots=5, queries=5, k=5, first_order=False, acc=1, tag="BASELINE configs[2]: 1 task per GPU, 8 tasks on 8 GPUs"),
+    "config4": dict(shots=5, queries=5, k=5, first_order=True, acc=4, tag="BASELINE configs[3]: grad_acc_step 4, 32 tasks on 8 GPUs"),
+}
+
+
+def set_workload(name):
+    global SHOTS, QUERIES, K_INNER, FIRST_ORDER, GRAD_ACC, WORKLOAD
+    w = WORKLOADS[name]
+    SHOTS, QUERIES, K_INNER, FIRST_ORDER, GRAD_ACC, WORKLOAD = w["shots"], w["queries"], w["k"], w["first_order"], w["acc"], name
 _JSON_OUT = sys.stdout
 METRIC = "mel-frames/sec per outer meta-step"
 UNIT = "mel-frames/s"
@@ -42,10 +55,11 @@ UNIT = "mel-frames/s"
 
 def workload_config(n_gpus, split, dropout=True):
     return {
-        "workload": f"second-order MAML K={K_INNER}, 1 task/GPU, {SHOTS}-shot support + {QUERIES} queries, "
-                    f"{L_PHON} phonemes -> {T_MEL} frames (BASELINE configs[1])",
-        "tasks_per_step": n_gpus, "shots": SHOTS, "queries": QUERIES, "phonemes": L_PHON, "frames": T_MEL,
-        "inner_steps": K_INNER, "order": "second", "precision": "bf16x3 hi/lo split (fp32-grade)" if split == 3 else "bf16",
+        "workload": f"{'first' if FIRST_ORDER else 'second'}-order MAML K={K_INNER}, 1 task/GPU"
+                    f"{'' if GRAD_ACC == 1 else f' x {GRAD_ACC} accumulated micro-steps'}, {SHOTS}-shot support + {QUERIES} queries, "
+                    f"{L_PHON} phonemes -> {T_MEL} frames ({WORKLOADS[WORKLOAD]['tag']})",
+        "tasks_per_step": n_gpus * GRAD_ACC, "shots": SHOTS, "queries": QUERIES, "phonemes": L_PHON, "frames": T_MEL,
+        "inner_steps": K_INNER, "order": "first" if FIRST_ORDER else "second", "precision": "bf16x3 hi/lo split (fp32-grade)" if split == 3 else "bf16",
         "dropout": ("train mode, ACTIVE (enc/dec 0.2, variance predictors 0.5, postnet 0.5): counter-hash masks fused into the "
                     "LN/BN kernels, fresh per step" if dropout else "identity (--no-dropout)"), "parallelism": f"dp{n_gpus} (1 task per GPU)",
         "l2": "per-step working set (activation tapes ~GBs + 280 MB weights) >> 126 MB L2: no flush needed",
@@ -56,10 +70,15 @@ def frames_per_task():
     return (SHOTS + QUERIES) * T_MEL
 
 
+def frames_per_step():
+    """Distinct mel frames one rank consumes per optimizer step (n_tasks x (S + Q) x T)."""
+    return GRAD_ACC * frames_per_task()
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (restated reference path) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_arm(steps, warmup, shots=SHOTS, queries=QUERIES, budget_s=150.0):
+def cpu_arm(steps, warmup, shots=None, queries=None, budget_s=150.0):
     from oracle import fs2_oracle as O
 
     cfg = O.BASE_MODEL_CONFIG
@@ -82,12 +101,12 @@ def cpu_arm(steps, warmup, shots=SHOTS, queries=QUERIES, budget_s=150.0):
     torch.set_num_threads(best[0])
     times = []
     total = steps + warmup
-    sample_shots, sample_q = shots, queries
+    sample_shots, sample_q = (SHOTS if shots is None else shots), (QUERIES if queries is None else queries)
     t_start = time.perf_counter()
     for i in range(total):
         sup, qry = O.synth_task(task=i, shots=sample_shots, queries=sample_q, L=L_PHON, T=T_MEL)
         t0 = time.perf_counter()
-        O.maml_task_step(P, cfg, sup, qry, K_INNER, 0.001, first_order=False, drop_seed="torch")
+        O.maml_task_step(P, cfg, sup, qry, K_INNER, 0.001, first_order=FIRST_ORDER, drop_seed="torch")
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append((dt, (sample_shots + sample_q) * T_MEL))
@@ -301,8 +320,10 @@ def run_own_arm(args):
     algo = copy.deepcopy(DEFAULT_ALGORITHM_CONFIG)
     algo["adapt"]["train"]["steps"] = K_INNER
     algo["adapt"]["test"]["steps"] = K_INNER
-    sysm = MetaSystem(None, DEFAULT_MODEL_CONFIG, DEFAULT_TRAIN_CONFIG, algo, n_speaker=16, device=dev, split=split,
-                      dropout=not args.no_dropout, seed=rank)
+    train_cfg = copy.deepcopy(DEFAULT_TRAIN_CONFIG)
+    train_cfg["optimizer"]["grad_acc_step"] = GRAD_ACC
+    sysm = MetaSystem(None, DEFAULT_MODEL_CONFIG, train_cfg, algo, n_speaker=16, device=dev, split=split,
+                      dropout=not args.no_dropout, seed=rank, second_order=not FIRST_ORDER)
     P = O.init_params(seed=0)
     sysm.load_state_dict({k: v.detach() for k, v in P.items()})
     n_steps_total = args.warmup + args.steps
@@ -365,10 +386,11 @@ def run_own_arm(args):
     key, ent = next(iter(sysm._graphs.items()))
     graph = ent[2]
     launches_task = sysm.launches_per_task_step
-    launches_step = launches_task + 2               # + sumsq + adam_clip (the allreduce is NCCL's kernel)
+    launches_step = GRAD_ACC * launches_task + 2    # + sumsq + adam_clip (the allreduce is NCCL's kernel)
 
     def device_step():
-        graph.replay()
+        for _ in range(GRAD_ACC):                   # micro-steps accumulate into the NCCL buffer; one allreduce + Adam per step
+            graph.replay()
         sysm.optimizer_step()
 
     for _ in range(args.warmup):
@@ -388,7 +410,7 @@ def run_own_arm(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = ms.item() / args.steps
-    value = world * frames_per_task() / (ms_per_step * 1e-3)
+    value = world * frames_per_step() / (ms_per_step * 1e-3)
 
     # ---------- (2) end-to-end through the public API with host buffers ----------
     for i in range(min(args.warmup, 3)):
@@ -408,7 +430,8 @@ def run_own_arm(args):
         wait_ms = []
         for i in range(args.steps):
             t0 = time.perf_counter()
-            out = sysm.training_step(batches[i % len(batches)], i)   # H2D of this step's batch + async D2H of its 6 losses
+            for a_ in range(GRAD_ACC):
+                out = sysm.training_step(batches[(i * GRAD_ACC + a_) % len(batches)], i)   # H2D of this step's batch + async D2H of its 6 losses
             sysm.optimizer_step()
             t_host += time.perf_counter() - t0
             pending.append(out)
@@ -438,7 +461,7 @@ def run_own_arm(args):
                   {k_: round(1e3 * v_ / args.steps, 3) for k_, v_ in sysm.host_prof.items()}, file=sys.stderr)
     ms2 = torch.tensor([min(e2e_runs) * args.steps], device=dev)
     e2e_ms = ms2.item() / args.steps
-    e2e_value = world * frames_per_task() / (e2e_ms * 1e-3)
+    e2e_value = world * frames_per_step() / (e2e_ms * 1e-3)
     line = None
     if rank == 0:
         # ---------- (3) roofline of the dominant kernel: record one eager step's GEMM launches, then time each
@@ -484,7 +507,7 @@ def run_own_arm(args):
                 print(f"{ms_g:7.3f} ms {100 * ms_g / tot:5.1f}%  n={n:3d}  {1e3 * ms_g / n:6.1f} us/launch  {fl / ms_g / 1e9:6.1f} TF/s(alg)  "
                       f"{key[0]:28s} MNK/taps/kb/z/terms={key[1]} flags={key[2]} ksplit={key[3]} out={key[4]} {key[5]}", file=sys.stderr)
         sysm.be.zero_(sysm.maml.g_outer)
-        fft_block = fft_block_roofline(sysm, peaks["bf16_tflops"])
+        fft_block = fft_block_roofline(sysm, peaks["bf16_tflops"], B=SHOTS)
         vstats.sort(key=lambda d: -d["ms_per_step"])
         dom = vstats[0]
         gemm_ms = sum(v["ms_per_step"] for v in vstats)
@@ -518,7 +541,7 @@ def run_own_arm(args):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16x3" if split == 3 else "bf16", "data": "synthetic", "config": workload_config(world, split, not args.no_dropout),
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": sysm.h2d_bytes_per_step,
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": GRAD_ACC * sysm.h2d_bytes_per_step,
                         "d2h_bytes_per_step": sysm.d2h_bytes_per_step, "api": f"MetaSystem.training_step(host batch) + optimizer_step; losses read back on the host {args.lag} step(s) later",
                         "runs_ms_per_step": e2e_runs, "host_enqueue_ms_per_step": host_ms},
                 "gpu_launches": launches_step * args.steps, "gpu_launches_per_step": launches_step,
@@ -542,6 +565,9 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--split", type=int, default=3, choices=[1, 3], help="3: bf16x3 (parity-grade, default); 1: plain bf16")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS),
+                    help="config2 = BASELINE configs[1] (the driver's line); config3 / config4 = the K=5 second-order / first-order "
+                         "configurations at full size (extra lines for profiles/)")
     ap.add_argument("--lag", type=int, default=2, help="e2e: the host reads step i-lag's losses after enqueueing step i (1..2)")
     ap.add_argument("--trace-e2e", action="store_true", help="diagnostic: CUDA events around every graph replay of the e2e loop")
     ap.add_argument("--gemm-table", action="store_true", help="diagnostic: per-shape GEMM time table on stderr")
@@ -552,6 +578,7 @@ def main():
                          "--profile-from-start off); prints nothing to judge")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
+    set_workload(args.workload)
     if args.impl == "reference":
         run_reference_arm(args)
     else:
