@@ -301,8 +301,10 @@ def griffin_lim_fm(mag: torch.Tensor, stft_fn: STFT, n_iters: int, init_angles: 
     """Frame-major Griffin-Lim (audio_processing.py:63-82): mag, init_angles [B, F, im_off] on the device -> signal
     [B, hop*(F-1)].  Per iteration: reflect-pad+split, Fourier GEMM, angle+recombine, inverse GEMM, normalise = 5 kernels
     (+ a memset when the inverse GEMM is split along its contraction).  The iteration is a fixed launch sequence on fixed
-    shapes, so on the GPU it is captured ONCE in a CUDA graph (signal buffer in place) and replayed: at one utterance the
-    loop is launch-bound on the host otherwise (measured 0.55 ms per eager iteration for ~0.08 ms of device work)."""
+    shapes, so it CAN be captured in a CUDA graph (`use_graph=True`: signal buffer updated in place, one capture + n-1
+    replays).  Measured on a B200 at 931 frames x 60 iterations (tools/config5_bench.py): eager 7.5 ms (125 us per
+    iteration: the host keeps up), capture + replays 23.9 ms (the capture itself costs more than it saves for a single
+    utterance) — so eager is the default and the graph is worth it only when the caller reuses it for many utterances."""
     B, F_, _ = mag.shape
     X_hi, X_lo = stft_fn.recombine_fm(mag, init_angles, None)
     signal = stft_fn.inverse_fm(X_hi, X_lo, B, F_)
@@ -312,8 +314,6 @@ def griffin_lim_fm(mag: torch.Tensor, stft_fn: STFT, n_iters: int, init_angles: 
         xh, xl = stft_fn.recombine_fm(mag, None, ri)                  # keeps only the angles of the new transform
         return stft_fn.inverse_fm(xh, xl, B, F_)
 
-    if use_graph is None:
-        use_graph = signal.is_cuda and n_iters >= 4
     if not use_graph:
         for _ in range(n_iters):
             signal = iteration(signal)

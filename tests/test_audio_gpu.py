@@ -72,6 +72,13 @@ def test_griffin_lim_vs_reference_goldens(prod):
         r = _rel(a, G[f"gl_audio_{iters}"])
         print(f"[audio] griffin-lim {iters} iterations: rel {r:.2e}")
         assert a.shape == G[f"gl_audio_{iters}"].shape and r < tol
+    # the CUDA-graph form of the loop (one captured iteration replayed) gives the same waveform as the eager loop
+    st = prod.stft_fn
+    spec = st._to_fm(torch.from_numpy(G["gl_spec"])[:, :, :-1])
+    ang = st._to_fm(torch.from_numpy(G["gl_init_angles"]))
+    eager = PA.griffin_lim_fm(spec, st, 8, ang, use_graph=False).clone()
+    graph = PA.griffin_lim_fm(spec, st, 8, ang, use_graph=True)
+    assert _rel(graph, eager.cpu().numpy()) < 1e-5
 
 
 def test_config5_size_griffin_lim_60_iterations(prod):
