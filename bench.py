@@ -304,7 +304,7 @@ def run_own_arm(args):
 
     from meta_tts_b200 import ops as mops
     from meta_tts_b200.systems import DEFAULT_ALGORITHM_CONFIG, DEFAULT_MODEL_CONFIG, DEFAULT_TRAIN_CONFIG, MetaSystem
-    from oracle import fs2_oracle as O   # synthetic task generator + seeded init only (never on the measured path)
+    from meta_tts_b200 import synthetic as SYN   # synthetic tasks + random-init weights (product side; oracle/ is not touched here)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -324,10 +324,10 @@ def run_own_arm(args):
     train_cfg["optimizer"]["grad_acc_step"] = GRAD_ACC
     sysm = MetaSystem(None, DEFAULT_MODEL_CONFIG, train_cfg, algo, n_speaker=16, device=dev, split=split,
                       dropout=not args.no_dropout, seed=rank, second_order=not FIRST_ORDER)
-    P = O.init_params(seed=0)
+    P = SYN.init_state_dict(DEFAULT_MODEL_CONFIG, n_speaker=16, seed=0)
     sysm.load_state_dict({k: v.detach() for k, v in P.items()})
     n_steps_total = args.warmup + args.steps
-    tasks = [O.synth_task(task=rank + world * i, shots=SHOTS, queries=QUERIES, L=L_PHON, T=T_MEL) for i in range(4)]
+    tasks = [SYN.synth_task(task=rank + world * i, shots=SHOTS, queries=QUERIES, L=L_PHON, T=T_MEL) for i in range(4)]
     batches = [[([t[0]], [t[1]])] for t in tasks]
 
     def barrier():

@@ -416,15 +416,28 @@ class FastSpeech2(_B200Module):
 
     def forward(self, speaker_args, texts, src_lens, max_src_len, mels=None, mel_lens=None, max_mel_len=None,
                 p_targets=None, e_targets=None, d_targets=None, p_control=1.0, e_control=1.0, d_control=1.0):
-        assert d_targets is not None and p_targets is not None and e_targets is not None, \
-            "free-running synthesis (predicted durations) is outside the teacher-forced hot path"
         rt = self._rt()
-        B, Lq, T = texts.shape[0], int(max_src_len), int(max_mel_len)
+        B, Lq = texts.shape[0], int(max_src_len)
+        free = d_targets is None
+        assert (p_targets is None) == free and (e_targets is None) == free, "give all of (p, e, d) targets or none of them"
+        if free:
+            # free-running synthesis (fastspeech2.py:73-92 with targets None -> modules.py:85-99,132-139): predicted pitch /
+            # energy / durations; model.eval() -> BatchNorm running statistics, train mode -> batch statistics
+            bt = Batch(spk_ids=rt.dev(speaker_args, torch.int64), average_spk=False, texts=rt.dev(texts, torch.int64),
+                       src_lens=rt.dev(src_lens, torch.int64), mels=None, mel_lens=None, pitches=None, energies=None, durations=None,
+                       B=B, L=Lq, T=0)
+            out = rt.engine.synthesize(rt.params(), bt, rt.engine.new_tape(), p_control, e_control, d_control,
+                                       update_bn=self.training, eval_mode=not self.training)
+            src_masks = get_mask_from_lengths(bt.src_lens, Lq)
+            mel_masks = get_mask_from_lengths(out["mel_len"], int(out["mel"].shape[1]))
+            return (out["mel"], out["postnet"], out["pitch"], out["energy"], out["logd"], out["d_rounded"], src_masks, mel_masks,
+                    bt.src_lens, out["mel_len"])
+        T = int(max_mel_len)
         bt = Batch(spk_ids=rt.dev(speaker_args, torch.int64), average_spk=False, texts=rt.dev(texts, torch.int64),
                    src_lens=rt.dev(src_lens, torch.int64), mels=rt.dev(mels, torch.float32),
                    mel_lens=rt.dev(mel_lens, torch.int64), pitches=rt.dev(p_targets, torch.float32),
                    energies=rt.dev(e_targets, torch.float32), durations=rt.dev(d_targets, torch.int64), B=B, L=Lq, T=T)
-        out = rt.engine.forward(rt.params(), bt, rt.tape(("fs2", B, Lq, T)), update_bn=self.training)
+        out = rt.engine.forward(rt.params(), bt, rt.tape(("fs2", B, Lq, T)), update_bn=self.training, eval_mode=not self.training)
         src_masks = get_mask_from_lengths(bt.src_lens, Lq)
         mel_masks = get_mask_from_lengths(bt.mel_lens, T)
         return (out["mel"], out["postnet"], out["pitch"], out["energy"], out["logd"], bt.durations, src_masks, mel_masks,

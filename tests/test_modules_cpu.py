@@ -80,3 +80,28 @@ def test_product_modules_refuse_to_run_without_gpu(pre_cfg):
     enc = M.Encoder(CFG)
     with pytest.raises(Exception):
         enc(torch.ones(1, 4, dtype=torch.long), torch.zeros(1, 4, dtype=torch.bool))
+
+
+def test_free_running_forward_matches_oracle(pre_cfg):
+    """`FastSpeech2.forward(spk, texts, src_lens, max_src_len)` without targets (fastspeech2.py:73-92): eval and train mode."""
+    be = RefOps(split=3)
+    M._B200Module._backend = be
+    try:
+        torch.manual_seed(0)
+        model = M.FastSpeech2(pre_cfg, CFG, ALGO)
+        sd = model.state_dict()
+        sd["variance_adaptor.duration_predictor.linear_layer.bias"] = sd["variance_adaptor.duration_predictor.linear_layer.bias"] + 1.3
+        model.load_state_dict(sd)
+        b12 = O.synth_batch(2, 7, 20, seed=4, speaker=1, ragged=True)
+        for train in (False, True):
+            model.train(train)
+            P = {k: v.detach().clone() for k, v in model.state_dict().items()}
+            with torch.no_grad():
+                ref = O.fs2_forward(P, CFG, *b12[2:6], d_control=1.2, training=train)
+            out = model(*b12[2:6], d_control=1.2)
+            assert torch.equal(out[5], ref[5]) and torch.equal(out[9], ref[9]) and int(ref[9].max()) > 7
+            assert torch.equal(out[6], ref[6]) and torch.equal(out[7], ref[7])
+            for i in range(5):
+                assert out[i].shape == ref[i].shape and _rel(out[i], ref[i]) < 5e-5, (train, i)
+    finally:
+        M._B200Module._backend = None

@@ -13,7 +13,7 @@ from meta_tts_b200 import audio as PA  # noqa: E402
 from meta_tts_b200 import ops as _ops  # noqa: E402
 from meta_tts_b200.maml import batch_from_tuple  # noqa: E402
 from meta_tts_b200.systems import DEFAULT_ALGORITHM_CONFIG, DEFAULT_MODEL_CONFIG, DEFAULT_TRAIN_CONFIG, MetaSystem  # noqa: E402
-from oracle import fs2_oracle as O  # noqa: E402  (synthetic task generator + seeded init only)
+from meta_tts_b200 import synthetic as O  # noqa: E402  (synthetic task generator + random-init weights)
 
 
 def timed(fn, reps=3):
@@ -35,7 +35,7 @@ def main():
     algo["adapt"]["train"]["steps"] = 5
     algo["adapt"]["test"] = {"steps": 20, "saving_steps": [20]}
     sysm = MetaSystem(None, DEFAULT_MODEL_CONFIG, DEFAULT_TRAIN_CONFIG, algo, n_speaker=16, device="cuda:0", use_cuda_graph=False, dropout=True, seed=0)
-    P = O.init_params(seed=0)
+    P = O.init_state_dict(DEFAULT_MODEL_CONFIG, seed=0)
     P["variance_adaptor.duration_predictor.linear_layer.bias"] = P["variance_adaptor.duration_predictor.linear_layer.bias"] + 2.0   # ~6.4 frames / phoneme
     sysm.load_state_dict(P)
     sup, qry = O.synth_task(task=9, shots=16, queries=1, L=128, T=864)
