@@ -302,6 +302,9 @@ class BMat:
     f32: Optional[torch.Tensor] = None
 
 
+# Narrow tiles + deeper split-K for SMALL accumulate GEMMs: measured on B200 12.00 ms/step vs 11.87 with the widest-tile rule
+# (the extra CTAs of the off-critical-path weight gradients take SMs from the main chain), so it stays off.
+SMALL_SPLITK_MODEL = os.environ.get("MTTS_SMALL_SPLITK", "0") == "1"
 USE_PAIR = True        # 2-CTA (cta_group::2) tiles; set False to fall back to the 1-CTA kernel everywhere
 
 
@@ -326,17 +329,27 @@ def _pick_cfg(mt: int, nz: int, N: int, k_iters: int, can_splitk: bool):
         rows = 2 * ((mt + 1) // 2) if pair else mt
         return nz * rows * ((N + bn - 1) // bn)
 
-    if can_splitk:
-        o = opts[0]                      # widest tile; fill the machine along the contraction instead
-        ks = max(1, min(148 // max(ctas(o), 1), max(1, k_iters // 6), 16))
-        return o[0], o[1], ks
     # no split-K: in-graph launch-time model fitted to tools/gemm_floor.py on B200 (profiles/r01_gemm_floor_in_graph.txt):
     # a wave costs  fixed(tile) + k_iters * per_iter(tile)  and a launch runs ceil(ctas / 148) waves.  (The former
     # ">= 96 CTAs" rule picked 128-wide pairs for the QKV projection: 23.9 us where the 256-wide pair takes 16.2.)
     fixed = {(64, False): 5.9, (128, False): 7.2, (128, True): 7.8, (256, False): 11.0, (256, True): 11.0}
     # us per k-block: narrow tiles and the 128-wide pair run two k-blocks per stage fill (KD = 2)
     per_it = {(64, False): 0.59, (128, False): 0.80, (128, True): 0.55, (256, False): 1.5, (256, True): 0.87}
+    if can_splitk:
+        o = opts[0]                      # widest tile; fill the machine along the contraction instead
+        ks = max(1, min(148 // max(ctas(o), 1), max(1, k_iters // 6), 16))
+        if SMALL_SPLITK_MODEL and ctas(o) * ks < 48:
+            # a small accumulate GEMM (weight gradients of the 256-wide layers on 512 ... 3456 rows): the widest tile leaves
+            # it on a handful of CTAs that each pay the 11 us fixed cost of a 256-wide tile; narrower tiles split further
+            # along the contraction reach more SMs with a cheaper prologue / epilogue
+            def cost_k(o2):
+                c = max(ctas(o2), 1)
+                k2 = max(1, min(148 // c, max(1, k_iters // 2), 16))
+                return fixed[o2] + -(-k_iters // k2) * per_it[o2] + 0.15 * k2, k2     # + red traffic of k2 partial tiles
 
+            o = min(opts, key=lambda o2: cost_k(o2)[0])
+            ks = cost_k(o)[1]
+        return o[0], o[1], ks
     def cost(o):
         waves = -(-ctas(o) // 148)
         return (fixed[o] + k_iters * per_it[o]) * (1.0 + 0.7 * (waves - 1))   # later waves overlap the previous one's tail
