@@ -69,3 +69,73 @@ def test_two_ranks_equal_one_rank_accumulating():
     assert ((g1 - g2).norm() / g1.norm()).item() < 1e-6
     assert ((m.theta - th2).abs().max()).item() < 1e-6
     assert (m.theta - _engine().theta).abs().max().item() > 1e-7      # the update moved the weights (lr(step 0) = 2.5e-7)
+
+
+# ---- iMAML: clip on each rank, THEN mean-reduce, then a plain Adam step (lightning/systems/imaml.py:123-147) ------------------------
+def _imaml_system():
+    import copy
+
+    from meta_tts_b200.imaml import IMAMLSystem
+    from meta_tts_b200.systems import DEFAULT_ALGORITHM_CONFIG, DEFAULT_TRAIN_CONFIG
+    algo = copy.deepcopy(DEFAULT_ALGORITHM_CONFIG)
+    algo["adapt"]["train"]["steps"] = 2
+    algo["adapt"]["test"]["steps"] = 2
+    algo["adapt"]["imaml"] = {"batch_size": 2, "reg_param": 1.0, "K": 2, "stochastic": False}
+    s = IMAMLSystem(None, CFG, DEFAULT_TRAIN_CONFIG, algo, n_speaker=16, device="cpu", backend=RefOps(split=3), dropout=False)
+    s.load_state_dict({k: v.detach().clone() for k, v in O.init_params(seed=0, model_config=CFG).items()})
+    return s
+
+
+def _imaml_batch(t):
+    sup, qry = O.synth_task(task=t + 3, shots=2, queries=2, L=5, T=12, ragged=True)
+    return [([sup], [qry])]
+
+
+def _imaml_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    s = _imaml_system()
+    torch.manual_seed(7)
+    s.training_step(_imaml_batch(rank), 0)
+    if rank == 0:
+        q.put(s.maml.theta.numpy().copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_imaml_two_ranks_clip_then_mean():
+    from meta_tts_b200.imaml import Task, imaml_adapt, imaml_hypergradient
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_imaml_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    th2 = torch.from_numpy(q.get(timeout=500))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    torch.set_num_threads(4)
+    # one process: each task's hypergradient from the meta parameters, clipped by ITS OWN norm, averaged, plain Adam
+    acc = None
+    for t in range(world):
+        s1 = _imaml_system()
+        torch.manual_seed(7)
+        b = _imaml_batch(t)
+        task = Task(b[0][0][0], b[0][1][0], batch_size=2)
+        imaml_adapt(s1.maml, task, 2, 1.0)
+        imaml_hypergradient(s1.maml, task, b[0][0][0], b[0][1][0], 2, 1.0, 2, False)
+        g = s1.maml.g_task.clone()
+        coef = min(1.0, 1.0 / (float(g.norm()) + 1e-6))
+        acc = coef * g / world if acc is None else acc + coef * g / world
+    ref = _imaml_system()
+    ref.maml.g_outer.copy_(acc)
+    ref.maml.outer_update(1.0, 0.0)
+    assert (ref.maml.theta - th2).abs().max().item() < 1e-6
+    assert (th2 - _imaml_system().maml.theta).abs().max().item() > 1e-7
