@@ -282,11 +282,16 @@ def encoder(P: Params, cfg, src_seq, mask, drop_seed: Optional[int] = None):
     return x
 
 
-def decoder(P: Params, cfg, enc_seq, mask, drop_seed: Optional[int] = None):
-    """transformer/Models.py:139-171 (training branch: truncate to max_seq_len)."""
-    max_len = min(enc_seq.shape[1], cfg["max_seq_len"])
-    x = enc_seq[:, :max_len, :] + P["decoder.position_enc"][:, :max_len, :]
-    mask = mask[:, :max_len]
+def decoder(P: Params, cfg, enc_seq, mask, drop_seed: Optional[int] = None, training: bool = True):
+    """transformer/Models.py:139-171: train mode truncates to max_seq_len (:161-166); under model.eval() a longer sequence
+    keeps its length and gets a freshly computed sinusoid table (:148-156)."""
+    if not training and enc_seq.shape[1] > cfg["max_seq_len"]:
+        max_len = enc_seq.shape[1]
+        x = enc_seq + sinusoid_table(max_len, enc_seq.shape[2])[:max_len, :].unsqueeze(0).to(enc_seq.dtype)
+    else:
+        max_len = min(enc_seq.shape[1], cfg["max_seq_len"])
+        x = enc_seq[:, :max_len, :] + P["decoder.position_enc"][:, :max_len, :]
+        mask = mask[:, :max_len]
     for i in range(cfg["transformer"]["decoder_layer"]):
         x = fft_block(P, f"decoder.layer_stack.{i}", x, mask, cfg["transformer"]["decoder_head"],
                       cfg["transformer"]["decoder_dropout"], drop_seed)
@@ -390,7 +395,7 @@ def fs2_forward(P: Params, cfg, speaker_args, texts, src_lens, max_src_len, mels
         P, output, src_masks, mel_masks, max_mel_len, p_targets, e_targets, d_targets, p_control, e_control, d_control,
         cfg["variance_predictor"]["dropout"], drop_seed)
     output = output + spk_emb.unsqueeze(1).expand(-1, int(max(mel_lens_out)), -1)   # base_adaptor.py:80-84
-    output, mel_masks = decoder(P, cfg, output, mel_masks, drop_seed)
+    output, mel_masks = decoder(P, cfg, output, mel_masks, drop_seed, training)
     output = F.linear(output, P["mel_linear.weight"], P["mel_linear.bias"])
     postnet_output = postnet(P, output, training, drop_seed) + output
     return (output, postnet_output, p_pred, e_pred, log_d_pred, d_rounded, src_masks, mel_masks, src_lens, mel_lens_out)

@@ -99,3 +99,33 @@ def test_config5_full_size(cuda_device):
     torch.cuda.synchronize()
     print(f"[config5] Griffin-Lim x60 on {T} frames: {ev0.elapsed_time(ev1):.1f} ms")
     assert wav.shape == (256 * (T - 2),) and bool(torch.isfinite(torch.from_numpy(wav)).all())
+
+
+def test_sequences_at_and_beyond_max_seq_len(cuda_device):
+    """Maximum sizes: a teacher-forced batch of exactly max_seq_len = 1000 frames, and free-running synthesis that predicts MORE
+    than max_seq_len frames — eval mode keeps the length with a recomputed sinusoid table (Models.py:148-156), train mode keeps
+    the first 1000 frames while mel_len reports the full sum of durations (Models.py:161-166)."""
+    from meta_tts_b200.maml import batch_from_tuple
+    cfg = O.small_model_config(1, 1)
+    P = talkative_params(cfg)
+    P["variance_adaptor.duration_predictor.linear_layer.bias"] = P["variance_adaptor.duration_predictor.linear_layer.bias"] + 1.2   # ~ 11 frames / phoneme
+    sysm = _system(cfg, 1, 1, (1,), False)
+    sysm.load_state_dict({k: v.detach().clone() for k, v in P.items()})
+    sup, qry = O.synth_task(task=4, shots=1, queries=1, L=120, T=1000)
+    m = sysm.maml
+    out = m.predict(batch_from_tuple(qry, "cuda:0", spk_ids=sup[2], average_spk=True), adapted=False, eval_mode=True)
+    with torch.no_grad():
+        ref = O.fs2_forward({k: v.detach().clone() for k, v in P.items()}, cfg, sup[2], *qry[3:], average_spk_emb=True, training=False)
+    assert rel(out["postnet"], ref[1]) < 1e-3 and out["postnet"].shape[1] == 1000
+    bt = batch_from_tuple(qry, "cuda:0", spk_ids=sup[2], average_spk=True, targets=False)
+    for train in (False, True):
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        out = m.predict(bt, adapted=False, free_running=True, eval_mode=not train)
+        with torch.no_grad():
+            ref = O.fs2_forward(sd, cfg, sup[2], *qry[3:6], average_spk_emb=True, training=train)
+        total = int(ref[9].max())
+        assert total > 1000, total
+        assert torch.equal(out["d_rounded"].cpu(), ref[5]) and torch.equal(out["mel_len"].cpu(), ref[9])
+        assert out["postnet"].shape == ref[1].shape and out["postnet"].shape[1] == (1000 if train else total)
+        print(f"[adapt] beyond max_seq_len ({total} frames), train={train}: postnet rel {rel(out['postnet'], ref[1]):.2e}")
+        assert rel(out["postnet"], ref[1]) < 1e-3
