@@ -784,6 +784,29 @@ extern "C" int mtts_rowdot_bwd(const float* dout, const float* ddout, const floa
   return MTTS_OK;
 }
 
+// Forward softmax for rows LONGER than 1024 keys: only reachable under model.eval(), where a sequence beyond max_seq_len keeps
+// its length (Models.py:148-156) — three passes over the row (max, sum, write), one warp per row; no backward forms exist
+// because train mode truncates to max_seq_len (Models.py:161-166).
+__global__ void __launch_bounds__(ROW_THREADS) softmax_long_fwd_kernel(const float* __restrict__ A, const int64_t* __restrict__ klens, int H, int Lq,
+                                                                       int Lk, int ld, long long rows, bf16* __restrict__ o_hi,
+                                                                       bf16* __restrict__ o_lo) {
+  pdl_enter();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long r = static_cast<long long>(blockIdx.x) * ROW_WARPS + warp; r < rows; r += static_cast<long long>(gridDim.x) * ROW_WARPS) {
+    const int b = static_cast<int>((r / Lq) / H);
+    const int kl = klens ? static_cast<int>(min(static_cast<long long>(Lk), static_cast<long long>(klens[b]))) : Lk;
+    const long long base = r * ld;
+    float m = -INFINITY;
+    for (int j = lane; j < kl; j += 32) m = fmaxf(m, A[base + j]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int j = lane; j < kl; j += 32) s += __expf(A[base + j] - m);
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+    for (int j = lane; j < ld; j += 32) st_split(o_hi, o_lo, base + j, j < kl ? __expf(A[base + j] - m) * inv : 0.f);
+  }
+}
+
 extern "C" int mtts_softmax(int mode, const float* A, const float* Bm, const void* p_hi, const void* p_lo, const void* pd_hi,
                             const void* pd_lo, const int64_t* klens, int nz, int H, int Lq, int Lk, int ld, void* o_hi,
                             void* o_lo, mtts_stream stream_) {
@@ -792,7 +815,13 @@ extern "C" int mtts_softmax(int mode, const float* A, const float* Bm, const voi
   MTTS_REQUIRE(mode == 0 || p_hi, "softmax: mode %d needs P", mode);
   MTTS_REQUIRE(mode != 2 || (pd_hi && Bm), "softmax: mode 2 needs Pdot and ddP");
   const long long rows = static_cast<long long>(nz) * Lq;
-  MTTS_REQUIRE(ld <= 1024, "softmax: rows longer than 1024 keys are not supported (max_seq_len = 1000)");
+  if (ld > 1024) {
+    MTTS_REQUIRE(mode == 0, "softmax: rows longer than 1024 keys exist only in eval-mode forwards (train mode truncates to max_seq_len)");
+    MTTS_CHECK_CUDA(mtts_launch(softmax_long_fwd_kernel, dim3(row_grid(rows)), dim3(ROW_THREADS), 0, s, A, klens, H, Lq, Lk, ld, rows,
+                                static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo)));
+    MTTS_CHECK_LAUNCH();
+    return MTTS_OK;
+  }
 #define SM_LAUNCH_M(NPL, MODE)                                                                                                  \
   MTTS_CHECK_CUDA(mtts_launch(softmax_kernel<NPL, MODE>, dim3(row_grid(rows)), dim3(ROW_THREADS), 0, s, mode, A, Bm, static_cast<const bf16*>(p_hi),                  \
                                                               static_cast<const bf16*>(p_lo), static_cast<const bf16*>(pd_hi), \

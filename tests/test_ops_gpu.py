@@ -154,6 +154,22 @@ def test_softmax_family(cuda_device, Lq, ld):
     _hl_check(c2[13], c2[14], g2[13], g2[14])
 
 
+def test_softmax_long_rows_forward_only(cuda_device):
+    """Rows longer than 1024 keys (eval-mode sequences beyond max_seq_len, Models.py:148-156): forward works, the backward /
+    tangent forms refuse (train mode truncates to max_seq_len, so they cannot occur)."""
+    B, H, Lq, ld = 1, 2, 1573, 1576
+    nz = B * H
+    kl = torch.tensor([1500])
+    S = 3 * R_(nz, Lq, ld, seed=1)
+    S[..., Lq:] = float("nan")
+    c, g = _both(cuda_device, "softmax", [0, S, None, None, None, None, None, kl, nz, H, Lq, Lq, ld, bf(nz, Lq, ld), bf(nz, Lq, ld)], skip=(1, 2))
+    _hl_check(c[13], c[14], g[13], g[14])
+    from meta_tts_b200.lib import MttsError
+    with pytest.raises(MttsError):
+        CudaOps(split=3).softmax(1, S.to(cuda_device), None, g[13].to(cuda_device), g[14].to(cuda_device), None, None, kl.to(cuda_device), nz, H,
+                                 Lq, Lq, ld, bf(nz, Lq, ld).to(cuda_device), bf(nz, Lq, ld).to(cuda_device))
+
+
 def test_gathers_and_sums(cuda_device):
     B, T, C, V = 3, 11, 256, 40
     R = B * T
