@@ -1,6 +1,6 @@
 """Roofline of the HBM-bound kernels (GPU tool): each kernel is launched back to back on ROTATING buffer sets whose total size
 exceeds 2x the 126 MB L2, so every launch streams cold data; achieved GB/s = algorithmic bytes (stated per kernel below) / average
-launch time (CUDA events), against the measured copy bandwidth in MEASURED_PEAKS.json.  Sizes are those of BASELINE configs[1]
+launch time (CUDA events around CUDA-graph replays of the launch sequence), against the measured copy bandwidth in MEASURED_PEAKS.json.  Sizes are those of BASELINE configs[1]
 (4 utterances x 864 frames, 256 / 512 / 1024 channels; 34.65 M parameters).  Writes a markdown table (profiles/ material)."""
 import json
 import os
@@ -29,12 +29,18 @@ def run(name, bytes_per_launch, make, launch, note, rows):
     for s in sets[:2]:
         launch(s)
     torch.cuda.synchronize()
+    # the launches are replayed from a CUDA graph: eager ctypes launches cost ~8 us of host time each, more than the small kernels run
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for s in sets:
+            launch(s)
+    graph.replay()
+    torch.cuda.synchronize()
     reps = max(3, 200 // nset)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        for s in sets:
-            launch(s)
+        graph.replay()
     e1.record()
     torch.cuda.synchronize()
     us = 1e3 * e0.elapsed_time(e1) / (reps * nset)
