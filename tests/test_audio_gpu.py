@@ -78,7 +78,7 @@ def test_griffin_lim_vs_reference_goldens(prod):
     ang = st._to_fm(torch.from_numpy(G["gl_init_angles"]))
     eager = PA.griffin_lim_fm(spec, st, 8, ang, use_graph=False).clone()
     graph = PA.griffin_lim_fm(spec, st, 8, ang, use_graph=True)
-    assert _rel(graph, eager.cpu().numpy()) < 1e-5
+    assert _rel(graph, eager.cpu().numpy()) < 2e-4      # (not bit-equal: the split-K inverse GEMM reduces with fp32 atomics)
 
 
 def test_config5_size_griffin_lim_60_iterations(prod):
