@@ -223,8 +223,36 @@ __global__ void bn_reduce_kernel(BnArgs a, float* __restrict__ ws) {
   if (MODE == 4) { atomicAdd(ws + 2 * a.C + c, s2); atomicAdd(ws + 3 * a.C + c, s3); }
 }
 
+// Batch statistics in ONE pass over x: shifted sums  sum(x - s), sum((x - s)^2)  with the per-channel shift s = x[0, c]
+// (a value of the same magnitude as the mean, so the textbook cancellation of E[x^2] - E[x]^2 does not arise:
+// var = (S2 - S1^2/R)/R loses ~log2(1 + (s - mean)^2/var) bits, a handful for any realistic activation).  Four rows are
+// in flight per thread (the row loop is otherwise a chain of dependent-latency loads: 12 us for 7 MB).
+__global__ void bn_stats_kernel(const float* __restrict__ x, long long R, int C, int rows_per_cta, float* __restrict__ ws) {
+  pdl_enter();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_cta;
+  const long long r1 = min(R, r0 + rows_per_cta);
+  const float sh = x[c];
+  float s1 = 0.f, s2 = 0.f;
+  long long r = r0;
+  for (; r + 4 <= r1; r += 4) {
+    const float v0 = x[r * C + c], v1 = x[(r + 1) * C + c], v2 = x[(r + 2) * C + c], v3 = x[(r + 3) * C + c];
+    const float d0 = v0 - sh, d1 = v1 - sh, d2 = v2 - sh, d3 = v3 - sh;
+    s1 += (d0 + d1) + (d2 + d3);
+    s2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+  }
+  for (; r < r1; ++r) {
+    const float d = x[r * C + c] - sh;
+    s1 += d;
+    s2 += d * d;
+  }
+  atomicAdd(ws + c, s1);
+  atomicAdd(ws + C + c, s2);
+}
+
 // forward apply: y = (x-mean)*rstd*gamma + beta; o = tanh? tanh(y) : y ; running stats update by CTA row 0
-__global__ void bn_fwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ ws /*sum x, sum (x-mean)^2*/,
+__global__ void bn_fwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ ws /*shifted sums: sum(x-s), sum((x-s)^2), s = x[0,c]*/,
                                     const float* __restrict__ gamma, const float* __restrict__ beta, long long R, int C,
                                     float eps, float momentum, int tanh_flag, float* __restrict__ running_mean,
                                     float* __restrict__ running_var, float* __restrict__ stats, float* __restrict__ out,
@@ -232,8 +260,10 @@ __global__ void bn_fwd_apply_kernel(const float* __restrict__ x, const float* __
   pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float mean = ws[c] / R;
-  const float var = ws[C + c] / R;
+  const float invR = 1.f / static_cast<float>(R);
+  const float m1 = ws[c] * invR;
+  const float mean = x[c] + m1;
+  const float var = fmaxf(ws[C + c] * invR - m1 * m1, 0.f);
   const float rstd = rsqrtf(var + eps);
   if (blockIdx.y == 0) {
     stats[c] = mean;
@@ -247,9 +277,8 @@ __global__ void bn_fwd_apply_kernel(const float* __restrict__ x, const float* __
   const float g = gamma[c], b = beta[c];
   const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_cta;
   const long long r1 = min(R, r0 + rows_per_cta);
-  for (long long r = r0; r < r1; ++r) {
-    const long long i = r * C + c;
-    float y = (x[i] - mean) * rstd * g + b;
+  auto emit = [&](long long i, float xv) {
+    float y = (xv - mean) * rstd * g + b;
     if (tanh_flag) y = tanhf(y);
     y *= drop_factor(drop, static_cast<uint32_t>(i));
     if (out) out[i] = y;
@@ -259,7 +288,17 @@ __global__ void bn_fwd_apply_kernel(const float* __restrict__ x, const float* __
       hi[i] = h;
       if (lo) lo[i] = l;
     }
+  };
+  long long r = r0;
+  for (; r + 4 <= r1; r += 4) {                   // four independent loads in flight per thread
+    const long long i0 = r * C + c;
+    const float v0 = x[i0], v1 = x[i0 + C], v2 = x[i0 + 2LL * C], v3 = x[i0 + 3LL * C];
+    emit(i0, v0);
+    emit(i0 + C, v1);
+    emit(i0 + 2LL * C, v2);
+    emit(i0 + 3LL * C, v3);
   }
+  for (; r < r1; ++r) emit(r * C + c, x[r * C + c]);
 }
 // backward apply: dx = rstd*gamma*(g - m1 - xh*m2); dgamma += sum g*xh; dbeta += sum g
 __global__ void bn_bwd_apply_kernel(BnArgs a, const float* __restrict__ ws, const float* __restrict__ gamma,
@@ -650,8 +689,7 @@ extern "C" int mtts_bn_fwd(const float* x, const float* gamma, const float* beta
   a.x = x; a.R = R; a.C = C; a.tanh_flag = tanh_flag; a.rows_per_cta = rpc; a.ws_in = ws;
   a.drop = DropSite{drop_thr, drop_seed, drop_scale, drop_salt};
   MTTS_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s));
-  MTTS_CHECK_CUDA(mtts_launch(bn_reduce_kernel<0>, dim3(grid), dim3(block), 0, s, a, ws));
-  MTTS_CHECK_CUDA(mtts_launch(bn_reduce_kernel<1>, dim3(grid), dim3(block), 0, s, a, ws + C));
+  MTTS_CHECK_CUDA(mtts_launch(bn_stats_kernel, dim3(grid), dim3(block), 0, s, x, R, C, rpc, ws));
   MTTS_CHECK_CUDA(mtts_launch(bn_fwd_apply_kernel, dim3(grid), dim3(block), 0, s, x, ws, gamma, beta, R, C, eps, momentum, tanh_flag, running_mean, running_var, stats,
                                              out, static_cast<bf16*>(hi), static_cast<bf16*>(lo), rpc, a.drop));
   MTTS_CHECK_LAUNCH();

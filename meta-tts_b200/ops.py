@@ -291,7 +291,7 @@ class CudaOps:
         t.zero_()          # cudaMemsetAsync on the current stream
 
     # kernels launched per C-ABI call (memsets not counted)
-    KERNELS = {"mtts_bn_fwd": 3, "mtts_bn_bwd": 2, "mtts_bn_tfwd": 2, "mtts_bn_tbwd": 2, "mtts_loss_fwd": 2}
+    KERNELS = {"mtts_bn_fwd": 2, "mtts_bn_bwd": 2, "mtts_bn_tfwd": 2, "mtts_bn_tbwd": 2, "mtts_loss_fwd": 2}
 
     def _call(self, name, *args):
         global launch_count
