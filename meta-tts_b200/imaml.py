@@ -24,7 +24,7 @@ import torch
 from torch.utils.data import BatchSampler, RandomSampler
 
 from .collate import split_reprocess
-from .engine import Batch, ParamSet
+from .engine import ParamSet
 from .maml import batch_from_tuple
 from . import systems as S
 

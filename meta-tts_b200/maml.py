@@ -18,12 +18,11 @@ The whole task step is a fixed launch sequence on static buffers => captured onc
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, List, Optional, Sequence
 
 import torch
 
-from .engine import Batch, FS2Engine, N_MEL, ParamLayout, ParamSet, Tape, const_names
+from .engine import Batch, FS2Engine, ParamLayout, ParamSet, Tape, const_names
 
 
 def batch_from_tuple(b12, device, spk_ids=None, average_spk=False, targets: bool = True) -> Batch:

@@ -21,8 +21,7 @@ buffers (pinned H2D) and reads back the 6 query losses.
 """
 from __future__ import annotations
 
-import os
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Tuple
 
 import time
 

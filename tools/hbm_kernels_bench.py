@@ -9,7 +9,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from meta_tts_b200.ops import CudaOps, NO_DROP  # noqa: E402
+from meta_tts_b200.ops import CudaOps  # noqa: E402
 
 DEV = "cuda:0"
 L2 = 126e6
