@@ -129,3 +129,41 @@ def test_sequences_at_and_beyond_max_seq_len(cuda_device):
         assert out["postnet"].shape == ref[1].shape and out["postnet"].shape[1] == (1000 if train else total)
         print(f"[adapt] beyond max_seq_len ({total} frames), train={train}: postnet rel {rel(out['postnet'], ref[1]):.2e}")
         assert rel(out["postnet"], ref[1]) < 1e-3
+
+
+def test_against_goldens_from_the_real_reference_modules(cuda_device):
+    """Free-running synthesis (eval / train, within and beyond max_seq_len) and the test-step protocol straight against
+    tests/golden/synth_golden.npz, produced by the REAL reference modules (oracle/make_golden_synth.py)."""
+    import os
+
+    import numpy as np
+    from meta_tts_b200.maml import batch_from_tuple
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "synth_golden.npz"), allow_pickle=False)
+    cfg = O.BASE_MODEL_CONFIG
+    t, S, Q, L, T = [int(v) for v in G["task_cfg"]]
+    sup, qry = O.synth_task(task=t, shots=S, queries=Q, L=L, T=T, ragged=True)
+
+    def fresh(steps=2, total=4):
+        P = O.init_params(seed=0)
+        P["variance_adaptor.duration_predictor.linear_layer.bias"] = P["variance_adaptor.duration_predictor.linear_layer.bias"] + float(G["bias"])
+        s = _system(cfg, steps, total, (2, 4), False)
+        s.load_state_dict(P)
+        return s
+
+    def check(tag, post, d_rounded, mel_len, tol):
+        assert tuple(post.shape) == tuple(int(v) for v in G[f"{tag}_shape"]), tag
+        assert np.array_equal(d_rounded.float().cpu().numpy(), G[f"{tag}_d_rounded"]) and np.array_equal(mel_len.cpu().numpy(), G[f"{tag}_mel_len"]), tag
+        r = rel(post[:, ::8], torch.from_numpy(G[f"{tag}_postnet"]))
+        print(f"[adapt] real-reference golden {tag}: T = {post.shape[1]}, postnet rel {r:.2e}")
+        assert r < tol, (tag, r)
+
+    bt = batch_from_tuple(qry, "cuda:0", spk_ids=sup[2], average_spk=True, targets=False)
+    for tag, train, dc in (("free_eval", False, 1.0), ("free_train", True, 1.0), ("free_eval_long", False, 12.0), ("free_train_long", True, 12.0)):
+        out = fresh().maml.predict(bt, adapted=False, free_running=True, eval_mode=not train, d_control=dc)
+        check(tag, out["postnet"], out["d_rounded"], out["mel_len"], 1e-3)
+    outs = fresh().test_step([([sup], [qry])], 0)[0]
+    for k in ("step_0", "step_2", "step_4"):
+        o = outs[k]["synth"]["output"]
+        check(f"tta_{k}_synth", o[1], o[5], o[9], 1e-3 if k == "step_0" else 5e-3)
+        got = torch.stack([x.cpu() for x in outs[k]["recon"]["losses"]])
+        assert rel(got, torch.from_numpy(G[f"tta_{k}_losses"]).float()) < (1e-3 if k == "step_0" else 5e-3), k
