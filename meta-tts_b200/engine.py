@@ -268,6 +268,57 @@ class Tape:
         return sum(t.numel() * t.element_size() for t in self.t.values())
 
 
+class TapeView:
+    """Utterances [b0, b1) of a batch-major Tape: every buffer whose leading extent is B or B*T rows is allocated for the FULL
+    batch in the parent tape and handed out as the contiguous slice of this group, so a pass may fill (or read) the tape
+    group by group on concurrent chains while every other pass keeps seeing ordinary full-batch buffers."""
+
+    def __init__(self, parent: "Tape", b0: int, b1: int, B: int, rows_per_item: int):
+        self.p, self.b0, self.b1, self.B = parent, b0, b1, B
+        self.split = parent.split
+        self.row0 = b0 * rows_per_item           # first token row of the group (dropout element indices are global)
+
+    @property
+    def drop_pass(self):
+        return getattr(self.p, "drop_pass", None)
+
+    def buf(self, name, shape, dtype=torch.float32, zero=False):
+        nb = self.b1 - self.b0
+        assert shape[0] % nb == 0, f"tape view: {name} {tuple(shape)} is not batch-major"
+        k = shape[0] // nb
+        full = self.p.buf(name, (k * self.B,) + tuple(shape[1:]), dtype, zero)
+        return full[self.b0 * k:self.b1 * k]
+
+    def f32(self, name, shape):
+        return self.buf(name + ":f", shape)
+
+    def bf(self, name, shape):
+        hi = self.buf(name + ":h", shape, torch.bfloat16)
+        lo = self.buf(name + ":l", shape, torch.bfloat16) if self.split == 3 else None
+        return hi, lo
+
+    def act(self, name, B, T, C, f32=True, bf=True) -> Act:
+        f = self.f32(name, (B, T, C)) if f32 else None
+        h, l = self.bf(name, (B, T, C)) if bf else (None, None)
+        return Act(f, h, l, B, T, C)
+
+
+def _act_rows(a: Optional[Act], b0: int, b1: int) -> Optional[Act]:
+    if a is None:
+        return None
+    sl = lambda t: None if t is None else t[b0:b1]  # noqa: E731
+    return Act(sl(a.f32), sl(a.hi), sl(a.lo), b1 - b0, a.T, a.C)
+
+
+# Forward-type passes (forward, tangent forward) of the FFT stacks run as TWO concurrent chains over half of the utterances each
+# when the batch is small: per-kernel latency (launch + prologue + epilogue, 5-11 us) dominates the under-filled GEMMs of a 4-utterance
+# batch, so two half-size chains finish in about the time of one (DESIGN.md section 6).  Backward-type passes keep one chain: there
+# the weight-gradient GEMMs already run beside the data-gradient chain and fill the machine.
+SPLIT_FWD = os.environ.get("MTTS_SPLIT_FWD", "0") == "1"
+SPLIT_FWD_MAX_ROWS = 8192
+_HASH_G_INV = pow(0x9E3779B9, -1, 1 << 32)       # the dropout hash adds element_index to seed * 0x9E3779B9 (mod 2^32)
+
+
 @dataclass
 class Batch:
     """Device-resident teacher-forced batch (the reference 12-tuple's tensor fields, collate.py:47-60)."""
@@ -524,16 +575,22 @@ class FS2Engine:
 
     # ---- dropout sites (include/mtts.h): launch scalar = crc32(site) ^ (pass_index * 2654435761); the device adds the
     #      per-step salt.  The pass index lives on the primal tape, so every pass over it draws the same mask. ----
-    def _site(self, tp: Tape, site: str, p: float):
+    def _site(self, tp: Tape, site: str, p: float, C: int = 0):
         idx = getattr(tp, "drop_pass", None)
         if idx is None or p <= 0.0:
             return NO_DROP
         scalar = (zlib.crc32(site.encode()) ^ ((int(idx) * 2654435761) & 0xFFFFFFFF)) & 0xFFFFFFFF
+        row0 = getattr(tp, "row0", 0)
+        if row0:
+            # a group of utterances launched on its own: the kernel numbers its elements from 0, the mask is defined on the index
+            # in the full batch.  keep(i + off) hashes (i + off + seed_eff * G) mod 2^32 = (i + (seed_eff + off * G^-1) * G), so the
+            # element offset folds into the launch-time seed.
+            scalar = (scalar + row0 * C * _HASH_G_INV) & 0xFFFFFFFF
         return (int(p * (1 << 24)), scalar, 1.0 / (1.0 - p))
 
     def _fft_drop(self, tp: Tape, pf: str):
         p = self.cfg["transformer"]["encoder_dropout" if pf.startswith("encoder") else "decoder_dropout"]
-        return self._site(tp, f"{pf}.slf_attn", p), self._site(tp, f"{pf}.pos_ffn", p)
+        return self._site(tp, f"{pf}.slf_attn", p, self.d), self._site(tp, f"{pf}.pos_ffn", p, self.d)
 
     def _vp_drop(self, tp: Tape, pf: str):
         p = self.cfg["variance_predictor"]["dropout"]
@@ -935,15 +992,82 @@ class FS2Engine:
         with self.be.branch("enc"), FS2Engine._BranchScratch(self):
             return self.encoder_fwd(P, bt.texts, bt.src_lens, bt.B, bt.L, tp)
 
+    # ---- forward-type passes of an FFT stack as concurrent chains over groups of utterances (see SPLIT_FWD) ----
+    def _groups(self, B: int, T: int):
+        if not SPLIT_FWD or B < 2 or B * T > SPLIT_FWD_MAX_ROWS:
+            return [(0, B)]
+        return [(0, B // 2), (B // 2, B)]
+
+    class _ChainScratch:
+        """Scratch buffers of one chain: chains run concurrently, so they must not share `scr` (keyed by the enclosing branch too:
+        the query encoder's chains run beside the main stream's)."""
+
+        def __init__(self, eng, h):
+            self.eng, self.h = eng, h
+
+        def __enter__(self):
+            e = self.eng
+            key = (getattr(e.be, "_cur_branch", None), self.h)
+            pool = e.__dict__.setdefault("_chain_scr", {})
+            if key not in pool:
+                pool[key] = Tape(e.be, e.split)
+            self.saved = e.scr
+            e.scr = pool[key]
+
+        def __exit__(self, *a):
+            self.eng.scr = self.saved
+
+    def _stack_fwd(self, P: ParamSet, stack: str, n_layers: int, tp: Tape, x: Act, lens, H: int) -> Act:
+        groups = self._groups(x.B, x.T)
+        if len(groups) == 1:
+            for i in range(n_layers):
+                x = self.fft_fwd(P, f"{stack}.layer_stack.{i}", tp, x, lens, H)
+            return x
+        be = self.be
+        for h, (b0, b1) in enumerate(groups):
+            with be.branch(f"grp{h}", local=True), FS2Engine._ChainScratch(self, h):
+                tv = TapeView(tp, b0, b1, x.B, x.T)
+                xh = _act_rows(x, b0, b1)
+                for i in range(n_layers):
+                    xh = self.fft_fwd(P, f"{stack}.layer_stack.{i}", tv, xh, lens[b0:b1], H)
+        for h in range(len(groups)):
+            be.join(f"grp{h}", local=True)
+        return tp.act(f"{stack}.layer_stack.{n_layers - 1}.out", x.B, x.T, self.d)
+
+    def _stack_tfwd(self, P: ParamSet, Pd: ParamSet, stack: str, n_layers: int, tp: Tape, tt: Tape, y: Act, yd: Optional[Act], lens, H: int):
+        """Tangent forward through a stack; y = the stack's primal input (layer i's input is layer i-1's saved output)."""
+        B, T, d = y.B, y.T, self.d
+        be = self.be
+        groups = self._groups(B, T)
+        for h, (b0, b1) in enumerate(groups):
+            one = len(groups) == 1
+            tpv = tp if one else TapeView(tp, b0, b1, B, T)
+            ttv = tt if one else TapeView(tt, b0, b1, B, T)
+
+            def chain():
+                yh, ydh = (y, yd) if one else (_act_rows(y, b0, b1), _act_rows(yd, b0, b1))
+                for i in range(n_layers):
+                    pf = f"{stack}.layer_stack.{i}"
+                    ynext = tpv.act(f"{pf}.out", b1 - b0, T, d)
+                    ydh = self.fft_tfwd(P, Pd, pf, tpv, ttv, yh, ydh, lens if one else lens[b0:b1], H)
+                    yh = ynext
+                return ydh
+
+            if one:
+                return chain()
+            with be.branch(f"grp{h}", local=True), FS2Engine._ChainScratch(self, h):
+                chain()
+        for h in range(len(groups)):
+            be.join(f"grp{h}", local=True)
+        return tt.act(f"{stack}.layer_stack.{n_layers - 1}.outd", B, T, d)
+
     def encoder_fwd(self, P: ParamSet, texts, src_lens, B: int, Lq: int, tp: Tape) -> Act:
         """Encoder.forward (Models.py:73-100): embedding + position_enc, then the FFT blocks."""
         d = self.d
         x = tp.act("enc.x0", B, Lq, d)
         self.be.embed_fwd(texts, P.get("encoder.src_word_emb.weight").f32, None, self.consts["encoder.position_enc"], Lq,
                           B * Lq, d, x.f32, x.hi, x.lo)
-        for i in range(self.n_enc):
-            x = self.fft_fwd(P, f"encoder.layer_stack.{i}", tp, x, src_lens, self.h_enc)
-        return x
+        return self._stack_fwd(P, "encoder", self.n_enc, tp, x, src_lens, self.h_enc)
 
     def _position_table(self, name: str, T: int, eval_mode: bool):
         """Models.py:82-91 / 148-160: the stored table covers max_seq_len + 1 positions; under model.eval() a longer
@@ -971,9 +1095,7 @@ class FS2Engine:
         d = self.d
         y = tp.act("dec.x0", B, T, d)
         self.be.add_rowvec(xin_f32, spk, d, self._position_table("decoder.position_enc", T, eval_mode), B, T, d, y.f32, y.hi, y.lo)
-        for i in range(self.n_dec):
-            y = self.fft_fwd(P, f"decoder.layer_stack.{i}", tp, y, mel_lens, self.h_dec)
-        return y
+        return self._stack_fwd(P, "decoder", self.n_dec, tp, y, mel_lens, self.h_dec)
 
     def postnet_fwd(self, P: ParamSet, mel: Act, tp: Tape, update_bn: bool = True, eval_mode: bool = False) -> Act:
         """PostNet.forward (Layers.py:129-137): 4 x tanh(BN(conv5)) + BN(conv5); batch statistics in train mode,
@@ -1271,11 +1393,8 @@ class FS2Engine:
         yd = tt.act("dec.x0d", B, T, d)
         be.add_rowvec(xrd, spkd, d, None, B, T, d, yd.f32, yd.hi, yd.lo)
         y = tp.act("dec.x0", B, T, d)
-        for i in range(self.n_dec):
-            pf = f"decoder.layer_stack.{i}"
-            ynext = tp.act(f"{pf}.out", B, T, d)
-            yd = self.fft_tfwd(P, Pd, pf, tp, tt, y, yd, bt.mel_lens, self.h_dec)
-            y = ynext
+        yd = self._stack_tfwd(P, Pd, "decoder", self.n_dec, tp, tt, y, yd, bt.mel_lens, self.h_dec)
+        y = tp.act(f"decoder.layer_stack.{self.n_dec - 1}.out", B, T, d)
         mel = tp.act("mel", B, T, N_MEL)
         meld = tt.act("meld", B, T, N_MEL)
         self._lin_t(y, yd, P.get("mel_linear.weight"), wdt("mel_linear.weight"), gd("mel_linear.bias"), meld.f32, meld.hi, meld.lo)
