@@ -310,10 +310,12 @@ def _act_rows(a: Optional[Act], b0: int, b1: int) -> Optional[Act]:
     return Act(sl(a.f32), sl(a.hi), sl(a.lo), b1 - b0, a.T, a.C)
 
 
-# Forward-type passes (forward, tangent forward) of the FFT stacks run as TWO concurrent chains over half of the utterances each
-# when the batch is small: per-kernel latency (launch + prologue + epilogue, 5-11 us) dominates the under-filled GEMMs of a 4-utterance
-# batch, so two half-size chains finish in about the time of one.  Backward-type passes keep one chain: there
-# the weight-gradient GEMMs already run beside the data-gradient chain and fill the machine.
+# EXPERIMENT (off): forward-type passes (forward, tangent forward) of the FFT stacks as TWO concurrent chains over half of the
+# utterances each.  Idea: per-kernel latency dominates the under-filled GEMMs of a 4-utterance batch, so two half-size chains
+# might finish in about the time of one.  Measured on B200 (configs[1]): parity green (24 GPU tests with MTTS_SPLIT_FWD=1) but
+# 12.18 ms/step vs 11.80 (+234 launches): the step does not get faster by running more kernels side by side — the extra launches
+# cost more than the concurrency returns, the same outcome as the narrow split-K tiles (SMALL_SPLITK_MODEL).  Kept because the
+# mechanism (TapeView slices, per-chain scratch, seed-folded dropout offsets) is what a fused per-block kernel will need.
 SPLIT_FWD = os.environ.get("MTTS_SPLIT_FWD", "0") == "1"
 SPLIT_FWD_MAX_ROWS = 8192
 _HASH_G_INV = pow(0x9E3779B9, -1, 1 << 32)       # the dropout hash adds element_index to seed * 0x9E3779B9 (mod 2^32)
