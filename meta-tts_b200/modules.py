@@ -261,13 +261,14 @@ class Decoder(_B200Module):
 
     def forward(self, enc_seq, mask, return_attns=False):
         rt = self._rt()
-        max_len = min(enc_seq.shape[1], self.max_seq_len)               # Models.py:154 (training branch)
+        long_eval = (not self.training) and enc_seq.shape[1] > self.max_seq_len    # Models.py:148-156: keep the length, fresh table
+        max_len = enc_seq.shape[1] if long_eval else min(enc_seq.shape[1], self.max_seq_len)      # Models.py:161-166: truncate
         x = rt.dev(enc_seq[:, :max_len, :], torch.float32)
         mask = mask[:, :max_len]
         B, T, _ = x.shape
         tp = rt.tape(("dec", B, T))
         lens = _lens_from_mask(rt.dev(mask, torch.bool))
-        out = rt.engine.decoder_fwd(rt.params(), x, None, lens, B, T, tp)
+        out = rt.engine.decoder_fwd(rt.params(), x, None, lens, B, T, tp, eval_mode=long_eval)
         return out.f32, mask
 
 

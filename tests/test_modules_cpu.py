@@ -105,3 +105,26 @@ def test_free_running_forward_matches_oracle(pre_cfg):
                 assert out[i].shape == ref[i].shape and _rel(out[i], ref[i]) < 5e-5, (train, i)
     finally:
         M._B200Module._backend = None
+
+
+def test_decoder_beyond_max_seq_len(pre_cfg):
+    """Decoder.forward on a sequence longer than max_seq_len: train mode truncates (Models.py:161-166), eval mode keeps the length
+    with a recomputed sinusoid table (Models.py:148-156)."""
+    import copy
+    cfg = copy.deepcopy(CFG)
+    cfg["max_seq_len"] = 24
+    M._B200Module._backend = RefOps(split=3)
+    try:
+        torch.manual_seed(0)
+        dec = M.Decoder(cfg)
+        P = {"decoder." + k: v.detach().clone() for k, v in dec.state_dict().items()}
+        x = torch.randn(2, 40, 256, generator=torch.Generator().manual_seed(3))
+        mask = O.get_mask_from_lengths(torch.tensor([40, 31]), 40)
+        for train in (True, False):
+            dec.train(train)
+            out, m = dec(x, mask)
+            ref, mref = O.decoder(P, cfg, x, mask, training=train)
+            assert out.shape == ref.shape and out.shape[1] == (24 if train else 40) and torch.equal(m, mref)
+            assert _rel(out, ref) < 2e-5, train
+    finally:
+        M._B200Module._backend = None
