@@ -282,7 +282,8 @@ class _FFTParams(nn.Module):
 
 
 class PostNet(_B200Module):
-    """transformer/Layers.py:67-137.  forward(x [B,T,80]) -> [B,T,80] (train-mode BatchNorm statistics)."""
+    """transformer/Layers.py:67-137.  forward(x [B,T,80]) -> [B,T,80]; BatchNorm uses batch statistics in train mode (and advances
+    the running ones), the running statistics under eval()."""
     _prefix = "postnet."
 
     def __init__(self, n_mel_channels=80, postnet_embedding_dim=512, postnet_kernel_size=5, postnet_n_convolutions=5):
@@ -303,7 +304,7 @@ class PostNet(_B200Module):
         tp = rt.tape(("post", B, T))
         mel = tp.act("mel", B, T, N_MEL)
         rt.be.add_rowvec(rt.dev(x, torch.float32), None, 0, None, B, T, N_MEL, mel.f32, mel.hi, mel.lo)
-        out = rt.engine.postnet_fwd(rt.params(), mel, tp, update_bn=self.training)
+        out = rt.engine.postnet_fwd(rt.params(), mel, tp, update_bn=self.training, eval_mode=not self.training)   # eval: running statistics
         if self.training:                                                    # running stats live in the runtime: mirror back
             for i in range(5):
                 bn = self.convolutions[i][1]

@@ -128,3 +128,22 @@ def test_decoder_beyond_max_seq_len(pre_cfg):
             assert _rel(out, ref) < 2e-5, train
     finally:
         M._B200Module._backend = None
+
+
+def test_postnet_eval_mode_uses_running_statistics(pre_cfg):
+    M._B200Module._backend = RefOps(split=3)
+    try:
+        torch.manual_seed(0)
+        post = M.PostNet()
+        x = torch.randn(2, 30, 80, generator=torch.Generator().manual_seed(2))
+        post.train()
+        post(x)                                                             # advances the running statistics once
+        P = {"postnet." + k: v.detach().clone() for k, v in post.state_dict().items()}
+        assert float(P["postnet.convolutions.0.1.running_mean"].abs().max()) > 0 and int(P["postnet.convolutions.0.1.num_batches_tracked"]) == 1
+        post.eval()
+        out = post(x)
+        ref = O.postnet(P, x, training=False)
+        assert _rel(out, ref) < 2e-5
+        assert _rel(out, O.postnet({k: v.clone() for k, v in P.items()}, x, training=True)) > 1e-2     # and differs from batch statistics
+    finally:
+        M._B200Module._backend = None
