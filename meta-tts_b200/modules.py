@@ -452,8 +452,14 @@ class _SpeakerTable(nn.Module):
         self.model = nn.Embedding(n_speaker, d)
 
 
-class _VarianceAdaptorParams(nn.Module):
-    """Parameter container mirroring VarianceAdaptor.__init__ (modules.py:20-78)."""
+class _VarianceAdaptorParams(_B200Module):
+    """lightning/model/modules.py:17-158 `VarianceAdaptor`: same constructor, parameter names and
+    `forward(x, src_mask, mel_mask, max_len, pitch_target, energy_target, duration_target, p_control, e_control, d_control)`
+    -> `(x [B,T,d], pitch_prediction, energy_prediction, log_duration_prediction, duration_rounded, mel_len, mel_mask)`
+    (phoneme-level pitch / energy, linear quantisation: preprocess/LibriTTS.yaml:37,40).  Inside FastSpeech2 the same steps run
+    as part of one engine pass; this standalone forward exists for drop-in use of the module alone.  Dropout of the predictors
+    (modules.py:223,235) is not applied here: the standalone module has no step salt (use MetaSystem / FastSpeech2 for training)."""
+    _prefix = "variance_adaptor."
 
     def __init__(self, preprocess_config, model_config):
         super().__init__()
@@ -475,6 +481,58 @@ class _VarianceAdaptorParams(nn.Module):
         d = model_config["transformer"]["encoder_hidden"]
         self.pitch_embedding = nn.Embedding(n_bins, d)
         self.energy_embedding = nn.Embedding(n_bins, d)
+        self._cfg = model_config
+
+    def forward(self, x, src_mask, mel_mask=None, max_len=None, pitch_target=None, energy_target=None, duration_target=None,
+                p_control=1.0, e_control=1.0, d_control=1.0):
+        from . import lib as L
+        rt = self._rt()
+        eng, be, P = rt.engine, rt.be, rt.params()
+        va = "variance_adaptor"
+        B, Lq, d = x.shape
+        tp = eng.new_tape()
+        tp.drop_pass = None
+        x0 = tp.act("va.x0", B, Lq, d)
+        be.add_rowvec(rt.dev(x, torch.float32), None, 0, None, B, Lq, d, x0.f32, x0.hi, x0.lo)
+        lens = _lens_from_mask(rt.dev(src_mask, torch.bool))
+        logd, ppred, epred = tp.f32("logd", (B, Lq)), tp.f32("ppred", (B, Lq)), tp.f32("epred", (B, Lq))
+        eng.vp_fwd(P, f"{va}.duration_predictor", tp, x0, lens, logd)
+        eng.vp_fwd(P, f"{va}.pitch_predictor", tp, x0, lens, ppred)
+
+        def embed(pred, target, control, bins, table, base, out: Act):
+            if target is not None:
+                src = rt.dev(target, torch.float32)
+            else:
+                if control != 1.0:
+                    be.unary(L.UN_SCALE, pred, control, 0.0, pred)          # prediction * control (modules.py:86,97)
+                src = pred
+            idx = tp.buf(f"idx.{bins}", (B, Lq), torch.int64)
+            be.bucketize(src, rt.consts[f"{va}.{bins}"], eng.nbins - 1, B * Lq, idx)
+            be.embed_fwd(idx, P.get(f"{va}.{table}.weight").f32, base, None, Lq, B * Lq, d, out.f32, out.hi, out.lo)
+
+        x1 = tp.act("va.x1", B, Lq, d)
+        embed(ppred, pitch_target, p_control, "pitch_bins", "pitch_embedding", x0.f32, x1)
+        eng.vp_fwd(P, f"{va}.energy_predictor", tp, x1, lens, epred)
+        x2 = tp.act("va.x2", B, Lq, d, bf=False)
+        embed(epred, energy_target, e_control, "energy_bins", "energy_embedding", x1.f32, x2)
+        if duration_target is not None:
+            dur = rt.dev(duration_target, torch.int64 if not torch.as_tensor(duration_target).is_floating_point() else torch.float32)
+            d_rounded = duration_target
+        else:
+            dur = tp.f32("d_rounded", (B, Lq))
+            be.duration_round(logd, d_control, dur)
+            d_rounded = dur
+        if max_len is None:                                                   # pad() without a max: data dependent, one sync
+            max_len = int(dur.detach().to("cpu").to(torch.int64).clamp_(min=0).sum(dim=1).max())
+        T = int(max_len)
+        idx = tp.buf("lr.idx", (B, T), torch.int32)
+        mel_len = tp.buf("lr.mel_len", (B,), torch.int64)
+        be.lr_index(dur, T, idx, mel_len)
+        out = tp.f32("lr.out", (B, T, d))
+        be.lr_fwd(x2.f32, idx, out)
+        if duration_target is None:
+            mel_mask = get_mask_from_lengths(mel_len)                          # modules.py:139
+        return out, ppred, epred, logd, d_rounded, mel_len, mel_mask
 
 
-VarianceAdaptor = _VarianceAdaptorParams      # teacher-forced use goes through FastSpeech2.forward / the engine
+VarianceAdaptor = _VarianceAdaptorParams

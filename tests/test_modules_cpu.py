@@ -147,3 +147,32 @@ def test_postnet_eval_mode_uses_running_statistics(pre_cfg):
         assert _rel(out, O.postnet({k: v.clone() for k, v in P.items()}, x, training=True)) > 1e-2     # and differs from batch statistics
     finally:
         M._B200Module._backend = None
+
+
+def test_variance_adaptor_standalone_forward(pre_cfg):
+    """VarianceAdaptor.forward alone (modules.py:102-158): teacher forced and free running (with controls)."""
+    M._B200Module._backend = RefOps(split=3)
+    try:
+        torch.manual_seed(0)
+        va = M.VarianceAdaptor(pre_cfg, CFG)
+        sd = va.state_dict()
+        sd["duration_predictor.linear_layer.bias"] = sd["duration_predictor.linear_layer.bias"] + 1.3
+        va.load_state_dict(sd)
+        P = {"variance_adaptor." + k: v.detach().clone() for k, v in va.state_dict().items()}
+        b12 = O.synth_batch(2, 7, 20, seed=4, speaker=1, ragged=True)
+        x = torch.randn(2, 7, 256, generator=torch.Generator().manual_seed(8))
+        src_mask = O.get_mask_from_lengths(b12[4], 7)
+        mel_mask = O.get_mask_from_lengths(b12[7], 20)
+        with torch.no_grad():
+            ref_t = O.variance_adaptor(P, x, src_mask, mel_mask, 20, b12[9], b12[10], b12[11])
+            ref_f = O.variance_adaptor(P, x, src_mask, None, None, None, None, None, 1.1, 0.9, 1.4)
+        out_t = va(x, src_mask, mel_mask, 20, b12[9], b12[10], b12[11])
+        out_f = va(x, src_mask, p_control=1.1, e_control=0.9, d_control=1.4)
+        for out, ref in ((out_t, ref_t), (out_f, ref_f)):
+            assert len(out) == 7 and out[0].shape == ref[0].shape
+            for i in range(4):
+                assert _rel(out[i], ref[i]) < 5e-5, i
+            assert torch.equal(torch.as_tensor(out[4]).float(), ref[4].float()) and torch.equal(out[5], ref[5]) and torch.equal(out[6], ref[6])
+        assert int(ref_f[5].max()) > 7
+    finally:
+        M._B200Module._backend = None
