@@ -170,6 +170,17 @@ class _B200Module(nn.Module):
     _prefix = ""
     _backend = None          # tests may inject the CPU restatement; the product default is CudaOps (raises w/o B200)
 
+    def _mirror_bn(self, rt: "_Runtime", postnet: nn.Module) -> None:
+        """After a train-mode pass: the engine advanced the BatchNorm running statistics in its constants; copy them into the
+        module's buffers (state_dict / checkpoints see them) without triggering a re-pack of the parameters."""
+        with torch.no_grad():
+            for i in range(5):
+                bn = postnet.convolutions[i][1]
+                bn.running_mean.copy_(rt.consts[f"postnet.convolutions.{i}.1.running_mean"])
+                bn.running_var.copy_(rt.consts[f"postnet.convolutions.{i}.1.running_var"])
+                bn.num_batches_tracked += 1
+        rt._versions = tuple((k, v._version, v.data_ptr()) for k, v in _named(self, self._prefix).items())
+
     def _rt(self) -> _Runtime:
         rt = self.__dict__.get("_runtime")
         if rt is None:
@@ -306,11 +317,7 @@ class PostNet(_B200Module):
         rt.be.add_rowvec(rt.dev(x, torch.float32), None, 0, None, B, T, N_MEL, mel.f32, mel.hi, mel.lo)
         out = rt.engine.postnet_fwd(rt.params(), mel, tp, update_bn=self.training, eval_mode=not self.training)   # eval: running statistics
         if self.training:                                                    # running stats live in the runtime: mirror back
-            for i in range(5):
-                bn = self.convolutions[i][1]
-                bn.running_mean.copy_(rt.consts[f"postnet.convolutions.{i}.1.running_mean"])
-                bn.running_var.copy_(rt.consts[f"postnet.convolutions.{i}.1.running_var"])
-                bn.num_batches_tracked += 1
+            self._mirror_bn(rt, self)
         return out.f32
 
 
@@ -430,6 +437,8 @@ class FastSpeech2(_B200Module):
                        B=B, L=Lq, T=0)
             out = rt.engine.synthesize(rt.params(), bt, rt.engine.new_tape(), p_control, e_control, d_control,
                                        update_bn=self.training, eval_mode=not self.training)
+            if self.training:
+                self._mirror_bn(rt, self.postnet)
             src_masks = get_mask_from_lengths(bt.src_lens, Lq)
             mel_masks = get_mask_from_lengths(out["mel_len"], int(out["mel"].shape[1]))
             return (out["mel"], out["postnet"], out["pitch"], out["energy"], out["logd"], out["d_rounded"], src_masks, mel_masks,
@@ -440,6 +449,8 @@ class FastSpeech2(_B200Module):
                    mel_lens=rt.dev(mel_lens, torch.int64), pitches=rt.dev(p_targets, torch.float32),
                    energies=rt.dev(e_targets, torch.float32), durations=rt.dev(d_targets, torch.int64), B=B, L=Lq, T=T)
         out = rt.engine.forward(rt.params(), bt, rt.tape(("fs2", B, Lq, T)), update_bn=self.training, eval_mode=not self.training)
+        if self.training:
+            self._mirror_bn(rt, self.postnet)
         src_masks = get_mask_from_lengths(bt.src_lens, Lq)
         mel_masks = get_mask_from_lengths(bt.mel_lens, T)
         return (out["mel"], out["postnet"], out["pitch"], out["energy"], out["logd"], bt.durations, src_masks, mel_masks,

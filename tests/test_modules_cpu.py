@@ -176,3 +176,29 @@ def test_variance_adaptor_standalone_forward(pre_cfg):
         assert int(ref_f[5].max()) > 7
     finally:
         M._B200Module._backend = None
+
+
+def test_train_mode_forward_advances_the_module_bn_buffers(pre_cfg):
+    """After a train-mode FastSpeech2 forward the module's own BatchNorm buffers (state_dict / checkpoints) hold the advanced
+    running statistics, exactly as the reference's nn.BatchNorm1d would, and a following eval() forward uses them."""
+    M._B200Module._backend = RefOps(split=3)
+    try:
+        torch.manual_seed(0)
+        model = M.FastSpeech2(pre_cfg, CFG, ALGO).train()
+        P = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        b12 = O.synth_batch(2, 7, 20, seed=4, speaker=1, ragged=True)
+        model(*b12[2:])
+        with torch.no_grad():
+            O.fs2_forward(P, CFG, *b12[2:], training=True)                    # the oracle updates P's running statistics in place
+        sd = model.state_dict()
+        for i in range(5):
+            for k in ("running_mean", "running_var"):
+                assert _rel(sd[f"postnet.convolutions.{i}.1.{k}"], P[f"postnet.convolutions.{i}.1.{k}"]) < 1e-4, (i, k)
+            assert int(sd[f"postnet.convolutions.{i}.1.num_batches_tracked"]) == 1
+        model.eval()
+        out = model(*b12[2:])
+        with torch.no_grad():
+            ref = O.fs2_forward({k: v.detach().clone() for k, v in sd.items()}, CFG, *b12[2:], training=False)
+        assert _rel(out[1], ref[1]) < 2e-5
+    finally:
+        M._B200Module._backend = None
