@@ -173,7 +173,7 @@ class MamlEngine:
         the rolling fast weights of `adapt_rolling`; teacher forced (+ loss) or free running; eval or train mode.
         Shapes differ call to call, so the activations go to a throw-away tape."""
         eng = self.engine
-        P = self.params(1) if adapted else self.params(0)
+        P = self.params(int(adapted))                          # False / 0: meta parameters; True / k: fast weights after k held steps
         tape = eng.new_tape()
         if free_running:
             out = eng.synthesize(P, bt, tape, p_control, e_control, d_control, update_bn=not eval_mode, drop_pass=drop_pass,

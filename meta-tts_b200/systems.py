@@ -434,6 +434,30 @@ def _set_salt(self, salt: int) -> None:
     self.be.drop_salt = torch.tensor([salt - (1 << 32) if salt >= (1 << 31) else salt], dtype=torch.int32, device=self.device)
 
 
+def forward_learner(self, learner, speaker_args, texts, src_lens, max_src_len, mels=None, mel_lens=None, max_mel_len=None,
+                    p_targets=None, e_targets=None, d_targets=None, p_control=1.0, e_control=1.0, d_control=1.0,
+                    average_spk_emb=False):
+    """base_adaptor.py:41-95: one model forward with the learner's (adapted) modules where it has them -> the reference's 10-tuple.
+    `learner` is what `adapt()` returned — the number of inner steps held in the fast-weight arenas — or None / 0 / `self.learner`
+    for the meta parameters.  Teacher forced when the targets are given, free running otherwise.  Mode follows the reference: an
+    adapted learner is in train mode (`adapt()` calls `learner.train()`), the un-adapted one follows `self.training`
+    (`.train()` / `.eval()`; Lightning's test loop puts the module in eval mode).  Dropout needs a step salt and is applied only
+    inside `training_step` / `test_step`; here it is off."""
+    k = 0 if (learner is None or learner is getattr(self, "learner", None)) else int(learner)
+    free = d_targets is None
+    assert (p_targets is None) == free and (e_targets is None) == free, "give all of (p, e, d) targets or none of them"
+    b12 = (None, None, speaker_args, texts, src_lens, max_src_len, mels, mel_lens, max_mel_len, p_targets, e_targets, d_targets)
+    bt = batch_from_tuple(b12, self.device, average_spk=average_spk_emb, targets=not free)
+    eval_mode = (k == 0) and not getattr(self, "training", True)
+    out = self.maml.predict(bt, k, free, eval_mode, None, p_control, e_control, d_control)
+    return _pred10(out, bt, free)
+
+
+def _train(self, mode: bool = True):
+    self.training = bool(mode)
+    return self
+
+
 def _test_step(self, batch, batch_idx):
     """base_adaptor.py:153-189 — few-shot adaptation inference (BASELINE configs[4]): evaluate the un-adapted learner
     (eval mode), then `test.steps / train.steps` rounds of first-order adaptation on the support set, after each of which the
@@ -582,6 +606,11 @@ class MetaSystem:
     validation_step = validation_step
     test_step = test_step
     _test_step = _test_step
+    forward_learner = forward_learner
+    training = True
+    learner = None                      # the reference's `self.learner` handle: the un-adapted meta parameters
+    train = _train
+    eval = lambda self: _train(self, False)  # noqa: E731
     on_load_checkpoint = on_load_checkpoint
     load_checkpoint = load_checkpoint
     save_checkpoint = save_checkpoint

@@ -66,3 +66,34 @@ def test_one_shot_protocol_and_controls():
                             d_control=1.5, average_spk_emb=True, training=False)
     assert torch.equal(out["d_rounded"], ref[5]) and torch.equal(out["mel_len"], ref[9])
     assert rel(out["pitch"], ref[2]) < 1e-4 and rel(out["energy"], ref[3]) < 1e-4 and rel(out["postnet"], ref[1]) < 1e-3
+
+
+def test_forward_learner_signature_and_modes():
+    """base_adaptor.py:41-95 as a public call: meta parameters vs the learner returned by adapt(), teacher forced vs free running,
+    eval vs train mode of the un-adapted learner."""
+    algo = copy.deepcopy(DEFAULT_ALGORITHM_CONFIG)
+    algo["adapt"]["train"]["steps"] = 2
+    algo["adapt"]["test"] = {"steps": 2}
+    sysm = MetaSystem(None, CFG, DEFAULT_TRAIN_CONFIG, algo, n_speaker=16, device="cpu", use_cuda_graph=False, backend=RefOps(split=3), dropout=False)
+    P = talkative_params(CFG)
+    sysm.load_state_dict({k: v.detach().clone() for k, v in P.items()})
+    sup, qry = O.synth_task(task=2, shots=3, queries=1, L=7, T=20, ragged=True)
+    # un-adapted, eval mode, teacher forced and free running
+    sysm.eval()
+    with torch.no_grad():
+        ref_t = O.fs2_forward({k: v.detach().clone() for k, v in P.items()}, CFG, sup[2], *qry[3:], average_spk_emb=True, training=False)
+        ref_f = O.fs2_forward({k: v.detach().clone() for k, v in P.items()}, CFG, sup[2], *qry[3:6], d_control=1.3, average_spk_emb=True, training=False)
+    out_t = sysm.forward_learner(sysm.learner, sup[2], *qry[3:], average_spk_emb=True)
+    out_f = sysm.forward_learner(None, sup[2], *qry[3:6], d_control=1.3, average_spk_emb=True)
+    for out, ref in ((out_t, ref_t), (out_f, ref_f)):
+        assert len(out) == 10 and all(rel(out[i], ref[i]) < 1e-4 for i in range(5))
+        assert torch.equal(out[6], ref[6]) and torch.equal(out[7], ref[7]) and torch.equal(out[9], ref[9])
+    assert torch.equal(out_f[5], ref_f[5])
+    # adapted learner (2 first-order... here second-order-capable adapt(), same weights): train mode, batch statistics
+    sysm.train()
+    learner = sysm.adapt([([sup], [qry])], 2, train=False)
+    assert learner == 2
+    Pc = {k: v.detach().clone() for k, v in P.items()}
+    ref, theta = O.test_time_adaptation(Pc, CFG, sup, qry, 2, 2, saving_steps=(2,))
+    out = sysm.forward_learner(learner, sup[2], *qry[3:], average_spk_emb=True)
+    assert rel(out[1], ref["step_2"]["recon"]["output"][1]) < 1e-3
