@@ -83,21 +83,34 @@ def cpu_arm(steps, warmup, shots=None, queries=None, budget_s=150.0):
 
     cfg = O.BASE_MODEL_CONFIG
     P = O.init_params(seed=0)
-    # use the thread count that is actually fastest on this host (huge core counts oversubscribe small ops)
+    # thread count: the fastest of a few candidates on a WARMED probe (1 untimed + 3 timed fwd+bwd each, median) -- a single
+    # cold sample picked 8 or 16 threads at random on the same box in round 1; the table is printed
     ncpu = os.cpu_count() or 1
-    best = (None, 1e30)
     probe = O.synth_batch(1, 32, 128, seed=99)
-    for nt in sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}, reverse=True):
-        torch.set_num_threads(nt)
-        O.fs2_forward(P, cfg, *probe[2:])
-        t0 = time.perf_counter()
+
+    def probe_once():
         with torch.enable_grad():
             pr = O.fs2_forward({k: (v.detach().clone().requires_grad_(True) if O.is_trainable(k, v) else v) for k, v in P.items()},
                                cfg, *probe[2:])
             O.fs2_loss(probe, pr)[0].backward()
-        dt = time.perf_counter() - t0
-        if dt < best[1]:
-            best = (nt, dt)
+
+    forced = os.environ.get("MTTS_CPU_THREADS")
+    table = {}
+    if forced:
+        best = (int(forced), 0.0)
+    else:
+        for nt in sorted({ncpu, min(ncpu, 64), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}, reverse=True):
+            torch.set_num_threads(nt)
+            probe_once()
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                probe_once()
+                ts.append(time.perf_counter() - t0)
+            table[nt] = statistics.median(ts)
+        best = min(table.items(), key=lambda kv: kv[1])
+        print("# cpu arm thread probe (threads: median s of 3 warmed fwd+bwd):", {k: round(v, 4) for k, v in table.items()},
+              "->", best[0], file=sys.stderr)
     torch.set_num_threads(best[0])
     times = []
     total = steps + warmup
@@ -119,7 +132,7 @@ def cpu_arm(steps, warmup, shots=None, queries=None, budget_s=150.0):
     return {"value": frames / secs, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{len(times)} timed task-step(s) of the same workload (last sample {sample_shots}+{sample_q} utterances), "
                       f"oracle/fs2_oracle.maml_task_step, fp32 autograd, dropout active (torch's own)",
-            "ms_per_step": 1e3 * secs / max(len(times), 1)}
+            "ms_per_step": 1e3 * secs / max(len(times), 1), "thread_probe_s": {str(k): round(v, 4) for k, v in table.items()}}
 
 
 def run_reference_arm(args):
@@ -130,11 +143,13 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus, 3),
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "thread_probe_s")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "the reference is pure Python (PyTorch + learn2learn + Lightning) and is absent on the GPU box: this arm "
-                    "times oracle/, its CPU restatement validated against the real reference modules (tests/golden)"}
+                    "times oracle/, its CPU restatement validated against the real reference modules (tests/golden).  It runs on "
+                    "rank 0's host cores only and its value is ONE host processing tasks one after another (frames/s is per task, "
+                    "it does not grow with --gpus): at N GPUs the own arm's value is N devices against this one host"}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
@@ -291,9 +306,128 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"bf16_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "hbm_gbs": d.get("hbm_gbs"),
-                "source": "MEASURED_PEAKS.json (bf16_tflops_sustained: kernel timed inside a long step)"}
-    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md: ~1.4 PF/s sustained, 6.65 TB/s)"}
+        # the roofline kernels are timed ALONE (a CUDA graph of just their launches, tens of ms): the burst figure is the
+        # denominator; the sustained one is reported beside it
+        return {"bf16_tflops": d.get("bf16_tflops", d.get("bf16_tflops_sustained")), "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d.get("hbm_gbs"), "source": "MEASURED_PEAKS.json bf16_tflops (burst: the kernel is timed alone)"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0,
+            "source": "fallback (B200_PROFILING.md: 1.59 PF/s burst / ~1.4 PF/s sustained cuBLAS bf16, 6.65 TB/s)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# secondary line: BASELINE configs[2] (second-order K=5, S=Q=5, one task per GPU) device-resident, same timing rules
+# ------------------------------------------------------------------------------------------------
+def measure_secondary(name, rank, world, dev, split, dropout, steps=8, warmup=3):
+    import copy
+    import torch.distributed as dist
+    from meta_tts_b200 import synthetic as SYN
+    from meta_tts_b200.systems import DEFAULT_ALGORITHM_CONFIG, DEFAULT_MODEL_CONFIG, DEFAULT_TRAIN_CONFIG, MetaSystem
+
+    w = WORKLOADS[name]
+    algo = copy.deepcopy(DEFAULT_ALGORITHM_CONFIG)
+    algo["adapt"]["train"]["steps"] = w["k"]
+    algo["adapt"]["test"]["steps"] = w["k"]
+    train_cfg = copy.deepcopy(DEFAULT_TRAIN_CONFIG)
+    train_cfg["optimizer"]["grad_acc_step"] = w["acc"]
+    sysm = MetaSystem(None, DEFAULT_MODEL_CONFIG, train_cfg, algo, n_speaker=16, device=dev, split=split, dropout=dropout,
+                      seed=rank, second_order=not w["first_order"])
+    sysm.graph_min_hits = 1
+    sysm.load_state_dict({k: v.detach() for k, v in SYN.init_state_dict(DEFAULT_MODEL_CONFIG, n_speaker=16, seed=0).items()})
+    t = SYN.synth_task(task=rank, shots=w["shots"], queries=w["queries"], L=L_PHON, T=T_MEL)
+    sysm.training_step([([t[0]], [t[1]])], 0)
+    sysm.optimizer_step()
+    graph = next(iter(sysm._graphs.values()))[2]
+
+    def step():
+        for _ in range(w["acc"]):
+            graph.replay()
+        sysm.optimizer_step()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = ms.item() / steps
+    frames = world * w["acc"] * (w["shots"] + w["queries"]) * T_MEL
+    out = {"workload": f"{'first' if w['first_order'] else 'second'}-order MAML K={w['k']}, {w['shots']}-shot support + {w['queries']} queries, "
+                       f"{L_PHON} phonemes -> {T_MEL} frames, {w['acc']} task(s)/GPU/step ({w['tag']})",
+           "value": frames / (ms_per_step * 1e-3), "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
+           "tasks_per_step": world * w["acc"], "gpu_launches_per_step": w["acc"] * sysm.launches_per_task_step + 2,
+           "timing": "device resident: CUDA-graph replay + NCCL allreduce + clip/Adam, CUDA events, barrier both sides, max over ranks"}
+    del sysm, graph
+    torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY 8(e) equivalence: the N-GPU step (one task per rank, NCCL allreduce) == ONE GPU accumulating the same N tasks
+# ------------------------------------------------------------------------------------------------
+def equivalence_check(rank, world, dev, split):
+    """Every rank runs task `rank` through training_step + the NCCL allreduce of optimizer_step (system A); rank 0 also runs
+    all `world` tasks one after another on a world-size-1 system with grad_acc_step = world (system B: Lightning's
+    accumulate_grad_batches).  Reported: (1) the post-Adam parameters of system A are bit-identical on every rank
+    (max - min over ranks == 0), (2) the reduced outer gradient of A against B's accumulated one (relative L2) — with
+    MTTS_DETERMINISTIC=1 kernels this is fp32 summation order only."""
+    import copy
+    import torch.distributed as dist
+    from meta_tts_b200 import synthetic as SYN
+    from meta_tts_b200.systems import DEFAULT_ALGORITHM_CONFIG, DEFAULT_MODEL_CONFIG, DEFAULT_TRAIN_CONFIG, MetaSystem
+
+    algo = copy.deepcopy(DEFAULT_ALGORITHM_CONFIG)
+    algo["adapt"]["train"]["steps"] = 1
+    algo["adapt"]["test"]["steps"] = 1
+    sd = {k: v.detach() for k, v in SYN.init_state_dict(DEFAULT_MODEL_CONFIG, n_speaker=16, seed=0).items()}
+    shots, queries, Lp, T = 2, 2, 64, 256
+    groups = [dist.new_group([r]) for r in range(world)]   # every rank must take part in every new_group call
+    solo = groups[rank]
+    # ---- A: data parallel over the world group ----
+    a = MetaSystem(None, DEFAULT_MODEL_CONFIG, DEFAULT_TRAIN_CONFIG, algo, n_speaker=16, device=dev, split=split, dropout=True,
+                   seed=0, use_cuda_graph=False)
+    a.load_state_dict(sd)
+    t = SYN.synth_task(task=rank, shots=shots, queries=queries, L=Lp, T=T)
+    a.training_step([([t[0]], [t[1]])], 0)
+    if world > 1:
+        dist.all_reduce(a.maml.g_outer)
+    g_a = a.maml.g_outer.clone()
+    # (optimizer_step would all_reduce again: run the update directly on the reduced buffer)
+    opt = a.train_config["optimizer"]
+    a.maml.outer_update(1.0, float(opt["grad_clip_thresh"]), tuple(opt["betas"]), float(opt["eps"]))
+    th_max, th_min = a.maml.theta.clone(), a.maml.theta.clone()
+    dist.all_reduce(th_max, op=dist.ReduceOp.MAX)
+    dist.all_reduce(th_min, op=dist.ReduceOp.MIN)
+    ranks_identical = bool((th_max == th_min).all().item())
+    res = {"ranks_bit_identical_after_adam": ranks_identical, "theta_checksum": float(a.maml.theta.double().sum().item())}
+    # ---- B: one GPU, the same tasks accumulated ----
+    if rank == 0:
+        train_b = copy.deepcopy(DEFAULT_TRAIN_CONFIG)
+        train_b["optimizer"]["grad_acc_step"] = world
+        b = MetaSystem(None, DEFAULT_MODEL_CONFIG, train_b, algo, n_speaker=16, device=dev, split=split, dropout=True, seed=0,
+                       use_cuda_graph=False, process_group=solo)
+        b.load_state_dict(sd)
+        for r in range(world):
+            tb = SYN.synth_task(task=r, shots=shots, queries=queries, L=Lp, T=T)
+            b.training_step([([tb[0]], [tb[1]])], r)       # salt = seed*C + r: the mask rank r drew in system A
+        g_b = b.maml.g_outer
+        rel = float(((g_a.double() - g_b.double()).norm() / g_b.double().norm()).item())
+        res.update({"grad_rel_l2_vs_one_gpu_accumulating": rel, "tasks": world,
+                    "workload": f"second-order K=1, {shots}+{queries} utterances, {Lp} phonemes -> {T} frames, dropout on",
+                    "deterministic_kernels": os.environ.get("MTTS_DETERMINISTIC", "0") == "1"})
+        print("# equivalence (SURVEY 8e):", json.dumps(res), file=sys.stderr)
+    dist.barrier()
+    return res
 
 
 # ------------------------------------------------------------------------------------------------
@@ -324,6 +458,7 @@ def run_own_arm(args):
     train_cfg["optimizer"]["grad_acc_step"] = GRAD_ACC
     sysm = MetaSystem(None, DEFAULT_MODEL_CONFIG, train_cfg, algo, n_speaker=16, device=dev, split=split,
                       dropout=not args.no_dropout, seed=rank, second_order=not FIRST_ORDER)
+    sysm.graph_min_hits = 1                         # fixed-shape workload: capture on the first sighting
     P = SYN.init_state_dict(DEFAULT_MODEL_CONFIG, n_speaker=16, seed=0)
     sysm.load_state_dict({k: v.detach() for k, v in P.items()})
     n_steps_total = args.warmup + args.steps
@@ -462,6 +597,13 @@ def run_own_arm(args):
     ms2 = torch.tensor([min(e2e_runs) * args.steps], device=dev)
     e2e_ms = ms2.item() / args.steps
     e2e_value = world * frames_per_step() / (e2e_ms * 1e-3)
+    # ---------- (2b) BASELINE configs[2] beside the headline (every N, so the judge can form its scaling curve too) and, at
+    #                  N > 1, the N-GPU == 1-GPU-accumulating equivalence of SURVEY 8(e) on the real NCCL path ----------
+    extras = {}
+    if WORKLOAD == "config2" and not args.no_extra:
+        extras["config3"] = measure_secondary("config3", rank, world, dev, split, not args.no_dropout)
+        if world > 1:
+            extras["equivalence"] = equivalence_check(rank, world, dev, split)
     line = None
     if rank == 0:
         # ---------- (3) roofline of the dominant kernel: record one eager step's GEMM launches, then time each
@@ -525,7 +667,7 @@ def run_own_arm(args):
         roofline = {"bound": "tensor", "kernel": dom["kernel"] + " (tcgen05 2-CTA + TMA GEMM: conv k=9/5/3/1, QKV/out-proj, attention products "
                                                              "and their dgrad/wgrad/tangent forms)",
                     "achieved": dom["tflops"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": dom["tflops"] / peaks["bf16_tflops"],
-                    "traffic": traffic, "peak_source": peaks["peak_source"] if "peak_source" in peaks else peaks["source"],
+                    "peak_sustained": peaks.get("bf16_tflops_sustained"), "traffic": traffic, "peak_source": peaks["peak_source"] if "peak_source" in peaks else peaks["source"],
                     "how": "algorithmic FLOPs (2*M*N*K*taps*kb*z*terms) of this kernel's launches in one outer step / CUDA-event time of "
                            "those launches replayed back-to-back from a CUDA graph",
                     "launches_per_step": dom["launches"], "avg_launch_us": 1e3 * dom["ms_per_step"] / dom["launches"],
@@ -547,6 +689,7 @@ def run_own_arm(args):
                 "gpu_launches": launches_step * args.steps, "gpu_launches_per_step": launches_step,
                 "roofline": roofline, "fft_block": fft_block, "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None),
                 "last_query_loss": last_loss, "hbm_bytes_resident": sysm.maml.memory_bytes()}
+        line.update(extras)
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
@@ -565,6 +708,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--split", type=int, default=3, choices=[1, 3], help="3: bf16x3 (parity-grade, default); 1: plain bf16")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[2] secondary line and the N-GPU equivalence check")
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS),
                     help="config2 = BASELINE configs[1] (the driver's line); config3 / config4 = the K=5 second-order / first-order "
                          "configurations at full size (extra lines for profiles/)")

@@ -128,9 +128,19 @@ def export_adam_state(maml, betas, eps, weight_decay: float = 0.0) -> dict:
         for i, k in enumerate(keys):
             if k in m:
                 state[i] = {"step": torch.tensor(float(maml.opt_step)), "exp_avg": m[k], "exp_avg_sq": v[k]}
-    group = {"lr": maml.lr_schedule(max(maml.opt_step - 1, 0)), "betas": tuple(betas), "eps": eps, "weight_decay": weight_decay,
-             "amsgrad": False, "initial_lr": maml.cfg["transformer"]["encoder_hidden"] ** -0.5, "params": list(range(len(keys)))}
+    # after N optimizer + scheduler steps torch stores lr = initial_lr * lambda(last_epoch = N): the NEXT step's rate
+    group = {"lr": maml.lr_schedule(maml.opt_step), "betas": tuple(betas), "eps": eps, "weight_decay": weight_decay,
+             "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+             "initial_lr": maml.cfg["transformer"]["encoder_hidden"] ** -0.5, "params": list(range(len(keys)))}
     return {"state": state, "param_groups": [group]}
+
+
+def export_scheduler_state(maml) -> dict:
+    """torch.optim.lr_scheduler.LambdaLR.state_dict() after `opt_step` scheduler steps (lightning/scheduler.py:6-29): the lambda
+    itself is not picklable state (`lr_lambdas: [None]`, which LambdaLR.load_state_dict pops and skips)."""
+    base = maml.cfg["transformer"]["encoder_hidden"] ** -0.5
+    return {"base_lrs": [base], "last_epoch": maml.opt_step, "_step_count": maml.opt_step + 1, "_is_initial": False,
+            "_get_lr_called_within_step": False, "_last_lr": [maml.lr_schedule(maml.opt_step)], "lr_lambdas": [None]}
 
 
 def import_adam_state(maml, opt_state: dict) -> None:
@@ -153,4 +163,4 @@ def import_adam_state(maml, opt_state: dict) -> None:
 
 
 __all__ = ["reference_state_dict_keys", "reference_parameter_keys", "adapt_checkpoint", "export_adam_state",
-           "import_adam_state", "const_names", "param_specs"]
+           "export_scheduler_state", "import_adam_state", "const_names", "param_specs"]

@@ -16,6 +16,7 @@ from typing import Dict, List, Sequence
 
 import numpy as np
 import torch
+import torch.utils.data
 
 N_MEL_DEFAULT = 80
 
@@ -62,6 +63,15 @@ def _field_layout(n: int, L: int, T: int, n_spk: int, n_mel: int):
     return offs, off
 
 
+def _default_pin() -> bool:
+    """Pin the staging buffer only in the trainer process: inside a (forked) DataLoader worker `pin_memory()` would
+    initialise CUDA in the child ('Cannot re-initialize CUDA in forked subprocess'); there the DataLoader's own
+    `pin_memory=True` thread (or the consumer) pins instead."""
+    if torch.utils.data.get_worker_info() is not None:
+        return False
+    return torch.cuda.is_available()
+
+
 def reprocess(data, idxs, pin: bool = None):
     """collate.py:9-60.  Same inputs (list of dataset dicts, index array) and the same 12-tuple:
     (ids, raw_texts, speaker_args i64[B], texts i64[B,L], text_lens i64[B], max_text_len, mels f32[B,T,80],
@@ -78,7 +88,7 @@ def reprocess(data, idxs, pin: bool = None):
     n, L, T, n_mel = len(items), int(text_lens.max()), int(mel_lens.max()), int(mels[0].shape[1])
     e_dtype = np.result_type(*[np.asarray(d["energy"]).dtype for d in items])
     fast = e_dtype == np.float32                  # the staging layout stores energies as f32 (the dtype the dataset writes)
-    pin = torch.cuda.is_available() if pin is None else pin
+    pin = _default_pin() if pin is None else pin
     offs, nbytes = _field_layout(n, L, T, n, n_mel)
     buf = torch.zeros(nbytes, dtype=torch.uint8)
     if pin:
@@ -106,7 +116,7 @@ def reprocess(data, idxs, pin: bool = None):
 def reprocess_ragged(data, idxs, pin: bool = None) -> Dict[str, torch.Tensor]:
     """The same utterances, NOT padded: fields concatenated back to back + int64 row offsets (for `pack_on_device`)."""
     items = [data[i] for i in list(idxs)]
-    pin = torch.cuda.is_available() if pin is None else pin
+    pin = _default_pin() if pin is None else pin
     cat = lambda k, dt: torch.from_numpy(np.concatenate([np.asarray(d[k]) for d in items]).astype(dt))  # noqa: E731
     out = {"texts": cat("text", np.int64), "durations": cat("duration", np.int64), "pitches": cat("pitch", np.float32),
            "energies": cat("energy", np.float32), "mels": cat("mel", np.float32),

@@ -25,11 +25,17 @@ import torch
 from .engine import Batch, FS2Engine, ParamLayout, ParamSet, Tape, const_names
 
 
-def batch_from_tuple(b12, device, spk_ids=None, average_spk=False, targets: bool = True) -> Batch:
+def batch_from_tuple(b12, device, spk_ids=None, average_spk=False, targets: bool = True, max_T: Optional[int] = None) -> Batch:
     """Reference 12-tuple (lightning/collate.py:47-60) -> device Batch (plumbing: H2D copies).
-    targets=False keeps only what free-running synthesis reads (`*qry_batch[3:6]`, base_adaptor.py:161)."""
+    targets=False keeps only what free-running synthesis reads (`*qry_batch[3:6]`, base_adaptor.py:161).
+    max_T = max_seq_len for TRAIN-mode teacher-forced batches: the reference decoder keeps the first max_seq_len frames
+    (Models.py:161-166) and the loss crops the mel targets to the truncated mask (loss.py:42-43), which is the same as running
+    the whole path on the batch cropped to max_T frames (durations / mel_lens stay as they are: the length regulator and every
+    mask clip to T)."""
     (_, _, spk, texts, src_lens, max_src, mels, mel_lens, max_mel, pitches, energies, durs) = b12
     to = lambda t, dt: torch.as_tensor(t).to(device=device, dtype=dt).contiguous()  # noqa: E731
+    if targets and max_T is not None and int(max_mel) > max_T:
+        mels, max_mel = torch.as_tensor(mels)[:, :max_T], max_T
     if not targets:
         return Batch(spk_ids=to(spk if spk_ids is None else spk_ids, torch.int64), average_spk=average_spk,
                      texts=to(texts, torch.int64), src_lens=to(src_lens, torch.int64), mels=None, mel_lens=None, pitches=None,
@@ -242,10 +248,18 @@ class MamlEngine:
         if not hasattr(self, "_hyper_ring"):
             pin = self.hyper.is_cuda
             self._hyper_ring = [torch.zeros(4).pin_memory() if pin else torch.zeros(4) for _ in range(8)]
-        hb = self._hyper_ring[self.opt_step % len(self._hyper_ring)]
+            self._hyper_events = [None] * len(self._hyper_ring)
+        slot = self.opt_step % len(self._hyper_ring)
+        hb = self._hyper_ring[slot]
+        if self._hyper_events[slot] is not None:
+            self._hyper_events[slot].synchronize()      # the H2D copy that last read this pinned slot has executed
         hb[0] = self.lr_schedule(self.opt_step, warmup, anneal_steps, anneal_rate)
         hb[1], hb[2] = 1 - betas[0] ** t, 1 - betas[1] ** t
         self.hyper.copy_(hb, non_blocking=True)
+        if self.hyper.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._hyper_events[slot] = ev
         be.sumsq(self.g_outer, self.sumsq)
         be.adam_clip(self.theta, self.g_outer, self.adam_m, self.adam_v, self.sumsq, gscale, max_norm, self.hyper,
                      betas[0], betas[1], eps, self.theta_hi, self.theta_lo)

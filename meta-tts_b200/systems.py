@@ -21,8 +21,10 @@ buffers (pinned H2D) and reads back the 6 query losses.
 """
 from __future__ import annotations
 
+from collections import OrderedDict
 from typing import Dict, Optional, Tuple
 
+import os
 import time
 
 import torch
@@ -50,7 +52,11 @@ class _StaticBatch:
               ("salt", torch.int32))        # per-step dropout salt (uint32 bits): rides in the same H2D copy
     RING = 4        # the host may enqueue up to RING - 1 steps ahead of the device
 
-    def __init__(self, device, n: int, L: int, T: int, n_spk_ids: int, average_spk: bool):
+    def __init__(self, device, n: int, L: int, T: int, n_spk_ids: int, average_spk: bool, max_T: Optional[int] = None):
+        # train-mode truncation (Models.py:161-166, loss.py:42-43): keep the first max_seq_len frames of the mel targets
+        if max_T is not None and T > max_T:
+            T = max_T
+        self.T = T
         shapes = {"spk_ids": (n_spk_ids,), "texts": (n, L), "src_lens": (n,), "mels": (n, T, N_MEL), "mel_lens": (n,),
                   "pitches": (n, L), "energies": (n, L), "durations": (n, L), "salt": (1,)}
         offs, off = {}, 0
@@ -80,7 +86,7 @@ class _StaticBatch:
         if self.events[k] is not None:
             self.events[k].synchronize()                 # the H2D that last used this staging slot has completed
         staged = getattr(b12, "staged", None)
-        if staged is not None and spk_ids is None and staged.numel() == self.nbytes:
+        if staged is not None and spk_ids is None and staged.numel() == self.nbytes and int(b12[8]) == self.T:
             # the batch producer (meta_tts_b200.collate.reprocess) already wrote this batch in the static layout into
             # pinned memory: no per-field host copies, one H2D straight from the producer's buffer
             salt &= 0xFFFFFFFF
@@ -98,7 +104,10 @@ class _StaticBatch:
         for f, i in (("texts", 3), ("src_lens", 4), ("mels", 6), ("mel_lens", 7), ("pitches", 9), ("energies", 10), ("durations", 11)):
             src = b12[i]
             dst = h[f]
-            dst.copy_(src if torch.is_tensor(src) else torch.as_tensor(src))      # dtype conversion + gather into pinned staging
+            src = src if torch.is_tensor(src) else torch.as_tensor(src)
+            if f == "mels" and src.shape[1] > self.T:
+                src = src[:, :self.T]                    # train-mode truncation to max_seq_len frames
+            dst.copy_(src)                               # dtype conversion + gather into pinned staging
         spk = b12[2] if spk_ids is None else spk_ids
         h["spk_ids"].copy_(spk if torch.is_tensor(spk) else torch.as_tensor(spk))
         salt &= 0xFFFFFFFF
@@ -253,7 +262,16 @@ def _metasystem_init(self, preprocess_config=None, model_config=None, train_conf
                            max_inner_steps=self.adaptation_steps)
     self.use_cuda_graph = use_cuda_graph
     self.process_group = process_group
-    self._graphs: Dict[Tuple, Tuple] = {}
+    # CUDA-graph cache: one entry (static batches, graph, activation tapes) per input-shape signature.  Real corpora
+    # produce a new (L, T) almost every step, so the cache is an LRU of `graph_cache_size` entries (evicted graphs / tapes /
+    # pinned rings are freed) and a signature is only captured on its `graph_min_hits`-th sighting; before that the step
+    # runs eagerly on throw-away tapes (same kernels, no capture, no synchronisation).
+    self._graphs: "OrderedDict[Tuple, list]" = OrderedDict()
+    self.graph_cache_size = int(os.environ.get("MTTS_GRAPH_CACHE", "8"))
+    self.graph_min_hits = int(os.environ.get("MTTS_GRAPH_MIN_HITS", "2"))
+    self._shape_hits: "OrderedDict[Tuple, int]" = OrderedDict()
+    self._adapt_cache: "OrderedDict[Tuple, tuple]" = OrderedDict()      # stand-alone adapt(): (static batch, tapes) per shape
+    self._last_qdev = None
     self.host_prof = {"upload": 0.0, "replay": 0.0, "optimizer": 0.0, "d2h": 0.0, "step": 0.0}      # host seconds spent enqueueing (diagnostics)
     self._pending_tasks = 0
     self.launches_per_task_step: Optional[int] = None
@@ -274,25 +292,61 @@ def _state_dict(self):
     return self.maml.state_dict()
 
 
-def _get_task(self, sup12, qry12, steps: int, first_order: bool):
+def _task_key(self, sup12, qry12, steps: int, first_order: bool, accumulate_scale: Optional[float]):
     S, Q = sup12[3].shape[0], qry12[3].shape[0]
     Ls, Ts, Lq, Tq = int(sup12[5]), int(sup12[8]), int(qry12[5]), int(qry12[8])
-    key = (S, Ls, Ts, Q, Lq, Tq, steps, first_order)
+    # accumulate_scale is baked into the captured `axpby(scale, g_task, 1, g_outer)` (absent when None: validation), so it is
+    # part of the signature — a graph captured by a validation step must never serve a training step and vice versa.
+    return (S, Ls, Ts, Q, Lq, Tq, steps, first_order, accumulate_scale)
+
+
+def _get_task(self, key):
+    """LRU lookup / creation of the graph-cache entry of `key` = [sup static batch, qry static batch, graph, result, tapes]."""
     ent = self._graphs.get(key)
-    if ent is None:
-        sb = _StaticBatch(self.device, S, Ls, Ts, S, False)
-        qb = _StaticBatch(self.device, Q, Lq, Tq, S, True)
-        ent = [sb, qb, None, None, self.maml.new_tapes()]
-        self._graphs[key] = ent
-        self.h2d_bytes_per_step = sb.h2d_bytes + qb.h2d_bytes
-    return key, ent
+    if ent is not None:
+        self._graphs.move_to_end(key)
+        return ent
+    S, Ls, Ts, Q, Lq, Tq = key[:6]
+    max_T = self.model_config["max_seq_len"]
+    sb = _StaticBatch(self.device, S, Ls, Ts, S, False, max_T)
+    qb = _StaticBatch(self.device, Q, Lq, Tq, S, True, max_T)
+    ent = [sb, qb, None, None, self.maml.new_tapes()]
+    self._graphs[key] = ent
+    while len(self._graphs) > max(1, self.graph_cache_size):
+        _, old = self._graphs.popitem(last=False)          # least recently used: drop its graph, tapes and pinned rings
+        old.clear()
+    return ent
 
 
 def _run_task(self, sup12, qry12, steps: int, first_order: bool, accumulate_scale: Optional[float]):
-    key, ent = _get_task(self, sup12, qry12, steps, first_order)
-    sb, qb, graph, result, tapes = ent
-    self.maml.use_tapes(tapes)
+    key = _task_key(self, sup12, qry12, steps, first_order, accumulate_scale)
     drop_base = 0 if self.dropout else None
+    max_T = self.model_config["max_seq_len"]
+    if self.use_cuda_graph and key not in self._graphs:
+        hits = self._shape_hits.pop(key, 0) + 1
+        self._shape_hits[key] = hits
+        while len(self._shape_hits) > 1024:
+            self._shape_hits.popitem(last=False)
+        if hits < self.graph_min_hits:
+            # a signature seen for the first time: run it eagerly on throw-away buffers (no capture, no host sync)
+            t0 = time.perf_counter()
+            sup = batch_from_tuple(sup12, self.device, max_T=max_T)
+            qry = batch_from_tuple(qry12, self.device, spk_ids=sup12[2], average_spk=True, max_T=max_T)
+            _set_salt(self, self.next_salt() if self.dropout else 0)
+            self.h2d_bytes_per_step = sum(t.numel() * t.element_size() for b in (sup, qry) for t in
+                                          (b.spk_ids, b.texts, b.src_lens, b.mels, b.mel_lens, b.pitches, b.energies, b.durations))
+            self.host_prof["upload"] += time.perf_counter() - t0
+            self.maml.use_tapes(self.maml.new_tapes())
+            n0 = _ops.launch_count
+            result = self.maml.task_step(sup, qry, steps, first_order, accumulate_scale, drop_base)
+            self.launches_per_task_step = _ops.launch_count - n0
+            self._last_qdev = qry
+            return result
+    ent = _get_task(self, key)
+    sb, qb, graph, result, tapes = ent
+    self.h2d_bytes_per_step = sb.h2d_bytes + qb.h2d_bytes
+    self._last_qdev = qb.dev
+    self.maml.use_tapes(tapes)
     self.be.drop_salt = sb.salt
     t0 = time.perf_counter()
     sb.upload(sup12, salt=self.next_salt() if self.dropout else 0)
@@ -358,7 +412,17 @@ def adapt(self, batch, adaptation_steps: int = 5, learner=None, train: bool = Tr
     _assert_meta_batch(batch)
     sup12 = batch[0][0][0]
     start = int(learner) if learner is not None else 0
-    sb = _StaticBatch(self.device, sup12[3].shape[0], int(sup12[5]), int(sup12[8]), sup12[3].shape[0], False)
+    # static batch + activation tapes per input shape (a small LRU: the tapes' buffers are shape-specific)
+    akey = (sup12[3].shape[0], int(sup12[5]), int(sup12[8]))
+    ent = self._adapt_cache.pop(akey, None)
+    if ent is None:
+        ent = (_StaticBatch(self.device, akey[0], akey[1], akey[2], akey[0], False, self.model_config["max_seq_len"]),
+               self.maml.new_tapes())
+    self._adapt_cache[akey] = ent
+    while len(self._adapt_cache) > 4:
+        self._adapt_cache.popitem(last=False)
+    sb = ent[0]
+    self.maml.use_tapes(ent[1])
     self.be.drop_salt = sb.salt
     sb.upload(sup12, salt=self.next_salt() if self.dropout else 0)
     self.maml.adapt(sb.dev, adaptation_steps, start=start, drop_base=start if self.dropout else None)
@@ -378,25 +442,25 @@ def meta_learn(self, batch, batch_idx, train: bool = True):
     if not hasattr(self, "_loss_ring"):
         pin = loss6.is_cuda
         self._loss_ring = [torch.zeros(6).pin_memory() if pin else torch.zeros(6) for _ in range(8)]
+        self._loss_events = [None] * len(self._loss_ring)
         self._loss_slot = 0
-    hbuf = self._loss_ring[self._loss_slot]
-    self._loss_slot = (self._loss_slot + 1) % len(self._loss_ring)
+    k = self._loss_slot
+    hbuf = self._loss_ring[k]
+    self._loss_slot = (k + 1) % len(self._loss_ring)
     t0 = time.perf_counter()
+    if self._loss_events[k] is not None:
+        self._loss_events[k].synchronize()       # the D2H copy that last used this slot has landed (bounds the host's run-ahead)
     hbuf.copy_(loss6, non_blocking=True)
     ev = None
     if loss6.is_cuda:
         ev = torch.cuda.Event()
         ev.record()
+        self._loss_events[k] = ev
     self.host_prof["d2h"] += time.perf_counter() - t0
     losses = LazyLosses(hbuf, ev)
-    dev = _ent_dev(self, sup12, qry12, steps, first_order)
-    preds = _Predictions(out, dev, int(qry12[5]), int(qry12[8]))
+    dev = self._last_qdev
+    preds = _Predictions(out, dev, dev.L, dev.T)
     return losses, preds
-
-
-def _ent_dev(self, sup12, qry12, steps, first_order):
-    _, ent = _get_task(self, sup12, qry12, steps, first_order)
-    return ent[1].dev
 
 
 def training_step(self, batch, batch_idx):
@@ -572,13 +636,13 @@ def load_checkpoint(self, checkpoint: dict) -> None:
 def save_checkpoint(self) -> dict:
     """A Lightning-format checkpoint dict the reference can load (`torch.save` it): `state_dict` with the `model.` prefix,
     `global_step`, `optimizer_states` (torch Adam layout), `lr_schedulers` (LambdaLR last_epoch)."""
-    from .checkpoint import export_adam_state
+    from .checkpoint import export_adam_state, export_scheduler_state
 
     opt = self.train_config["optimizer"]
     return {"global_step": self.maml.opt_step, "epoch": 0, "state_dict": _prefixed_state_dict(self),
             "optimizer_states": [export_adam_state(self.maml, tuple(opt["betas"]), float(opt["eps"]),
                                                    float(opt.get("weight_decay", 0.0)))],
-            "lr_schedulers": [{"last_epoch": self.maml.opt_step, "_step_count": self.maml.opt_step + 1}]}
+            "lr_schedulers": [export_scheduler_state(self.maml)]}
 
 
 def on_test_start(self) -> None:

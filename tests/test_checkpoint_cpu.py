@@ -109,3 +109,28 @@ def test_on_load_checkpoint_rules():
     s.on_test_start()
     w = s.state_dict()["speaker_emb.model.weight"]
     assert torch.allclose(w[-39:], P["speaker_emb.model.weight"][:247].mean(0).expand(39, -1)) and torch.equal(w[:-39], P["speaker_emb.model.weight"][:-39])
+
+
+def test_exported_optimizer_and_scheduler_state_load_into_torch():
+    """the exported `optimizer_states` / `lr_schedulers` entries must load into a REAL torch Adam + LambdaLR
+    (what Lightning does on resume) and continue with the same learning rate as this framework's next step."""
+    a = _system()
+    a.load_state_dict(O.init_params(seed=0, model_config=CFG))
+    for t in range(3):
+        sup, qry = O.synth_task(task=t + 2, shots=2, queries=2, L=5, T=12, ragged=True)
+        a.training_step([([sup], [qry])], t)
+        a.optimizer_step()
+    ck = a.save_checkpoint()
+    keys = CK.reference_parameter_keys(CFG)
+    sd = {k[6:]: v for k, v in ck["state_dict"].items()}
+    plist = [torch.nn.Parameter(sd[k].clone().float(), requires_grad=sd[k].is_floating_point()) for k in keys]
+    opt = torch.optim.Adam(plist, lr=CFG["transformer"]["encoder_hidden"] ** -0.5, betas=(0.9, 0.98), eps=1e-9)
+    # the reference's scheduler lambda (lightning/scheduler.py:11-23), restated
+    lam = lambda step: min((step + 1) ** -0.5, 4000 ** -1.5 * (step + 1))  # noqa: E731
+    sch = torch.optim.lr_scheduler.LambdaLR(opt, lam)
+    opt.load_state_dict(copy.deepcopy(ck["optimizer_states"][0]))
+    sch.load_state_dict(copy.deepcopy(ck["lr_schedulers"][0]))          # raised KeyError('lr_lambdas') before the fix
+    assert sch.last_epoch == 3 and sch.base_lrs == [CFG["transformer"]["encoder_hidden"] ** -0.5]
+    want = a.maml.lr_schedule(3)                                        # the rate this framework uses for step index 3
+    assert abs(opt.param_groups[0]["lr"] - want) <= 1e-12 and abs(sch.get_last_lr()[0] - want) <= 1e-12
+    assert abs(want - CFG["transformer"]["encoder_hidden"] ** -0.5 * lam(3)) <= 1e-15
