@@ -190,6 +190,50 @@ int mtts_softmax(int mode, const float* A, const float* Bm, const void* p_hi, co
                  mtts_stream stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused scaled-dot-product attention (csrc/mtts_attn.cu): scores, key-masked softmax and the value /
+ * gradient products in one tcgen05 kernel per pass; the [T,T] score matrix stays in tensor memory.
+ * Replaces ScaledDotProductAttention.forward, Modules.py:14-25 (bmm(q, k^T)/temperature,
+ * masked_fill(mask, -inf), softmax(dim=2), bmm(attn, v)) as called from MultiHeadAttention.forward,
+ * SubLayers.py:43-52, and its autograd backward.
+ *
+ *   q | k | v live in ONE [B*T, 3*H*dk] bf16 (hi/lo) buffer (the fused w_qs|w_ks|w_vs projection,
+ *   SubLayers.py:39-41): column block `which*H + h` (which = 0 q, 1 k, 2 v) holds head h.  dk == 128.
+ *   o / do are [B*T, H*dk].  keys j >= klens[b] are masked (klens NULL: none).
+ *
+ * mtts_attn_fwd:  o = softmax(scale * q k^T) v ;  lse[b,h,t] = log2-domain log-sum-exp of row t's scaled
+ *   scores (the backward recomputes P from it).  p_hi != NULL additionally EMITS the probabilities
+ *   P[B,H,T,Tp] (hi/lo) for passes that re-read them (the Hessian-vector passes).
+ * mtts_attn_bwd(parts):  MTTS_ATTN_PREP  dvec[b,h,t] = sum_c do*o   (softmax-backward row term)
+ *                        MTTS_ATTN_DQ    dqkv[.., q block] = scale * dS k,  dS = P*(dP - dvec), dP = do v^T
+ *                                        (ds_hi != NULL: EMIT dP (fp32) and dS (hi/lo) as [B,H,T,Tp])
+ *                        MTTS_ATTN_DKV   dqkv[.., v block] = P^T do ;  dqkv[.., k block] = scale * dS^T q
+ *   DQ and DKV only depend on PREP and may run concurrently on different streams.
+ * lse / dvec: fp32 [B,H,Tl], Tl >= T rounded up to 128 (Tl % 4 == 0); entries beyond T are never read as
+ * meaningful values but must be finite.
+ * ------------------------------------------------------------------------------------------ */
+enum { MTTS_ATTN_PREP = 1, MTTS_ATTN_DQ = 2, MTTS_ATTN_DKV = 4 };
+
+typedef struct {
+  int32_t B, H, T, dk;
+  int32_t Tp;              /* leading dimension of the emitted [B,H,T,Tp] tensors (multiple of 8, >= T) */
+  int32_t Tl;              /* leading dimension of lse / dvec                                          */
+  int32_t split;           /* 1 (bf16) or 3 (bf16x3 hi/lo)                                             */
+  float   scale;           /* 1 / temperature = d_k^-0.5 (SubLayers.py:27)                             */
+  const void* qkv_hi;  const void* qkv_lo;
+  const int64_t* klens;    /* [B] or NULL */
+  void* o_hi;  void* o_lo; /* fwd: out; bwd PREP: in */
+  float* lse;              /* fwd: out; bwd: in  */
+  void* p_hi;  void* p_lo; /* fwd: optional emit */
+  const void* do_hi;  const void* do_lo;
+  float* dvec;             /* bwd PREP: out; DQ / DKV: in */
+  void* dqkv_hi;  void* dqkv_lo;
+  float* dp;  void* ds_hi;  void* ds_lo;   /* bwd DQ: optional emit */
+} mtts_attn_desc;
+
+int mtts_attn_fwd(const mtts_attn_desc* desc, mtts_stream stream);
+int mtts_attn_bwd(const mtts_attn_desc* desc, int parts, mtts_stream stream);
+
+/* ------------------------------------------------------------------------------------------
  * Gathers, broadcasts, column sums
  * ------------------------------------------------------------------------------------------ */
 /* out[r,:] = table[idx[r],:] (+ base[r,:]) (+ pos[r % T,:]).  nn.Embedding + position_enc Models.py:89-91;

@@ -358,6 +358,9 @@ class BMat:
 # Narrow tiles + deeper split-K for SMALL accumulate GEMMs: measured on B200 12.00 ms/step vs 11.87 with the widest-tile rule
 # (the extra CTAs of the off-critical-path weight gradients take SMs from the main chain), so it stays off.
 SMALL_SPLITK_MODEL = os.environ.get("MTTS_SMALL_SPLITK", "0") == "1"
+# Fused attention (csrc/mtts_attn.cu) for the forward / backward passes: scores -> softmax -> P V (and the recomputing backward)
+# as ONE kernel per pass, S / dP never written.  MTTS_FUSED_ATTN=0 restores the three-launch chain (A/B measurements).
+FUSED_ATTN = os.environ.get("MTTS_FUSED_ATTN", "1") == "1"
 USE_PAIR = True        # 2-CTA (cta_group::2) tiles; set False to fall back to the 1-CTA kernel everywhere
 
 
@@ -575,6 +578,19 @@ class FS2Engine:
         om = lambda hi, lo, f32=None: BMat(hi, lo, 0, T * d, dk, d, T, dk, f32)  # noqa: E731
         return dk, Tp, q, pm, om
 
+    def _fused_attn(self, dk: int) -> bool:
+        return FUSED_ATTN and dk == 128 and hasattr(self.be, "attn_fwd")
+
+    def _attn_emit(self, tp, pf: str) -> bool:
+        """Write P / dP / dS out of the fused kernels?  Only tapes that a Hessian-vector pass re-reads need them (second-order
+        support passes: `tp.attn_emit`, unknown = keep), and only layers that have a tangent pass (adapted modules)."""
+        return bool(getattr(tp, "attn_emit", True)) and self.layout.is_adapted_module(pf)
+
+    @staticmethod
+    def _attn_vec(tp, name: str, B: int, H: int, T: int):
+        """Per-row attention statistics [B, H, Tl] (log-sum-exp / softmax-backward row term), Tl = T rounded up to 128."""
+        return tp.buf(name + ":f", (B, H, _rup(T, 128)), zero=True)
+
     # ---- dropout sites (include/mtts.h): launch scalar = crc32(site) ^ (pass_index * 2654435761); the device adds the
     #      per-step salt.  The pass index lives on the primal tape, so every pass over it draws the same mask. ----
     def _site(self, tp: Tape, site: str, p: float, C: int = 0):
@@ -618,12 +634,17 @@ class FS2Engine:
         wqkv, bqkv = self._qkv(P, pf)
         qkv_h, qkv_l = tp.bf(f"{pf}.qkv", (R, 3 * d))
         g.conv_fwd(x, wqkv, bqkv.f32, None, qkv_h, qkv_l)
-        S = scr.scratch("S", (B, H, T, Tp))
-        g.bmm(qm(qkv_h, qkv_l, 0), False, qm(qkv_h, qkv_l, 1), False, pm(None, None, S), B, H, alpha=1.0 / math.sqrt(dk))
-        p_h, p_l = tp.bf(f"{pf}.P", (B, H, T, Tp))
-        be.softmax(0, S, None, None, None, None, None, lens, B * H, H, T, T, Tp, p_h, p_l)
         o = tp.act(f"{pf}.o", B, T, d, f32=False)
-        g.bmm(pm(p_h, p_l), False, qm(qkv_h, qkv_l, 2), True, om(o.hi, o.lo), B, H)
+        if self._fused_attn(dk):
+            # P is only written out for tapes a Hessian-vector pass will re-read (tp.attn_emit; unknown = keep it)
+            p_h, p_l = tp.bf(f"{pf}.P", (B, H, T, Tp)) if self._attn_emit(tp, pf) else (None, None)
+            be.attn_fwd(qkv_h, qkv_l, lens, B, H, T, dk, o.hi, o.lo, self._attn_vec(tp, f"{pf}.lse", B, H, T), p_h, p_l, Tp)
+        else:
+            S = scr.scratch("S", (B, H, T, Tp))
+            g.bmm(qm(qkv_h, qkv_l, 0), False, qm(qkv_h, qkv_l, 1), False, pm(None, None, S), B, H, alpha=1.0 / math.sqrt(dk))
+            p_h, p_l = tp.bf(f"{pf}.P", (B, H, T, Tp))
+            be.softmax(0, S, None, None, None, None, None, lens, B * H, H, T, T, Tp, p_h, p_l)
+            g.bmm(pm(p_h, p_l), False, qm(qkv_h, qkv_l, 2), True, om(o.hi, o.lo), B, H)
         y0 = scr.scratch("y0", (B, T, d))
         g.conv_fwd(o, P.get(f"{a_}.fc.weight"), P.get(f"{a_}.fc.bias").f32, y0, None, None)
         y1 = tp.act(f"{pf}.y1", B, T, d)
@@ -652,7 +673,6 @@ class FS2Engine:
         wqkv, _ = self._qkv(P, pf)
         gwqkv, gbqkv = self._qkv(G, pf)
         qkv_h, qkv_l = tp.bf(f"{pf}.qkv", (R, 3 * d))
-        p_h, p_l = tp.bf(f"{pf}.P", (B, H, T, Tp))
         o = tp.act(f"{pf}.o", B, T, d, f32=False)
         y1 = tp.act(f"{pf}.y1", B, T, d)
         h = tp.act(f"{pf}.h", B, T, self.d_inner, f32=False)
@@ -679,18 +699,33 @@ class FS2Engine:
         with be.side():
             g.conv_wgrad(dz1, o, G.get(f"{a_}.fc.weight").f32)
         # attention
-        dP = tp.f32(f"{pf}.dP", (B, H, T, Tp))
         dq_h, dq_l = tp.bf(f"{pf}.dqkv", (R, 3 * d))
-        with be.branch("att", local=True):                  # dV needs only dO and P: beside dP -> softmax-bwd -> dQ
-            g.bmm(pm(p_h, p_l), True, om(do.hi, do.lo), True, qm(dq_h, dq_l, 2), B, H)                  # dV = P^T dO
-        g.bmm(om(do.hi, do.lo), False, qm(qkv_h, qkv_l, 2), False, pm(None, None, dP), B, H)
-        ds_h, ds_l = tp.bf(f"{pf}.dS", (B, H, T, Tp))
-        be.softmax(1, dP, None, p_h, p_l, None, None, lens, B * H, H, T, T, Tp, ds_h, ds_l)
-        sc = 1.0 / math.sqrt(dk)
-        g.bmm(pm(ds_h, ds_l), False, qm(qkv_h, qkv_l, 1), True, qm(dq_h, dq_l, 0), B, H, alpha=sc)       # dQ = dS K
-        with be.branch("att", local=True):                  # dK runs beside dQ (disjoint column blocks of dqkv)
-            g.bmm(pm(ds_h, ds_l), True, qm(qkv_h, qkv_l, 0), True, qm(dq_h, dq_l, 1), B, H, alpha=sc)    # dK = dS^T Q
-        be.join("att", local=True)
+        if self._fused_attn(dk):
+            # P is recomputed from q, k and the saved log-sum-exp; the key-tile kernel (dK, dV) and the query-tile kernel (dQ)
+            # run side by side.  dP / dS are only written out for tapes a Hessian-vector pass will re-read.
+            emit = self._attn_emit(tp, pf)
+            dP = tp.f32(f"{pf}.dP", (B, H, T, Tp)) if emit else None
+            ds_h, ds_l = tp.bf(f"{pf}.dS", (B, H, T, Tp)) if emit else (None, None)
+            args = (qkv_h, qkv_l, lens, B, H, T, dk, o.hi, o.lo, self._attn_vec(tp, f"{pf}.lse", B, H, T), do.hi, do.lo,
+                    self._attn_vec(tp, f"{pf}.dvec", B, H, T), dq_h, dq_l)
+            be.attn_bwd(L.ATTN_PREP, *args)
+            with be.branch("att", local=True):
+                be.attn_bwd(L.ATTN_DKV, *args)
+            be.attn_bwd(L.ATTN_DQ, *args, dP, ds_h, ds_l, Tp)
+            be.join("att", local=True)
+        else:
+            p_h, p_l = tp.bf(f"{pf}.P", (B, H, T, Tp))
+            dP = tp.f32(f"{pf}.dP", (B, H, T, Tp))
+            with be.branch("att", local=True):                  # dV needs only dO and P: beside dP -> softmax-bwd -> dQ
+                g.bmm(pm(p_h, p_l), True, om(do.hi, do.lo), True, qm(dq_h, dq_l, 2), B, H)                  # dV = P^T dO
+            g.bmm(om(do.hi, do.lo), False, qm(qkv_h, qkv_l, 2), False, pm(None, None, dP), B, H)
+            ds_h, ds_l = tp.bf(f"{pf}.dS", (B, H, T, Tp))
+            be.softmax(1, dP, None, p_h, p_l, None, None, lens, B * H, H, T, T, Tp, ds_h, ds_l)
+            sc = 1.0 / math.sqrt(dk)
+            g.bmm(pm(ds_h, ds_l), False, qm(qkv_h, qkv_l, 1), True, qm(dq_h, dq_l, 0), B, H, alpha=sc)       # dQ = dS K
+            with be.branch("att", local=True):                  # dK runs beside dQ (disjoint column blocks of dqkv)
+                g.bmm(pm(ds_h, ds_l), True, qm(qkv_h, qkv_l, 0), True, qm(dq_h, dq_l, 1), B, H, alpha=sc)    # dK = dS^T Q
+            be.join("att", local=True)
         dqkv = Act(None, dq_h, dq_l, B, T, 3 * d)
         with be.side():
             g.conv_wgrad(dqkv, x, gwqkv.f32)
@@ -1348,6 +1383,7 @@ class FS2Engine:
     # (Pd is non-zero on adapted parameters only; encoder = non-adapted => zero forward tangent.)
     # ---------------------------------------------------------------------------------------------
     def hvp(self, P: ParamSet, Pd: ParamSet, HV: ParamSet, bt: Batch, tp: Tape, tt: Tape, loss_scale: float = 1.0):
+        assert getattr(tp, "attn_emit", True), "this tape was recorded without the attention probabilities (attn_emit = False)"
         self.g.split_override = self.hvp_split if self.hvp_split != self.split else None
         try:
             self._hvp(P, Pd, HV, bt, tp, tt, loss_scale)

@@ -50,6 +50,26 @@ class GemmDesc(C.Structure):
     ]
 
 
+ATTN_PREP, ATTN_DQ, ATTN_DKV = 1, 2, 4
+
+
+class AttnDesc(C.Structure):
+    """mtts_attn_desc (include/mtts.h)."""
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("T", C.c_int32), ("dk", C.c_int32),
+        ("Tp", C.c_int32), ("Tl", C.c_int32), ("split", C.c_int32), ("scale", C.c_float),
+        ("qkv_hi", C.c_void_p), ("qkv_lo", C.c_void_p),
+        ("klens", C.c_void_p),
+        ("o_hi", C.c_void_p), ("o_lo", C.c_void_p),
+        ("lse", C.c_void_p),
+        ("p_hi", C.c_void_p), ("p_lo", C.c_void_p),
+        ("do_hi", C.c_void_p), ("do_lo", C.c_void_p),
+        ("dvec", C.c_void_p),
+        ("dqkv_hi", C.c_void_p), ("dqkv_lo", C.c_void_p),
+        ("dp", C.c_void_p), ("ds_hi", C.c_void_p), ("ds_lo", C.c_void_p),
+    ]
+
+
 class MttsError(RuntimeError):
     pass
 
@@ -84,6 +104,8 @@ SIGNATURES: dict[str, list] = {
     "mtts_check_device": [],
     "mtts_set_pdl": [_i],
     "mtts_gemm": [C.POINTER(GemmDesc), _vp],
+    "mtts_attn_fwd": [C.POINTER(AttnDesc), _vp],
+    "mtts_attn_bwd": [C.POINTER(AttnDesc), _i, _vp],
     "mtts_pack_rows": [_vp, _vp, _i, _i, _i, _vp, _vp],
     "mtts_length_regulate_index": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
     "mtts_length_regulate_fwd": [_vp, _vp, _i, _i, _i, _i, _vp, _vp],

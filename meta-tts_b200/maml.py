@@ -138,7 +138,7 @@ class MamlEngine:
         return {n: sd[n] for n, e in self.layout.entries.items() if e.adapted}
 
     # ---- one task ---------------------------------------------------------------------------------
-    def adapt(self, sup: Batch, steps: int, start: int = 0, drop_base: Optional[int] = None) -> None:
+    def adapt(self, sup: Batch, steps: int, start: int = 0, drop_base: Optional[int] = None, second_order: bool = True) -> None:
         """Inner loop (base_adaptor.py:98-112): fast weights theta_{start+1..start+steps}.
         drop_base: None = dropout off; else support pass k uses dropout pass index drop_base + k (learner.train(),
         base_adaptor.py:103)."""
@@ -146,6 +146,7 @@ class MamlEngine:
         a0 = lay.adapt_begin
         for k in range(start, start + steps):
             P = self.params(k)
+            self.tapes[k].attn_emit = second_order       # only a Hessian-vector pass re-reads the attention probabilities
             eng.forward(P, sup, self.tapes[k], drop_pass=None if drop_base is None else drop_base + k)
             g_ad = self.g_inner[a0:]
             be.zero_(g_ad)
@@ -163,6 +164,7 @@ class MamlEngine:
         be, eng, lay = self.be, self.engine, self.layout
         a0 = lay.adapt_begin
         dst = self.fast[0]
+        tape.attn_emit = False
         for s in range(steps):
             first = fresh and s == 0
             P = self.params(0) if first else self.params(1)
@@ -181,6 +183,7 @@ class MamlEngine:
         eng = self.engine
         P = self.params(int(adapted))                          # False / 0: meta parameters; True / k: fast weights after k held steps
         tape = eng.new_tape()
+        tape.attn_emit = False
         if free_running:
             out = eng.synthesize(P, bt, tape, p_control, e_control, d_control, update_bn=not eval_mode, drop_pass=drop_pass,
                                  eval_mode=eval_mode)
@@ -199,8 +202,9 @@ class MamlEngine:
         a0 = lay.adapt_begin
         dq = None if drop_base is None else drop_base + steps
         # the encoder is not adapted: the query's encoder pass does not depend on the inner loop -> 'enc' branch
+        self.tape_q.attn_emit = False
         xq = eng.encoder_early(self.params(0), qry, self.tape_q, drop_pass=dq)
-        self.adapt(sup, steps, drop_base=drop_base)
+        self.adapt(sup, steps, drop_base=drop_base, second_order=not first_order)
         PK = self.params(steps)
         out = eng.forward(PK, qry, self.tape_q, drop_pass=dq, enc=xq)
         self.bn_batches += 1

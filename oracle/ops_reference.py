@@ -379,6 +379,58 @@ class RefOps:
         _put_split(o_hi, o_lo, full)
 
     # ------------------------------------------------------------------------------------------
+    # fused attention (mtts_attn_fwd / mtts_attn_bwd): ScaledDotProductAttention, Modules.py:14-25, and its autograd,
+    # restated with torch ops.  lse is kept in the log2 domain like the kernels do.
+    # ------------------------------------------------------------------------------------------
+    def _attn_parts(self, qkv_hi, qkv_lo, klens, B, H, T, dk):
+        x = _val(qkv_hi, qkv_lo if self.split == 3 else None).reshape(B, T, 3, H, dk).to(self.acc)
+        q, k, v = (x[:, :, i].permute(0, 2, 1, 3) for i in range(3))                     # [B,H,T,dk]
+        kl = klens.clamp(max=T) if klens is not None else torch.full((B,), T)
+        km = (torch.arange(T)[None, :] < kl[:, None])[:, None, None, :]                    # [B,1,1,T] valid keys
+        s = (q @ k.transpose(-1, -2)) / math.sqrt(dk)
+        return q, k, v, s.masked_fill(~km, -math.inf), km
+
+    def attn_fwd(self, qkv_hi, qkv_lo, klens, B, H, T, dk, o_hi, o_lo, lse, p_hi=None, p_lo=None, Tp=0):
+        self.n_calls += 1
+        q, k, v, s, km = self._attn_parts(qkv_hi, qkv_lo, klens, B, H, T, dk)
+        P = torch.softmax(s, -1)
+        lse[..., :T] = (torch.logsumexp(s, -1) / math.log(2.0)).float()
+        _put_split(o_hi, o_lo if self.split == 3 else None, (P @ v).permute(0, 2, 1, 3).reshape(B * T, H * dk))
+        if p_hi is not None:
+            full = torch.zeros(B, H, T, Tp, dtype=self.acc)
+            full[..., :T] = P
+            _put_split(p_hi, p_lo if self.split == 3 else None, full)
+
+    def attn_bwd(self, parts, qkv_hi, qkv_lo, klens, B, H, T, dk, o_hi, o_lo, lse, do_hi, do_lo, dvec, dqkv_hi, dqkv_lo,
+                 dp=None, ds_hi=None, ds_lo=None, Tp=0):
+        self.n_calls += 1
+        lo = (lambda t: t if self.split == 3 else None)
+        dO = _val(do_hi, lo(do_lo)).reshape(B, T, H, dk).permute(0, 2, 1, 3).to(self.acc)
+        if parts & 1:
+            O = _val(o_hi, lo(o_lo)).reshape(B, T, H, dk).permute(0, 2, 1, 3).to(self.acc)
+            dvec[..., :T] = (dO * O).sum(-1).float()
+        if not parts & 6:
+            return
+        q, k, v, s, km = self._attn_parts(qkv_hi, qkv_lo, klens, B, H, T, dk)
+        P = torch.exp(s - (lse[..., :T].to(self.acc) * math.log(2.0))[..., None])          # recomputed from the saved log-sum-exp
+        dP = dO @ v.transpose(-1, -2)
+        dS = P * (dP - dvec[..., :T].to(self.acc)[..., None])
+        sc = 1.0 / math.sqrt(dk)
+        cur = _val(dqkv_hi, lo(dqkv_lo)).reshape(B, T, 3, H, dk).to(self.acc).clone()
+        if parts & 2:
+            cur[:, :, 0] = (sc * (dS @ k)).permute(0, 2, 1, 3)
+            if ds_hi is not None:
+                full = torch.zeros(B, H, T, Tp, dtype=self.acc)
+                full[..., :T] = dS
+                _put_split(ds_hi, lo(ds_lo), full)
+                full[..., :T] = dP
+                _put(dp, full)
+        if parts & 4:
+            cur[:, :, 1] = (sc * (dS.transpose(-1, -2) @ q)).permute(0, 2, 1, 3)
+            cur[:, :, 2] = (P.transpose(-1, -2) @ dO).permute(0, 2, 1, 3)
+        _put_split(dqkv_hi, lo(dqkv_lo), cur.reshape(B * T, 3 * H * dk))
+
+    # ------------------------------------------------------------------------------------------
     # gathers / broadcasts / sums
     # ------------------------------------------------------------------------------------------
     def embed_fwd(self, idx, table, base, pos, T, R, C, out, hi, lo):
