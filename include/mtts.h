@@ -206,12 +206,13 @@ int mtts_softmax(int mode, const float* A, const float* Bm, const void* p_hi, co
  * mtts_attn_bwd(parts):  MTTS_ATTN_PREP  dvec[b,h,t] = sum_c do*o   (softmax-backward row term)
  *                        MTTS_ATTN_DQ    dqkv[.., q block] = scale * dS k,  dS = P*(dP - dvec), dP = do v^T
  *                                        (ds_hi != NULL: EMIT dP (fp32) and dS (hi/lo) as [B,H,T,Tp])
- *                        MTTS_ATTN_DKV   dqkv[.., v block] = P^T do ;  dqkv[.., k block] = scale * dS^T q
- *   DQ and DKV only depend on PREP and may run concurrently on different streams.
+ *                        MTTS_ATTN_DK    dqkv[.., k block] = scale * dS^T q
+ *                        MTTS_ATTN_DV    dqkv[.., v block] = P^T do
+ *   DQ, DK and DV only depend on PREP, write disjoint column blocks and may run concurrently on different streams.
  * lse / dvec: fp32 [B,H,Tl], Tl >= T rounded up to 128 (Tl % 4 == 0); entries beyond T are never read as
  * meaningful values but must be finite.
  * ------------------------------------------------------------------------------------------ */
-enum { MTTS_ATTN_PREP = 1, MTTS_ATTN_DQ = 2, MTTS_ATTN_DKV = 4 };
+enum { MTTS_ATTN_PREP = 1, MTTS_ATTN_DQ = 2, MTTS_ATTN_DK = 4, MTTS_ATTN_DV = 8 };
 
 typedef struct {
   int32_t B, H, T, dk;

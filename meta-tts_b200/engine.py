@@ -701,7 +701,7 @@ class FS2Engine:
         # attention
         dq_h, dq_l = tp.bf(f"{pf}.dqkv", (R, 3 * d))
         if self._fused_attn(dk):
-            # P is recomputed from q, k and the saved log-sum-exp; the key-tile kernel (dK, dV) and the query-tile kernel (dQ)
+            # P is recomputed from q, k and the saved log-sum-exp; the two key-tile kernels (dK, dV) and the query-tile kernel (dQ)
             # run side by side.  dP / dS are only written out for tapes a Hessian-vector pass will re-read.
             emit = self._attn_emit(tp, pf)
             dP = tp.f32(f"{pf}.dP", (B, H, T, Tp)) if emit else None
@@ -710,9 +710,12 @@ class FS2Engine:
                     self._attn_vec(tp, f"{pf}.dvec", B, H, T), dq_h, dq_l)
             be.attn_bwd(L.ATTN_PREP, *args)
             with be.branch("att", local=True):
-                be.attn_bwd(L.ATTN_DKV, *args)
+                be.attn_bwd(L.ATTN_DK, *args)
+            with be.branch("att2", local=True):
+                be.attn_bwd(L.ATTN_DV, *args)
             be.attn_bwd(L.ATTN_DQ, *args, dP, ds_h, ds_l, Tp)
             be.join("att", local=True)
+            be.join("att2", local=True)
         else:
             p_h, p_l = tp.bf(f"{pf}.P", (B, H, T, Tp))
             dP = tp.f32(f"{pf}.dP", (B, H, T, Tp))

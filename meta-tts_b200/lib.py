@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmtts.so")
+LIB_PATH = os.environ.get("MTTS_LIB_PATH") or os.path.join(_HERE, "libmtts.so")     # override: instrumented debug builds
 
 # enums (include/mtts.h)
 SRC_ZERO, SRC_Z0, SRC_Z1, SRC_TAP, SRC_KB = 0, 1, 2, 3, 4
@@ -50,7 +50,8 @@ class GemmDesc(C.Structure):
     ]
 
 
-ATTN_PREP, ATTN_DQ, ATTN_DKV = 1, 2, 4
+ATTN_PREP, ATTN_DQ, ATTN_DK, ATTN_DV = 1, 2, 4, 8
+ATTN_DKV = ATTN_DK | ATTN_DV
 
 
 class AttnDesc(C.Structure):

@@ -371,7 +371,7 @@ class CudaOps:
     def attn_bwd(self, parts, qkv_hi, qkv_lo, klens, B, H, T, dk, o_hi, o_lo, lse, do_hi, do_lo, dvec, dqkv_hi, dqkv_lo,
                  dp=None, ds_hi=None, ds_lo=None, Tp=0):
         """parts: mask of L.ATTN_PREP (dvec = rowsum(do*o)), L.ATTN_DQ (dq block of dqkv; optional emit of dP / dS),
-        L.ATTN_DKV (dk, dv blocks of dqkv)."""
+        L.ATTN_DK, L.ATTN_DV (dk / dv blocks of dqkv)."""
         global launch_count
         _need_cuda(qkv_hi, do_hi, lse, dvec)
         d = self._attn_desc(qkv_hi, qkv_lo, klens, B, H, T, dk, lse)

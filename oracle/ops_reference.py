@@ -409,7 +409,7 @@ class RefOps:
         if parts & 1:
             O = _val(o_hi, lo(o_lo)).reshape(B, T, H, dk).permute(0, 2, 1, 3).to(self.acc)
             dvec[..., :T] = (dO * O).sum(-1).float()
-        if not parts & 6:
+        if not parts & 14:
             return
         q, k, v, s, km = self._attn_parts(qkv_hi, qkv_lo, klens, B, H, T, dk)
         P = torch.exp(s - (lse[..., :T].to(self.acc) * math.log(2.0))[..., None])          # recomputed from the saved log-sum-exp
@@ -427,6 +427,7 @@ class RefOps:
                 _put(dp, full)
         if parts & 4:
             cur[:, :, 1] = (sc * (dS.transpose(-1, -2) @ q)).permute(0, 2, 1, 3)
+        if parts & 8:
             cur[:, :, 2] = (P.transpose(-1, -2) @ dO).permute(0, 2, 1, 3)
         _put_split(dqkv_hi, lo(dqkv_lo), cur.reshape(B * T, 3 * H * dk))
 

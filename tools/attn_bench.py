@@ -96,8 +96,9 @@ timeit("chain  fwd: scores + softmax + PV", chain_fwd, f_fwd)
 timeit("fused  fwd", lambda a: fused_fwd(a, False), f_fwd)
 timeit("fused  fwd + emit P", lambda a: fused_fwd(a, True), f_fwd)
 timeit("chain  bwd: dV, dP, softmax', dQ, dK (serial)", chain_bwd, 2 * f_fwd)
-timeit("fused  bwd: prep + dQ + dKV (serial)", lambda a: fused_bwd(a, 7, False), 2 * f_fwd)
+timeit("fused  bwd: prep + dQ + dK + dV (serial)", lambda a: fused_bwd(a, 15, False), 2 * f_fwd)
 timeit("fused  bwd: dQ only", lambda a: fused_bwd(a, L.ATTN_DQ, False), 0.75 * f_fwd)
 timeit("fused  bwd: dQ only + emit dP, dS", lambda a: fused_bwd(a, L.ATTN_DQ, True), 0.75 * f_fwd)
-timeit("fused  bwd: dKV only", lambda a: fused_bwd(a, L.ATTN_DKV, False), 1.0 * f_fwd)
+timeit("fused  bwd: dK only", lambda a: fused_bwd(a, L.ATTN_DK, False), 0.75 * f_fwd)
+timeit("fused  bwd: dV only", lambda a: fused_bwd(a, L.ATTN_DV, False), 0.5 * f_fwd)
 timeit("fused  bwd: prep only", lambda a: fused_bwd(a, L.ATTN_PREP, False), 0.0)
