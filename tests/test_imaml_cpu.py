@@ -88,3 +88,24 @@ def test_imaml_hypergradient_matches_oracle(dropout, stochastic):
     th = sysm.maml.theta.clone()
     v = sysm.validation_step([([sup], [qry])], 0)
     assert len(v["losses"]) == 6 and torch.equal(sysm.maml.theta, th) and sysm.maml.opt_step == 1
+
+
+def test_imaml_task_matches_real_hypergrad_golden():
+    """`oracle.fs2_oracle.imaml_task_step` against the golden of one whole iMAML task driven through the REAL
+    hypertorch `hypergrad.hypergradients.CG` over the REAL reference modules (oracle/make_golden_imaml.py: proximal inner loop and
+    fixed-point map of lightning/systems/imaml.py:51-112): adapted weights, query losses and the hypergradient."""
+    task, shots, queries, L, T, steps, cg_iters, batch_size, seed = (int(v) for v in G["imaml_case"])
+    lr, reg = (float(v) for v in G["imaml_lr_reg"])
+    P = O.init_params(seed=0, model_config=CFG)
+    sup, qry = O.synth_task(task=task, shots=shots, queries=queries, L=L, T=T, ragged=True)
+    torch.manual_seed(seed)                                  # the support mini-batches are drawn by torch's RandomSampler
+    losses, _, grads, w = O.imaml_task_step(P, CFG, sup, qry, steps, lr, reg, cg_iters, batch_size, stochastic=True)
+    names = [str(n) for n in G["imaml_names"]]
+    assert sorted(grads) == names
+    np.testing.assert_allclose(np.array([v.item() for v in losses]), G["imaml_losses"], rtol=1e-5)
+    np.testing.assert_allclose(np.array([w[k].double().norm().item() for k in names]), G["imaml_w_norm"], rtol=1e-6)
+    gn = np.array([grads[k].double().norm().item() for k in names])
+    tot = np.sqrt((G["imaml_grad_norm"] ** 2).sum())
+    assert np.abs(gn - G["imaml_grad_norm"]).max() / tot < 1e-5
+    head = np.stack([np.pad(grads[k].flatten()[:8].numpy(), (0, max(0, 8 - grads[k].numel()))) for k in names])
+    assert np.abs(head - G["imaml_grad_head"]).max() / np.abs(G["imaml_grad_head"]).max() < 1e-4
