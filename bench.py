@@ -53,13 +53,27 @@ METRIC = "mel-frames/sec per outer meta-step"
 UNIT = "mel-frames/s"
 
 
+def precision_label(split):
+    """(dtype, description) of the arithmetic: bf16x3 everywhere, or the engine's per-class policy."""
+    if split != 3:
+        return "bf16", "bf16 (single pass)"
+    from meta_tts_b200.engine import split_policy_from_env
+    single = sorted(k for k, v in split_policy_from_env().items() if v == 1)
+    if not single:
+        return "bf16x3", "bf16x3 hi/lo split (fp32-grade) for every tensor-core product"
+    return ("bf16x3", "bf16x3 hi/lo split (fp32-grade) for every product that reaches an output or a data gradient (forward, dgrad, "
+            "attention, tangent dgrad); single-pass bf16 for the classes " + ", ".join(single) + " (p = forward/backward passes, t = "
+            "Hessian-vector passes) — chosen from the measured per-class error budget profiles/r02_precision_budget.md: outputs 7e-5, "
+            "outer gradient 5.9e-4 of its norm vs the fp32 oracle; MTTS_SPLIT_POLICY=strict runs everything bf16x3")
+
+
 def workload_config(n_gpus, split, dropout=True):
     return {
         "workload": f"{'first' if FIRST_ORDER else 'second'}-order MAML K={K_INNER}, 1 task/GPU"
                     f"{'' if GRAD_ACC == 1 else f' x {GRAD_ACC} accumulated micro-steps'}, {SHOTS}-shot support + {QUERIES} queries, "
                     f"{L_PHON} phonemes -> {T_MEL} frames ({WORKLOADS[WORKLOAD]['tag']})",
         "tasks_per_step": n_gpus * GRAD_ACC, "shots": SHOTS, "queries": QUERIES, "phonemes": L_PHON, "frames": T_MEL,
-        "inner_steps": K_INNER, "order": "first" if FIRST_ORDER else "second", "precision": "bf16x3 hi/lo split (fp32-grade)" if split == 3 else "bf16",
+        "inner_steps": K_INNER, "order": "first" if FIRST_ORDER else "second", "precision": precision_label(split)[1],
         "dropout": ("train mode, ACTIVE (enc/dec 0.2, variance predictors 0.5, postnet 0.5): counter-hash masks fused into the "
                     "LN/BN kernels, fresh per step" if dropout else "identity (--no-dropout)"), "parallelism": f"dp{n_gpus} (1 task per GPU)",
         "l2": "per-step working set (activation tapes ~GBs + 280 MB weights) >> 126 MB L2: no flush needed",
@@ -681,7 +695,7 @@ def run_own_arm(args):
         cb = cpu_arm(steps=2, warmup=1, budget_s=60.0) if not args.no_cpu else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16x3" if split == 3 else "bf16", "data": "synthetic", "config": workload_config(world, split, not args.no_dropout),
+                "dtype": precision_label(split)[0], "data": "synthetic", "config": workload_config(world, split, not args.no_dropout),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": GRAD_ACC * sysm.h2d_bytes_per_step,
                         "d2h_bytes_per_step": sysm.d2h_bytes_per_step, "api": f"MetaSystem.training_step(host batch) + optimizer_step; losses read back on the host {args.lag} step(s) later",

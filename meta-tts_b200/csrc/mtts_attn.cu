@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) mtts_attn_kernel(const __grid_
   constexpr int NS = C::NS;
   constexpr bool WIDE = C::WIDE;
   constexpr int NSWEEP = MODE == ATT_FWD ? 2 : 1;
+  constexpr int PK = (SPLIT == 3 || EMIT) ? 3 : 1;      // the lo halves of P / dS exist when they are an MMA operand or are emitted
   // WIDE modes:   ring 1 feeds the score product only (free once it has been read), ring 2 feeds the accumulated product.
   // narrow modes: both rings feed the score products, ring 1 also feeds the accumulated product.
   pdl_launch_dependents();
@@ -558,7 +559,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) mtts_attn_kernel(const __grid_
 #pragma unroll
         for (int j = 0; j < 32; ++j) pv[j] = (c0 + j < klen) ? ex2_approx(fmaf(__uint_as_float(v[j]), cs, -L2)) : 0.f;
         uint32_t hi[16], lo[16];
-        pack_split<SPLIT, 16>(pv, hi, lo);
+        pack_split<PK, 16>(pv, hi, lo);
         tmem_st_32x32_x16(acc, hi);              // this warp's 32 fp32 columns become [hi: 16 columns | lo: 16 columns]
         if (SPLIT == 3) tmem_st_32x32_x16(acc + 16, lo);
         tmem_st_wait();
@@ -566,7 +567,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) mtts_attn_kernel(const __grid_
         if (EMIT && row < T) {
           const long long off = (zrow * T + row) * p.Tp + c0;
           store_bf16_row<16>(p.p_hi + off, hi, c0, p.Tp, tp16);
-          if (SPLIT == 3) store_bf16_row<16>(p.p_lo + off, lo, c0, p.Tp, tp16);
+          if (p.p_lo) store_bf16_row<16>(p.p_lo + off, lo, c0, p.Tp, tp16);
         }
       }
     } else if constexpr (MODE == ATT_DV) {
@@ -637,7 +638,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) mtts_attn_kernel(const __grid_
           }
         }
         uint32_t hi[8], lo[8];
-        pack_split<SPLIT, 8>(dsv, hi, lo);         // dS (dS^T) over this warp's 16 columns of dP (dP^T): [hi: 8 | lo: 8]
+        pack_split<PK, 8>(dsv, hi, lo);            // dS (dS^T) over this warp's 16 columns of dP (dP^T): [hi: 8 | lo: 8]
         tmem_st_32x32_x8(acc + NS, hi);
         if (SPLIT == 3) tmem_st_32x32_x8(acc + NS + 8, lo);
         tmem_st_wait();
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) mtts_attn_kernel(const __grid_
         if (EMIT && MODE == ATT_DQ && row < T) {
           const long long off = (zrow * T + row) * p.Tp + c0;
           store_bf16_row<8>(p.ds_hi + off, hi, c0, p.Tp, tp16);
-          if (SPLIT == 3) store_bf16_row<8>(p.ds_lo + off, lo, c0, p.Tp, tp16);
+          if (p.ds_lo) store_bf16_row<8>(p.ds_lo + off, lo, c0, p.Tp, tp16);
           const bool tp8 = (p.Tp & 7) == 0;
 #pragma unroll
           for (int k = 0; k < 2; ++k) {            // dP: 16 fp32 = two 32-byte stores
@@ -689,10 +690,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) mtts_attn_kernel(const __grid_
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * alpha;
         uint32_t hi[16], lo[16];
-        pack_split<SPLIT, 16>(f, hi, lo);
+        pack_split<3, 16>(f, hi, lo);            // outputs carry their lo half whenever the caller passes a buffer for it
         if (row < T) {
           store_bf16_row<16>(dst_hi + off + ch * 32, hi, 0, 32, true);
-          if (SPLIT == 3 && dst_lo) store_bf16_row<16>(dst_lo + off + ch * 32, lo, 0, 32, true);
+          if (dst_lo) store_bf16_row<16>(dst_lo + off + ch * 32, lo, 0, 32, true);
         }
       }
     }
@@ -829,7 +830,7 @@ extern "C" int mtts_attn_fwd(const mtts_attn_desc* d, mtts_stream stream_) {
   if (rc != MTTS_OK) return rc;
   MTTS_REQUIRE(d->o_hi && (d->split == 1 || d->o_lo), "attn_fwd: missing output");
   p.o_hi = static_cast<bf16*>(d->o_hi);
-  p.o_lo = static_cast<bf16*>(d->o_lo);
+  p.o_lo = static_cast<bf16*>(d->o_lo);          // written whenever given (also in single-pass mode)
   const bool emit = d->p_hi != nullptr;
   if (emit) {
     MTTS_REQUIRE(d->Tp >= d->T && (d->Tp & 7) == 0 && (d->split == 1 || d->p_lo), "attn_fwd: bad P emit buffers (Tp %d)", d->Tp);

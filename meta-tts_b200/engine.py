@@ -414,6 +414,24 @@ def _pick_cfg(mt: int, nz: int, N: int, k_iters: int, can_splitk: bool):
     return o[0], o[1], 1
 
 
+# Per-class precision policy.  Classes: p.* = forward / backward passes, t.* = Hessian-vector (tangent) passes;
+# fwd = Linear / Conv forward products, dgrad = data gradients, wgrad = weight gradients, bmm = attention products.  Measured on
+# BASELINE configs[1] against the fp32 oracle (tools/precision_budget.py, profiles/r02_precision_budget.md): running the four
+# classes below single-pass bf16 leaves the outputs untouched (7e-5) and moves the outer gradient by 5.9e-4 of its norm (2.2e-4
+# with everything bf16x3), while p.fwd / p.dgrad / p.bmm / t.dgrad each cost > 2e-3 and stay bf16x3.
+DEFAULT_SPLIT_POLICY = {"t.fwd": 1, "t.bmm": 1, "t.wgrad": 1, "p.wgrad": 1}
+
+
+def split_policy_from_env() -> Dict[str, int]:
+    """MTTS_SPLIT_POLICY: unset = DEFAULT_SPLIT_POLICY; "strict" (or empty) = every product bf16x3; else "class=1,class=3,..."."""
+    v = os.environ.get("MTTS_SPLIT_POLICY")
+    if v is None:
+        return dict(DEFAULT_SPLIT_POLICY)
+    if v.strip() in ("", "strict"):
+        return {}
+    return dict((k.strip(), int(x)) for k, x in (kv.split("=") for kv in v.split(",") if kv.strip()))
+
+
 class Gemm:
     """Descriptor construction for the contractions of the model (all through be.gemm).
     `x2/w2`-style arguments add a SECOND product term in the same launch (tangent passes)."""
@@ -421,10 +439,18 @@ class Gemm:
     def __init__(self, be):
         self.be = be
         self.split_override = None      # engine.hvp() sets 1: the lr-scaled curvature terms run single-pass bf16
+        self.tangent = False            # inside a Hessian-vector pass (engine.hvp)
+        self.policy = split_policy_from_env()
 
-    def _gemm(self, *a, **kw):
-        if self.split_override is not None:
-            kw["split"] = self.split_override
+    def split_of(self, kind: str):
+        """Operand split (1 = single-pass bf16, 3 = bf16x3) of GEMM class `kind` in the current pass type, or None = backend default."""
+        s = self.policy.get(("t." if self.tangent else "p.") + kind) if self.be.split == 3 else None
+        return s if s is not None else self.split_override
+
+    def _gemm(self, kind, *a, **kw):
+        s = self.split_of(kind)
+        if s is not None:
+            kw["split"] = s
         self.be.gemm(*a, **kw)
 
     # y[b,t,:] = sum_j x[b,t+j-p,:] W_j^T (+bias) [+ sum_j x2[b,t+j-p,:] W2_j^T] ; W: [k, N, Cin]
@@ -443,7 +469,7 @@ class Gemm:
             if x2 is not None:
                 a.hi2, a.lo2 = x2.hi, x2.lo
             bn, pair, _ = _pick_cfg((x.B * x.T + 127) // 128, 1, N, 0, False)
-            self._gemm(a, wop, x.B * x.T, N, Cin, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=N, bias=bias,
+            self._gemm("fwd", a, wop, x.B * x.T, N, Cin, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=N, bias=bias,
                          gate=gate, flags=flags, block_n=bn, pair=pair)
         else:
             a = Opnd(x.hi, x.lo, L.MAJOR_K, (Cin, x.T, x.B), (1, Cin, x.T * Cin), src2=L.SRC_Z0,
@@ -451,7 +477,7 @@ class Gemm:
             if x2 is not None:
                 a.hi2, a.lo2 = x2.hi, x2.lo
             bn, pair, _ = _pick_cfg((x.T + 127) // 128, x.B, N, 0, False)
-            self._gemm(a, wop, x.T, N, Cin, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=N, c_sz0=x.T * N, bias=bias,
+            self._gemm("fwd", a, wop, x.T, N, Cin, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=N, c_sz0=x.T * N, bias=bias,
                          gate=gate, flags=flags, ntaps=k, nz0=x.B, block_n=bn, pair=pair)
 
     # dx[b,t,:] = sum_j dy[b,t-j+p,:] W_j  [+ sum_j dy2[b,t-j+p,:] W2_j]
@@ -476,14 +502,14 @@ class Gemm:
             a = Opnd(dy.hi, dy.lo, L.MAJOR_K, (N, dy.B * dy.T), (1, N))
             if dy2 is not None:
                 a.hi2, a.lo2 = dy2.hi, dy2.lo
-            self._gemm(a, wop, dy.B * dy.T, Cin, N, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=Cin, gate=gate,
+            self._gemm("dgrad", a, wop, dy.B * dy.T, Cin, N, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=Cin, gate=gate,
                          flags=flags, block_n=bn, pair=pair, ksplit=ks)
         else:
             a = Opnd(dy.hi, dy.lo, L.MAJOR_K, (N, dy.T, dy.B), (1, N, dy.T * N), src2=L.SRC_Z0,
                      shift_src=L.SRC_TAP, shift_base=p, shift_step=-1)
             if dy2 is not None:
                 a.hi2, a.lo2 = dy2.hi, dy2.lo
-            self._gemm(a, wop, dy.T, Cin, N, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=Cin, c_sz0=dy.T * Cin,
+            self._gemm("dgrad", a, wop, dy.T, Cin, N, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=Cin, c_sz0=dy.T * Cin,
                          gate=gate, flags=flags, ntaps=k, nz0=dy.B, block_n=bn, pair=pair, ksplit=ks)
 
     # dW_j[n,c] += sum_{b,t} dy[b,t,n] x[b,t+j-p,c]  [+ dy2 (x) x2]
@@ -502,7 +528,7 @@ class Gemm:
             b = Opnd(x.hi, x.lo, L.MAJOR_MN, (Cin, R), (1, Cin))
             if dy2 is not None:
                 a.hi2, a.lo2, b.hi2, b.lo2 = dy2.hi, dy2.lo, x2.hi, x2.lo
-            self._gemm(a, b, N, Cin, R, c_f32=dw_f32, ldc=Cin, flags=L.EPI_ACCUM, alpha=scale, ksplit=ks, block_n=bn,
+            self._gemm("wgrad", a, b, N, Cin, R, c_f32=dw_f32, ldc=Cin, flags=L.EPI_ACCUM, alpha=scale, ksplit=ks, block_n=bn,
                          pair=pair)
         else:
             a = Opnd(dy.hi, dy.lo, L.MAJOR_MN, (N, dy.T, dy.B), (1, N, dy.T * N), src2=L.SRC_KB)
@@ -510,7 +536,7 @@ class Gemm:
                      shift_src=L.SRC_Z0, shift_base=-p, shift_step=1)
             if dy2 is not None:
                 a.hi2, a.lo2, b.hi2, b.lo2 = dy2.hi, dy2.lo, x2.hi, x2.lo
-            self._gemm(a, b, N, Cin, dy.T, c_f32=dw_f32, ldc=Cin, c_sz0=N * Cin, flags=L.EPI_ACCUM, alpha=scale,
+            self._gemm("wgrad", a, b, N, Cin, dy.T, c_f32=dw_f32, ldc=Cin, c_sz0=N * Cin, flags=L.EPI_ACCUM, alpha=scale,
                          nkb=dy.B, nz0=k, ksplit=ks, block_n=bn, pair=pair)
 
     # C[b,h] = alpha * ( op(A) op(B)^T [+ op(A2) op(B2)^T] )   (op = identity or transpose, see BMat)
@@ -528,7 +554,7 @@ class Gemm:
             assert (A2.off, A2.sr, A2.sh, A2.sb) == (A.off, A.sr, A.sh, A.sb) and (B2.off, B2.sr, B2.sh, B2.sb) == (Bm.off, Bm.sr, Bm.sh, Bm.sb)
             a.hi2, a.lo2, b.hi2, b.lo2 = A2.hi, A2.lo, B2.hi, B2.lo
         bn, pair, _ = _pick_cfg((M + 127) // 128, nb * nh, N, 0, False)
-        self._gemm(a, b, M, N, K, c_f32=Cm.f32, c_hi=Cm.hi, c_lo=Cm.lo, ldc=Cm.sr, c_off=Cm.off, c_sz0=Cm.sh,
+        self._gemm("bmm", a, b, M, N, K, c_f32=Cm.f32, c_hi=Cm.hi, c_lo=Cm.lo, ldc=Cm.sr, c_off=Cm.off, c_sz0=Cm.sh,
                      c_sz1=Cm.sb, alpha=alpha, flags=(L.EPI_ADD_C if add_c else 0), nz0=nh, nz1=nb,
                      block_n=bn, pair=pair)
 
@@ -638,7 +664,8 @@ class FS2Engine:
         if self._fused_attn(dk):
             # P is only written out for tapes a Hessian-vector pass will re-read (tp.attn_emit; unknown = keep it)
             p_h, p_l = tp.bf(f"{pf}.P", (B, H, T, Tp)) if self._attn_emit(tp, pf) else (None, None)
-            be.attn_fwd(qkv_h, qkv_l, lens, B, H, T, dk, o.hi, o.lo, self._attn_vec(tp, f"{pf}.lse", B, H, T), p_h, p_l, Tp)
+            be.attn_fwd(qkv_h, qkv_l, lens, B, H, T, dk, o.hi, o.lo, self._attn_vec(tp, f"{pf}.lse", B, H, T), p_h, p_l, Tp,
+                        split=g.split_of("bmm"))
         else:
             S = scr.scratch("S", (B, H, T, Tp))
             g.bmm(qm(qkv_h, qkv_l, 0), False, qm(qkv_h, qkv_l, 1), False, pm(None, None, S), B, H, alpha=1.0 / math.sqrt(dk))
@@ -708,12 +735,13 @@ class FS2Engine:
             ds_h, ds_l = tp.bf(f"{pf}.dS", (B, H, T, Tp)) if emit else (None, None)
             args = (qkv_h, qkv_l, lens, B, H, T, dk, o.hi, o.lo, self._attn_vec(tp, f"{pf}.lse", B, H, T), do.hi, do.lo,
                     self._attn_vec(tp, f"{pf}.dvec", B, H, T), dq_h, dq_l)
+            sp = g.split_of("bmm")
             be.attn_bwd(L.ATTN_PREP, *args)
             with be.branch("att", local=True):
-                be.attn_bwd(L.ATTN_DK, *args)
+                be.attn_bwd(L.ATTN_DK, *args, split=sp)
             with be.branch("att2", local=True):
-                be.attn_bwd(L.ATTN_DV, *args)
-            be.attn_bwd(L.ATTN_DQ, *args, dP, ds_h, ds_l, Tp)
+                be.attn_bwd(L.ATTN_DV, *args, split=sp)
+            be.attn_bwd(L.ATTN_DQ, *args, dP, ds_h, ds_l, Tp, split=sp)
             be.join("att", local=True)
             be.join("att2", local=True)
         else:
@@ -1388,10 +1416,12 @@ class FS2Engine:
     def hvp(self, P: ParamSet, Pd: ParamSet, HV: ParamSet, bt: Batch, tp: Tape, tt: Tape, loss_scale: float = 1.0):
         assert getattr(tp, "attn_emit", True), "this tape was recorded without the attention probabilities (attn_emit = False)"
         self.g.split_override = self.hvp_split if self.hvp_split != self.split else None
+        self.g.tangent = True
         try:
             self._hvp(P, Pd, HV, bt, tp, tt, loss_scale)
         finally:
             self.g.split_override = None
+            self.g.tangent = False
 
     def _hvp(self, P: ParamSet, Pd: ParamSet, HV: ParamSet, bt: Batch, tp: Tape, tt: Tape, loss_scale: float = 1.0):
         be, g, scr, d = self.be, self.g, self.scr, self.d

@@ -359,22 +359,22 @@ class CudaOps:
         d.qkv_hi, d.qkv_lo, d.klens, d.lse = _p(qkv_hi), _p(qkv_lo), _p(klens), _p(lse)
         return d
 
-    def attn_fwd(self, qkv_hi, qkv_lo, klens, B, H, T, dk, o_hi, o_lo, lse, p_hi=None, p_lo=None, Tp=0):
+    def attn_fwd(self, qkv_hi, qkv_lo, klens, B, H, T, dk, o_hi, o_lo, lse, p_hi=None, p_lo=None, Tp=0, split=None):
         """o = softmax(q k^T / sqrt(dk), keys >= klens masked) v; lse [B,H,Tl] (log2 domain); optional emit of P [B,H,T,Tp]."""
         global launch_count
         _need_cuda(qkv_hi, o_hi, lse)
-        d = self._attn_desc(qkv_hi, qkv_lo, klens, B, H, T, dk, lse)
+        d = self._attn_desc(qkv_hi, qkv_lo, klens, B, H, T, dk, lse, split)
         d.o_hi, d.o_lo, d.p_hi, d.p_lo, d.Tp = _p(o_hi), _p(o_lo), _p(p_hi), _p(p_lo), Tp
         L.call("mtts_attn_fwd", C.byref(d), _stream())
         launch_count += 1
 
     def attn_bwd(self, parts, qkv_hi, qkv_lo, klens, B, H, T, dk, o_hi, o_lo, lse, do_hi, do_lo, dvec, dqkv_hi, dqkv_lo,
-                 dp=None, ds_hi=None, ds_lo=None, Tp=0):
+                 dp=None, ds_hi=None, ds_lo=None, Tp=0, split=None):
         """parts: mask of L.ATTN_PREP (dvec = rowsum(do*o)), L.ATTN_DQ (dq block of dqkv; optional emit of dP / dS),
         L.ATTN_DK, L.ATTN_DV (dk / dv blocks of dqkv)."""
         global launch_count
         _need_cuda(qkv_hi, do_hi, lse, dvec)
-        d = self._attn_desc(qkv_hi, qkv_lo, klens, B, H, T, dk, lse)
+        d = self._attn_desc(qkv_hi, qkv_lo, klens, B, H, T, dk, lse, split)
         d.o_hi, d.o_lo, d.do_hi, d.do_lo, d.dvec = _p(o_hi), _p(o_lo), _p(do_hi), _p(do_lo), _p(dvec)
         d.dqkv_hi, d.dqkv_lo, d.dp, d.ds_hi, d.ds_lo, d.Tp = _p(dqkv_hi), _p(dqkv_lo), _p(dp), _p(ds_hi), _p(ds_lo), Tp
         L.call("mtts_attn_bwd", C.byref(d), int(parts), _stream())

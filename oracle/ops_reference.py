@@ -390,7 +390,7 @@ class RefOps:
         s = (q @ k.transpose(-1, -2)) / math.sqrt(dk)
         return q, k, v, s.masked_fill(~km, -math.inf), km
 
-    def attn_fwd(self, qkv_hi, qkv_lo, klens, B, H, T, dk, o_hi, o_lo, lse, p_hi=None, p_lo=None, Tp=0):
+    def attn_fwd(self, qkv_hi, qkv_lo, klens, B, H, T, dk, o_hi, o_lo, lse, p_hi=None, p_lo=None, Tp=0, split=None):
         self.n_calls += 1
         q, k, v, s, km = self._attn_parts(qkv_hi, qkv_lo, klens, B, H, T, dk)
         P = torch.softmax(s, -1)
@@ -402,7 +402,7 @@ class RefOps:
             _put_split(p_hi, p_lo if self.split == 3 else None, full)
 
     def attn_bwd(self, parts, qkv_hi, qkv_lo, klens, B, H, T, dk, o_hi, o_lo, lse, do_hi, do_lo, dvec, dqkv_hi, dqkv_lo,
-                 dp=None, ds_hi=None, ds_lo=None, Tp=0):
+                 dp=None, ds_hi=None, ds_lo=None, Tp=0, split=None):
         self.n_calls += 1
         lo = (lambda t: t if self.split == 3 else None)
         dO = _val(do_hi, lo(do_lo)).reshape(B, T, H, dk).permute(0, 2, 1, 3).to(self.acc)

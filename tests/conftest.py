@@ -3,6 +3,11 @@ import sys
 
 import pytest
 
+# Parity tests hold the CUDA path to its tightest tolerances with every tensor-core product in bf16x3 ("strict"); the default
+# mixed policy (engine.DEFAULT_SPLIT_POLICY: single-pass weight-gradient / tangent-forward products, what bench.py times) has its
+# own tests (tests/test_engine_gpu.py::test_default_precision_policy*, smoke()).
+os.environ.setdefault("MTTS_SPLIT_POLICY", "strict")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -194,3 +194,28 @@ def test_bf16_single_pass_mode_runs(cuda_device):
     r = _rel(out["mel"].reshape(preds[0].shape), preds[0])
     print(f"[engine] bf16 single-pass mel rel {r:.2e}, loss rel {_rel(loss6, torch.stack(losses)):.2e}")
     assert r < 3e-2 and _rel(loss6, torch.stack(losses)) < 3e-2
+
+
+def test_default_precision_policy_config2_full_size(cuda_device):
+    """What bench.py times: BASELINE configs[1] with dropout ON under the DEFAULT per-class precision policy (weight-gradient and
+    tangent-forward products single-pass bf16, everything that reaches the outputs or a data gradient bf16x3).  Outputs keep the
+    north_star bar (1e-3; measured 7e-5), the outer gradient stays within 1.5e-3 of its norm (measured 5.9e-4)."""
+    from meta_tts_b200.engine import DEFAULT_SPLIT_POLICY
+    cfg = O.BASE_MODEL_CONFIG
+    P = O.init_params(seed=0)
+    m = _engine(P, cfg, K=1)
+    m.engine.g.policy = dict(DEFAULT_SPLIT_POLICY)
+    sup, qry = O.synth_task(task=0, shots=4, queries=4, L=128, T=864)
+    _check_task(m, P, cfg, sup, qry, 1, False, 1.5e-3, "config2 full size, DEFAULT precision policy, dropout ON", salt=20260925, fast_tol=2e-2,
+                median_tol=3e-3)
+
+
+def test_default_precision_policy_k5(cuda_device):
+    """Five inner steps / five Hessian-vector passes under the default policy (BASELINE configs[2] structure)."""
+    from meta_tts_b200.engine import DEFAULT_SPLIT_POLICY
+    cfg = O.small_model_config(2, 2)
+    P = O.init_params(seed=0, model_config=cfg)
+    m = _engine(P, cfg, K=5)
+    m.engine.g.policy = dict(DEFAULT_SPLIT_POLICY)
+    sup, qry = O.synth_task(task=4, shots=5, queries=5, L=16, T=64, ragged=True)
+    _check_task(m, P, cfg, sup, qry, 5, False, 2e-2, "K=5 second order, DEFAULT precision policy", fast_tol=2e-2, median_tol=1e-2)
