@@ -225,7 +225,8 @@ def instrument_gemm(be):
         flops = 2.0 * M * N * K * kw.get("ntaps", 1) * kw.get("nkb", 1) * nz * terms
         bn, pair = kw.get("block_n", 0), bool(kw.get("pair", False))
         variant = f"mtts_gemm_{'pair_' if pair else ''}kernel<{bn},{kw.get('split', be.split)}>"
-        rec.append({"variant": variant, "flops": flops, "call": (a, b, M, N, K, dict(kw)),
+        kw2 = dict(kw)
+        rec.append({"variant": variant, "flops": flops, "call": (a, b, M, N, K, kw2), "fn": (lambda: orig(a, b, M, N, K, **kw2)),
                     "shape": (M, N, K, kw.get("ntaps", 1), kw.get("nkb", 1), nz, terms)})
         orig(a, b, M, N, K, **kw)
 
@@ -233,16 +234,42 @@ def instrument_gemm(be):
     return rec, orig
 
 
+def instrument_attn(be, rec):
+    """Wrap be.attn_fwd / be.attn_bwd the same way (fused attention kernels, csrc/mtts_attn.cu).  Algorithmic FLOPs: forward
+    4 B H T^2 d_k (scores + P V); backward 8 B H T^2 d_k = dP, dQ (DQ kernel), dK (DK kernel), dV (DV kernel) — the recomputed
+    score products of the three kernels are overhead, not algorithmic work."""
+    from meta_tts_b200 import lib as L
+    o_fwd, o_bwd = be.attn_fwd, be.attn_bwd
+
+    def fwd(qh, ql, kl, B_, H, T, dk, *a, **kw):
+        f = 4.0 * B_ * H * T * T * dk
+        emit = (len(a) > 3 and a[3] is not None) or kw.get("p_hi") is not None
+        rec.append({"variant": f"mtts_attn_kernel<FWD{',emit P' if emit else ''}>", "flops": f, "shape": ("attn", B_, H, T, dk),
+                    "fn": (lambda: o_fwd(qh, ql, kl, B_, H, T, dk, *a, **kw))})
+        o_fwd(qh, ql, kl, B_, H, T, dk, *a, **kw)
+
+    def bwd(parts, qh, ql, kl, B_, H, T, dk, *a, **kw):
+        unit = 2.0 * B_ * H * T * T * dk
+        for bit, name, nprod in ((L.ATTN_DQ, "DQ", 2), (L.ATTN_DK, "DK", 1), (L.ATTN_DV, "DV", 1)):
+            if parts & bit:
+                rec.append({"variant": f"mtts_attn_kernel<{name}>", "flops": nprod * unit, "shape": ("attn", B_, H, T, dk),
+                            "fn": (lambda bit=bit: o_bwd(bit, qh, ql, kl, B_, H, T, dk, *a, **kw))})
+        o_bwd(parts, qh, ql, kl, B_, H, T, dk, *a, **kw)
+
+    be.attn_fwd, be.attn_bwd = fwd, bwd
+    return o_fwd, o_bwd
+
+
 def time_variant(orig_gemm, calls, reps=5):
     """CUDA-event time of one kernel variant's launches of a step, replayed back-to-back from a CUDA graph
     (same descriptors, same resident operands) on the current stream."""
     for c in calls[:2]:
-        orig_gemm(*c["call"][:5], **c["call"][5])
+        c["fn"]()
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         for c in calls:
-            orig_gemm(*c["call"][:5], **c["call"][5])
+            c["fn"]()
     g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -623,6 +650,7 @@ def run_own_arm(args):
         # ---------- (3) roofline of the dominant kernel: record one eager step's GEMM launches, then time each
         #                kernel variant's launches back-to-back from a CUDA graph with CUDA events ----------
         rec, orig = instrument_gemm(sysm.be)
+        orig_attn = instrument_attn(sysm.be, rec)
         sysm.use_cuda_graph = False
         sysm.training_step(batches[0], 0)
         torch.cuda.synchronize()
@@ -630,6 +658,7 @@ def run_own_arm(args):
         sysm.training_step(batches[1], 1)
         torch.cuda.synchronize()
         sysm.be.gemm = orig
+        sysm.be.attn_fwd, sysm.be.attn_bwd = orig_attn
         sysm.use_cuda_graph = True
         by_var = {}
         for r in rec:
@@ -641,11 +670,14 @@ def run_own_arm(args):
             ms_v = time_variant(orig, calls)
             fl = sum(c["flops"] for c in calls)
             vstats.append({"kernel": v, "launches": len(calls), "ms_per_step": ms_v, "algorithmic_gflop": fl / 1e9,
-                           "tflops": fl / (ms_v * 1e-3) / 1e12})
+                           "tflops": fl / (ms_v * 1e-3) / 1e12,
+                           "mma_passes": 1 if (",1>" in v or split == 1) else 3})
         if args.gemm_table:
             # diagnostic: time per (variant, shape, epilogue) group, each group's launches replayed back-to-back
             groups = {}
             for r in rec:
+                if "call" not in r:
+                    continue
                 kw = r["call"][5]
                 out = "f32" if kw.get("c_f32") is not None and kw.get("c_hi") is None else ("hilo" if kw.get("c_f32") is None else "f32+hilo")
                 key = (r["variant"], r["shape"], kw.get("flags", 0), kw.get("ksplit", 1), out,
@@ -686,11 +718,12 @@ def run_own_arm(args):
                            "those launches replayed back-to-back from a CUDA graph",
                     "launches_per_step": dom["launches"], "avg_launch_us": 1e3 * dom["ms_per_step"] / dom["launches"],
                     "share_of_step": dom["ms_per_step"] / ms_per_step,
-                    "tensor_pipe_work_multiplier": mma_mult, "frac_of_issued_mma": mma_mult * dom["tflops"] / peaks["bf16_tflops"],
+                    "tensor_pipe_work_multiplier": dom["mma_passes"], "frac_of_issued_mma": dom["mma_passes"] * dom["tflops"] / peaks["bf16_tflops"],
                     "top_shapes_MNK_taps_kb_z_terms": [{"shape": list(k), "launches": v[1], "gflop": v[0] / 1e9} for k, v in top],
                     "all_gemm_kernels": vstats,
                     "all_gemm": {"ms_per_step": gemm_ms, "algorithmic_gflop_per_step": gemm_flops / 1e9,
-                                 "tflops": gemm_flops / (gemm_ms * 1e-3) / 1e12, "share_of_step": gemm_ms / ms_per_step}}
+                                 "tflops": gemm_flops / (gemm_ms * 1e-3) / 1e12, "share_of_step": gemm_ms / ms_per_step,
+                                 "note": "all tensor-core kernels: the GEMM family and the fused attention kernels (mtts_attn_kernel<...>)"}}
         # ---------- (4) CPU baseline (bounded sample) ----------
         cb = cpu_arm(steps=2, warmup=1, budget_s=60.0) if not args.no_cpu else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

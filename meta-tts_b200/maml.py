@@ -66,8 +66,13 @@ class MamlEngine:
         self.theta_lo = z((n,), bf) if be.split == 3 else None
         self.fast = [(z((na,)), z((na,), bf), z((na,), bf) if be.split == 3 else None) for _ in range(self.K_max)]
         self.g_inner = z((n,))           # inner-step gradient (adapted region used)
-        self.g_task = z((n,))            # this task's outer gradient (lambda | gphi)
-        self.g_outer = z((n,))           # accumulated over tasks (allreduce buffer)
+        # The 6 query losses ride on the TAIL of the gradient arenas (8 extra floats): the task's accumulation `axpby` and the
+        # ONE NCCL allreduce of the outer gradient then also produce the mean losses of all tasks of the step on every rank —
+        # meta.py:77-79 `self.log_dict(..., sync_dist=True)` without a second collective.
+        self.g_task_full = z((n + 8,))
+        self.g_task = self.g_task_full[:n]       # this task's outer gradient (lambda | gphi)
+        self.g_outer_full = z((n + 8,))
+        self.g_outer = self.g_outer_full[:n]     # accumulated over tasks (allreduce buffer)
         self.hv = z((n,))
         self.g_enc = z((lay.adapt_begin,))   # query-pass gradient of the (non-adapted) prefix, accumulated on the 'enc' branch
         self.lam_hi = z((na,), bf)
@@ -106,7 +111,9 @@ class MamlEngine:
 
     def new_tapes(self):
         """(support tapes x K_max, query tape, tangent tape): one set per input-shape signature."""
-        return ([self.engine.new_tape() for _ in range(self.K_max)], self.engine.new_tape(), self.engine.new_tape())
+        tq = self.engine.new_tape()
+        tq.t["loss6:f"] = self.g_task_full[self.layout.total:self.layout.total + 6]     # the query losses land on the arena tail
+        return ([self.engine.new_tape() for _ in range(self.K_max)], tq, self.engine.new_tape())
 
     def use_tapes(self, tapes) -> None:
         self.tapes, self.tape_q, self.tape_t = tapes
@@ -227,7 +234,7 @@ class MamlEngine:
             be.join("enc")
             be.axpby(1.0, self.g_enc, 1.0, self.g_task[:a0])
         if accumulate_scale is not None:
-            be.axpby(accumulate_scale, self.g_task, 1.0, self.g_outer)
+            be.axpby(accumulate_scale, self.g_task_full, 1.0, self.g_outer_full)      # gradient + the 6 losses on the tail
         return out["loss6"], out
 
     def task_grads(self) -> Dict[str, torch.Tensor]:

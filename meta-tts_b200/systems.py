@@ -361,12 +361,12 @@ def _run_task(self, sup12, qry12, steps: int, first_order: bool, accumulate_scal
         # eager warm-up run: allocates every tape buffer and sets kernel attributes outside capture
         bn0 = self.maml.bn_batches
         saved = {k: v.clone() for k, v in self.maml.consts.items() if k.endswith(("running_mean", "running_var"))}
-        g_outer_saved = self.maml.g_outer.clone()
+        g_outer_saved = self.maml.g_outer_full.clone()
         self.maml.task_step(sb.dev, qb.dev, steps, first_order, accumulate_scale, drop_base)
         torch.cuda.synchronize()
         for k, v in saved.items():
             self.maml.consts[k].copy_(v)           # the warm-up must not advance BatchNorm running statistics
-        self.maml.g_outer.copy_(g_outer_saved)
+        self.maml.g_outer_full.copy_(g_outer_saved)
         self.maml.bn_batches = bn0
         graph = torch.cuda.CUDAGraph()
         n0 = _ops.launch_count
@@ -589,12 +589,14 @@ def optimizer_step(self):
     m = self.maml
     t0 = time.perf_counter()
     if torch.distributed.is_initialized() and torch.distributed.get_world_size(self.process_group) > 1:
-        torch.distributed.all_reduce(m.g_outer, group=self.process_group)
+        torch.distributed.all_reduce(m.g_outer_full, group=self.process_group)
+    # mean of the 6 query losses over every task of the step (all ranks x accumulated micro-steps): meta.py:77-79 sync_dist=True
+    self.synced_losses = m.g_outer_full[m.layout.total:m.layout.total + 6].clone()
     opt = self.train_config["optimizer"]
     m.outer_update(1.0, float(opt.get("grad_clip_thresh", 1.0)), tuple(opt["betas"]), float(opt["eps"]),
                    warmup=int(opt.get("warm_up_step", 4000)), anneal_steps=tuple(opt.get("anneal_steps", ())),
                    anneal_rate=float(opt.get("anneal_rate", 0.3)))
-    self.be.zero_(m.g_outer)
+    self.be.zero_(m.g_outer_full)
     self._pending_tasks = 0
     self.host_prof["optimizer"] += time.perf_counter() - t0
 

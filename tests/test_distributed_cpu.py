@@ -35,8 +35,12 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(2)
     m = _engine()
-    _task(m, rank, 1.0 / world)                     # rank r processes task r (1 task per device, base_adaptor.py:128)
-    dist.all_reduce(m.g_outer)                      # the single collective of the path
+    loss = _task(m, rank, 1.0 / world).clone()      # rank r processes task r (1 task per device, base_adaptor.py:128)
+    dist.all_reduce(m.g_outer_full)                 # the single collective of the path: gradient + the 6 losses on its tail
+    synced = m.g_outer_full[m.layout.total:m.layout.total + 6].clone()
+    gathered = [torch.zeros(6) for _ in range(world)]
+    dist.all_gather(gathered, loss)                 # (test only) every rank's own losses
+    assert torch.allclose(synced, torch.stack(gathered).mean(0), rtol=1e-6, atol=1e-7), "tail != mean of the ranks' losses"
     m.outer_update(1.0, 1.0)
     if rank == 0:
         q.put((m.g_outer.numpy().copy(), m.theta.numpy().copy()))
