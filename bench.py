@@ -64,7 +64,7 @@ def precision_label(split):
     return ("bf16x3", "bf16x3 hi/lo split (fp32-grade) for every product that reaches an output or a data gradient (forward, dgrad, "
             "attention, tangent dgrad); single-pass bf16 for the classes " + ", ".join(single) + " (p = forward/backward passes, t = "
             "Hessian-vector passes) — chosen from the measured per-class error budget profiles/r02_precision_budget.md: outputs 7e-5, "
-            "outer gradient 5.9e-4 of its norm vs the fp32 oracle; MTTS_SPLIT_POLICY=strict runs everything bf16x3")
+            "outer gradient 3.1e-4 of its norm vs the fp32 oracle (2.2e-4 all-bf16x3); MTTS_SPLIT_POLICY=strict runs everything bf16x3")
 
 
 def workload_config(n_gpus, split, dropout=True):

@@ -199,14 +199,16 @@ def test_bf16_single_pass_mode_runs(cuda_device):
 def test_default_precision_policy_config2_full_size(cuda_device):
     """What bench.py times: BASELINE configs[1] with dropout ON under the DEFAULT per-class precision policy (weight-gradient and
     tangent-forward products single-pass bf16, everything that reaches the outputs or a data gradient bf16x3).  Outputs keep the
-    north_star bar (1e-3; measured 7e-5), the outer gradient stays within 1.5e-3 of its norm (measured 5.9e-4)."""
+    north_star bar (1e-3; measured 2e-5).  The outer gradient is held to the tolerance of the all-bf16x3 dropout test above (4e-3):
+    with dropout on both land at ~2e-3 of the gradient norm (1.9e-3 strict / 2.1e-3 default policy: ReLU / L1 kink flips dominate);
+    without dropout the policy measures 3.1e-4 against 2.2e-4 (profiles/r02_precision_budget.md)."""
     from meta_tts_b200.engine import DEFAULT_SPLIT_POLICY
     cfg = O.BASE_MODEL_CONFIG
     P = O.init_params(seed=0)
     m = _engine(P, cfg, K=1)
     m.engine.g.policy = dict(DEFAULT_SPLIT_POLICY)
     sup, qry = O.synth_task(task=0, shots=4, queries=4, L=128, T=864)
-    _check_task(m, P, cfg, sup, qry, 1, False, 1.5e-3, "config2 full size, DEFAULT precision policy, dropout ON", salt=20260925, fast_tol=2e-2,
+    _check_task(m, P, cfg, sup, qry, 1, False, 4e-3, "config2 full size, DEFAULT precision policy, dropout ON", salt=20260925, fast_tol=2e-2,
                 median_tol=3e-3)
 
 

@@ -47,10 +47,21 @@ if len(sys.argv) > 1 and sys.argv[-1] == "policy":
     variants = [variants[0]] + variants[-3:]
 print("| single-pass bf16 classes | max output rel err | loss rel err | outer grad rel err (total) | median per-tensor grad rel err | p90 |")
 print("|---|---|---|---|---|---|")
-for name, pol in variants:
+SALT = 20260925
+losses_d = preds_d = grads_d = None
+variants += [("(dropout ON) all bf16x3", {}, True), ("(dropout ON) POLICY", {"t.fwd": 1, "t.bmm": 1, "t.wgrad": 1, "p.wgrad": 1}, True)]
+for var in variants:
+    name, pol, drop = var if len(var) == 3 else (var[0], var[1], False)
+    if drop and grads_d is None:
+        losses_d, preds_d, grads_d = O.maml_task_step({k: v.detach().clone() for k, v in P.items()}, cfg, sup, qry, 1, 0.001, False,
+                                                      drop_seed=(0, SALT))
+    if drop:
+        losses, preds, grads = losses_d, preds_d, grads_d
+        tot_ref = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values()))
+        be.drop_salt = torch.tensor([SALT], dtype=torch.int32, device=dev)
     m.load_state_dict({k: v.detach().clone() for k, v in P.items()})
     m.engine.g.policy = dict(pol)
-    loss6, out = m.task_step(bs, bq, 1, False, drop_base=None)
+    loss6, out = m.task_step(bs, bq, 1, False, drop_base=0 if drop else None)
     torch.cuda.synchronize()
     r_out = max(rel(out["mel"].reshape(preds[0].shape), preds[0]), rel(out["postnet"].reshape(preds[1].shape), preds[1]),
                 rel(out["pitch"], preds[2]), rel(out["energy"], preds[3]), rel(out["logd"], preds[4]))
