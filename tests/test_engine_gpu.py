@@ -221,3 +221,17 @@ def test_default_precision_policy_k5(cuda_device):
     m.engine.g.policy = dict(DEFAULT_SPLIT_POLICY)
     sup, qry = O.synth_task(task=4, shots=5, queries=5, L=16, T=64, ragged=True)
     _check_task(m, P, cfg, sup, qry, 5, False, 2e-2, "K=5 second order, DEFAULT precision policy", fast_tol=2e-2, median_tol=1e-2)
+
+
+@pytest.mark.parametrize("first_order", [False, True])
+def test_config3_config4_full_size_parity(cuda_device, first_order):
+    """BASELINE configs[2] (second order) / configs[3] (first order) at FULL size: one task step with 5-shot support + 5 queries,
+    128 phonemes -> 864 frames, K = 5 inner steps, base model, dropout off (the oracle's 5-step double backward takes ~1 min of
+    CPU).  Outputs to the north_star bar; the outer gradient to 4e-3 of its norm and 3e-3 median per tensor (five inner steps let
+    the ReLU / L1 kink flips documented above reach the fast weights)."""
+    cfg = O.BASE_MODEL_CONFIG
+    P = O.init_params(seed=0)
+    m = _engine(P, cfg, K=5)
+    sup, qry = O.synth_task(task=0, shots=5, queries=5, L=128, T=864)
+    _check_task(m, P, cfg, sup, qry, 5, first_order, 4e-3, f"config{'4' if first_order else '3'} FULL size K=5", fast_tol=2e-2,
+                median_tol=3e-3)
