@@ -43,6 +43,10 @@ const char* mtts_last_error(void);
 int         mtts_check_device(void);
 /* Programmatic Dependent Launch on/off (default on; env MTTS_PDL=0 disables). */
 int         mtts_set_pdl(int on);
+/* Deterministic mode on/off (default off; env MTTS_DETERMINISTIC=1 enables): no split-K, every cross-CTA atomic reduction
+ * (bias / LayerNorm / BatchNorm channel sums, loss and norm scalars, embedding scatter-add) runs in a fixed order, so results are
+ * bit-reproducible run to run — the counterpart of the reference's Trainer(deterministic=True), main.py:35.  ~10x slower (a debugging mode). */
+int         mtts_set_deterministic(int on);
 
 /* ------------------------------------------------------------------------------------------
  * Generic tcgen05 GEMM:   for every z = (z0, z1):

@@ -50,6 +50,7 @@ void mtts_set_error(const char* fmt, ...);
 // executes griddepcontrol.wait before its first global-memory access, so ordering is unchanged.
 // ------------------------------------------------------------------------------------------------
 int mtts_pdl_enabled();
+int mtts_deterministic();   // 1: fixed-order reductions (no split-K, one contributing CTA per reduced element)
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 static inline cudaError_t mtts_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

@@ -802,7 +802,7 @@ extern "C" int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream_) {
   MTTS_REQUIRE(d->c_f32 || d->c_hi, "gemm: no output");
   MTTS_REQUIRE(!(d->c_lo && !d->c_hi), "gemm: c_lo without c_hi");
   MTTS_REQUIRE(!(d->flags & MTTS_EPI_GATE) || d->gate, "gemm: GATE flag without gate pointer");
-  const int ksplit = d->ksplit < 1 ? 1 : d->ksplit;
+  const int ksplit = (d->ksplit < 1 || mtts_deterministic()) ? 1 : d->ksplit;   // deterministic mode: one CTA per output tile
   MTTS_REQUIRE(ksplit == 1 || ((d->flags & MTTS_EPI_ACCUM) && d->c_f32 && !d->c_hi),
                "gemm: ksplit>1 requires ACCUM into c_f32 only");
   MTTS_REQUIRE(!(d->flags & MTTS_EPI_ACCUM) || d->c_f32, "gemm: ACCUM requires c_f32");

@@ -71,6 +71,18 @@ __global__ void embed_bwd_kernel(const int64_t* __restrict__ idx, const float* _
     atomicAdd(dtable + j * C + c, scale * dy[i]);
   }
 }
+// deterministic variant: thread = one column c, which it owns in every table row; rows are added in row order (no atomics)
+__global__ void embed_bwd_ordered_kernel(const int64_t* __restrict__ idx, const float* __restrict__ dy, long long R, int C,
+                                         long long skip_idx, float scale, float* __restrict__ dtable) {
+  pdl_enter();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  for (long long r = 0; r < R; ++r) {
+    const long long j = idx[r];
+    if (j == skip_idx) continue;
+    dtable[j * C + c] += scale * dy[r * C + c];
+  }
+}
 // torch.bucketize(v, bins) (right=False): out = #{ bins < v }  (lower bound)
 __global__ void bucketize_kernel(const float* __restrict__ v, const float* __restrict__ bins, int nb, long long R,
                                  int64_t* __restrict__ out) {
@@ -407,7 +419,7 @@ __global__ void bn_tbwd_apply_kernel(BnArgs a, const float* __restrict__ ws, con
 inline void bn_launch_dims(long long R, int C, dim3& grid, dim3& block, int& rows_per_cta) {
   block = dim3(128);
   const int col_blocks = mtts_cdiv(C, 128);
-  int row_chunks = static_cast<int>(mtts_cdiv64(148LL * 4, col_blocks));
+  int row_chunks = mtts_deterministic() ? 1 : static_cast<int>(mtts_cdiv64(148LL * 4, col_blocks));   // deterministic: one CTA per column block
   if (row_chunks > R) row_chunks = static_cast<int>(R);
   rows_per_cta = static_cast<int>(mtts_cdiv64(R, row_chunks));
   row_chunks = static_cast<int>(mtts_cdiv64(R, rows_per_cta));
@@ -624,7 +636,10 @@ extern "C" int mtts_embed_bwd(const int64_t* idx, const float* dy, int64_t R, in
                               float* dtable, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(idx && dy && dtable && R > 0 && C > 0, "embed_bwd: bad args");
-  MTTS_CHECK_CUDA(mtts_launch(embed_bwd_kernel, dim3(ew_grid(R * C, 1)), dim3(EW_THREADS), 0, s, idx, dy, R, C, skip_idx, scale, dtable));
+  if (mtts_deterministic())
+    MTTS_CHECK_CUDA(mtts_launch(embed_bwd_ordered_kernel, dim3(mtts_cdiv(C, 128)), dim3(128), 0, s, idx, dy, R, C, skip_idx, scale, dtable));
+  else
+    MTTS_CHECK_CUDA(mtts_launch(embed_bwd_kernel, dim3(ew_grid(R * C, 1)), dim3(EW_THREADS), 0, s, idx, dy, R, C, skip_idx, scale, dtable));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -666,7 +681,7 @@ extern "C" int mtts_colsum(const float* f32, const void* hi, const void* lo, int
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE((f32 || hi) && out && nb > 0 && R > 0 && C > 0, "colsum: bad args");
   const int col_blocks = mtts_cdiv(C, 128);
-  int row_chunks = static_cast<int>(mtts_cdiv64(148LL * 4, static_cast<long long>(col_blocks) * nb));
+  int row_chunks = mtts_deterministic() ? 1 : static_cast<int>(mtts_cdiv64(148LL * 4, static_cast<long long>(col_blocks) * nb));
   if (row_chunks < 1) row_chunks = 1;
   if (row_chunks > R) row_chunks = static_cast<int>(R);
   const int rows_per_cta = static_cast<int>(mtts_cdiv64(R, row_chunks));
@@ -766,7 +781,7 @@ extern "C" int mtts_loss_fwd(const float* mel, const float* post, const float* m
                "loss_fwd: null argument");
   LossArgs a = make_loss_args(mel, post, mel_tgt, mel_lens, p, p_tgt, e, e_tgt, logd, dur, src_lens, B, T, L, NM);
   MTTS_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 8, s));
-  MTTS_CHECK_CUDA(mtts_launch(loss_sums_kernel, dim3(ew_grid(static_cast<long long>(B) * T * NM, 4)), dim3(EW_THREADS), 0, s, a, ws));
+  MTTS_CHECK_CUDA(mtts_launch(loss_sums_kernel, dim3(mtts_deterministic() ? 1 : ew_grid(static_cast<long long>(B) * T * NM, 4)), dim3(EW_THREADS), 0, s, a, ws));
   MTTS_CHECK_CUDA(mtts_launch(loss_finalize_kernel, dim3(1), dim3(1), 0, s, a, ws, out6, counts));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
@@ -813,7 +828,7 @@ extern "C" int mtts_sumsq(const float* x, int64_t n, float* out /* zeroed here *
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   REQ_N4(n, x);
   MTTS_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
-  MTTS_CHECK_CUDA(mtts_launch(sumsq_kernel, dim3(ew_grid(n / 4, 4)), dim3(EW_THREADS), 0, s, x, n / 4, out));
+  MTTS_CHECK_CUDA(mtts_launch(sumsq_kernel, dim3(mtts_deterministic() ? 1 : ew_grid(n / 4, 4)), dim3(EW_THREADS), 0, s, x, n / 4, out));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -822,7 +837,7 @@ extern "C" int mtts_dot(const float* x, const float* y, int64_t n, float* out /*
   REQ_N4(n, x);
   MTTS_REQUIRE(y != nullptr && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "dot: bad second operand");
   MTTS_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
-  MTTS_CHECK_CUDA(mtts_launch(dot_kernel, dim3(ew_grid(n / 4, 4)), dim3(EW_THREADS), 0, s, x, y, n / 4, out));
+  MTTS_CHECK_CUDA(mtts_launch(dot_kernel, dim3(mtts_deterministic() ? 1 : ew_grid(n / 4, 4)), dim3(EW_THREADS), 0, s, x, y, n / 4, out));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }

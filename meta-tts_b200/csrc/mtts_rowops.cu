@@ -17,7 +17,9 @@ namespace {
 constexpr int ROW_THREADS = 256;   // 8 warps / CTA
 constexpr int ROW_WARPS = ROW_THREADS / 32;
 
-inline int row_grid(long long rows) {
+// reduces = the kernel also accumulates per-channel sums over its rows (atomics across CTAs): ONE CTA in deterministic mode
+inline int row_grid(long long rows, bool reduces = false) {
+  if (reduces && mtts_deterministic()) return 1;
   int sms = 148;
   long long need = (rows + ROW_WARPS - 1) / ROW_WARPS;
   long long cap = static_cast<long long>(sms) * 4;
@@ -731,7 +733,7 @@ extern "C" int mtts_ln_bwd(const float* dy, const float* z, const float* stats, 
                            float* dbias, uint32_t pre_thr, uint32_t pre_seed, float pre_scale, uint32_t post_thr, uint32_t post_seed, float post_scale, const uint32_t* drop_salt, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(dy && z && stats && gamma && R > 0, "ln_bwd: bad args");
-  DISPATCH_NV(C, MTTS_CHECK_CUDA(mtts_launch(ln_bwd_kernel<NV>, dim3(row_grid(R)), dim3(ROW_THREADS), 0, s, dy, z, stats, gamma, lens, T, R, relu_gate, dz,
+  DISPATCH_NV(C, MTTS_CHECK_CUDA(mtts_launch(ln_bwd_kernel<NV>, dim3(row_grid(R, true)), dim3(ROW_THREADS), 0, s, dy, z, stats, gamma, lens, T, R, relu_gate, dz,
                                                                         static_cast<bf16*>(dz_hi), static_cast<bf16*>(dz_lo),
                                                                         dgamma, dbeta, dbias, DropSite{pre_thr, pre_seed, pre_scale, drop_salt}, DropSite{post_thr, post_seed, post_scale, drop_salt})));
   MTTS_CHECK_LAUNCH();
@@ -756,7 +758,7 @@ extern "C" int mtts_ln_tbwd(const float* dy, const float* ddy, const float* z, c
                             mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(dy && ddy && z && zdot && stats && gamma && R > 0, "ln_tbwd: bad args");
-  DISPATCH_NV(C, MTTS_CHECK_CUDA(mtts_launch(ln_tbwd_kernel<NV>, dim3(row_grid(R)), dim3(ROW_THREADS), 0, s, dy, ddy, z, zdot, stats, gamma, gdot, lens, T, R,
+  DISPATCH_NV(C, MTTS_CHECK_CUDA(mtts_launch(ln_tbwd_kernel<NV>, dim3(row_grid(R, true)), dim3(ROW_THREADS), 0, s, dy, ddy, z, zdot, stats, gamma, gdot, lens, T, R,
                                                                          relu_gate, ddz, static_cast<bf16*>(ddz_hi),
                                                                          static_cast<bf16*>(ddz_lo), ddgamma, ddbeta, ddbias, DropSite{pre_thr, pre_seed, pre_scale, drop_salt}, DropSite{post_thr, post_seed, post_scale, drop_salt})));
   MTTS_CHECK_LAUNCH();
@@ -779,7 +781,7 @@ extern "C" int mtts_rowdot_bwd(const float* dout, const float* ddout, const floa
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(dout && h && w && dh && R > 0, "rowdot_bwd: bad args");
   MTTS_REQUIRE(!ddout || hdot, "rowdot_bwd: tangent mode needs hdot");
-  DISPATCH_NV(C, MTTS_CHECK_CUDA(mtts_launch(rowdot_bwd_kernel<NV>, dim3(row_grid(R)), dim3(ROW_THREADS), 0, s, dout, ddout, h, hdot, w, wdot, lens, T, R, dh, dw, db)));
+  DISPATCH_NV(C, MTTS_CHECK_CUDA(mtts_launch(rowdot_bwd_kernel<NV>, dim3(row_grid(R, true)), dim3(ROW_THREADS), 0, s, dout, ddout, h, hdot, w, wdot, lens, T, R, dh, dw, db)));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }

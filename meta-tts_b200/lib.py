@@ -104,6 +104,7 @@ _D1 = [_u32, _u32, _f, _vp]
 SIGNATURES: dict[str, list] = {
     "mtts_check_device": [],
     "mtts_set_pdl": [_i],
+    "mtts_set_deterministic": [_i],
     "mtts_gemm": [C.POINTER(GemmDesc), _vp],
     "mtts_attn_fwd": [C.POINTER(AttnDesc), _vp],
     "mtts_attn_bwd": [C.POINTER(AttnDesc), _i, _vp],
