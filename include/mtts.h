@@ -47,6 +47,9 @@ int         mtts_set_pdl(int on);
  * (bias / LayerNorm / BatchNorm channel sums, loss and norm scalars, embedding scatter-add) runs in a fixed order, so results are
  * bit-reproducible run to run — the counterpart of the reference's Trainer(deterministic=True), main.py:35.  ~10x slower (a debugging mode). */
 int         mtts_set_deterministic(int on);
+/* Zero `bytes` bytes at p on the stream (cudaMemsetAsync; a memset node under graph capture).  Replaces optimizer.zero_grad()
+ * (Lightning, main.py:57-64) / the zero-initialised gradient buffers of autograd on the flat gradient arenas. */
+int         mtts_zero(void* p, int64_t bytes, mtts_stream stream);
 
 /* ------------------------------------------------------------------------------------------
  * Generic tcgen05 GEMM:   for every z = (z0, z1):

@@ -28,7 +28,7 @@ from scipy.signal import get_window
 
 from . import lib as L
 from .engine import _pick_cfg
-from .ops import Opnd
+from .ops import Opnd, _stream
 
 
 def _rup(x: int, m: int) -> int:
@@ -224,12 +224,23 @@ class STFT:
 
 
 def dynamic_range_compression(x, C=1, clip_val=1e-5):
-    """audio_processing.py:85-91 (host/torch tensors in, same out; used by callers outside the GEMM path)."""
+    """audio_processing.py:85-91: log(clamp(x, min=clip_val) * C).  CUDA tensors go through mtts_unary (no torch kernels on the
+    device path); host tensors (the reference calls it on numpy-backed tensors during preprocessing) use torch on the CPU."""
+    if x.is_cuda:
+        xin = x.contiguous().float()
+        out = torch.empty_like(xin)
+        L.call("mtts_unary", L.UN_LOGCLAMP, xin.data_ptr(), xin.numel(), float(clip_val), float(C), out.data_ptr(), None, None, _stream())
+        return out
     return torch.log(torch.clamp(x, min=clip_val) * C)
 
 
 def dynamic_range_decompression(x, C=1):
-    """audio_processing.py:94-100."""
+    """audio_processing.py:94-100: exp(x) / C (CUDA tensors: mtts_unary)."""
+    if x.is_cuda:
+        xin = x.contiguous().float()
+        out = torch.empty_like(xin)
+        L.call("mtts_unary", L.UN_EXP, xin.data_ptr(), xin.numel(), 1.0 / float(C), 0.0, out.data_ptr(), None, None, _stream())
+        return out
     return torch.exp(x) / C
 
 

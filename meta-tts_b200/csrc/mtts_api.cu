@@ -57,3 +57,11 @@ extern "C" int mtts_set_deterministic(int on) {
   g_det = on ? 1 : 0;
   return MTTS_OK;
 }
+
+// Zero a buffer on the stream (cudaMemsetAsync: a memset node in a captured graph, no kernel).  Replaces the torch fill kernels
+// of `tensor.zero_()` on the accumulation arenas (optimizer.zero_grad / the gradient buffers autograd would allocate zeroed).
+extern "C" int mtts_zero(void* p, int64_t bytes, mtts_stream stream) {
+  MTTS_REQUIRE(p != nullptr && bytes >= 0, "zero: bad args");
+  if (bytes) MTTS_CHECK_CUDA(cudaMemsetAsync(p, 0, static_cast<size_t>(bytes), static_cast<cudaStream_t>(stream)));
+  return MTTS_OK;
+}

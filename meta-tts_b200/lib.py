@@ -105,6 +105,7 @@ SIGNATURES: dict[str, list] = {
     "mtts_check_device": [],
     "mtts_set_pdl": [_i],
     "mtts_set_deterministic": [_i],
+    "mtts_zero": [_vp, _i64, _vp],
     "mtts_gemm": [C.POINTER(GemmDesc), _vp],
     "mtts_attn_fwd": [C.POINTER(AttnDesc), _vp],
     "mtts_attn_bwd": [C.POINTER(AttnDesc), _i, _vp],

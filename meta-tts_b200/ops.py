@@ -288,7 +288,8 @@ class CudaOps:
         return torch.zeros(shape, dtype=dtype, device=self.device)
 
     def zero_(self, t):
-        t.zero_()          # cudaMemsetAsync on the current stream
+        assert t.is_contiguous()
+        L.call("mtts_zero", t.data_ptr(), t.numel() * t.element_size(), _stream())     # cudaMemsetAsync: no fill kernel
 
     # kernels launched per C-ABI call (memsets not counted)
     KERNELS = {"mtts_bn_fwd": 2, "mtts_bn_bwd": 2, "mtts_bn_tfwd": 2, "mtts_bn_tbwd": 2, "mtts_loss_fwd": 2}
