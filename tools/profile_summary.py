@@ -17,11 +17,11 @@ w(f"bench.py (CUDA-graph replay, clocks {bench['clocks']}): **{bench['ms_per_ste
   f"{e2e['value']:.0f} mel-frames/s ({e2e['ms_per_step']:.2f} ms/step, runs {['%.2f' % x for x in e2e['runs_ms_per_step']]}); "
   f"CPU oracle on the same box: {cb.get('value', float('nan')):.0f} mel-frames/s ({cb.get('cores')} threads).\n")
 w(f"Dominant kernel `{rf['kernel'].split(' ')[0]}`: {rf['launches_per_step']} launches/step, {100 * rf['share_of_step']:.0f}% of the step, "
-  f"**{rf['achieved']:.1f} algorithmic TFLOP/s = {100 * rf['frac']:.1f}% of the measured sustained bf16 peak ({rf['peak']} TF/s)**; "
-  f"bf16x3 issues 3 MMAs per algorithmic FLOP => {100 * rf['frac_of_issued_mma']:.1f}% of peak as issued tensor work.  "
+  f"**{rf['achieved']:.1f} algorithmic TFLOP/s = {100 * rf['frac']:.1f}% of the measured BURST bf16 peak ({rf['peak']} TF/s; the kernel is timed alone)**; "
+  f"it issues {rf.get('tensor_pipe_work_multiplier', 3)} MMA pass(es) per algorithmic FLOP => {100 * rf['frac_of_issued_mma']:.1f}% of peak as issued tensor work.  "
   f"All GEMM kernels: {rf['all_gemm']['ms_per_step']:.2f} ms/step of kernel time ({rf['all_gemm']['tflops']:.1f} TFLOP/s; they overlap "
   f"across the main / side / branch streams, so the sum exceeds their share of the step).\n")
-w("| GEMM kernel variant | launches/step | ms/step (graph replay of that variant's launches, CUDA events) | algorithmic GFLOP | TFLOP/s |")
+w("| tensor-core kernel variant | launches/step | ms/step (graph replay of that variant's launches, CUDA events) | algorithmic GFLOP | TFLOP/s |")
 w("|---|---|---|---|---|")
 for v in rf["all_gemm_kernels"]:
     w(f"| `{v['kernel']}` | {v['launches']} | {v['ms_per_step']:.3f} | {v['algorithmic_gflop']:.1f} | {v['tflops']:.1f} |")
@@ -71,10 +71,11 @@ for row in f:
     key = (k, row[col[names["grid"]]])
     g = groups.setdefault(key, [])
     g.append([float(row[col[names[x]]].replace(",", "")) for x in ("dur", "tensor", "dr", "dw", "l2hit", "l2thr")])
-w(f"## ncu --set full capture of the support decoder forward's GEMMs (raw page: `profiles/{tag}_ncu_gemm_raw.csv`)\n")
+w(f"## ncu --set full capture of tensor-core launches of the support forward pass (raw page: `profiles/{tag}_ncu_gemm_raw.csv`)\n")
 w("| kernel | grid | launches | duration us | tensor pipe active % | DRAM read MB | DRAM write KB | L2 hit % | L2 throughput % | what it is |")
 w("|---|---|---|---|---|---|---|---|---|---|")
-what = {"(84, 1, 1)": "QKV projection 3456x768x256", "(49, 1, 8)": "attention scores 864x864x128 x 8 (b,h)", "(14, 1, 8)": "P.V 864x128x864 x 8",
+what = {"(7, 2, 4)": "fused attention, 7 query (key) tiles x 2 heads x 4 utterances", "(1, 2, 4)": "fused attention, encoder (128 phonemes)",
+        "(84, 1, 1)": "QKV projection 3456x768x256", "(49, 1, 8)": "attention scores 864x864x128 x 8 (b,h)", "(14, 1, 8)": "P.V 864x128x864 x 8",
         "(108, 1, 1)": "out-proj 3456x256x256 / conv k=1 3456x256x1024", "(32, 1, 4)": "conv k=9 864x1024x(9x256) x 4", "(4, 1, 4)": "encoder conv k=1 (tail of the query encoder branch)"}
 for (k, grid), rows in groups.items():
     m = [sum(c) / len(rows) for c in zip(*rows)]
