@@ -406,7 +406,7 @@ def measure_secondary(name, rank, world, dev, split, dropout, steps=8, warmup=3)
     out = {"workload": f"{'first' if w['first_order'] else 'second'}-order MAML K={w['k']}, {w['shots']}-shot support + {w['queries']} queries, "
                        f"{L_PHON} phonemes -> {T_MEL} frames, {w['acc']} task(s)/GPU/step ({w['tag']})",
            "value": frames / (ms_per_step * 1e-3), "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
-           "tasks_per_step": world * w["acc"], "gpu_launches_per_step": w["acc"] * sysm.launches_per_task_step + 2,
+           "tasks_per_step": world * w["acc"], "gpu_launches_per_step": w["acc"] * sysm.launches_per_task_step + 3,
            "timing": "device resident: CUDA-graph replay + NCCL allreduce + clip/Adam, CUDA events, barrier both sides, max over ranks"}
     del sysm, graph
     torch.cuda.empty_cache()
@@ -553,7 +553,7 @@ def run_own_arm(args):
         sysm.optimizer_step()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
-        print(json.dumps({"profile_step": True, "launches": sysm.launches_per_task_step + 2}))
+        print(json.dumps({"profile_step": True, "launches": sysm.launches_per_task_step + 3}))
         return
 
     # ---------- (1) device-resident timing: graph replay + allreduce + Adam ----------
@@ -562,7 +562,7 @@ def run_own_arm(args):
     key, ent = next(iter(sysm._graphs.items()))
     graph = ent[2]
     launches_task = sysm.launches_per_task_step
-    launches_step = GRAD_ACC * launches_task + 2    # + sumsq + adam_clip (the allreduce is NCCL's kernel)
+    launches_step = GRAD_ACC * launches_task + 3    # + sumsq (partials, finalize) + adam_clip (the allreduce is NCCL's kernel)
 
     def device_step():
         for _ in range(GRAD_ACC):                   # micro-steps accumulate into the NCCL buffer; one allreduce + Adam per step

@@ -303,8 +303,11 @@ int mtts_split(const float* src, void* hi, void* lo, int64_t n, mtts_stream stre
 /* l2l maml_update: out = theta - lr*g, fused with the bf16 hi/lo operand preparation. */
 int mtts_sgd_split(const float* theta, const float* g, float lr, float* out, void* hi, void* lo, int64_t n, mtts_stream stream);
 int mtts_axpby(float a, const float* x, float b, float* y, int64_t n, mtts_stream stream);
+/* out[0] = sum x^2 (the global gradient norm of clip_grad_norm_, main.py:61).  `out` holds MTTS_SCALAR_WS floats: out[1..] are
+ * per-CTA partials, added in a fixed order (no atomics) — every rank that holds the same reduced gradient gets the same bits. */
+#define MTTS_SCALAR_WS 2048
 int mtts_sumsq(const float* x, int64_t n, float* out, mtts_stream stream);
-/* out = <x, y>  (conjugate-gradient scalars of the iMAML hypergradient, hypertorch/hypergrad/CG_torch.py:21-35). */
+/* out[0] = <x, y>  (conjugate-gradient scalars of the iMAML hypergradient, hypertorch/hypergrad/CG_torch.py:21-35); out as above. */
 int mtts_dot(const float* x, const float* y, int64_t n, float* out, mtts_stream stream);
 /* clip_grad_norm_(max_norm) + Adam (lightning/optimizer.py:6-16, main.py:61).  sumsq = sum g^2 of
  * the UNSCALED buffer, gscale multiplies g first (1/(n_tasks)); hyper = device (lr, 1-b1^t, 1-b2^t). */

@@ -568,7 +568,7 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n4, float* _
     s += (u.x * u.x + u.y * u.y) + (u.z * u.z + u.w * u.w);
   }
   s = block_sum(s);
-  if (threadIdx.x == 0) atomicAdd(out, s);
+  if (threadIdx.x == 0) out[1 + blockIdx.x] = s;       // per-CTA partial; scalar_finalize_kernel adds them in CTA order
 }
 __global__ void dot_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n4, float* __restrict__ out) {
   pdl_enter();
@@ -579,7 +579,17 @@ __global__ void dot_kernel(const float* __restrict__ x, const float* __restrict_
     s += (u.x * w.x + u.y * w.y) + (u.z * w.z + u.w * w.w);
   }
   s = block_sum(s);
-  if (threadIdx.x == 0) atomicAdd(out, s);
+  if (threadIdx.x == 0) out[1 + blockIdx.x] = s;
+}
+// out[0] = sum of the n per-CTA partials out[1 .. n] in a FIXED order (thread t takes partials t, t + 256, ...; then the fixed
+// shuffle tree): the global gradient norm — and with it the clip coefficient and the Adam update — is bit-identical on every
+// rank that holds the same reduced gradient, as torch's deterministic sum kernels make it in the reference (main.py:61).
+__global__ void scalar_finalize_kernel(float* __restrict__ out, int n) {
+  pdl_enter();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += out[1 + i];
+  s = block_sum(s);
+  if (threadIdx.x == 0) out[0] = s;
 }
 // clip-by-global-norm (torch clip_grad_norm_: coef = min(1, max_norm/(norm+1e-6))) + Adam (no weight decay)
 // hyper[0] = lr, hyper[1] = bias_correction1 = 1-beta1^t, hyper[2] = bias_correction2 = 1-beta2^t  (device, so graphs replay)
@@ -824,20 +834,25 @@ extern "C" int mtts_axpby(float a, const float* x, float b, float* y, int64_t n,
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
-extern "C" int mtts_sumsq(const float* x, int64_t n, float* out /* zeroed here */, mtts_stream stream_) {
+// out: MTTS_SCALAR_WS floats — out[0] the result, out[1..] per-CTA partials (fixed-order two-stage reduction, no atomics)
+extern "C" int mtts_sumsq(const float* x, int64_t n, float* out, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   REQ_N4(n, x);
-  MTTS_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
-  MTTS_CHECK_CUDA(mtts_launch(sumsq_kernel, dim3(mtts_deterministic() ? 1 : ew_grid(n / 4, 4)), dim3(EW_THREADS), 0, s, x, n / 4, out));
+  int grid = ew_grid(n / 4, 4);
+  if (grid > MTTS_SCALAR_WS - 1) grid = MTTS_SCALAR_WS - 1;
+  MTTS_CHECK_CUDA(mtts_launch(sumsq_kernel, dim3(grid), dim3(EW_THREADS), 0, s, x, n / 4, out));
+  MTTS_CHECK_CUDA(mtts_launch(scalar_finalize_kernel, dim3(1), dim3(256), 0, s, out, grid));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
-extern "C" int mtts_dot(const float* x, const float* y, int64_t n, float* out /* zeroed here */, mtts_stream stream_) {
+extern "C" int mtts_dot(const float* x, const float* y, int64_t n, float* out, mtts_stream stream_) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   REQ_N4(n, x);
   MTTS_REQUIRE(y != nullptr && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "dot: bad second operand");
-  MTTS_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
-  MTTS_CHECK_CUDA(mtts_launch(dot_kernel, dim3(mtts_deterministic() ? 1 : ew_grid(n / 4, 4)), dim3(EW_THREADS), 0, s, x, y, n / 4, out));
+  int grid = ew_grid(n / 4, 4);
+  if (grid > MTTS_SCALAR_WS - 1) grid = MTTS_SCALAR_WS - 1;
+  MTTS_CHECK_CUDA(mtts_launch(dot_kernel, dim3(grid), dim3(EW_THREADS), 0, s, x, y, n / 4, out));
+  MTTS_CHECK_CUDA(mtts_launch(scalar_finalize_kernel, dim3(1), dim3(256), 0, s, out, grid));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }

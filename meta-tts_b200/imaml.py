@@ -119,7 +119,7 @@ def imaml_hypergradient(maml, task: Task, sup12, qry12, steps: int, reg_param: f
     # ---- CG (CG_torch.py:6-41) on flat arenas: x = 0, r = p = b ----
     n_ad = lay.n_adapt
     if not hasattr(maml, "_cg"):
-        maml._cg = [be.zeros((n_ad,)) for _ in range(3)] + [be.zeros((1,)) for _ in range(3)]
+        maml._cg = [be.zeros((n_ad,)) for _ in range(3)] + [be.zeros((2048,)) for _ in range(3)]     # scalar results: [0] value, [1..] partials
     x, r, p, s_rr, s_pap, s_new = maml._cg
     be.zero_(x)
     r.copy_(maml.g_task[a0:])
@@ -138,11 +138,11 @@ def imaml_hypergradient(maml, task: Task, sup12, qry12, steps: int, reg_param: f
         be.axpby(0.0, p, lr, hv_ad)                          # A p = lr * (H + reg I) p      (v - J_fp^T v, utils.py:163-171)
         be.dot(r, r, s_rr)
         be.dot(p, hv_ad, s_pap)
-        rTr, pAp = float(s_rr), float(s_pap)                 # the reference syncs here too (float(torch.norm(r_vec)))
+        rTr, pAp = float(s_rr[0]), float(s_pap[0])                 # the reference syncs here too (float(torch.norm(r_vec)))
         alpha = rTr / pAp
         be.axpby(-alpha, hv_ad, 1.0, r)                      # r <- r - alpha A p
         be.dot(r, r, s_new)
-        rr_new = float(s_new)
+        rr_new = float(s_new[0])
         if rr_new ** 0.5 < cg_eps:
             break                                            # x_last is returned WITHOUT this iteration's update
         be.axpby(alpha, p, 1.0, x)                           # x <- x + alpha p
@@ -200,7 +200,7 @@ class IMAMLSystem(S.MetaSystem):
             if world > 1:
                 # clip on this rank (imaml.py:123-129), then mean-reduce (imaml.py:130), then a plain Adam step
                 be.sumsq(m.g_task, m.sumsq)
-                coef = min(1.0, max_norm / (float(m.sumsq) ** 0.5 + 1e-6))
+                coef = min(1.0, max_norm / (float(m.sumsq[0]) ** 0.5 + 1e-6))
                 be.zero_(m.g_outer)
                 be.axpby(coef / world, m.g_task, 1.0, m.g_outer)
                 torch.distributed.all_reduce(m.g_outer, group=self.process_group)

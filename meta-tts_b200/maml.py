@@ -86,7 +86,7 @@ class MamlEngine:
         # Adam state (outer optimiser)
         self.adam_m = z((n,))
         self.adam_v = z((n,))
-        self.sumsq = z((1,))
+        self.sumsq = z((2048,))          # [0] = |g|^2, [1..] per-CTA partials of the fixed-order reduction (MTTS_SCALAR_WS)
         self.hyper = z((4,))
         self.opt_step = 0
 

@@ -292,7 +292,8 @@ class CudaOps:
         L.call("mtts_zero", t.data_ptr(), t.numel() * t.element_size(), _stream())     # cudaMemsetAsync: no fill kernel
 
     # kernels launched per C-ABI call (memsets not counted)
-    KERNELS = {"mtts_bn_fwd": 2, "mtts_bn_bwd": 2, "mtts_bn_tfwd": 2, "mtts_bn_tbwd": 2, "mtts_loss_fwd": 2}
+    KERNELS = {"mtts_bn_fwd": 2, "mtts_bn_bwd": 2, "mtts_bn_tfwd": 2, "mtts_bn_tbwd": 2, "mtts_loss_fwd": 2, "mtts_sumsq": 2, "mtts_dot": 2}
+    SCALAR_WS = 2048        # floats behind a sumsq / dot result (include/mtts.h MTTS_SCALAR_WS): [0] = the value, [1..] = per-CTA partials
 
     def _call(self, name, *args):
         global launch_count
@@ -472,9 +473,11 @@ class CudaOps:
         self._call("mtts_axpby", a, _p(x), b, _p(y), x.numel())
 
     def sumsq(self, x, out):
+        assert out.numel() >= self.SCALAR_WS, "sumsq: the result buffer carries the per-CTA partials (SCALAR_WS floats)"
         self._call("mtts_sumsq", _p(x), x.numel(), _p(out))
 
     def dot(self, x, y, out):
+        assert out.numel() >= self.SCALAR_WS, "dot: the result buffer carries the per-CTA partials (SCALAR_WS floats)"
         self._call("mtts_dot", _p(x), _p(y), x.numel(), _p(out))
 
     def adam_clip(self, p, g, m, v, sumsq, gscale, max_norm, hyper, beta1, beta2, eps, hi, lo):

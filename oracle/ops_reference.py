@@ -693,15 +693,15 @@ class RefOps:
 
     def sumsq(self, x, out):
         self.n_calls += 1
-        out.copy_((x.double() ** 2).sum().float().reshape(out.shape))
+        out.reshape(-1)[0] = (x.double() ** 2).sum().float()       # [0] = the value ([1..]: the kernels' per-CTA partials)
 
     def dot(self, x, y, out):
         self.n_calls += 1
-        out.copy_((x.double() * y.double()).sum().float().reshape(out.shape))
+        out.reshape(-1)[0] = (x.double() * y.double()).sum().float()
 
     def adam_clip(self, p, g, m, v, sumsq, gscale, max_norm, hyper, beta1, beta2, eps, hi, lo):
         self.n_calls += 1
-        norm = torch.sqrt(sumsq.double()).item() * gscale
+        norm = torch.sqrt(sumsq.reshape(-1)[0].double()).item() * gscale
         coef = min(1.0, max_norm / (norm + 1e-6)) if max_norm > 0 else 1.0
         gg = g * (coef * gscale)
         lr, bc1, bc2 = [float(x) for x in hyper[:3]]

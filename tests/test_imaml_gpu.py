@@ -23,11 +23,11 @@ def _rel(a, b):
 def test_dot_kernel(cuda_device):
     g = torch.Generator().manual_seed(0)
     x, y = torch.randn(1 << 20, generator=g), torch.randn(1 << 20, generator=g)
-    out = torch.zeros(1, device=cuda_device)
+    out = torch.zeros(2048, device=cuda_device)
     CudaOps(split=3).dot(x.to(cuda_device), y.to(cuda_device), out)
-    ref = torch.zeros(1)
+    ref = torch.zeros(2048)
     RefOps().dot(x, y, ref)
-    assert abs(float(out) - float(ref)) < 1e-4 * float(x.norm() * y.norm()) / 1000
+    assert abs(float(out[0]) - float(ref[0])) < 1e-4 * float(x.norm() * y.norm()) / 1000
 
 
 @pytest.mark.parametrize("model,dropout,stochastic,shape", [("small", False, True, (4, 2, 6, 16)), ("small", True, True, (4, 2, 6, 16)),

@@ -242,7 +242,14 @@ def test_elementwise(cuda_device):
     _hl_check(c[1], c[2], gg[1], gg[2])
     _both(cuda_device, "sgd_split", [x, g, 0.001, torch.zeros(n), bf(n), bf(n)])
     _both(cuda_device, "axpby", [-0.3, x, 1.5, g.clone()])
-    _both(cuda_device, "sumsq", [x, torch.zeros(1)])
+    cu = CudaOps(split=3)
+    ws = torch.zeros(2048, device=cuda_device)
+    cu.sumsq(x.to(cuda_device), ws)
+    ref = (x.double() ** 2).sum().item()
+    assert abs(float(ws[0]) - ref) < 1e-5 * ref
+    ws2 = torch.full((2048,), 7.0, device=cuda_device)       # stale workspace contents must not matter; same bits run to run
+    cu.sumsq(x.to(cuda_device), ws2)
+    assert float(ws2[0]) == float(ws[0])
     hyper = torch.tensor([0.01, 1 - 0.9, 1 - 0.98, 0.0])
     ss = (g.double() ** 2).sum().float().reshape(1)
     _both(cuda_device, "adam_clip", [x.clone(), g, 0.1 * R_(n, seed=3), R_(n, seed=4).abs(), ss, 0.5, 1.0, hyper, 0.9, 0.98, 1e-9,

@@ -101,7 +101,7 @@ def main():
         "read p, g, m, v (16 B); write p, m, v, hi, lo (16 B)", rows)
     run("axpby (G <- G - lr*HV), 34.65 M", n * 12, lambda: (f(n), f(n)), lambda s: be.axpby(-1e-3, s[0], 1.0, s[1]),
         "read x, y; write y", rows)
-    out1 = z(1)
+    out1 = z(2048)
     run("sumsq (global gradient norm), 34.65 M", n * 4, lambda: (f(n),), lambda s: be.sumsq(s[0], out1), "read x", rows)
     # vocoder side
     F_, NP, io = 864, 1040, 520
