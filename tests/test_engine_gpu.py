@@ -235,3 +235,26 @@ def test_config3_config4_full_size_parity(cuda_device, first_order):
     sup, qry = O.synth_task(task=0, shots=5, queries=5, L=128, T=864)
     _check_task(m, P, cfg, sup, qry, 5, first_order, 4e-3, f"config{'4' if first_order else '3'} FULL size K=5", fast_tol=2e-2,
                 median_tol=3e-3)
+
+
+@pytest.mark.parametrize("eval_mode", [False, True])
+def test_config1_single_utterance_forward(cuda_device, eval_mode):
+    """BASELINE configs[0]: FastSpeech2-base single-utterance forward, 64 phonemes -> 512 mel frames (no MAML): every output of
+    `FastSpeech2.forward` (fastspeech2.py:40-112) and the 6 losses against the oracle, in train mode (batch statistics in the
+    postnet) and under model.eval() (running statistics)."""
+    cfg = O.BASE_MODEL_CONFIG
+    P = O.init_params(seed=0)
+    m = _engine(P, cfg, K=1)
+    b12 = O.synth_batch(1, 64, 512, seed=21, speaker=5)
+    with torch.no_grad():
+        preds = O.fs2_forward({k: v.detach().clone() for k, v in P.items()}, cfg, *b12[2:], training=not eval_mode)
+        losses = O.fs2_loss(b12, preds)
+    out = m.engine.forward(m.params(0), batch_from_tuple(b12, m.theta.device), m.engine.new_tape(), update_bn=not eval_mode,
+                           eval_mode=eval_mode)
+    torch.cuda.synchronize()
+    errs = {"mel": _rel(out["mel"].reshape(preds[0].shape), preds[0]), "postnet": _rel(out["postnet"].reshape(preds[1].shape), preds[1]),
+            "pitch": _rel(out["pitch"], preds[2]), "energy": _rel(out["energy"], preds[3]), "logd": _rel(out["logd"], preds[4]),
+            "loss6": _rel(out["loss6"], torch.stack(losses))}
+    print(f"[engine] config1 single utterance 64 -> 512, eval={eval_mode}: " + " ".join(f"{k} {v:.2e}" for k, v in errs.items()))
+    assert torch.equal(out["mel_len"].cpu(), preds[9])
+    assert max(errs.values()) < REL_OUT
