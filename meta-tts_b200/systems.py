@@ -425,7 +425,8 @@ def adapt(self, batch, adaptation_steps: int = 5, learner=None, train: bool = Tr
     self.maml.use_tapes(ent[1])
     self.be.drop_salt = sb.salt
     sb.upload(sup12, salt=self.next_salt() if self.dropout else 0)
-    self.maml.adapt(sb.dev, adaptation_steps, start=start, drop_base=start if self.dropout else None)
+    self.maml.adapt(sb.dev, adaptation_steps, start=start, drop_base=start if self.dropout else None,
+                    second_order=False)          # no Hessian-vector pass follows a stand-alone adapt(): nothing re-reads P / dP / dS
     return start + adaptation_steps
 
 
