@@ -377,11 +377,13 @@ def measure_secondary(name, rank, world, dev, split, dropout, steps=8, warmup=3)
     t = SYN.synth_task(task=rank, shots=w["shots"], queries=w["queries"], L=L_PHON, T=T_MEL)
     sysm.training_step([([t[0]], [t[1]])], 0)
     sysm.optimizer_step()
-    graph = next(iter(sysm._graphs.values()))[2]
+    gkey, gent = next(reversed(sysm._graphs.items()))       # the graph of the LAST micro-step (it carries the in-step allreduce)
+    graphs = [e[2] for e in sysm._graphs.values()]
 
     def step():
-        for _ in range(w["acc"]):
-            graph.replay()
+        for i_ in range(w["acc"]):
+            (graphs[0] if i_ + 1 < w["acc"] else gent[2]).replay()
+        sysm._reduced_in_step = bool(gkey[-1])          # replaying the graph directly: tell optimizer_step what it contained
         sysm.optimizer_step()
 
     def barrier():
@@ -439,9 +441,10 @@ def equivalence_check(rank, world, dev, split):
                    seed=0, use_cuda_graph=False)
     a.load_state_dict(sd)
     t = SYN.synth_task(task=rank, shots=shots, queries=queries, L=Lp, T=T)
-    a.training_step([([t[0]], [t[1]])], 0)
-    if world > 1:
+    a.training_step([([t[0]], [t[1]])], 0)          # world > 1: the step itself reduces the outer gradient (overlapped)
+    if world > 1 and not a._reduced_in_step:
         dist.all_reduce(a.maml.g_outer)
+    res_in_step = bool(a._reduced_in_step)
     g_a = a.maml.g_outer.clone()
     # (optimizer_step would all_reduce again: run the update directly on the reduced buffer)
     opt = a.train_config["optimizer"]
@@ -450,7 +453,8 @@ def equivalence_check(rank, world, dev, split):
     dist.all_reduce(th_max, op=dist.ReduceOp.MAX)
     dist.all_reduce(th_min, op=dist.ReduceOp.MIN)
     ranks_identical = bool((th_max == th_min).all().item())
-    res = {"ranks_bit_identical_after_adam": ranks_identical, "theta_checksum": float(a.maml.theta.double().sum().item())}
+    res = {"ranks_bit_identical_after_adam": ranks_identical, "theta_checksum": float(a.maml.theta.double().sum().item()),
+           "allreduce_issued_inside_the_step": res_in_step}
     # ---- B: one GPU, the same tasks accumulated ----
     if rank == 0:
         train_b = copy.deepcopy(DEFAULT_TRAIN_CONFIG)
@@ -559,14 +563,16 @@ def run_own_arm(args):
     # ---------- (1) device-resident timing: graph replay + allreduce + Adam ----------
     sysm.training_step(batches[0], 0)              # builds static buffers, warm-up + CUDA-graph capture
     sysm.optimizer_step()
-    key, ent = next(iter(sysm._graphs.items()))
+    key, ent = next(reversed(sysm._graphs.items()))          # the graph of the last micro-step (carries the in-step allreduce)
     graph = ent[2]
+    first_graph = next(iter(sysm._graphs.values()))[2]
     launches_task = sysm.launches_per_task_step
     launches_step = GRAD_ACC * launches_task + 3    # + sumsq (partials, finalize) + adam_clip (the allreduce is NCCL's kernel)
 
     def device_step():
-        for _ in range(GRAD_ACC):                   # micro-steps accumulate into the NCCL buffer; one allreduce + Adam per step
-            graph.replay()
+        for i_ in range(GRAD_ACC):                  # micro-steps accumulate into the NCCL buffer; one allreduce + Adam per step
+            (first_graph if i_ + 1 < GRAD_ACC else graph).replay()
+        sysm._reduced_in_step = bool(key[-1])       # replaying the graph directly: tell optimizer_step what it contained
         sysm.optimizer_step()
 
     for _ in range(args.warmup):

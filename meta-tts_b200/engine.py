@@ -1433,17 +1433,20 @@ class FS2Engine:
     # Hessian-vector product at the tape's parameters:  HV += d/d(eps) grad L(P + eps*Pd)
     # (Pd is non-zero on adapted parameters only; encoder = non-adapted => zero forward tangent.)
     # ---------------------------------------------------------------------------------------------
-    def hvp(self, P: ParamSet, Pd: ParamSet, HV: ParamSet, bt: Batch, tp: Tape, tt: Tape, loss_scale: float = 1.0):
+    def hvp(self, P: ParamSet, Pd: ParamSet, HV: ParamSet, bt: Batch, tp: Tape, tt: Tape, loss_scale: float = 1.0, before_encoder=None):
+        """before_encoder: called when the ADAPTED region of HV is final (every adapted module's tangent backward has been issued),
+        just before the pass walks back through the non-adapted encoder — the data-parallel step starts reducing the adapted 2/3 of
+        the outer gradient there."""
         assert getattr(tp, "attn_emit", True), "this tape was recorded without the attention probabilities (attn_emit = False)"
         self.g.split_override = self.hvp_split if self.hvp_split != self.split else None
         self.g.tangent = True
         try:
-            self._hvp(P, Pd, HV, bt, tp, tt, loss_scale)
+            self._hvp(P, Pd, HV, bt, tp, tt, loss_scale, before_encoder)
         finally:
             self.g.split_override = None
             self.g.tangent = False
 
-    def _hvp(self, P: ParamSet, Pd: ParamSet, HV: ParamSet, bt: Batch, tp: Tape, tt: Tape, loss_scale: float = 1.0):
+    def _hvp(self, P: ParamSet, Pd: ParamSet, HV: ParamSet, bt: Batch, tp: Tape, tt: Tape, loss_scale: float = 1.0, before_encoder=None):
         be, g, scr, d = self.be, self.g, self.scr, self.d
         B, Lq, T = bt.B, bt.L, bt.T
         R = B * T
@@ -1570,6 +1573,9 @@ class FS2Engine:
         be.axpby(1.0, ddx0, 1.0, ddx)
         be.colsum(ddx, None, None, B, Lq, d, ddspk)
         be.spk_embed_bwd(bt.spk_ids, ddspk, bt.spk_ids.numel(), d, bt.average_spk, B, 1.0, hv("speaker_emb.model.weight"))
+        if before_encoder is not None:
+            be.join_side()                       # the adapted modules' weight-gradient products (side stream) are in HV
+            before_encoder()
         # encoder: zero forward tangent => the tangent backward is a plain backward of ddx (mixed partials)
         self._encoder_bwd(P, HV, bt, tp, ddx)
         be.join_side()

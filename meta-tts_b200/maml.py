@@ -201,7 +201,7 @@ class MamlEngine:
         return out
 
     def task_step(self, sup: Batch, qry: Batch, steps: int, first_order: bool, accumulate_scale: Optional[float] = None,
-                  drop_base: Optional[int] = None):
+                  drop_base: Optional[int] = None, reduce=None):
         """meta_learn (base_adaptor.py:114-124) + the task's outer gradient into self.g_task.
         Returns the query loss 6-vector tensor (device) and the query predictions dict."""
         assert steps <= self.K_max
@@ -223,18 +223,42 @@ class MamlEngine:
             be.zero_(self.g_enc)
         eng.backward(PK, self.grads(self.g_task), qry, self.tape_q, 1.0, into_encoder=True,
                      enc_G=self.grads(self.g_enc) if overlap_enc else None)
+        # reduce(tensor): the data-parallel sum over ranks (the step's ONE exchange, issued in two pieces).  The adapted region of the
+        # outer gradient is final before the last Hessian-vector pass walks back through the encoder, so its 2/3 of the buffer is
+        # reduced on a 'comm' branch UNDER that walk (and under the query-encoder backward on the 'enc' branch); only the encoder
+        # third is reduced at the end.  Same arithmetic: every element is accumulated once and reduced once.
+        early = reduce is not None and accumulate_scale is not None and not first_order and steps > 0 and a0 > 0
+        split_done = [False]
+
+        def reduce_adapted():
+            be.axpby(-self.lr, self.hv[a0:], 1.0, self.g_task[a0:])
+            be.axpby(accumulate_scale, self.g_task_full[a0:], 1.0, self.g_outer_full[a0:])     # adapted gradient + the 6 losses
+            with be.branch("comm"):
+                reduce(self.g_outer_full[a0:])
+            split_done[0] = True
+
         if not first_order:
             for k in range(steps - 1, -1, -1):
                 be.split_(self.g_task[a0:], self.lam_hi, self.lam_lo)
                 Pd = ParamSet(lay, None, None, None, self.g_task[a0:], self.lam_hi, self.lam_lo, only_adapted=True)
                 be.zero_(self.hv)
-                eng.hvp(self.params(k), Pd, self.grads(self.hv), sup, self.tapes[k], self.tape_t)
-                be.axpby(-self.lr, self.hv, 1.0, self.g_task)              # lambda_k | gphi update in one pass
+                last = early and k == 0
+                eng.hvp(self.params(k), Pd, self.grads(self.hv), sup, self.tapes[k], self.tape_t, before_encoder=reduce_adapted if last else None)
+                if last:
+                    be.axpby(-self.lr, self.hv[:a0], 1.0, self.g_task[:a0])      # the encoder third (the adapted part went in reduce_adapted)
+                else:
+                    be.axpby(-self.lr, self.hv, 1.0, self.g_task)          # lambda_k | gphi update in one pass
         if overlap_enc:
             be.join("enc")
             be.axpby(1.0, self.g_enc, 1.0, self.g_task[:a0])
-        if accumulate_scale is not None:
+        if split_done[0]:
+            be.axpby(accumulate_scale, self.g_task[:a0], 1.0, self.g_outer[:a0])
+            reduce(self.g_outer[:a0])
+            be.join("comm")
+        elif accumulate_scale is not None:
             be.axpby(accumulate_scale, self.g_task_full, 1.0, self.g_outer_full)      # gradient + the 6 losses on the tail
+            if reduce is not None:
+                reduce(self.g_outer_full)
         return out["loss6"], out
 
     def task_grads(self) -> Dict[str, torch.Tensor]:

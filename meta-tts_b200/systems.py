@@ -238,7 +238,7 @@ DEFAULT_TRAIN_CONFIG = {
 def _metasystem_init(self, preprocess_config=None, model_config=None, train_config=None, algorithm_config=None,
                      log_dir=None, result_dir=None, *, n_speaker: int = 16, device: str = "cuda:0", split: int = 3,
                      use_cuda_graph: bool = True, second_order: bool = True, process_group=None, backend=None,
-                     dropout: bool = True, seed: int = 0):
+                     dropout: bool = True, seed: int = 0, overlap_allreduce: Optional[bool] = None):
     self.preprocess_config = preprocess_config
     self.model_config = model_config or DEFAULT_MODEL_CONFIG
     self.train_config = train_config or DEFAULT_TRAIN_CONFIG
@@ -262,6 +262,11 @@ def _metasystem_init(self, preprocess_config=None, model_config=None, train_conf
                            max_inner_steps=self.adaptation_steps)
     self.use_cuda_graph = use_cuda_graph
     self.process_group = process_group
+    # Data-parallel exchange INSIDE the task step: the allreduce of the outer gradient is issued by the step itself, the
+    # adapted 2/3 of the buffer under the last Hessian-vector pass' walk through the encoder (captured in the CUDA graph with the
+    # rest of the step).  MTTS_OVERLAP_ALLREDUCE=0 (or overlap_allreduce=False) restores the allreduce in optimizer_step().
+    self.overlap_allreduce = (os.environ.get("MTTS_OVERLAP_ALLREDUCE", "1") != "0") if overlap_allreduce is None else bool(overlap_allreduce)
+    self._reduced_in_step = False
     # CUDA-graph cache: one entry (static batches, graph, activation tapes) per input-shape signature.  Real corpora
     # produce a new (L, T) almost every step, so the cache is an LRU of `graph_cache_size` entries (evicted graphs / tapes /
     # pinned rings are freed) and a signature is only captured on its `graph_min_hits`-th sighting; before that the step
@@ -292,12 +297,12 @@ def _state_dict(self):
     return self.maml.state_dict()
 
 
-def _task_key(self, sup12, qry12, steps: int, first_order: bool, accumulate_scale: Optional[float]):
+def _task_key(self, sup12, qry12, steps: int, first_order: bool, accumulate_scale: Optional[float], reduce_now: bool = False):
     S, Q = sup12[3].shape[0], qry12[3].shape[0]
     Ls, Ts, Lq, Tq = int(sup12[5]), int(sup12[8]), int(qry12[5]), int(qry12[8])
     # accumulate_scale is baked into the captured `axpby(scale, g_task, 1, g_outer)` (absent when None: validation), so it is
     # part of the signature — a graph captured by a validation step must never serve a training step and vice versa.
-    return (S, Ls, Ts, Q, Lq, Tq, steps, first_order, accumulate_scale)
+    return (S, Ls, Ts, Q, Lq, Tq, steps, first_order, accumulate_scale, reduce_now)
 
 
 def _get_task(self, key):
@@ -318,8 +323,11 @@ def _get_task(self, key):
     return ent
 
 
-def _run_task(self, sup12, qry12, steps: int, first_order: bool, accumulate_scale: Optional[float]):
-    key = _task_key(self, sup12, qry12, steps, first_order, accumulate_scale)
+def _run_task(self, sup12, qry12, steps: int, first_order: bool, accumulate_scale: Optional[float], reduce_now: bool = False):
+    """reduce_now: this is the last accumulated task of a data-parallel step — the step issues the allreduce itself."""
+    key = _task_key(self, sup12, qry12, steps, first_order, accumulate_scale, reduce_now)
+    pg = self.process_group
+    reduce = (lambda t: torch.distributed.all_reduce(t, group=pg)) if reduce_now else None
     drop_base = 0 if self.dropout else None
     max_T = self.model_config["max_seq_len"]
     if self.use_cuda_graph and key not in self._graphs:
@@ -338,7 +346,7 @@ def _run_task(self, sup12, qry12, steps: int, first_order: bool, accumulate_scal
             self.host_prof["upload"] += time.perf_counter() - t0
             self.maml.use_tapes(self.maml.new_tapes())
             n0 = _ops.launch_count
-            result = self.maml.task_step(sup, qry, steps, first_order, accumulate_scale, drop_base)
+            result = self.maml.task_step(sup, qry, steps, first_order, accumulate_scale, drop_base, reduce=reduce)
             self.launches_per_task_step = _ops.launch_count - n0
             self._last_qdev = qry
             return result
@@ -354,7 +362,7 @@ def _run_task(self, sup12, qry12, steps: int, first_order: bool, accumulate_scal
     self.host_prof["upload"] += time.perf_counter() - t0
     if not self.use_cuda_graph:
         n0 = _ops.launch_count
-        result = self.maml.task_step(sb.dev, qb.dev, steps, first_order, accumulate_scale, drop_base)
+        result = self.maml.task_step(sb.dev, qb.dev, steps, first_order, accumulate_scale, drop_base, reduce=reduce)
         self.launches_per_task_step = _ops.launch_count - n0
         return result
     if graph is None:
@@ -362,7 +370,7 @@ def _run_task(self, sup12, qry12, steps: int, first_order: bool, accumulate_scal
         bn0 = self.maml.bn_batches
         saved = {k: v.clone() for k, v in self.maml.consts.items() if k.endswith(("running_mean", "running_var"))}
         g_outer_saved = self.maml.g_outer_full.clone()
-        self.maml.task_step(sb.dev, qb.dev, steps, first_order, accumulate_scale, drop_base)
+        self.maml.task_step(sb.dev, qb.dev, steps, first_order, accumulate_scale, drop_base, reduce=reduce)     # (every rank warms up: the collective matches)
         torch.cuda.synchronize()
         for k, v in saved.items():
             self.maml.consts[k].copy_(v)           # the warm-up must not advance BatchNorm running statistics
@@ -370,8 +378,9 @@ def _run_task(self, sup12, qry12, steps: int, first_order: bool, accumulate_scal
         self.maml.bn_batches = bn0
         graph = torch.cuda.CUDAGraph()
         n0 = _ops.launch_count
-        with torch.cuda.graph(graph):
-            result = self.maml.task_step(sb.dev, qb.dev, steps, first_order, accumulate_scale, drop_base)
+        # thread_local: the NCCL watchdog thread's event queries must not invalidate a capture that contains the collective
+        with torch.cuda.graph(graph, capture_error_mode="thread_local" if reduce_now else "global"):
+            result = self.maml.task_step(sb.dev, qb.dev, steps, first_order, accumulate_scale, drop_base, reduce=reduce)
         self.launches_per_task_step = _ops.launch_count - n0
         self.maml.bn_batches = bn0
         ent[2], ent[3] = graph, result
@@ -437,8 +446,12 @@ def meta_learn(self, batch, batch_idx, train: bool = True):
     sup12, qry12 = batch[0][0][0], batch[0][1][0]
     steps = min(self.adaptation_steps, self.test_adaptation_steps)
     first_order = (not train) or (not self.second_order)
-    loss6, out = _run_task(self, sup12, qry12, steps, first_order, _scale(self) if train else None)
+    acc = self.train_config["optimizer"].get("grad_acc_step", 1)
+    dist_on = torch.distributed.is_initialized() and torch.distributed.get_world_size(self.process_group) > 1
+    reduce_now = bool(train and dist_on and self.overlap_allreduce and (self._pending_tasks + 1) % acc == 0)
+    loss6, out = _run_task(self, sup12, qry12, steps, first_order, _scale(self) if train else None, reduce_now)
     self._pending_tasks += 1 if train else 0
+    self._reduced_in_step = self._reduced_in_step or reduce_now
     # D2H read of the 6 losses (the step's result): asynchronous copy into a pinned ring, waited on access
     if not hasattr(self, "_loss_ring"):
         pin = loss6.is_cuda
@@ -589,7 +602,8 @@ def optimizer_step(self):
     clip_grad_norm_(grad_clip_thresh), Adam, LambdaLR; then zero the accumulation buffer."""
     m = self.maml
     t0 = time.perf_counter()
-    if torch.distributed.is_initialized() and torch.distributed.get_world_size(self.process_group) > 1:
+    if (torch.distributed.is_initialized() and torch.distributed.get_world_size(self.process_group) > 1
+            and not self._reduced_in_step):          # (else the last task step of the accumulation window has already reduced it)
         torch.distributed.all_reduce(m.g_outer_full, group=self.process_group)
     # mean of the 6 query losses over every task of the step (all ranks x accumulated micro-steps): meta.py:77-79 sync_dist=True
     self.synced_losses = m.g_outer_full[m.layout.total:m.layout.total + 6].clone()
@@ -599,6 +613,7 @@ def optimizer_step(self):
                    anneal_rate=float(opt.get("anneal_rate", 0.3)))
     self.be.zero_(m.g_outer_full)
     self._pending_tasks = 0
+    self._reduced_in_step = False
     self.host_prof["optimizer"] += time.perf_counter() - t0
 
 

@@ -75,6 +75,56 @@ def test_two_ranks_equal_one_rank_accumulating():
     assert (m.theta - _engine().theta).abs().max().item() > 1e-7      # the update moved the weights (lr(step 0) = 2.5e-7)
 
 
+# ---- the allreduce issued INSIDE the task step (adapted region under the last Hessian-vector pass' encoder walk) ----------
+def _overlap_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    sup, qry = O.synth_task(task=rank, shots=2, queries=2, L=5, T=12, ragged=True)
+    bs = batch_from_tuple(sup, "cpu")
+    bq = batch_from_tuple(qry, "cpu", spk_ids=sup[2], average_spk=True)
+    a = _engine()                                   # reference: task step, THEN one allreduce of the whole buffer
+    a.task_step(bs, bq, 1, False, accumulate_scale=1.0 / world)
+    dist.all_reduce(a.g_outer_full)
+    b = _engine()                                   # the step reduces its own gradient, in two pieces
+    calls = []
+
+    def reduce(t):
+        calls.append(t.numel())
+        dist.all_reduce(t)
+
+    b.task_step(bs, bq, 1, False, accumulate_scale=1.0 / world, reduce=reduce)
+    n, a0 = b.layout.total, b.layout.adapt_begin
+    assert calls == [n + 8 - a0, a0], calls          # adapted region (+ the loss tail) first, the encoder third last
+    assert torch.equal(a.g_outer_full, b.g_outer_full), "in-step reduction differs from reducing after the step"
+    c = _engine()                                   # first order: nothing to overlap, one reduction at the end of the step
+    calls.clear()
+    c.task_step(bs, bq, 1, True, accumulate_scale=1.0 / world, reduce=reduce)
+    assert calls == [n + 8], calls
+    if rank == 0:
+        q.put(True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_in_step_allreduce_equals_allreduce_after_the_step():
+    world = 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    assert q.get(timeout=500) is True
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+
+
 # ---- iMAML: clip on each rank, THEN mean-reduce, then a plain Adam step (lightning/systems/imaml.py:123-147) ------------------------
 def _imaml_system():
     import copy

@@ -77,7 +77,7 @@ def test_graph_cache_key_separates_train_and_validation_and_is_bounded():
     sup, qry = O.synth_task(task=2, shots=2, queries=2, L=5, T=12, ragged=True)
     k_train = S._task_key(s, sup, qry, 1, True, 1.0)
     k_val = S._task_key(s, sup, qry, 1, True, None)
-    assert k_train != k_val and k_train[:-1] == k_val[:-1]
+    assert k_train != k_val and k_train[:-2] == k_val[:-2] and k_train[-1] == k_val[-1]      # (scale, reduce_now) are the last two fields
     s.graph_cache_size = 2
     for T in (10, 11, 12, 13):
         sup, qry = O.synth_task(task=2, shots=2, queries=2, L=5, T=T)
