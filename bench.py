@@ -410,7 +410,7 @@ def measure_secondary(name, rank, world, dev, split, dropout, steps=8, warmup=3)
            "value": frames / (ms_per_step * 1e-3), "unit": UNIT, "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
            "tasks_per_step": world * w["acc"], "gpu_launches_per_step": w["acc"] * sysm.launches_per_task_step + 3,
            "timing": "device resident: CUDA-graph replay + NCCL allreduce + clip/Adam, CUDA events, barrier both sides, max over ranks"}
-    del sysm, graph
+    del sysm, graphs, gent
     torch.cuda.empty_cache()
     return out
 
