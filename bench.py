@@ -657,6 +657,7 @@ def run_own_arm(args):
         #                kernel variant's launches back-to-back from a CUDA graph with CUDA events ----------
         rec, orig = instrument_gemm(sysm.be)
         orig_attn = instrument_attn(sysm.be, rec)
+        sysm.overlap_allreduce = False      # rank 0 alone from here on: its task steps must not issue the collective
         sysm.use_cuda_graph = False
         sysm.training_step(batches[0], 0)
         torch.cuda.synchronize()
