@@ -747,7 +747,20 @@ def run_own_arm(args):
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
+        # captured graphs that contain the in-step NCCL allreduce must be gone before the communicator is torn down (tearing it
+        # down under live graphs hung at exit); a timer guarantees the process ends even if the teardown stalls
+        import gc
+        import threading
+        sysm.close()
+        del graph, first_graph, ent
+        gc.collect()
+        torch.cuda.synchronize()
+        _JSON_OUT.flush()
+        guard = threading.Timer(30.0, lambda: os._exit(0))
+        guard.daemon = True
+        guard.start()
         dist.destroy_process_group()
+        guard.cancel()
 
 
 def main():

@@ -596,6 +596,15 @@ def test_step(self, batch, batch_idx):
     return all_outputs
 
 
+def close(self):
+    """Drop every captured graph, static batch and tape.  Call before `torch.distributed.destroy_process_group()`: the graphs of a
+    data-parallel run contain the in-step NCCL allreduce, and tearing the communicator down under live graphs can hang."""
+    self._graphs.clear()
+    self._adapt_cache.clear()
+    if torch.cuda.is_available() and self.device.type == "cuda":
+        torch.cuda.synchronize(self.device)
+
+
 def optimizer_step(self):
     """What Lightning does after `accumulate_grad_batches` training_steps: DDP mean-allreduce of the
     outer gradient (one flat buffer, summed; the 1/(acc*world) scale was folded in at accumulation),
@@ -699,6 +708,7 @@ class MetaSystem:
     on_save_checkpoint = staticmethod(lambda checkpoint: checkpoint)       # system.py:111-113
     on_test_start = on_test_start
     optimizer_step = optimizer_step
+    close = close
     next_salt = next_salt
     _on_meta_batch_start = staticmethod(_assert_meta_batch)
 
