@@ -262,10 +262,12 @@ def _metasystem_init(self, preprocess_config=None, model_config=None, train_conf
                            max_inner_steps=self.adaptation_steps)
     self.use_cuda_graph = use_cuda_graph
     self.process_group = process_group
-    # Data-parallel exchange INSIDE the task step: the allreduce of the outer gradient is issued by the step itself, the
-    # adapted 2/3 of the buffer under the last Hessian-vector pass' walk through the encoder (captured in the CUDA graph with the
-    # rest of the step).  MTTS_OVERLAP_ALLREDUCE=0 (or overlap_allreduce=False) restores the allreduce in optimizer_step().
-    self.overlap_allreduce = (os.environ.get("MTTS_OVERLAP_ALLREDUCE", "1") != "0") if overlap_allreduce is None else bool(overlap_allreduce)
+    # Data-parallel exchange INSIDE the task step (opt-in: MTTS_OVERLAP_ALLREDUCE=1 or overlap_allreduce=True): the allreduce
+    # of the outer gradient is issued by the step itself, the adapted 2/3 of the buffer under the last Hessian-vector pass' walk
+    # through the encoder, captured in the CUDA graph with the rest of the step.  Measured on B200: 10.93 -> 10.80 ms/step at 2 GPUs,
+    # no change at 8 GPUs (10.97 ms both ways) — so the default stays the single allreduce in optimizer_step(); call close()
+    # before destroying the process group when it is on (graphs that contain the collective must go first).
+    self.overlap_allreduce = (os.environ.get("MTTS_OVERLAP_ALLREDUCE", "0") == "1") if overlap_allreduce is None else bool(overlap_allreduce)
     self._reduced_in_step = False
     # CUDA-graph cache: one entry (static batches, graph, activation tapes) per input-shape signature.  Real corpora
     # produce a new (L, T) almost every step, so the cache is an LRU of `graph_cache_size` entries (evicted graphs / tapes /
