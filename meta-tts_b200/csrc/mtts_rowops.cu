@@ -26,6 +26,12 @@ inline int row_grid(long long rows, bool reduces = false) {
   return static_cast<int>(need < cap ? (need < 1 ? 1 : need) : cap);
 }
 
+// one row per warp when that stays under 8 CTAs per SM: a capped grid-stride loop would leave warps with 1 or 2 rows (a 2-row tail)
+inline int softmax_grid(long long rows) {
+  const long long need = (rows + ROW_WARPS - 1) / ROW_WARPS;
+  return need <= 148LL * 8 ? static_cast<int>(need < 1 ? 1 : need) : row_grid(rows);
+}
+
 __device__ __forceinline__ bool row_valid(const int64_t* lens, int T, long long r) {
   if (!lens) return true;
   const long long b = r / T;
@@ -595,7 +601,7 @@ __device__ __forceinline__ void st4_split(bf16* hi, bf16* lo, long long i, float
 #define F4_EACH(v, EXPR_X, EXPR_Y, EXPR_Z, EXPR_W) { (v).x = EXPR_X; (v).y = EXPR_Y; (v).z = EXPR_Z; (v).w = EXPR_W; }
 
 template <int NQ, int MODE>
-__global__ void __launch_bounds__(ROW_THREADS) softmax_vec_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+__global__ void __launch_bounds__(ROW_THREADS, (MODE == 2 && NQ > 4) ? 2 : 1) softmax_vec_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
                                                                   const bf16* __restrict__ p_hi, const bf16* __restrict__ p_lo,
                                                                   const bf16* __restrict__ pd_hi, const bf16* __restrict__ pd_lo,
                                                                   const int64_t* __restrict__ klens, int H, int Lq, int Lk, int ld,
@@ -841,7 +847,7 @@ extern "C" int mtts_softmax(int mode, const float* A, const float* Bm, const voi
                        reinterpret_cast<uintptr_t>(o_hi) | reinterpret_cast<uintptr_t>(o_lo);
   if ((ld & 3) == 0 && (al & 15) == 0) {
 #define SMV_LAUNCH_M(NQ, MODE)                                                                                                   \
-  MTTS_CHECK_CUDA(mtts_launch(softmax_vec_kernel<NQ, MODE>, dim3(row_grid(rows)), dim3(ROW_THREADS), 0, s, A, Bm, static_cast<const bf16*>(p_hi), \
+  MTTS_CHECK_CUDA(mtts_launch(softmax_vec_kernel<NQ, MODE>, dim3(softmax_grid(rows)), dim3(ROW_THREADS), 0, s, A, Bm, static_cast<const bf16*>(p_hi), \
                               static_cast<const bf16*>(p_lo), static_cast<const bf16*>(pd_hi), static_cast<const bf16*>(pd_lo), klens, H, Lq, \
                               Lk, ld, rows, static_cast<bf16*>(o_hi), static_cast<bf16*>(o_lo)))
 #define SMV_LAUNCH(NQ)                        \

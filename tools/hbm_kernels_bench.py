@@ -72,6 +72,14 @@ def main():
         lambda: (f(nz, T, Tp), h(nz, T, Tp), h(nz, T, Tp)),
         lambda s: be.softmax(0, s[0], None, None, None, None, None, lens, nz, 2, T, T, Tp, s[1], s[2]),
         "read S fp32 (4 B/elt); write P hi, lo (4 B/elt)", rows)
+    run(f"softmax tangent fwd (mode 1), {nz} x {T} rows of {T} keys (ld {Tp})", nz * T * Tp * 12,
+        lambda: (f(nz, T, Tp), h(nz, T, Tp), h(nz, T, Tp), h(nz, T, Tp), h(nz, T, Tp)),
+        lambda s: be.softmax(1, s[0], None, s[1], s[2], None, None, lens, nz, 2, T, T, Tp, s[3], s[4]),
+        "read dS fp32, P hi, lo (8 B/elt); write hi, lo (4 B/elt)", rows)
+    run(f"softmax tangent bwd (mode 2), {nz} x {T} rows of {T} keys (ld {Tp})", nz * T * Tp * 20,
+        lambda: (f(nz, T, Tp), f(nz, T, Tp), h(nz, T, Tp), h(nz, T, Tp), h(nz, T, Tp), h(nz, T, Tp), h(nz, T, Tp), h(nz, T, Tp)),
+        lambda s: be.softmax(2, s[0], s[1], s[2], s[3], s[4], s[5], lens, nz, 2, T, T, Tp, s[6], s[7]),
+        "read A, B fp32, P hi, lo, Pd hi, lo (16 B/elt); write hi, lo (4 B/elt)", rows)
     C = 512
     run(f"bn_fwd (batch stats + tanh + split), {R}x{C}", R * C * 12,
         lambda: (f(R, C), f(C), f(C), z(C), torch.ones(C, device=DEV), z(4 * 512), z(2 * C), z(R, C), h(R, C), h(R, C)),
