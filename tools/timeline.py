@@ -91,3 +91,25 @@ for k in sorted(cnt, key=lambda k: -(excl[k] + shared[k])):
     if excl[k] + shared[k] < 0.01 * wall:
         continue
     print(f"| `{k}` | {cnt[k]} | {excl[k] / 1e3:.3f} | {shared[k] / 1e3:.3f} | {100 * (excl[k] + shared[k]) / wall:.1f} |")
+
+# second table: exclusive time by (family, duration bucket) — which individual launches sit alone on the critical path
+if "--detail" in sys.argv:
+    excl_i = collections.Counter()
+    active, prev = set(), pts[0][0]
+    for tpt, kind, i in pts:
+        if tpt > prev and len(active) == 1:
+            excl_i[next(iter(active))] += tpt - prev
+        prev = tpt
+        (active.add if kind == 1 else active.discard)(i)
+    groups = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    for i, (a, b, n) in enumerate(evs):
+        dur = b - a
+        bucket = 2 ** max(0, int(dur).bit_length() - 1)          # power-of-two duration bucket (us)
+        g = groups[(fam(n), bucket)]
+        g[0] += 1
+        g[1] += dur
+        g[2] += excl_i[i]
+    print("\n| kernel family | duration bucket us | launches | mean us | exclusive ms |")
+    print("|---|---|---|---|---|")
+    for (k, bkt), (c, d, e) in sorted(groups.items(), key=lambda kv: -kv[1][2])[:45]:
+        print(f"| `{k}` | {bkt}-{2 * bkt} | {c} | {d / c:.1f} | {e / 1e3:.3f} |")
