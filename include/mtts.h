@@ -115,6 +115,33 @@ typedef struct {
 
 int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream);
 
+/* The same GEMM with `dropout -> + residual -> LayerNorm -> pad-row zeroing` as its epilogue: what MultiHeadAttention.forward does
+ * after `fc` (SubLayers.py:54-55: dropout(fc(o)) + residual, layer_norm), PositionwiseFeedForward.forward after `w_2`
+ * (SubLayers.py:88-91) and FFTBlock.forward's masked_fill (Layers.py:25,28) — i.e. mtts_gemm followed by mtts_ln_fwd in ONE launch.
+ * The output row (N = 256 columns) is spread over the four 64-wide tiles of a 4-CTA cluster, which exchange per-row partial
+ * (mean, M2) through distributed shared memory (Chan's parallel variance: one exchange, no cancellation).
+ *   v      = alpha * acc + bias;  v *= keep(drop, m * N + n);  v += res[m, n]         -> z_out (fp32, saved for backward)
+ *   stats  = (mean_m, rstd_m) of v over n
+ *   c_*    = row m valid (m % T < lens[m / T]) ? (v - mean) * rstd * gamma[n] + beta[n] : 0   (fp32 and / or bf16 hi, lo)
+ * Requires N == 256, ldc == N, nz0 == nz1 == 1, ksplit == 1, pair == 0, flags == 0 (block_n is forced to 64);
+ * every pointer 16-byte aligned. */
+typedef struct {
+  const float* res;        /* [M, N] or NULL                                                        */
+  const float* gamma;      /* [N]                                                                   */
+  const float* beta;       /* [N]                                                                   */
+  const int64_t* lens;     /* [M / T] valid rows per sequence, or NULL (all rows valid)             */
+  int32_t T;
+  float eps;
+  float* z_out;            /* [M, N] or NULL                                                        */
+  float* stats;            /* [M, 2] or NULL                                                        */
+  uint32_t drop_thr, drop_seed;   /* dropout on the GEMM result (thr == 0: off), as mtts_ln_fwd's `pre` site */
+  float drop_scale;
+  int32_t reserved;
+  const uint32_t* drop_salt;
+} mtts_ln_epilogue;
+
+int mtts_gemm_ln(const mtts_gemm_desc* d, const mtts_ln_epilogue* ln, mtts_stream stream);
+
 /* Ragged -> padded pack = the padding half of collate on the device.  Replaces utils/tools.py:270-301 (pad_1D / pad_2D:
  * np.pad per utterance + np.stack) as used by lightning/collate.py:22-26: dst[b, t, :] = src[row_off[b] + t, :] for
  * t < row_off[b+1] - row_off[b], else 0; rows are copied as bytes (row_bytes a multiple of 4), so every dtype is exact.

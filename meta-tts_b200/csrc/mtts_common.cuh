@@ -297,6 +297,18 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// ---- distributed shared memory between the CTAs of a cluster (row statistics of the LayerNorm epilogue) ----------------
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t cta_addr, uint32_t rank) {      // my smem address -> the same slot of CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+// remote store that also completes its 8 bytes on an mbarrier of the destination CTA (both addresses shared::cluster)
+__device__ __forceinline__ void st_async_f32x2(uint32_t cluster_addr, float x, float y, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(cluster_addr), "f"(x),
+               "f"(y), "r"(cluster_bar)
+               : "memory");
+}
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_slot) {   // one warp in EACH CTA of the pair
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "n"(NCOLS)

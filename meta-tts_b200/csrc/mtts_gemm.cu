@@ -27,6 +27,8 @@ constexpr int BK = 64;         // bf16 elements per k-block = 128 B = one swizzl
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two warps per TMEM lane quarter)
 constexpr int MAX_SMEM = 227 * 1024;
+constexpr int EPI_LN = 1 << 16;    // internal flag (not part of the public MTTS_EPI_* set): the LayerNorm epilogue of mtts_gemm_ln
+constexpr int LN_CLUSTER = 4;      // 4 CTAs x 64 columns = the 256-wide row
 
 struct OperandParams {
   int32_t major;
@@ -52,6 +54,16 @@ struct alignas(64) GemmParams {
   const float* bias;
   int64_t bias_sz0;
   const bf16* gate;
+  // LayerNorm epilogue (mtts_gemm_ln; flags & EPI_LN): dropout -> + residual -> LayerNorm -> pad-row zeroing
+  const float* ln_res;
+  const float* ln_gamma;
+  const float* ln_beta;
+  const int64_t* ln_lens;
+  float* ln_z;
+  float* ln_stats;
+  int32_t ln_T;
+  float ln_eps;
+  DropSite ln_drop;
   int32_t dbg;               // MTTS_GEMM_DBG (diagnostics only): bits 0-3 stage cap, 16 skip MMA, 32 skip TMA, 64 epilogue sleeps, 128 no stores
 };
 
@@ -64,7 +76,9 @@ struct Cfg {
   static constexpr int B_TILE = BN * BK * 2;
   static constexpr int SUB = (A_TILE + B_TILE) * (SPLIT == 3 ? 2 : 1);   // one k-block of A (hi, lo) and B (hi, lo)
   static constexpr int STAGE = SUB * KD;
-  static constexpr int BAR_BYTES = 1024;
+  // 64-wide tiles also hold the LayerNorm epilogue's row-statistics exchange area: [4 CTAs][2 column halves][128 rows] x (mean, M2)
+  static constexpr int LN_BYTES = BN == 64 ? LN_CLUSTER * 2 * BM * 8 : 0;
+  static constexpr int BAR_BYTES = 1024 + LN_BYTES;
   static constexpr int STAGES_RAW = (MAX_SMEM - BAR_BYTES - 1024 /*align slack*/) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int SMEM = STAGES * STAGE + BAR_BYTES + 1024;
@@ -259,6 +273,150 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
   }
 }
 
+// One warp's 32 x 32 chunk (thread = row, v = its 32 columns) -> global through the warp's staging buffer: every store instruction
+// covers 4 rows x 128 contiguous bytes (same transposition as epilogue_tile).
+__device__ __forceinline__ void store_chunk_staged(float4* stage, const float (&v)[32], int lane, int row0, int M, int64_t ld, int col0,
+                                                   float* f32, bf16* hi, bf16* lo) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) stage[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int jj = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + (lane >> 3);
+    const float4 t = stage[rr * 8 + (jj ^ (rr & 7))];
+    const int grow = row0 + rr;
+    if (grow < M) {
+      const int64_t off = int64_t(grow) * ld + col0 + jj * 4;
+      if (f32) *reinterpret_cast<float4*>(f32 + off) = t;
+      if (hi) {
+        bf16 h0, h1, h2, h3, l0, l1, l2, l3;
+        split_bf16(t.x, h0, l0); split_bf16(t.y, h1, l1); split_bf16(t.z, h2, l2); split_bf16(t.w, h3, l3);
+        uint2 h;
+        h.x = uint32_t(__bfloat16_as_ushort(h0)) | (uint32_t(__bfloat16_as_ushort(h1)) << 16);
+        h.y = uint32_t(__bfloat16_as_ushort(h2)) | (uint32_t(__bfloat16_as_ushort(h3)) << 16);
+        *reinterpret_cast<uint2*>(hi + off) = h;
+        if (lo) {
+          uint2 l;
+          l.x = uint32_t(__bfloat16_as_ushort(l0)) | (uint32_t(__bfloat16_as_ushort(l1)) << 16);
+          l.y = uint32_t(__bfloat16_as_ushort(l2)) | (uint32_t(__bfloat16_as_ushort(l3)) << 16);
+          *reinterpret_cast<uint2*>(lo + off) = l;
+        }
+      }
+    }
+  }
+  __syncwarp();                       // the staging buffer is rewritten by the next chunk
+}
+
+// LayerNorm epilogue of a 128 x 64 tile whose row continues in the three other CTAs of the cluster (mtts_gemm_ln, include/mtts.h).
+// Warp (q, half) owns rows q*32 .. +32 and columns half*32 .. +32 of the tile: 8 partial (mean, M2) per row in the cluster.  Every thread
+// writes its partial into the exchange area of ALL four CTAs with st.async, which also counts its bytes on that CTA's `ln_bar`
+// (4 CTAs x 256 threads x 8 bytes expected); a CTA reads only its own shared memory, and only after every writer's bytes have
+// landed, so no CTA can exit while a peer still needs it.
+__device__ __forceinline__ void epilogue_ln_tile(const GemmParams& p, uint32_t tmem_base, int q, int lane, int half, int m0, int n0,
+                                                 float4* stage, float2* part, uint64_t* ln_bar, uint64_t* tmem_full_bar) {
+  const int rl = q * 32 + lane;
+  const int row = m0 + rl;
+  const bool row_ok = row < p.M;
+  const int col0 = n0 + half * 32;
+  // Everything that does not depend on the accumulator is fetched while the main loop runs (these warps are idle until then):
+  //   v = (alpha * acc + bias) * keep + res  =  acc * mul + add,   mul = alpha * keep,  add = bias * keep + res
+  float mul[32], add[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { mul[j] = 0.f; add[j] = 0.f; }
+  if (row_ok) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mul[j] = p.alpha;
+    if (p.ln_drop.thr) {              // element index = m * N + n, as the stand-alone LayerNorm kernel's `pre` site
+      const uint32_t e0 = uint32_t(row) * uint32_t(p.N) + uint32_t(col0);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mul[j] *= drop_factor(p.ln_drop, e0 + j);
+    }
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        add[j] = bb.x; add[j + 1] = bb.y; add[j + 2] = bb.z; add[j + 3] = bb.w;
+      }
+      if (p.ln_drop.thr) {
+        const float ia = 1.f / p.alpha;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) add[j] *= mul[j] * ia;         // bias * keep
+      }
+    }
+    if (p.ln_res) {
+      const float4* rs = reinterpret_cast<const float4*>(p.ln_res + int64_t(row) * p.ldc + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = rs[j];
+        add[4 * j] += t.x; add[4 * j + 1] += t.y; add[4 * j + 2] += t.z; add[4 * j + 3] += t.w;
+      }
+    }
+  }
+  if (p.dbg & 64) mbar_wait_sleep(tmem_full_bar, 0); else mbar_wait(tmem_full_bar, 0);
+  tc_fence_after();
+  uint32_t r[32];
+  tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(half * 32), r);
+  tmem_ld_wait();
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), mul[j], add[j]);
+  // partial statistics of my 32 columns, centred on their own mean
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) s += v[j];
+  const float mi = s * (1.f / 32.f);
+  float m2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float d = v[j] - mi;
+    m2 = fmaf(d, d, m2);
+  }
+  // st.async: the store itself completes 8 transaction bytes on the destination CTA's mbarrier (which expects all 4 x 256 x 8)
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t slot = smem_u32(part + (rank * 2 + half) * BM + rl);
+  const uint32_t bar = smem_u32(ln_bar);
+#pragma unroll
+  for (uint32_t t = 0; t < LN_CLUSTER; ++t) st_async_f32x2(mapa_shared(slot, t), mi, m2, mapa_shared(bar, t));
+  mbar_wait(ln_bar, 0);
+  // Chan et al.: 8 groups of 32 -> mean, M2 of the 256-wide row (fixed order: bit-reproducible)
+  float2 pr[2 * LN_CLUSTER];
+  float mean = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2 * LN_CLUSTER; ++i) {
+    pr[i] = part[i * BM + rl];
+    mean += pr[i].x;
+  }
+  mean *= 1.f / (2 * LN_CLUSTER);
+  float M2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2 * LN_CLUSTER; ++i) {
+    const float d = pr[i].x - mean;
+    M2 += pr[i].y + 32.f * d * d;
+  }
+  const float rstd = rsqrtf(M2 * (1.f / (64.f * LN_CLUSTER)) + p.ln_eps);
+  if (row_ok && p.ln_stats && rank == 0 && half == 0) {
+    p.ln_stats[2 * int64_t(row)] = mean;
+    p.ln_stats[2 * int64_t(row) + 1] = rstd;
+  }
+  if (p.ln_z) store_chunk_staged(stage, v, lane, m0 + q * 32, p.M, p.ldc, col0, p.ln_z, nullptr, nullptr);
+  bool valid = row_ok;
+  if (valid && p.ln_lens) {
+    const int b = row / p.ln_T;
+    valid = (row - b * p.ln_T) < p.ln_lens[b];
+  }
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + col0 + j));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.ln_beta + col0 + j));
+    v[j] = valid ? fmaf((v[j] - mean) * rstd, g.x, b.x) : 0.f;
+    v[j + 1] = valid ? fmaf((v[j + 1] - mean) * rstd, g.y, b.y) : 0.f;
+    v[j + 2] = valid ? fmaf((v[j + 2] - mean) * rstd, g.z, b.z) : 0.f;
+    v[j + 3] = valid ? fmaf((v[j + 3] - mean) * rstd, g.w, b.w) : 0.f;
+  }
+  store_chunk_staged(stage, v, lane, m0 + q * 32, p.M, p.ldc, col0, p.c_f32, p.c_hi, p.c_lo);
+}
+
 // ================================================================================================
 template <int BN, int SPLIT, int KD>
 __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_constant__ GemmParams p) {
@@ -271,6 +429,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tmem_full_bar = empty_bar + C::STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* ln_bar = tmem_full_bar + 2;
+  const bool ln = (BN == 64) && (p.flags & EPI_LN);       // launched as 4-CTA clusters along the row (blockIdx.x % 4 = n_tile)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -311,6 +471,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
+    if (ln) {                                    // completes when every epilogue thread of the cluster has stored its 8 bytes here
+      mbar_init(ln_bar, 1);
+      mbar_arrive_expect_tx(ln_bar, LN_CLUSTER * 256 * 8);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -319,6 +483,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (ln) cluster_sync_all();                    // every CTA's ln_bar is initialised before a peer can arrive on it
   const uint32_t tmem_base = *tmem_slot;
   const int nstages = (p.dbg & 15) ? min(p.dbg & 15, C::STAGES) : C::STAGES;
   pdl_wait();                                    // everything above overlapped the previous kernel's tail
@@ -460,15 +625,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mtts_gemm_kernel(const __grid_
     // TMEM lane quarter accessible to a warp is (warp_id % 4); warps 2,3,4,5 -> quarters 2,3,0,1.
     const int q = warp & 3;
     if (n_iters > 0) {
-      if (p.dbg & 64) mbar_wait_sleep(tmem_full_bar, 0); else mbar_wait(tmem_full_bar, 0);
-      tc_fence_after();
       // two warps share a TMEM lane quarter (warp % 4) and split the BN columns between them
       constexpr int CH = BN / 32;
       const int half = (warp - 2) >> 2;
       const int c_begin = CH >= 2 ? half * (CH / 2) : 0;
       const int c_end = CH >= 2 ? c_begin + CH / 2 : (half == 0 ? CH : 0);
-      epilogue_tile<BN>(p, tmem_base, q, lane, m0, n0, z0, z1, c_begin, c_end,
-                        reinterpret_cast<float4*>(smem) + (warp - 2) * 256);
+      if (BN == 64 && ln) {
+        epilogue_ln_tile(p, tmem_base, q, lane, half, m0, n0, reinterpret_cast<float4*>(smem) + (warp - 2) * 256,
+                         reinterpret_cast<float2*>(bar_base + 1024), ln_bar, tmem_full_bar);
+      } else {
+        if (p.dbg & 64) mbar_wait_sleep(tmem_full_bar, 0); else mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        epilogue_tile<BN>(p, tmem_base, q, lane, m0, n0, z0, z1, c_begin, c_end,
+                          reinterpret_cast<float4*>(smem) + (warp - 2) * 256);
+      }
     }
   }
 
@@ -784,15 +954,55 @@ int launch(const GemmParams& p, dim3 grid, cudaStream_t stream) {
                                          C::SMEM));
     configured = true;
   }
-  MTTS_CHECK_CUDA(mtts_launch(mtts_gemm_kernel<BN, SPLIT, KD>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, p));
+  if (p.flags & EPI_LN) {
+    // the four 64-wide tiles of a row form one cluster (consecutive blockIdx.x): launch-time cluster dimension + PDL
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = LN_CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = mtts_pdl_enabled() ? 2 : 1;
+    MTTS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mtts_gemm_kernel<BN, SPLIT, KD>, p));
+  } else {
+    MTTS_CHECK_CUDA(mtts_launch(mtts_gemm_kernel<BN, SPLIT, KD>, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, p));
+  }
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
 
+int gemm_impl(const mtts_gemm_desc* d, const mtts_ln_epilogue* ln, cudaStream_t stream);
+
 }  // namespace
 
 extern "C" int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  return gemm_impl(d, nullptr, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int mtts_gemm_ln(const mtts_gemm_desc* d, const mtts_ln_epilogue* ln, mtts_stream stream_) {
+  MTTS_REQUIRE(d != nullptr && ln != nullptr, "gemm_ln: null descriptor");
+  MTTS_REQUIRE(d->N == 64 * LN_CLUSTER && d->ldc == d->N, "gemm_ln: N must be %d with ldc == N (N %d, ldc %lld)", 64 * LN_CLUSTER, d->N,
+               static_cast<long long>(d->ldc));
+  MTTS_REQUIRE(d->nz0 == 1 && d->nz1 == 1 && d->ksplit <= 1 && d->pair == 0 && d->flags == 0,
+               "gemm_ln: needs nz0 == nz1 == 1, ksplit == 1, pair == 0, flags == 0");
+  MTTS_REQUIRE(ln->gamma && ln->beta && ln->T > 0, "gemm_ln: gamma / beta / T missing");
+  const uintptr_t al = reinterpret_cast<uintptr_t>(d->c_f32) | reinterpret_cast<uintptr_t>(d->c_hi) | reinterpret_cast<uintptr_t>(d->c_lo) |
+                       reinterpret_cast<uintptr_t>(d->bias) | reinterpret_cast<uintptr_t>(ln->res) | reinterpret_cast<uintptr_t>(ln->gamma) |
+                       reinterpret_cast<uintptr_t>(ln->beta) | reinterpret_cast<uintptr_t>(ln->z_out);
+  MTTS_REQUIRE((al & 15) == 0, "gemm_ln: outputs, bias, residual, gamma and beta must be 16-byte aligned");
+  return gemm_impl(d, ln, static_cast<cudaStream_t>(stream_));
+}
+
+namespace {
+
+int gemm_impl(const mtts_gemm_desc* d, const mtts_ln_epilogue* ln, cudaStream_t stream) {
   MTTS_REQUIRE(d != nullptr, "gemm: null descriptor");
   MTTS_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "gemm: bad M/N/K %d %d %d", d->M, d->N, d->K);
   MTTS_REQUIRE(d->ntaps >= 1 && d->nkb >= 1 && d->nz0 >= 1 && d->nz1 >= 1, "gemm: bad loop extents");
@@ -809,7 +1019,7 @@ extern "C" int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream_) {
   MTTS_REQUIRE(!(d->flags & MTTS_EPI_ADD_C) || (d->c_f32 && ksplit == 1 && !(d->flags & MTTS_EPI_ACCUM)),
                "gemm: ADD_C requires c_f32, ksplit == 1 and no ACCUM");
 
-  int bn = d->block_n;
+  int bn = ln ? 64 : d->block_n;
   if (bn == 0) {
     if (d->N <= 64) bn = 64;
     else if (d->N <= 128) bn = 128;
@@ -872,6 +1082,12 @@ extern "C" int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream_) {
   p.ldc = d->ldc; p.c_sz0 = d->c_sz0; p.c_sz1 = d->c_sz1;
   p.bias = d->bias; p.bias_sz0 = d->bias_sz0;
   p.gate = static_cast<const bf16*>(d->gate);
+  if (ln) {
+    p.flags |= EPI_LN;
+    p.ln_res = ln->res; p.ln_gamma = ln->gamma; p.ln_beta = ln->beta; p.ln_lens = ln->lens;
+    p.ln_z = ln->z_out; p.ln_stats = ln->stats; p.ln_T = ln->T; p.ln_eps = ln->eps;
+    p.ln_drop = DropSite{ln->drop_thr, ln->drop_seed, ln->drop_scale, ln->drop_salt};
+  }
 
   const int m_tiles = mtts_cdiv(d->M, BM);
   dim3 grid(m_tiles * p.n_tiles, p.ksplit, d->nz0 * d->nz1);
@@ -893,3 +1109,5 @@ extern "C" int mtts_gemm(const mtts_gemm_desc* d, mtts_stream stream_) {
     return launch<256, 3>(p, grid, stream);
   }
 }
+
+}  // namespace

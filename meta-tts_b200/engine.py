@@ -361,6 +361,10 @@ SMALL_SPLITK_MODEL = os.environ.get("MTTS_SMALL_SPLITK", "0") == "1"
 # Fused attention (csrc/mtts_attn.cu) for the forward / backward passes: scores -> softmax -> P V (and the recomputing backward)
 # as ONE kernel per pass, S / dP never written.  MTTS_FUSED_ATTN=0 restores the three-launch chain (A/B measurements).
 FUSED_ATTN = os.environ.get("MTTS_FUSED_ATTN", "1") == "1"
+# dropout -> + residual -> LayerNorm -> pad-row zeroing as the EPILOGUE of the out-projection / conv k=1 GEMM that feeds it (mtts_gemm_ln:
+# the 256-wide row is spread over a 4-CTA cluster that exchanges row statistics through distributed shared memory) instead of a
+# LayerNorm launch of its own.  MTTS_FUSED_LN=0 restores GEMM + mtts_ln_fwd (A/B measurements).
+FUSED_LN = os.environ.get("MTTS_FUSED_LN", "1") == "1"
 USE_PAIR = True        # 2-CTA (cta_group::2) tiles; set False to fall back to the 1-CTA kernel everywhere
 
 
@@ -471,9 +475,16 @@ class Gemm:
 
     # y[b,t,:] = sum_j x[b,t+j-p,:] W_j^T (+bias) [+ sum_j x2[b,t+j-p,:] W2_j^T] ; W: [k, N, Cin]
     def conv_fwd(self, x: Act, w: Wt, bias, out_f32, out_hi, out_lo, relu=False, gate=None, add_c=False,
-                 x2: Optional[Act] = None, w2: Optional[Wt] = None):
+                 x2: Optional[Act] = None, w2: Optional[Wt] = None, ln: Optional[dict] = None):
+        """ln (k = 1, N = 256 only): the outputs receive LayerNorm(dropout(y) + res) with pad rows zeroed — see ops.gemm."""
         k, N, Cin = w.shape if len(w.shape) == 3 else (1,) + tuple(w.shape)
         assert Cin == x.C and (x2 is None) == (w2 is None)
+        if ln is not None:
+            assert k == 1 and N == 256 and x2 is None and not (relu or add_c) and gate is None
+            a = Opnd(x.hi, x.lo, L.MAJOR_K, (Cin, x.B * x.T), (1, Cin))
+            wop = Opnd(w.hi, w.lo, L.MAJOR_K, (Cin, N, k), (1, Cin, N * Cin), src2=L.SRC_TAP)
+            self._gemm("fwd", a, wop, x.B * x.T, N, Cin, c_f32=out_f32, c_hi=out_hi, c_lo=out_lo, ldc=N, bias=bias, block_n=64, ln=ln)
+            return
         p = (k - 1) // 2
         flags = (L.EPI_RELU if relu else 0) | (L.EPI_GATE if gate is not None else 0) | (L.EPI_ADD_C if add_c else 0)
         h2 = (lambda t: (t.hi, t.lo)) if x2 is not None else (lambda t: (None, None))
@@ -688,20 +699,31 @@ class FS2Engine:
             p_h, p_l = tp.bf(f"{pf}.P", (B, H, T, Tp))
             be.softmax(0, S, None, None, None, None, None, lens, B * H, H, T, T, Tp, p_h, p_l)
             g.bmm(pm(p_h, p_l), False, qm(qkv_h, qkv_l, 2), True, om(o.hi, o.lo), B, H)
-        y0 = scr.scratch("y0", (B, T, d))
-        g.conv_fwd(o, P.get(f"{a_}.fc.weight"), P.get(f"{a_}.fc.bias").f32, y0, None, None)
         y1 = tp.act(f"{pf}.y1", B, T, d)
-        be.ln_fwd(y0, x.f32, P.get(f"{a_}.layer_norm.weight").f32, P.get(f"{a_}.layer_norm.bias").f32, lens, T, R, d,
-                  tp.f32(f"{pf}.z1", (B, T, d)), tp.f32(f"{pf}.st1", (R, 2)), y1.f32, y1.hi, y1.lo,
-                  pre=self._fft_drop(tp, pf)[0])
+        fused_ln = FUSED_LN and d == 256
+        if fused_ln:     # out-projection with dropout + residual + LayerNorm + pad-row zeroing as its epilogue (SubLayers.py:54-55)
+            g.conv_fwd(o, P.get(f"{a_}.fc.weight"), P.get(f"{a_}.fc.bias").f32, y1.f32, y1.hi, y1.lo,
+                       ln=dict(res=x.f32, gamma=P.get(f"{a_}.layer_norm.weight").f32, beta=P.get(f"{a_}.layer_norm.bias").f32, lens=lens, T=T,
+                               z=tp.f32(f"{pf}.z1", (B, T, d)), stats=tp.f32(f"{pf}.st1", (R, 2)), pre=self._fft_drop(tp, pf)[0]))
+        else:
+            y0 = scr.scratch("y0", (B, T, d))
+            g.conv_fwd(o, P.get(f"{a_}.fc.weight"), P.get(f"{a_}.fc.bias").f32, y0, None, None)
+            be.ln_fwd(y0, x.f32, P.get(f"{a_}.layer_norm.weight").f32, P.get(f"{a_}.layer_norm.bias").f32, lens, T, R, d,
+                      tp.f32(f"{pf}.z1", (B, T, d)), tp.f32(f"{pf}.st1", (R, 2)), y1.f32, y1.hi, y1.lo,
+                      pre=self._fft_drop(tp, pf)[0])
         h = tp.act(f"{pf}.h", B, T, self.d_inner, f32=False)
         g.conv_fwd(y1, P.get(f"{f_}.w_1.weight"), P.get(f"{f_}.w_1.bias").f32, None, h.hi, h.lo, relu=True)
-        y2 = scr.scratch("y0", (B, T, d))
-        g.conv_fwd(h, P.get(f"{f_}.w_2.weight"), P.get(f"{f_}.w_2.bias").f32, y2, None, None)
         out = tp.act(f"{pf}.out", B, T, d)
-        be.ln_fwd(y2, y1.f32, P.get(f"{f_}.layer_norm.weight").f32, P.get(f"{f_}.layer_norm.bias").f32, lens, T, R, d,
-                  tp.f32(f"{pf}.z2", (B, T, d)), tp.f32(f"{pf}.st2", (R, 2)), out.f32, out.hi, out.lo,
-                  pre=self._fft_drop(tp, pf)[1])
+        if fused_ln and P.get(f"{f_}.w_2.weight").shape[0] == 1:     # conv k=1 (w_2) with the same epilogue (SubLayers.py:88-91)
+            g.conv_fwd(h, P.get(f"{f_}.w_2.weight"), P.get(f"{f_}.w_2.bias").f32, out.f32, out.hi, out.lo,
+                       ln=dict(res=y1.f32, gamma=P.get(f"{f_}.layer_norm.weight").f32, beta=P.get(f"{f_}.layer_norm.bias").f32, lens=lens, T=T,
+                               z=tp.f32(f"{pf}.z2", (B, T, d)), stats=tp.f32(f"{pf}.st2", (R, 2)), pre=self._fft_drop(tp, pf)[1]))
+        else:
+            y2 = scr.scratch("y0", (B, T, d))
+            g.conv_fwd(h, P.get(f"{f_}.w_2.weight"), P.get(f"{f_}.w_2.bias").f32, y2, None, None)
+            be.ln_fwd(y2, y1.f32, P.get(f"{f_}.layer_norm.weight").f32, P.get(f"{f_}.layer_norm.bias").f32, lens, T, R, d,
+                      tp.f32(f"{pf}.z2", (B, T, d)), tp.f32(f"{pf}.st2", (R, 2)), out.f32, out.hi, out.lo,
+                      pre=self._fft_drop(tp, pf)[1])
         return out
 
     def fft_bwd(self, P: ParamSet, G: ParamSet, pf: str, tp: Tape, x: Act, lens, H: int, dout: torch.Tensor,

@@ -50,6 +50,17 @@ class GemmDesc(C.Structure):
     ]
 
 
+class LnEpilogue(C.Structure):
+    """mtts_ln_epilogue (include/mtts.h): dropout -> + residual -> LayerNorm -> pad-row zeroing as the epilogue of mtts_gemm_ln."""
+    _fields_ = [
+        ("res", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("lens", C.c_void_p),
+        ("T", C.c_int32), ("eps", C.c_float),
+        ("z_out", C.c_void_p), ("stats", C.c_void_p),
+        ("drop_thr", C.c_uint32), ("drop_seed", C.c_uint32), ("drop_scale", C.c_float), ("reserved", C.c_int32),
+        ("drop_salt", C.c_void_p),
+    ]
+
+
 ATTN_PREP, ATTN_DQ, ATTN_DK, ATTN_DV = 1, 2, 4, 8
 ATTN_DKV = ATTN_DK | ATTN_DV
 
@@ -107,6 +118,7 @@ SIGNATURES: dict[str, list] = {
     "mtts_set_deterministic": [_i],
     "mtts_zero": [_vp, _i64, _vp],
     "mtts_gemm": [C.POINTER(GemmDesc), _vp],
+    "mtts_gemm_ln": [C.POINTER(GemmDesc), C.POINTER(LnEpilogue), _vp],
     "mtts_attn_fwd": [C.POINTER(AttnDesc), _vp],
     "mtts_attn_bwd": [C.POINTER(AttnDesc), _i, _vp],
     "mtts_pack_rows": [_vp, _vp, _i, _i, _i, _vp, _vp],

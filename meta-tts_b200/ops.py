@@ -80,7 +80,9 @@ def gemm(a: Opnd, b: Opnd, M: int, N: int, K: int, *,
          alpha: float = 1.0, bias: Optional[torch.Tensor] = None, bias_sz0: int = 0,
          gate: Optional[torch.Tensor] = None, flags: int = 0,
          ntaps: int = 1, nkb: int = 1, nz0: int = 1, nz1: int = 1,
-         split: int = 1, block_n: int = 0, ksplit: int = 1, pair: bool = False) -> None:
+         split: int = 1, block_n: int = 0, ksplit: int = 1, pair: bool = False, ln: Optional[dict] = None) -> None:
+    """ln = dict(res, gamma, beta, lens, T, z, stats, pre, salt[, eps]): the GEMM's epilogue is dropout -> + residual -> LayerNorm ->
+    pad-row zeroing (mtts_gemm_ln, include/mtts.h; N == 256): c_f32 / c_hi / c_lo receive the LayerNorm output."""
     global launch_count
     _need_cuda(a.hi, b.hi, c_f32, c_hi, c_lo, bias, gate)
     d = L.GemmDesc()
@@ -104,7 +106,18 @@ def gemm(a: Opnd, b: Opnd, M: int, N: int, K: int, *,
         d.a2_lo = (a.lo2.data_ptr() + 2 * a.offset) if a.lo2 is not None else None
         d.b2_hi = b.hi2.data_ptr() + 2 * b.offset
         d.b2_lo = (b.lo2.data_ptr() + 2 * b.offset) if b.lo2 is not None else None
-    L.call("mtts_gemm", C.byref(d), _stream())
+    if ln is not None:
+        _need_cuda(ln.get("res"), ln["gamma"], ln["beta"], ln.get("lens"), ln.get("z"), ln.get("stats"))
+        e = L.LnEpilogue()
+        e.res, e.gamma, e.beta, e.lens = _ptr(ln.get("res")), _ptr(ln["gamma"]), _ptr(ln["beta"]), _ptr(ln.get("lens"))
+        e.T, e.eps = int(ln["T"]), float(ln.get("eps", 1e-5))
+        e.z_out, e.stats = _ptr(ln.get("z")), _ptr(ln.get("stats"))
+        e.drop_thr, e.drop_seed, e.drop_scale = ln.get("pre", NO_DROP)
+        e.drop_salt = _ptr(ln.get("salt"))
+        d.block_n = 64
+        L.call("mtts_gemm_ln", C.byref(d), C.byref(e), _stream())
+    else:
+        L.call("mtts_gemm", C.byref(d), _stream())
     launch_count += 1
 
 
@@ -303,6 +316,8 @@ class CudaOps:
     # ---- GEMM ----
     def gemm(self, a: Opnd, b: Opnd, M, N, K, **kw):
         kw.setdefault("split", self.split)
+        if kw.get("ln") is not None:
+            kw["ln"] = dict(kw["ln"], salt=self.drop_salt)
         gemm(a, b, M, N, K, **kw)
 
     # ---- collate on the device: ragged -> padded ----

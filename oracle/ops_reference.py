@@ -124,8 +124,16 @@ class RefOps:
         return torch.where(valid, v, torch.zeros((), dtype=self.acc))
 
     def gemm(self, a, b, M, N, K, *, c_f32=None, c_hi=None, c_lo=None, ldc, c_off=0, c_sz0=0, c_sz1=0, alpha=1.0,
-             bias=None, bias_sz0=0, gate=None, flags=0, ntaps=1, nkb=1, nz0=1, nz1=1, split=None, block_n=0, ksplit=1, pair=False):
+             bias=None, bias_sz0=0, gate=None, flags=0, ntaps=1, nkb=1, nz0=1, nz1=1, split=None, block_n=0, ksplit=1, pair=False, ln=None):
         self.n_calls += 1
+        if ln is not None:      # mtts_gemm_ln: the same product, then dropout -> + residual -> LayerNorm -> pad rows as the epilogue
+            assert N == 256 and ldc == N and nz0 == nz1 == 1 and ksplit == 1 and not pair and flags == 0 and c_off == 0
+            y = torch.zeros(M, N)
+            self.gemm(a, b, M, N, K, c_f32=y, ldc=N, alpha=alpha, bias=bias, ntaps=ntaps, nkb=nkb, split=split)
+            self.n_calls -= 2
+            self.ln_fwd(y, ln.get("res"), ln["gamma"], ln["beta"], ln.get("lens"), ln["T"], M, N, ln.get("z"), ln.get("stats"),
+                        c_f32, c_hi, c_lo, eps=ln.get("eps", 1e-5), pre=ln.get("pre", NO_DROP))
+            return
         split = split or self.split
         assert c_f32 is not None or c_hi is not None
         if flags & EPI_ADD_C:

@@ -32,7 +32,7 @@ def _err(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
 
 
-def _run(dev, B, H, T, lens, split, emit, seed=0):
+def _run(dev, B, H, T, lens, split, emit, seed=0, tol=None):
     qkv, do, klens = _inputs(B, H, T, seed, lens)
     Tp, Tl = (T + 7) // 8 * 8, (T + 127) // 128 * 128
     qh, ql = split_bf16(qkv)
@@ -55,7 +55,7 @@ def _run(dev, B, H, T, lens, split, emit, seed=0):
         out[name] = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in a.items()}
     r, c = out["ref"], out["cuda"]
     val = (lambda d, k: d[k + "_h"].double() + d[k + "_l"].double()) if split == 3 else (lambda d, k: d[k + "_h"].double())
-    tol = 2e-5 if split == 3 else 2e-2
+    tol = tol or (2e-5 if split == 3 else 2e-2)
     errs = {"o": _err(val(c, "o"), val(r, "o")), "lse": _err(c["lse"][..., :T], r["lse"][..., :T]),
             "dvec": _err(c["dvec"][..., :T], r["dvec"][..., :T])}
     dq_c, dq_r = val(c, "dq").reshape(B * T, 3, H * DK), val(r, "dq").reshape(B * T, 3, H * DK)
@@ -74,13 +74,17 @@ def _run(dev, B, H, T, lens, split, emit, seed=0):
 
 @pytest.mark.parametrize("B,H,T,lens", [
     (2, 2, 24, [24, 17]),             # one partial tile
+    (2, 2, 40, [1, 40]),              # a sequence with ONE valid key (softmax over a single element)
+    (1, 2, 8, [5]),                   # shortest aligned sequence
     (1, 2, 128, None),                # exactly one resident tile, no mask (encoder-sized)
     (2, 2, 200, [200, 131]),          # T % 32 != 0, ragged
     (4, 2, 864, [864, 700, 515, 300]),  # configs[1] decoder shape
     (1, 2, 1000, [1000]),             # max_seq_len
 ])
 def test_attn_fused_matches_reference(cuda_device, B, H, T, lens):
-    _run(cuda_device, B, H, T, lens, split=3, emit=False)
+    # one valid key: P = 1 and dS = P (dP - D) is the difference of two equal numbers, each rounded on its own (the reference gets an
+    # exact 0): the cancellation noise, ~1e-6 of |dP|, times |q| shows up in dK at 3e-5 of the tensor's maximum
+    _run(cuda_device, B, H, T, lens, split=3, emit=False, tol=5e-5 if (lens and min(lens) == 1) else None)
 
 
 @pytest.mark.parametrize("T,lens", [(72, [72, 40]), (864, [864, 333])])

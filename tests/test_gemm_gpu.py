@@ -332,3 +332,57 @@ def test_pair_attention_products(cuda_device, split):
              Lq, dk, Lq, c_f32=dV, ldc=H * dk, c_sz0=dk, c_sz1=Lq * H * dk, nz0=H, nz1=B, split=split, block_n=128, pair=True)
     dVref = torch.einsum("bhlm,blhd->bmhd", pr[..., :Lq], dr.view(B, Lq, H, dk)).reshape(B * Lq, H * dk)
     _check("pair attn dV (A,B MN-major)", dV, dVref, split)
+
+
+@pytest.mark.parametrize("split", [1, 3])
+@pytest.mark.parametrize("M,K,T,lens,drop,with_res", [
+    (3456, 256, 864, [864, 700, 515, 300], True, True),     # out-projection of the configs[1] decoder (27 clusters of 4 CTAs)
+    (512, 1024, 128, [128, 90, 128, 7], False, True),       # conv k=1 (w_2) of the encoder
+    (200, 320, 50, None, True, False),                      # partial row tile, K tail, no mask, no residual
+])
+def test_gemm_ln_epilogue(cuda_device, split, M, K, T, lens, drop, with_res):
+    """mtts_gemm_ln: GEMM + bias -> dropout -> + residual -> LayerNorm -> pad-row zeroing in one launch (row statistics exchanged
+    between the 4 CTAs of a cluster) against RefOps' GEMM emulator followed by its LayerNorm (float64)."""
+    from oracle.ops_reference import RefOps
+
+    N = 256
+    g = torch.Generator().manual_seed(7)
+    X = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / math.sqrt(K)
+    bias = torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g) + 0.5 if with_res else None        # non-zero row means
+    gamma, beta = 1 + 0.1 * torch.randn(N, generator=g), 0.1 * torch.randn(N, generator=g)
+    klens = torch.tensor(lens, dtype=torch.int64) if lens is not None else None
+    xh, xl = ops.split_bf16(X)
+    wh, wl = ops.split_bf16(W)
+    pre = (int(0.2 * (1 << 24)), 0xC0FFEE11, 1.0 / 0.8) if drop else (0, 0, 1.0)
+    salt = torch.tensor([0x1234567], dtype=torch.int32)
+    outs = {}
+    for name, be, to in (("ref", RefOps(split=split), lambda t: t.clone()), ("cuda", ops.CudaOps(split=split), lambda t: t.to(cuda_device))):
+        be.drop_salt = to(salt)
+        o = dict(z=to(torch.zeros(M, N)), st=to(torch.zeros(M, 2)), out=to(torch.zeros(M, N)),
+                 oh=to(torch.zeros(M, N, dtype=torch.bfloat16)), ol=to(torch.zeros(M, N, dtype=torch.bfloat16)))
+        lo = (lambda t: to(t)) if split == 3 else (lambda t: None)
+        be.gemm(ops.Opnd(to(xh), lo(xl), L.MAJOR_K, (K, M), (1, K)), ops.Opnd(to(wh), lo(wl), L.MAJOR_K, (K, N), (1, K)), M, N, K,
+                c_f32=o["out"], c_hi=o["oh"], c_lo=o["ol"], ldc=N, bias=to(bias), block_n=64,
+                ln=dict(res=None if res is None else to(res), gamma=to(gamma), beta=to(beta), lens=None if klens is None else to(klens),
+                        T=T, z=o["z"], stats=o["st"], pre=pre))
+        if name == "cuda":
+            torch.cuda.synchronize()
+        outs[name] = {k: v.cpu() for k, v in o.items()}
+    r, c = outs["ref"], outs["cuda"]
+    errs = {}
+    for k in ("z", "st", "out"):
+        assert torch.isfinite(c[k]).all(), k
+        errs[k] = ((c[k].double() - r[k].double()).abs().max() / r[k].double().abs().max()).item()
+    errs["hi+lo"] = ((c["oh"].double() + c["ol"].double() - r["out"].double()).abs().max() / r["out"].double().abs().max()).item()
+    print(f"[gemm_ln] M{M} K{K} split{split} drop{drop}: " + " ".join(f"{k} {v:.1e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        assert v < 1e-4, f"{k}: {v:.3e}"
+    if klens is not None:                      # pad rows are exactly zero
+        rows = torch.arange(M)
+        pad = (rows % T) >= klens[rows // T]
+        assert pad.any() and (c["out"][pad] == 0).all() and (c["oh"][pad] == 0).all()
+    if drop:                                    # the epilogue's hash drops exactly the elements the host hash drops
+        zz = (c["z"] - (res if res is not None else 0)).abs()
+        assert abs((zz < 1e-12).float().mean().item() - 0.2) < 0.02

@@ -37,7 +37,11 @@ def test_training_step_graph_replay_matches_oracle(cuda_device, second_order, dr
         losses, preds, grads = O.maml_task_step(Pc, cfg, sup, qry, 2, 0.001, first_order=not second_order,
                                                 drop_seed=(0, sysm.last_salt) if dropout else None)
         got_l = torch.stack([out["losses"][i] for i in range(6)])
-        assert _rel(got_l, torch.stack(losses)) < 1e-4, f"step {step}"
+        # 1e-4 without dropout.  With dropout a rectifier unit of the SUPPORT passes can sit within 1e-6 of zero: it gates differently in
+        # two fp32 implementations, the inner gradient moves one weight row and the query's duration loss jumps by 6.6e-4 (1.02e-4 of
+        # the 6-vector) — task 11 with step 1's salt does exactly that on the CPU alone when the oracle's weights are perturbed by 1e-6
+        # (tools/kink_probe.py, profiles/r02_kink_probe.txt), and here when LayerNorm became the out-projection's epilogue.
+        assert _rel(got_l, torch.stack(losses)) < (3e-4 if dropout else 1e-4), f"step {step}"
         assert _rel(out["output"][0], preds[0]) < 1e-3 and _rel(out["output"][1], preds[1]) < 1e-3
         assert torch.equal(out["output"][9].cpu(), preds[9])
         got = sysm.maml.task_grads()
