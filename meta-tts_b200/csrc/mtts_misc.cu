@@ -426,6 +426,17 @@ inline void bn_launch_dims(long long R, int C, dim3& grid, dim3& block, int& row
   grid = dim3(col_blocks, row_chunks);
 }
 
+// The apply passes have no cross-CTA reduction (the per-channel sums arrive in `ws`): they take a finer row split than the
+// reduce passes — ~16 CTAs of 128 threads per SM instead of 4 — so that enough loads are in flight to reach the HBM rate
+// (bn_tfwd_apply 18 -> 9 us on 3456 x 512).
+inline void bn_apply_dims(long long R, int C, dim3& grid, int& rows_per_cta) {
+  const int col_blocks = mtts_cdiv(C, 128);
+  long long row_chunks = mtts_cdiv64(148LL * 16, col_blocks);
+  if (row_chunks > R) row_chunks = R;
+  rows_per_cta = static_cast<int>(mtts_cdiv64(R, row_chunks));
+  grid = dim3(col_blocks, static_cast<unsigned>(mtts_cdiv64(R, rows_per_cta)));
+}
+
 // ================================================================================================
 // FastSpeech2Loss (loss.py:19-92), phoneme-level pitch / energy
 // ================================================================================================
@@ -715,8 +726,11 @@ extern "C" int mtts_bn_fwd(const float* x, const float* gamma, const float* beta
   a.drop = DropSite{drop_thr, drop_seed, drop_scale, drop_salt};
   MTTS_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s));
   MTTS_CHECK_CUDA(mtts_launch(bn_stats_kernel, dim3(grid), dim3(block), 0, s, x, R, C, rpc, ws));
-  MTTS_CHECK_CUDA(mtts_launch(bn_fwd_apply_kernel, dim3(grid), dim3(block), 0, s, x, ws, gamma, beta, R, C, eps, momentum, tanh_flag, running_mean, running_var, stats,
-                                             out, static_cast<bf16*>(hi), static_cast<bf16*>(lo), rpc, a.drop));
+  dim3 agrid;
+  int arpc;
+  bn_apply_dims(R, C, agrid, arpc);
+  MTTS_CHECK_CUDA(mtts_launch(bn_fwd_apply_kernel, dim3(agrid), dim3(block), 0, s, x, ws, gamma, beta, R, C, eps, momentum, tanh_flag, running_mean, running_var, stats,
+                                             out, static_cast<bf16*>(hi), static_cast<bf16*>(lo), arpc, a.drop));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -733,7 +747,9 @@ extern "C" int mtts_bn_bwd(const float* dout, const float* o, const float* x, co
   a.drop = DropSite{drop_thr, drop_seed, drop_scale, drop_salt};
   MTTS_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s));
   MTTS_CHECK_CUDA(mtts_launch(bn_reduce_kernel<2>, dim3(grid), dim3(block), 0, s, a, ws));
-  MTTS_CHECK_CUDA(mtts_launch(bn_bwd_apply_kernel, dim3(grid), dim3(block), 0, s, a, ws, gamma, dx, static_cast<bf16*>(hi), static_cast<bf16*>(lo), dgamma, dbeta));
+  dim3 agrid;
+  bn_apply_dims(R, C, agrid, a.rows_per_cta);
+  MTTS_CHECK_CUDA(mtts_launch(bn_bwd_apply_kernel, dim3(agrid), dim3(block), 0, s, a, ws, gamma, dx, static_cast<bf16*>(hi), static_cast<bf16*>(lo), dgamma, dbeta));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -750,7 +766,9 @@ extern "C" int mtts_bn_tfwd(const float* xdot, const float* x, const float* stat
   a.drop = DropSite{drop_thr, drop_seed, drop_scale, drop_salt};
   MTTS_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 2 * C, s));
   MTTS_CHECK_CUDA(mtts_launch(bn_reduce_kernel<3>, dim3(grid), dim3(block), 0, s, a, ws));
-  MTTS_CHECK_CUDA(mtts_launch(bn_tfwd_apply_kernel, dim3(grid), dim3(block), 0, s, a, ws, gamma, gdot, bdot, tsums, odot, static_cast<bf16*>(hi), static_cast<bf16*>(lo)));
+  dim3 agrid;
+  bn_apply_dims(R, C, agrid, a.rows_per_cta);
+  MTTS_CHECK_CUDA(mtts_launch(bn_tfwd_apply_kernel, dim3(agrid), dim3(block), 0, s, a, ws, gamma, gdot, bdot, tsums, odot, static_cast<bf16*>(hi), static_cast<bf16*>(lo)));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
@@ -769,7 +787,9 @@ extern "C" int mtts_bn_tbwd(const float* dout, const float* ddout, const float* 
   a.drop = DropSite{drop_thr, drop_seed, drop_scale, drop_salt};
   MTTS_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * 4 * C, s));
   MTTS_CHECK_CUDA(mtts_launch(bn_reduce_kernel<4>, dim3(grid), dim3(block), 0, s, a, ws));
-  MTTS_CHECK_CUDA(mtts_launch(bn_tbwd_apply_kernel, dim3(grid), dim3(block), 0, s, a, ws, gamma, gdot, ddx, static_cast<bf16*>(hi), static_cast<bf16*>(lo), ddgamma, ddbeta));
+  dim3 agrid;
+  bn_apply_dims(R, C, agrid, a.rows_per_cta);
+  MTTS_CHECK_CUDA(mtts_launch(bn_tbwd_apply_kernel, dim3(agrid), dim3(block), 0, s, a, ws, gamma, gdot, ddx, static_cast<bf16*>(hi), static_cast<bf16*>(lo), ddgamma, ddbeta));
   MTTS_CHECK_LAUNCH();
   return MTTS_OK;
 }
