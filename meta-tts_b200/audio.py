@@ -22,6 +22,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional
 
+import math
+
 import numpy as np
 import torch
 from scipy.signal import get_window
@@ -313,9 +315,10 @@ def griffin_lim_fm(mag: torch.Tensor, stft_fn: STFT, n_iters: int, init_angles: 
     [B, hop*(F-1)].  Per iteration: reflect-pad+split, Fourier GEMM, angle+recombine, inverse GEMM, normalise = 5 kernels
     (+ a memset when the inverse GEMM is split along its contraction).  The iteration is a fixed launch sequence on fixed
     shapes, so it CAN be captured in a CUDA graph (`use_graph=True`: signal buffer updated in place, one capture + n-1
-    replays).  Measured on a B200 at 931 frames x 60 iterations (tools/config5_bench.py): eager 7.5 ms (125 us per
-    iteration: the host keeps up), capture + replays 23.9 ms (the capture itself costs more than it saves for a single
-    utterance) — so eager is the default and the graph is worth it only when the caller reuses it for many utterances."""
+    replays).  Measured on a B200 at 931 frames x 60 iterations (tools/config5_bench.py): eager 7.2 ms (120 us per
+    iteration: the host keeps up), so eager is the default; a capture per call does not pay for a single utterance.
+    (Round 1 recorded 23.9 ms for `inv_mel_spec` and blamed the capture: it was the reference-style HOST draw of the
+    initial angles — since moved to the device, `inv_mel_spec` now takes 7.4 ms.)"""
     B, F_, _ = mag.shape
     X_hi, X_lo = stft_fn.recombine_fm(mag, init_angles, None)
     signal = stft_fn.inverse_fm(X_hi, X_lo, B, F_)
@@ -368,8 +371,15 @@ def inv_mel_spec(mel, out_filename, _stft: TacotronSTFT, griffin_iters=60, init_
     mel_fm[0, :, :mel.shape[0]] = mel.to(st.device).t()
     spec = _stft.spec_from_mel_fm(mel_fm)[:, :T - 1].contiguous()                  # spec_from_mel[:, :, :-1]
     if init_angles is None:
-        init_angles = np.angle(np.exp(2j * np.pi * np.random.rand(1, st.cutoff, T - 1))).astype(np.float32)
-    audio = griffin_lim_fm(spec, st, griffin_iters, st._to_fm(torch.as_tensor(init_angles)))
+        # the reference draws np.angle(np.exp(2j*pi*U)), U ~ uniform[0,1) unseeded, on the host (audio_processing.py:70-72): the same
+        # distribution — 2*pi*U wrapped into (-pi, pi] — drawn on the device (the host draw + H2D was 17 of inv_mel_spec's 25 ms)
+        ang = 2.0 * math.pi * torch.rand((1, T - 1, st.cutoff), dtype=torch.float32, device=st.device)
+        ang = torch.where(ang > math.pi, ang - 2.0 * math.pi, ang)
+        angles_fm = torch.zeros((1, T - 1, st.im_off), dtype=torch.float32, device=st.device)
+        angles_fm[:, :, :st.cutoff] = ang
+    else:
+        angles_fm = st._to_fm(torch.as_tensor(init_angles))
+    audio = griffin_lim_fm(spec, st, griffin_iters, angles_fm)
     audio = audio.squeeze().cpu().numpy()
     if out_filename is not None:
         from scipy.io.wavfile import write

@@ -53,7 +53,7 @@ def main():
     T = int(out["T"])
     stft = PA.TacotronSTFT(1024, 256, 1024, 80, 22050, 0, 8000, device="cuda:0")
     mel = out["postnet"][0].t().contiguous()
-    PA.inv_mel_spec(mel, None, stft, 60)                                    # warm-up (graph capture inside)
+    PA.inv_mel_spec(mel, None, stft, 60)                                    # warm-up
     t_gl, wav = timed(lambda: PA.inv_mel_spec(mel, None, stft, 60))
     t_gl_eager, _ = timed(lambda: PA.griffin_lim_fm(stft.spec_from_mel_fm(torch.nn.functional.pad(mel.t()[None], (0, 0)).contiguous())[:, :T - 1].contiguous(),
                                                     stft.stft_fn, 60, stft.stft_fn._to_fm(torch.zeros(1, 513, T - 1)), use_graph=False))
