@@ -57,3 +57,30 @@ def test_no_cpu_fallback():
     from meta_tts_b200.systems import MetaSystem
     with pytest.raises(L.MttsError):
         MetaSystem(None, None, None, None, device="cuda:0")
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """sizeof / offsetof of every descriptor struct as gcc lays out include/mtts.h == the ctypes mirror in lib.py (an ABI drift would
+    otherwise only show up as wrong numbers on the GPU)."""
+    import subprocess
+
+    structs = {"mtts_operand": L.Operand, "mtts_gemm_desc": L.GemmDesc, "mtts_ln_epilogue": L.LnEpilogue, "mtts_attn_desc": L.AttnDesc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "mtts.h"', "int main(void) {"]
+    for cname, ct in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for line in out.splitlines():
+        cname, field, val = line.split()
+        ct = structs[cname]
+        want = ctypes.sizeof(ct) if field == "size" else getattr(ct, field).offset
+        assert int(val) == want, f"{cname}.{field}: header {val}, ctypes {want}"
+        seen += 1
+    assert seen == sum(len(ct._fields_) + 1 for ct in structs.values())
