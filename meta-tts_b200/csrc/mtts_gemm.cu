@@ -13,6 +13,8 @@
 //   warp 1      MMA issuer    (one elected lane)        tcgen05.mma  smem x smem -> TMEM (fp32)
 //   warps 2..9  epilogue      (2 warps per 32-lane TMEM quarter, each half of the columns)  tcgen05.ld -> regs -> global
 // Pipelines: full[s]/empty[s] mbarriers for the smem ring, one tmem_full mbarrier MMA -> epilogue.
+// mtts_gemm_ln: the 64-wide variant launched as 4-CTA clusters along the row with dropout -> + residual -> LayerNorm -> pad-row
+// zeroing as its epilogue (epilogue_ln_tile: row statistics exchanged through distributed shared memory).
 //
 // bf16x3 mode (SPLIT == 3): operands arrive as hi/lo bf16 pairs; each k-step issues
 // hi*hi + hi*lo + lo*hi into the same TMEM accumulator (error ~2^-17, i.e. fp32-grade), which is
